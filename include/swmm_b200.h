@@ -1,0 +1,242 @@
+/*
+ * swmm_b200.h -- C-ABI of libswmm_b200.so, the B200 (sm_100a) dynamic-wave flow routing and
+ * water-quality transport library.
+ *
+ * This is the "core" half of the drop-in boundary.  The other half, include/swmm_b200_seam.h,
+ * is the reference's own seam (dynwave_* / qualrout_*, funcs.h:229-237); the seam shim flattens
+ * the reference engine's global Node[]/Link[] objects into the swb_network_desc below and drives
+ * this API once per routing step.  Ensembles (many scenarios of one network, BASELINE.json
+ * configs[3]) have no counterpart in the reference's one-project-per-process API
+ * (swmm5.h:129-151) and are driven through this header directly.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array is caller-owned host memory unless stated;
+ *   - all hydraulic quantities are in the reference's internal units (ft, cfs, s; consts.h:31-50),
+ *     curve tables stay in user units exactly as the reference keeps them (link.c:1579-1620);
+ *   - every function returns 0 on success or one of SWB_ERR_*; swb_last_error() gives the text;
+ *   - host-side layout of a per-member field is [member][item] (one member is one contiguous
+ *     array, like the reference's Node[]/Link[]); the device layout is [item][member].
+ *   - integer codes (node/link/xsect/flow-class types) are the reference's enums.h values.
+ */
+#ifndef SWMM_B200_H
+#define SWMM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWB_VERSION 100
+
+/* error codes */
+#define SWB_OK            0
+#define SWB_ERR_ARG       1   /* bad argument / inconsistent descriptor                    */
+#define SWB_ERR_CUDA      2   /* CUDA runtime failure (no device, launch failure, ...)     */
+#define SWB_ERR_UNSUPP    3   /* network uses an element the device path does not cover    */
+#define SWB_ERR_NAN       4   /* device state became non-finite (maps to ERR_SYSTEM, 500)  */
+
+/* enums.h values used in the descriptor (restated so callers need no reference header) */
+enum { SWB_JUNCTION = 0, SWB_OUTFALL = 1, SWB_STORAGE = 2, SWB_DIVIDER = 3 };          /* enums.h:70  */
+enum { SWB_CONDUIT = 0, SWB_PUMP = 1, SWB_ORIFICE = 2, SWB_WEIR = 3, SWB_OUTLET = 4 }; /* enums.h:80  */
+enum { SWB_EXTRAN = 0, SWB_SLOT = 1 };                                                  /* enums.h:369 */
+enum { SWB_NO_DAMPING = 0, SWB_PARTIAL_DAMPING = 1, SWB_FULL_DAMPING = 2 };             /* enums.h:364 */
+enum { SWB_NF_SLOPE = 0, SWB_NF_FROUDE = 1, SWB_NF_BOTH = 2, SWB_NF_NEITHER = 3 };      /* enums.h:358 */
+enum { SWB_FREE_OUTFALL = 0, SWB_NORMAL_OUTFALL = 1, SWB_STAGE_OUTFALL = 2 };
+       /* FIXED/TIDAL/TIMESERIES outfalls (enums.h:389) all reduce to "stage given per step"   */
+enum { SWB_DRY = 0, SWB_UP_DRY, SWB_DN_DRY, SWB_SUBCRITICAL, SWB_SUPCRITICAL,
+       SWB_UP_CRITICAL, SWB_DN_CRITICAL, SWB_MAX_FLOW_CLASSES, SWB_UP_FULL, SWB_DN_FULL,
+       SWB_ALL_FULL };                                                                   /* enums.h:245 */
+
+/* Options block: [OPTIONS] values the path reads (dynwave.c:177-191, project.c:840-900) */
+typedef struct swb_options {
+    int    surcharge_method;   /* SurchargeMethod                                           */
+    int    inert_damping;      /* InertDamping                                              */
+    int    normal_flow_ltd;    /* NormalFlowLtd                                             */
+    int    allow_ponding;      /* AllowPonding                                              */
+    int    max_trials;         /* MaxTrials (after dynwave_validate: 0 -> 8)                */
+    int    force_main_eqn;     /* ForceMainEqn                                              */
+    int    unit_system;        /* UnitSystem (0 US, 1 SI) -- regulators evaluate in user units */
+    int    ignore_quality;     /* IgnoreQuality                                             */
+    double head_tol;           /* HeadTol, ft (after validate)                              */
+    double min_surf_area;      /* MinSurfArea, ft2 (after validate)                         */
+    double courant_factor;     /* CourantFactor (0 = fixed step)                            */
+    double min_route_step;     /* MinRouteStep, s                                           */
+    double route_step;         /* RouteStep, s (the user's fixed / maximum step)            */
+    double ucf_length;         /* UCF(LENGTH), UCF(VOLUME), UCF(FLOW) (swmm5.c:1378-1388)   */
+    double ucf_volume;
+    double ucf_flow;
+    double evap_rate;          /* Evap.rate, ft/s (per-step scalar, see swb_set_climate)    */
+    double hydcon_factor;      /* Adjust.hydconFactor                                       */
+} swb_options;
+
+/* Flattened network (static data).  Per-link arrays are indexed by LINK index for every link
+ * type; entries that do not apply to a link's type are ignored. */
+typedef struct swb_network_desc {
+    int n_nodes, n_links, n_pollut, n_curves, n_curve_pts, n_shape_tbls, shape_tbl_len;
+    int reserved0;
+
+    /* nodes (objects.h:490-530) */
+    const int    *node_type;        /* Node.type                                           */
+    const int    *node_degree;      /* Node.degree (sign set by flowrout.c:330)            */
+    const double *node_invert;      /* invertElev                                          */
+    const double *node_full_depth;  /* fullDepth                                           */
+    const double *node_sur_depth;   /* surDepth                                            */
+    const double *node_ponded_area; /* pondedArea                                          */
+    const double *node_full_volume; /* fullVolume                                          */
+    const double *node_crown_elev;  /* crownElev as set by dynwave_init (dynwave.c:137-153)*/
+    /* outfall / storage attributes, indexed by NODE (ignored for other node types) */
+    const int    *outfall_type;     /* SWB_*_OUTFALL                                       */
+    const int    *outfall_flap;     /* Outfall.hasFlapGate                                 */
+    const int    *storage_shape;    /* Storage.shape (enums.h:396)                         */
+    const int    *storage_curve;    /* Storage.aCurve (curve index or -1)                  */
+    const double *storage_a0, *storage_a1, *storage_a2;
+
+    /* links (objects.h:664-709) */
+    const int    *link_type, *link_node1, *link_node2, *link_direction, *link_has_flap;
+    const double *link_offset1, *link_offset2, *link_q_limit, *link_q_full;
+    const double *link_closs_in, *link_closs_out, *link_closs_avg, *link_seep_rate;
+    /* cross sections (objects.h:581-599) */
+    const int    *xs_type, *xs_culvert, *xs_table;  /* xs_table: index into shape tables or -1 */
+    const double *xs_yfull, *xs_wmax, *xs_ywmax, *xs_afull, *xs_rfull, *xs_sfull, *xs_smax;
+    const double *xs_ybot, *xs_abot, *xs_sbot, *xs_rbot;
+    /* conduits (objects.h:714-733) */
+    const int    *cond_barrels, *cond_has_losses;
+    const double *cond_length;      /* TRUE length, link_getLength (link.c:808,1195)       */
+    const double *cond_mod_length, *cond_rough_factor, *cond_slope, *cond_beta, *cond_q_max;
+    /* regulators, indexed by LINK */
+    const int    *pump_type, *pump_curve;           /* Pump.type (enums.h:418), pumpCurve  */
+    const double *pump_xmin, *pump_xmax;
+    const int    *orif_type;                        /* Orifice.type                        */
+    const double *orif_cdisch, *orif_length;
+    const int    *weir_type, *weir_can_surcharge, *weir_cd_curve;
+    const double *weir_cdisch1, *weir_cdisch2, *weir_end_con, *weir_slope, *weir_length;
+    const int    *outlet_curve, *outlet_curve_type; /* Outlet.qCurve, curveType            */
+    const double *outlet_qcoeff, *outlet_qexpon;
+
+    /* curves flattened from the reference's linked lists (table.c), CSR by curve */
+    const int    *curve_start;      /* n_curves+1                                          */
+    const int    *curve_type;       /* Curve.curveType (enums.h:437)                       */
+    const double *curve_x, *curve_y;
+    /* per-object geometry tables for IRREGULAR / CUSTOM / STREET (objects.h:604-659):
+     * n_shape_tbls tables of shape_tbl_len entries each, [table][entry]; table t has
+     * shape_tbl_n[t] valid entries (51 except for STREET transects) */
+    const int    *shape_tbl_n;
+    const double *shape_area_tbl, *shape_hrad_tbl, *shape_width_tbl;
+
+    /* pollutants */
+    const double *pollut_kdecay;    /* Pollut.kDecay, 1/s                                  */
+} swb_network_desc;
+
+/* Fields that can be read or written with swb_get_field / swb_set_field.
+ * NODE_* are n_nodes long per member, LINK_* n_links, *_QUAL and LINK_TOTAL_LOAD are
+ * [item][pollutant] per member on the host side.  Integer fields travel as doubles. */
+enum swb_field {
+    SWB_NODE_NEW_DEPTH = 0, SWB_NODE_OLD_DEPTH, SWB_NODE_NEW_VOLUME, SWB_NODE_OLD_VOLUME,
+    SWB_NODE_NEW_LATFLOW, SWB_NODE_LOSSES, SWB_NODE_INFLOW, SWB_NODE_OUTFLOW, SWB_NODE_OVERFLOW,
+    SWB_NODE_OLD_NET_INFLOW, SWB_NODE_NEW_SURF_AREA, SWB_NODE_OLD_SURF_AREA, SWB_NODE_SUMDQDH,
+    SWB_NODE_DYDT, SWB_NODE_CONVERGED, SWB_NODE_OUTFALL_STAGE, SWB_NODE_STORAGE_EVAP_LOSS,
+    SWB_NODE_STORAGE_EXFIL_LOSS, SWB_NODE_HRT, SWB_NODE_NEW_QUAL, SWB_NODE_OLD_QUAL,
+    SWB_LINK_NEW_FLOW = 32, SWB_LINK_OLD_FLOW, SWB_LINK_NEW_DEPTH, SWB_LINK_OLD_DEPTH,
+    SWB_LINK_NEW_VOLUME, SWB_LINK_OLD_VOLUME, SWB_LINK_SETTING, SWB_LINK_TARGET_SETTING,
+    SWB_LINK_DQDH, SWB_LINK_FROUDE, SWB_LINK_FLOW_CLASS, SWB_LINK_SURF_AREA1, SWB_LINK_SURF_AREA2,
+    SWB_LINK_BYPASSED, SWB_LINK_NORMAL_FLOW, SWB_LINK_INLET_CONTROL, SWB_COND_A1, SWB_COND_A2,
+    SWB_COND_Q1, SWB_COND_Q2, SWB_COND_FULL_STATE, SWB_COND_CAPACITY_LIMITED, SWB_COND_EVAP_LOSS,
+    SWB_COND_SEEP_LOSS, SWB_ORIF_CORIF, SWB_ORIF_CWEIR, SWB_ORIF_HCRIT, SWB_REG_SURF_AREA,
+    SWB_WEIR_CSURCHARGE, SWB_LINK_NEW_QUAL, SWB_LINK_OLD_QUAL, SWB_LINK_TOTAL_LOAD,
+    SWB_FIELD_COUNT = 96
+};
+
+/* per-member accumulators kept on the device (massbal.c:517-555, stats.c:522-540) */
+typedef struct swb_member_stats {
+    double sim_time;          /* elapsed simulated time, s                                  */
+    double last_dt;           /* routing step most recently used, s                         */
+    double next_dt;           /* variable step for the next call (dynwave_getRoutingStep)   */
+    long long steps;          /* routing steps taken                                        */
+    long long iterations;     /* sum of Picard iterations (dynwave_execute return values)   */
+    long long non_converged;  /* NonConvergeCount (dynwave.c:269)                           */
+    int    crit_node, crit_link;  /* arg-min of the last Courant search (dynwave.c:827)     */
+} swb_member_stats;
+
+typedef struct swb_network swb_network;   /* device-resident static data       */
+typedef struct swb_solver  swb_solver;    /* device-resident state of M members */
+
+const char *swb_last_error(void);
+int  swb_version(void);
+int  swb_device_count(void);
+
+/* static network -> HBM (SoA, shared by all members).  device = CUDA ordinal. */
+int  swb_network_create(const swb_network_desc *desc, const swb_options *opt, int device,
+                        swb_network **out);
+void swb_network_destroy(swb_network *net);
+
+/* M lockstep members of one network. */
+int  swb_solver_create(swb_network *net, int n_members, swb_solver **out);
+void swb_solver_destroy(swb_solver *s);
+int  swb_solver_members(const swb_solver *s);
+
+/* state exchange; buf is [n_members][items(*n_pollut)] doubles for members
+ * [member0, member0+n_members) */
+int  swb_set_field(swb_solver *s, int field, int member0, int n_members, const double *buf);
+int  swb_get_field(swb_solver *s, int field, int member0, int n_members, double *buf);
+/* same value for every member (a single-member image is broadcast) */
+int  swb_broadcast_field(swb_solver *s, int field, const double *buf);
+int  swb_set_climate(swb_solver *s, double evap_rate, double hydcon_factor);
+
+/* qualrout_init (qualrout.c:63-96): c = init_concen[p] where depth > ZeroDepth else 0 */
+int  swb_qual_init(swb_solver *s, const double *init_concen);
+
+/*
+ * The reference's per-step calls, one for one (all members in lockstep):
+ *   swb_old_state_swap  = routing.c:399-409 + flowrout.c:153-162 (+ routing.c:312-336 quality swap
+ *                         when with_quality): new->old, node_initFlows, overflow reset.  The seam
+ *                         shim does NOT call this (the host engine has already done it and the
+ *                         shim uploads the result); the ensemble driver does.
+ *   swb_dynwave_execute = dynwave_execute (dynwave.c:224-262); dt[member]; returns iteration
+ *                         counts in iters[member] (may be NULL).
+ *   swb_qualrout_execute= qualrout_execute (qualrout.c:100-142).
+ *   swb_get_routing_step= dynwave_getRoutingStep (dynwave.c:195-220) for every member.
+ */
+int  swb_old_state_swap(swb_solver *s, const double *dt, int with_quality);
+int  swb_dynwave_execute(swb_solver *s, const double *dt, int *iters);
+int  swb_qualrout_execute(swb_solver *s, const double *dt);
+int  swb_get_routing_step(swb_solver *s, double fixed_step, double *dt_out);
+
+/*
+ * Ensemble driver ("runoff once, route many"): lateral inflows are evaluated on the device from
+ * per-node hydrographs shared by all members and a per-member (scale, time shift) pair:
+ *   latflow[m][node] = baseline[node] + scale[m] * sfactor[node] * TS_node(t_m - shift[m])
+ * with TS linear between breakpoints and 0 outside them (table.c:745-806, extend = FALSE), and
+ * pollutant p enters as concentration inflow_concen[node][p] * latflow (routing.c:476-489).
+ */
+typedef struct swb_inflow_desc {
+    int n_inflow_nodes;
+    int n_ts_pts;                   /* total breakpoints                                     */
+    const int    *node;             /* node index per inflow                                 */
+    const int    *ts_start;         /* n_inflow_nodes+1, CSR into ts_t/ts_q                  */
+    const double *ts_t;             /* seconds since simulation start                        */
+    const double *ts_q;             /* cfs                                                   */
+    const double *sfactor;          /* per inflow node                                       */
+    const double *baseline;         /* per inflow node, cfs                                  */
+    const double *concen;           /* [n_inflow_nodes][n_pollut], mass/ft3                  */
+    const double *member_scale;     /* [n_members]                                           */
+    const double *member_shift;     /* [n_members], s                                        */
+} swb_inflow_desc;
+
+int  swb_set_inflows(swb_solver *s, const swb_inflow_desc *inflows);
+/* Advance every member n_steps routing steps entirely on the device (one cooperative launch):
+ * dt from the Courant search, inflows from swb_set_inflows, dynamic wave + quality routing.
+ * t_end: members stop stepping once their sim_time reaches it (last step shortened like
+ * swmm5.c:541-546). */
+int  swb_run_steps(swb_solver *s, int n_steps, double t_end);
+int  swb_get_stats(swb_solver *s, int member0, int n_members, swb_member_stats *out);
+/* conduit-updates performed so far: sum over members of iterations x true conduits */
+long long swb_conduit_updates(swb_solver *s);
+
+/* launch bookkeeping for bench.py ("gpu_launches") and device timing of the last call */
+long long swb_launch_count(const swb_solver *s);
+double    swb_last_kernel_ms(const swb_solver *s);
+int       swb_sync(swb_solver *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWMM_B200_H */

@@ -1,0 +1,333 @@
+"""Deterministic generators for the BASELINE.json configs.
+
+Each generator returns the text of a SWMM 5.2 ``.inp`` (formats per SURVEY.md Appendix E, parsers
+cited there: node.c:606-809, link.c:933-988,162-311, inflow.c:41-134, table.c:67-204).  The same
+scenario can also be built directly as flat arrays by ``network.build_*`` (no engine needed on the
+GPU box); tests check the two agree bit for bit.
+
+Configs:
+  c1  100-junction dendritic tree, circular pipes, 6 h triangular storm
+  c2  n x n looped grid (n=100 -> 10k nodes / 19 801 conduits), circular + rect_closed,
+      surcharge, 2 pollutants (TSS decays, DYE conservative); SLOT (strict gate) or EXTRAN
+  c3  mixed-element network (storage, pumps, orifices, weirs, outlet, outfalls, rules)
+  c4  members of c2 = (inflow scale, time shift) pairs, rng 2024
+  c5  c2 at 1000 x 500 (~1M links), no pollutants
+"""
+from __future__ import annotations
+
+import math
+import random
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+def _hms(hours: float) -> str:
+    s = int(round(hours * 3600))
+    return f"{s // 3600}:{(s % 3600) // 60:02d}:{s % 60:02d}"
+
+
+def _options(*, hours: float, route_step: float, variable_step: float, surcharge: str,
+             report_step_s: int, threads: int, extra: dict | None = None) -> list[str]:
+    days = int(hours // 24)
+    rem = hours - 24 * days
+    end_date = f"01/{1 + days:02d}/2020"
+    o = {
+        "FLOW_UNITS": "CFS",
+        "FLOW_ROUTING": "DYNWAVE",
+        "START_DATE": "01/01/2020",
+        "START_TIME": "00:00:00",
+        "REPORT_START_DATE": "01/01/2020",
+        "REPORT_START_TIME": "00:00:00",
+        "END_DATE": end_date,
+        "END_TIME": _hms(rem) if rem > 0 else "00:00:00",
+        "REPORT_STEP": _hms(report_step_s / 3600.0),
+        "ROUTING_STEP": f"{route_step:g}",
+        "VARIABLE_STEP": f"{variable_step:g}",
+        "SURCHARGE_METHOD": surcharge,
+        "MAX_TRIALS": "8",
+        "HEAD_TOLERANCE": "0.005",
+        "THREADS": str(threads),
+    }
+    if hours >= 24 and rem == 0:
+        o["END_TIME"] = "00:00:00"
+    if extra:
+        o.update(extra)
+    return ["[OPTIONS]"] + [f"{k} {v}" for k, v in o.items()]
+
+
+# --------------------------------------------------------------------------------------------
+# config 1: dendritic tree
+# --------------------------------------------------------------------------------------------
+@dataclass
+class TreeSpec:
+    n_junctions: int = 100
+    length: float = 400.0
+    roughness: float = 0.013
+    drop: float = 2.0            # invert drop per conduit, ft
+    max_depth: float = 8.0
+    peak_cfs: float = 0.6
+    hours: float = 6.0
+    route_step: float = 5.0
+    variable_step: float = 0.75
+    surcharge: str = "EXTRAN"
+    report_step_s: int = 300
+    threads: int = 1
+
+    def level(self, i: int) -> int:           # heap index i >= 1
+        return int(math.floor(math.log2(i)))
+
+    def diameter(self, i: int) -> float:
+        top = self.level(self.n_junctions)
+        return max(1.0, 4.0 - 3.0 * self.level(i) / max(top, 1))
+
+    def leaves(self) -> list[int]:
+        n = self.n_junctions
+        return [i for i in range(1, n + 1) if 2 * i > n]
+
+
+def c1_tree_inp(spec: TreeSpec | None = None) -> str:
+    s = spec or TreeSpec()
+    n = s.n_junctions
+    L = _options(hours=s.hours, route_step=s.route_step, variable_step=s.variable_step,
+                 surcharge=s.surcharge, report_step_s=s.report_step_s, threads=s.threads)
+    L += ["[JUNCTIONS]"]
+    for i in range(1, n + 1):
+        elev = 10.0 + s.drop * (s.level(i) + 1)
+        L.append(f"J{i} {elev:.4f} {s.max_depth:g} 0 0 0")
+    L += ["[OUTFALLS]", "OUT 10 FREE NO"]
+    L += ["[CONDUITS]"]
+    for i in range(1, n + 1):
+        dn = f"J{i // 2}" if i > 1 else "OUT"
+        L.append(f"C{i} J{i} {dn} {s.length:g} {s.roughness:g} 0 0 0 0")
+    L += ["[XSECTIONS]"]
+    for i in range(1, n + 1):
+        L.append(f"C{i} CIRCULAR {s.diameter(i):.6g} 0 0 0 1")
+    L += ["[INFLOWS]"]
+    for k, i in enumerate(s.leaves()):
+        scale = 0.5 + 0.5 * ((k * 7919) % 100) / 100.0
+        L.append(f"J{i} FLOW STORM FLOW 1.0 {scale:.4f}")
+    L += ["[TIMESERIES]", "STORM 0:00 0", f"STORM 2:00 {s.peak_cfs:g}", "STORM 4:00 0",
+          "STORM 6:00 0"]
+    L += ["[REPORT]", "NODES ALL", "LINKS ALL"]
+    return "\n".join(L) + "\n"
+
+
+# --------------------------------------------------------------------------------------------
+# config 2 / 5: looped urban grid
+# --------------------------------------------------------------------------------------------
+@dataclass
+class GridSpec:
+    nx: int = 100
+    ny: int = 100
+    length: float = 300.0
+    roughness: float = 0.013
+    size: float = 1.5            # circular diameter and rect_closed side, ft
+    max_depth: float = 6.0
+    hours: float = 2.0
+    route_step: float = 5.0
+    variable_step: float = 0.75
+    surcharge: str = "SLOT"
+    pollutants: bool = True
+    report_step_s: int = 300
+    threads: int = 1
+    seed: int = 1
+    inflow_scale: float = 1.0    # member scale (config 4)
+    inflow_shift_h: float = 0.0  # member time shift, hours (config 4)
+    # hydrograph breakpoints (hours, multiplier)
+    hydro: tuple = ((0.0, 0.0), (1.5, 1.0), (3.0, 4.0), (4.5, 1.0), (6.0, 0.0))
+
+    def node_id(self, i: int, j: int) -> str:
+        return f"N{i}_{j}"
+
+    def elev(self, i: int, j: int) -> float:
+        return 100.0 + 0.4 * ((self.nx - 1 - i) + (self.ny - 1 - j))
+
+    def inflow_nodes(self) -> list[tuple[int, int, float]]:
+        """(i, j, scale) for every 2nd node, scale ~ U(0.2, 0.5), random.seed(seed)."""
+        rng = random.Random(self.seed)
+        out = []
+        k = 0
+        for i in range(self.nx):
+            for j in range(self.ny):
+                if k % 2 == 0:
+                    out.append((i, j, rng.uniform(0.2, 0.5)))
+                k += 1
+        return out
+
+    def hydrograph(self) -> list[tuple[float, float]]:
+        """Breakpoints after the member time shift (hours >= 0, value)."""
+        pts = [(t + self.inflow_shift_h, v) for t, v in self.hydro]
+        return pts
+
+
+def c2_grid_inp(spec: GridSpec | None = None) -> str:
+    s = spec or GridSpec()
+    L = _options(hours=s.hours, route_step=s.route_step, variable_step=s.variable_step,
+                 surcharge=s.surcharge, report_step_s=s.report_step_s, threads=s.threads)
+    L += ["[JUNCTIONS]"]
+    for i in range(s.nx):
+        for j in range(s.ny):
+            L.append(f"{s.node_id(i, j)} {s.elev(i, j):.4f} {s.max_depth:g} 0 0 0")
+    out_elev = s.elev(s.nx - 1, s.ny - 1) - 0.4
+    L += ["[OUTFALLS]", f"OUT {out_elev:.4f} FREE NO"]
+    cond, xs = [], []
+    k = 0
+    for i in range(s.nx):
+        for j in range(s.ny):
+            for (di, dj) in ((1, 0), (0, 1)):
+                ii, jj = i + di, j + dj
+                if ii >= s.nx or jj >= s.ny:
+                    continue
+                cid = f"C{k}"
+                cond.append(f"{cid} {s.node_id(i, j)} {s.node_id(ii, jj)} {s.length:g} "
+                            f"{s.roughness:g} 0 0 0 0")
+                if k % 2 == 0:
+                    xs.append(f"{cid} CIRCULAR {s.size:g} 0 0 0 1")
+                else:
+                    xs.append(f"{cid} RECT_CLOSED {s.size:g} {s.size:g} 0 0 1")
+                k += 1
+    cond.append(f"COUT {s.node_id(s.nx - 1, s.ny - 1)} OUT {s.length:g} {s.roughness:g} 0 0 0 0")
+    xs.append(f"COUT CIRCULAR {2.0 * s.size:g} 0 0 0 1")
+    L += ["[CONDUITS]"] + cond + ["[XSECTIONS]"] + xs
+    if s.pollutants:
+        L += ["[POLLUTANTS]", "TSS MG/L 0 0 0 0.5", "DYE MG/L 0 0 0 0"]
+    L += ["[INFLOWS]"]
+    for (i, j, sc) in s.inflow_nodes():
+        nid = s.node_id(i, j)
+        L.append(f"{nid} FLOW HYDRO FLOW 1.0 {sc * s.inflow_scale:.6f}")
+        if s.pollutants:
+            L.append(f"{nid} TSS CTSS CONCEN 1.0 1.0")
+            L.append(f"{nid} DYE CDYE CONCEN 1.0 1.0")
+    L += ["[TIMESERIES]"]
+    for (t, v) in s.hydrograph():
+        L.append(f"HYDRO {_hms(t)} {v:g}")
+    if s.pollutants:
+        L += ["CTSS 0:00 100", "CTSS 48:00 100", "CDYE 0:00 50", "CDYE 48:00 50"]
+    L += ["[REPORT]", "NODES ALL", "LINKS ALL"]
+    return "\n".join(L) + "\n"
+
+
+def c4_members(n_members: int = 4096, seed: int = 2024):
+    """(scale, shift_hours) per member: LogNormal(0, 0.3) scale, U(-30, 30) min shift (8d).
+
+    Shifts are made non-negative by a common +30 min offset so every hydrograph starts at t >= 0.
+    """
+    rng = np.random.default_rng(seed)
+    scale = rng.lognormal(0.0, 0.3, n_members)
+    shift_min = rng.uniform(-30.0, 30.0, n_members)
+    # quantise to what an .inp can express exactly (6 decimals / whole seconds)
+    scale = np.round(scale, 6)
+    shift_h = np.round((shift_min + 30.0) * 60.0) / 3600.0
+    return scale, shift_h
+
+
+# --------------------------------------------------------------------------------------------
+# config 3: mixed elements (SURVEY.md Appendix E seed model, verified against the reference)
+# --------------------------------------------------------------------------------------------
+C3_MIXED_INP = """[OPTIONS]
+FLOW_UNITS CFS
+FLOW_ROUTING DYNWAVE
+START_DATE 01/01/2020
+START_TIME 00:00:00
+END_DATE 01/02/2020
+END_TIME 00:00:00
+REPORT_STEP 00:15:00
+ROUTING_STEP 5
+VARIABLE_STEP 0.75
+ALLOW_PONDING YES
+THREADS 1
+[JUNCTIONS]
+J1 110 8 0 0 500
+J2 108 8 0 0 0
+J3 100 8 0 0 0
+J4 99 8 0 0 0
+J5 98 8 0 0 0
+WW 90 15 0 0 0
+[OUTFALLS]
+O1 97 FREE NO
+O2 96 FIXED 97.5 YES
+O3 96 TIDAL TIDE NO
+[STORAGE]
+S1 104 12 2 FUNCTIONAL 1000 0 500 0 0
+S2 102 10 1 TABULAR SCURVE 0 0
+[CONDUITS]
+C1 J1 J2 400 0.013 0 0 0 0
+C2 J2 S1 400 0.013 0 1 0 0
+C3 J3 J4 400 0.013 0 0 0 0
+C4 J4 J5 300 0.015 0 0.5 0 0
+C5 J5 O1 300 0.013 0 0 0 0
+C6 J4 O2 300 0.013 0 0 0 0
+C7 S2 O3 300 0.013 0 0 0 0
+C8 J3 WW 200 0.013 0 0 0 0
+[PUMPS]
+P1 WW J4 PC3 ON 4 1
+[ORIFICES]
+OR1 S1 J3 SIDE 0 0.65 NO 0
+OR2 S1 S2 BOTTOM 0 0.6 NO 0.05
+[WEIRS]
+W1 S1 S2 TRANSVERSE 8 3.33 NO 0 0 YES
+W2 S2 J3 V-NOTCH 5 2.5 NO 0 0 YES
+[OUTLETS]
+OL1 S2 J3 0 FUNCTIONAL/DEPTH 2.0 0.5 NO
+[XSECTIONS]
+C1 CIRCULAR 2 0 0 0 1
+C2 RECT_CLOSED 2 3 0 0 1
+C3 CIRCULAR 3 0 0 0 1
+C4 TRAPEZOIDAL 4 3 1 1 1
+C5 EGG 3 0 0 0 1
+C6 CIRCULAR 2 0 0 0 2
+C7 CIRCULAR 2.5 0 0 0 1
+C8 CIRCULAR 2 0 0 0 1
+OR1 CIRCULAR 1 0 0 0
+OR2 RECT_CLOSED 1 1 0 0
+W1 RECT_OPEN 3 10 0 0
+W2 TRIANGULAR 4 6 0 0
+[LOSSES]
+C3 0.5 0.5 0 NO 0
+[CONTROLS]
+RULE R1
+IF NODE S1 DEPTH > 6
+THEN ORIFICE OR1 SETTING = 1.0
+ELSE ORIFICE OR1 SETTING = 0.3
+PRIORITY 1
+RULE R2
+IF SIMULATION TIME > 12
+THEN PUMP P1 STATUS = OFF
+[POLLUTANTS]
+TSS MG/L 0 0 0 0.5
+DYE MG/L 0 0 0 0
+[INFLOWS]
+J1 FLOW TS1 FLOW 1.0 1.0
+J1 TSS TSC CONCEN 1.0 1.0
+J2 FLOW TS1 FLOW 1.0 0.5 0.2
+J2 DYE TSC CONCEN 1.0 0.5
+[DWF]
+J3 FLOW 0.3 DAILYP
+[PATTERNS]
+DAILYP HOURLY 0.5 0.5 0.5 0.5 0.6 0.8 1.2 1.5 1.4 1.2 1.1 1.0 1.0 1.0 1.0 1.1 1.2 1.4 1.5 1.3 1.0 0.8 0.6 0.5
+[CURVES]
+SCURVE STORAGE 0 800 5 1500 10 3000
+PC3 PUMP3 0 8 5 6 10 3 15 0
+TIDE TIDAL 0 96.5 6 98 12 96.5 18 98 24 96.5
+[TIMESERIES]
+TS1 0:00 0
+TS1 2:00 10
+TS1 4:00 30
+TS1 8:00 5
+TS1 24:00 1
+TSC 0:00 100
+TSC 24:00 100
+[REPORT]
+NODES ALL
+LINKS ALL
+CONTROLS YES
+"""
+
+
+def c3_mixed_inp() -> str:
+    return C3_MIXED_INP
+
+
+def c5_mega_spec(hours: float = 1.0) -> GridSpec:
+    return GridSpec(nx=1000, ny=500, hours=hours, pollutants=False, surcharge="SLOT")

@@ -1,0 +1,37 @@
+// swb_common.h -- constants and macros shared by every device header.
+//
+// The device headers are plain C++ inline functions marked SWB_HD so that tests/emul can compile
+// the very same kernel arithmetic for the host and check it on a machine without a GPU.  That
+// host build is test scaffolding only: libswmm_b200.so contains the CUDA path alone and every
+// entry point fails with SWB_ERR_CUDA when no device is present.
+#ifndef SWB_COMMON_H
+#define SWB_COMMON_H
+
+#ifdef __CUDACC__
+#define SWB_HD __host__ __device__ __forceinline__
+#define SWB_D  __device__ __forceinline__
+#else
+#define SWB_HD
+#define SWB_D
+#endif
+
+// consts.h:31-50 and the module constants of dynwave.c:60-66, dwflow.c:37, qualrout.c:40-41.
+// PI is the reference's 10-digit value on purpose.
+#define SWB_FUDGE       0.0001
+#define SWB_TINY        1.E-6
+#define SWB_ZERO        1.E-10
+#define SWB_PI          3.141592654
+#define SWB_GRAVITY     32.2
+#define SWB_OMEGA       0.5
+#define SWB_MAXVELOCITY 50.
+#define SWB_MINTIMESTEP 0.001
+#define SWB_ZERO_VOLUME 0.0353147
+#define SWB_ZERO_DEPTH  0.003281
+#define SWB_M3_PER_FT3  0.028317
+
+// macros.h:25-33 semantics: MIN returns x when equal, SGN(0) = +1
+#define SWB_MIN(x, y) (((x) <= (y)) ? (x) : (y))
+#define SWB_MAX(x, y) (((x) >= (y)) ? (x) : (y))
+#define SWB_SGN(x)    (((x) < 0) ? (-1) : (1))
+
+#endif

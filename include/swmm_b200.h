@@ -101,6 +101,7 @@ typedef struct swb_network_desc {
     /* conduits (objects.h:714-733) */
     const int    *cond_barrels, *cond_has_losses;
     const double *cond_length;      /* TRUE length, link_getLength (link.c:808,1195)       */
+    const double *cond_user_length; /* Conduit.length as entered (dynwave.c:374)           */
     const double *cond_mod_length, *cond_rough_factor, *cond_slope, *cond_beta, *cond_q_max;
     /* regulators, indexed by LINK */
     const int    *pump_type, *pump_curve;           /* Pump.type (enums.h:418), pumpCurve  */
@@ -203,22 +204,27 @@ int  swb_get_routing_step(swb_solver *s, double fixed_step, double *dt_out);
 /*
  * Ensemble driver ("runoff once, route many"): lateral inflows are evaluated on the device from
  * per-node hydrographs shared by all members and a per-member (scale, time shift) pair:
- *   latflow[m][node] = baseline[node] + scale[m] * sfactor[node] * TS_node(t_m - shift[m])
- * with TS linear between breakpoints and 0 outside them (table.c:745-806, extend = FALSE), and
- * pollutant p enters as concentration inflow_concen[node][p] * latflow (routing.c:476-489).
+ *   latflow[m][node] = baseline[node] + scale[m] * sfactor[node] * TS_node(date_m - shift[m])
+ * Times use the reference's DateTime encoding (decimal days) so that the interpolation is the
+ * reference's own arithmetic: date_m = start_day + (start_secs + (elapsed_ms + 1) / 1000) / 86400
+ * (getDateTime, swmm5.c:1543-1552; datetime_addSeconds, datetime.c:381-393), TS linear between
+ * breakpoints and 0 outside them (table_tseriesLookup with extend = FALSE, table.c:745-806).
+ * Pollutant p enters as concentration concen[node][p] * latflow (routing.c:476-489).
  */
 typedef struct swb_inflow_desc {
     int n_inflow_nodes;
     int n_ts_pts;                   /* total breakpoints                                     */
     const int    *node;             /* node index per inflow                                 */
     const int    *ts_start;         /* n_inflow_nodes+1, CSR into ts_t/ts_q                  */
-    const double *ts_t;             /* seconds since simulation start                        */
+    const double *ts_t;             /* DateTime (days), as the reference stores Tseries x    */
     const double *ts_q;             /* cfs                                                   */
     const double *sfactor;          /* per inflow node                                       */
     const double *baseline;         /* per inflow node, cfs                                  */
-    const double *concen;           /* [n_inflow_nodes][n_pollut], mass/ft3                  */
-    const double *member_scale;     /* [n_members]                                           */
-    const double *member_shift;     /* [n_members], s                                        */
+    const double *concen;           /* [n_inflow_nodes][n_pollut], mass/ft3 (may be NULL)    */
+    const double *member_scale;     /* [n_members] (NULL = 1)                                */
+    const double *member_shift;     /* [n_members], days (NULL = 0)                          */
+    double start_day;               /* floor(StartDateTime)                                  */
+    double start_secs;              /* seconds of day of StartDateTime                       */
 } swb_inflow_desc;
 
 int  swb_set_inflows(swb_solver *s, const swb_inflow_desc *inflows);

@@ -57,6 +57,8 @@ class RefEngine:
         H.refhook_get_field.argtypes = [C.c_int, C.POINTER(C.c_double)]
         H.refhook_set_field.argtypes = [C.c_int, C.POINTER(C.c_double)]
         H.refhook_new_routing_time.restype = C.c_double
+        H.refhook_inflows.restype = C.POINTER(self.abi.InflowDesc)
+        H.refhook_total_duration.restype = C.c_double
         H.refhook_xsect_eval.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int,
                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]
         H.refhook_xsect_set.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double,
@@ -125,6 +127,22 @@ class RefEngine:
             fid = self.abi.FIELD[fid]
         buf = np.ascontiguousarray(arr, dtype=np.float64)
         self.hook.refhook_set_field(fid, buf.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def inflows(self) -> dict:
+        """External FLOW hydrographs of the open model as keyword arguments for Solver.set_inflows."""
+        d = self.hook.refhook_inflows().contents
+        F = self.abi.FIELD
+        n, npts = d.n_inflow_nodes, d.n_ts_pts
+        nP = self.hook.refhook_field_len(F['SWB_NODE_NEW_QUAL']) // self.hook.refhook_field_len(F['SWB_NODE_NEW_DEPTH'])
+        arr = lambda p, k, dt: np.ctypeslib.as_array(p, shape=(max(k, 1),))[:k].astype(dt).copy()
+        return dict(node=arr(d.node, n, np.int32), ts_start=arr(d.ts_start, n + 1, np.int32),
+                    ts_t=arr(d.ts_t, npts, np.float64), ts_q=arr(d.ts_q, npts, np.float64),
+                    sfactor=arr(d.sfactor, n, np.float64), baseline=arr(d.baseline, n, np.float64),
+                    concen=arr(d.concen, n * nP, np.float64) if nP else None,
+                    start_day=d.start_day, start_secs=d.start_secs)
+
+    def total_duration_s(self) -> float:
+        return self.hook.refhook_total_duration() / 1000.0
 
     def routing_time_ms(self) -> float:
         return self.hook.refhook_new_routing_time()

@@ -8,6 +8,8 @@
  * Nothing in the product path loads this file.
  */
 #include <string.h>
+#include <stdlib.h>
+#include <math.h>
 #include "headers.h"
 #include "flatten.h"
 
@@ -66,3 +68,60 @@ int refhook_xsect_set(int type, const double *geom4, double ucf, double *p)
     p[6] = x.sMax; p[7] = x.yBot; p[8] = x.aBot; p[9] = x.sBot; p[10] = x.rBot;
     return ok;
 }
+
+/* ---- external inflow hydrographs of the live engine -> swb_inflow_desc (ensemble driver) ----
+ * Nodes with a FLOW time-series inflow (no baseline pattern).  Concentration inflows are taken as
+ * constants evaluated at the start date (the BASELINE configs use constant series). */
+static swb_inflow_desc g_inf;
+static int *g_inf_node, *g_inf_start;
+static double *g_inf_t, *g_inf_q, *g_inf_sf, *g_inf_bl, *g_inf_c;
+
+const swb_inflow_desc *refhook_inflows(void)
+{
+    int nN = Nobjects[NODE], nP = Nobjects[POLLUT], i, n = 0, npts = 0, k, p;
+    TExtInflow *f;
+    for (i = 0; i < nN; i++)
+        for (f = Node[i].extInflow; f; f = f->next)
+            if (f->type == FLOW_INFLOW && f->tSeries >= 0) {
+                TTableEntry *e = Tseries[f->tSeries].firstEntry;
+                n++;
+                while (e) { npts++; e = e->next; }
+            }
+    free(g_inf_node); free(g_inf_start); free(g_inf_t); free(g_inf_q); free(g_inf_sf);
+    free(g_inf_bl); free(g_inf_c);
+    g_inf_node = calloc(n + 1, sizeof(int)); g_inf_start = calloc(n + 2, sizeof(int));
+    g_inf_t = calloc(npts + 1, sizeof(double)); g_inf_q = calloc(npts + 1, sizeof(double));
+    g_inf_sf = calloc(n + 1, sizeof(double)); g_inf_bl = calloc(n + 1, sizeof(double));
+    g_inf_c = calloc((size_t)(n + 1) * (nP ? nP : 1), sizeof(double));
+    k = 0; npts = 0;
+    for (i = 0; i < nN; i++) {
+        TExtInflow *flow = NULL;
+        for (f = Node[i].extInflow; f; f = f->next)
+            if (f->type == FLOW_INFLOW && f->tSeries >= 0) { flow = f; break; }
+        if (!flow) continue;
+        g_inf_node[k] = i; g_inf_start[k] = npts;
+        g_inf_sf[k] = flow->sFactor * flow->cFactor;      /* cFactor = 1 / UCF(FLOW) */
+        g_inf_bl[k] = flow->baseline * flow->cFactor;
+        { TTableEntry *e = Tseries[flow->tSeries].firstEntry;
+          while (e) { g_inf_t[npts] = e->x; g_inf_q[npts] = e->y; npts++; e = e->next; } }
+        for (f = Node[i].extInflow; f; f = f->next)
+            if (f->type == CONCEN_INFLOW) {
+                p = f->param;
+                g_inf_c[k * nP + p] = inflow_getExtInflow(f, StartDateTime);
+            }
+        k++;
+    }
+    g_inf_start[k] = npts;
+    memset(&g_inf, 0, sizeof(g_inf));
+    g_inf.n_inflow_nodes = n; g_inf.n_ts_pts = npts; g_inf.node = g_inf_node;
+    g_inf.ts_start = g_inf_start; g_inf.ts_t = g_inf_t; g_inf.ts_q = g_inf_q;
+    g_inf.sfactor = g_inf_sf; g_inf.baseline = g_inf_bl; g_inf.concen = g_inf_c;
+    {
+        int h, mi, s;
+        datetime_decodeTime(StartDateTime, &h, &mi, &s);
+        g_inf.start_day = floor(StartDateTime);
+        g_inf.start_secs = 3600.0 * h + 60.0 * mi + s;
+    }
+    return &g_inf;
+}
+double refhook_total_duration(void) { return TotalDuration; }

@@ -1,0 +1,377 @@
+// swb_api_impl.h -- the C-ABI of include/swmm_b200.h, written once against a tiny memory/launch
+// backend.  csrc/swb_api.cu instantiates it with the CUDA backend (the product); tests/emul
+// instantiates it with a host-thread backend so the CPU-only test suite can drive the very same
+// entry points.  The including file must define, before including this header:
+//
+//   namespace swb { namespace backend {
+//     bool  init(int device, std::string &err);
+//     void *alloc(size_t bytes);            void free_(void *p);
+//     void  upload(void *dst, const void *src, size_t bytes);
+//     void  download(void *dst, const void *src, size_t bytes);
+//     void  zero(void *dst, size_t bytes);
+//     bool  launch(const Net &, const State &, const RunArgs &, int device, float *ms, std::string &err);
+//     bool  sync(std::string &err);         int device_count();
+//   } }
+#ifndef SWB_API_IMPL_H
+#define SWB_API_IMPL_H
+
+#include <cstddef>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "swb_host.h"
+#include "swb_engine.h"
+
+using namespace swb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+struct swb_network {
+    Net net;
+    Derived der;
+    int device;
+    std::vector<void *> allocs;
+};
+
+struct swb_solver {
+    swb_network *net;
+    State st;
+    int M;
+    std::vector<void *> allocs;
+    Inflows inflows;
+    bool have_inflows;
+    long long launches;
+    float last_ms;
+    std::vector<double> h_dt;
+};
+
+template <class T>
+static T *dev_copy(std::vector<void *> &allocs, const T *src, size_t n)
+{
+    T *p = (T *)backend::alloc(sizeof(T) * (n ? n : 1));
+    if (n) backend::upload(p, src, sizeof(T) * n);
+    allocs.push_back(p);
+    return p;
+}
+template <class T>
+static T *dev_zero(std::vector<void *> &allocs, size_t n)
+{
+    T *p = (T *)backend::alloc(sizeof(T) * (n ? n : 1));
+    backend::zero(p, sizeof(T) * (n ? n : 1));
+    allocs.push_back(p);
+    return p;
+}
+
+extern "C" {
+
+const char *swb_last_error(void) { return g_err.c_str(); }
+int swb_version(void) { return SWB_VERSION; }
+int swb_device_count(void) { return backend::device_count(); }
+
+int swb_network_create(const swb_network_desc *d, const swb_options *o, int device, swb_network **out)
+{
+    if (!d || !o || !out) return fail(SWB_ERR_ARG, "null argument");
+    std::string why = validate_desc(*d, *o);
+    if (!why.empty())
+        return fail(why.find("not supported") != std::string::npos || why.find("dummy") != std::string::npos
+                        ? SWB_ERR_UNSUPP : SWB_ERR_ARG, why);
+    std::string err;
+    if (!backend::init(device, err)) return fail(SWB_ERR_CUDA, err);
+    swb_network *nw = new swb_network();
+    nw->device = device;
+    derive(*d, *o, nw->der);
+    fill_net_scalars(nw->net, *d, *o, nw->der);
+#define X(T, name, kind) nw->net.name = dev_copy<T>(nw->allocs, d->name, desc_count(*d, #kind[0], #kind[1]));
+    SWB_DESC_ARRAYS(X)
+#undef X
+    const Derived &r = nw->der;
+    nw->net.link_flags = dev_copy<int>(nw->allocs, r.link_flags.data(), r.link_flags.size());
+    nw->net.link_z1 = dev_copy<double>(nw->allocs, r.link_z1.data(), r.link_z1.size());
+    nw->net.link_z2 = dev_copy<double>(nw->allocs, r.link_z2.data(), r.link_z2.size());
+    nw->net.adj_start = dev_copy<int>(nw->allocs, r.adj_start.data(), r.adj_start.size());
+    nw->net.adj = dev_copy<int>(nw->allocs, r.adj.data(), r.adj.size());
+    nw->net.adjq_start = dev_copy<int>(nw->allocs, r.adjq_start.data(), r.adjq_start.size());
+    nw->net.adjq = dev_copy<int>(nw->allocs, r.adjq.data(), r.adjq.size());
+    nw->net.nc_links = dev_copy<int>(nw->allocs, r.nc_links.data(), r.nc_links.size());
+    nw->net.outfall_link = dev_copy<int>(nw->allocs, r.outfall_link.data(), r.outfall_link.size());
+    nw->net.xs_tables = dev_copy<double>(nw->allocs, r.xs_tables.data(), r.xs_tables.size());
+    *out = nw;
+    return SWB_OK;
+}
+
+void swb_network_destroy(swb_network *nw)
+{
+    if (!nw) return;
+    for (void *p : nw->allocs) backend::free_(p);
+    delete nw;
+}
+
+int swb_solver_create(swb_network *nw, int M, swb_solver **out)
+{
+    if (!nw || !out || M < 1) return fail(SWB_ERR_ARG, "bad solver arguments");
+    if (M > 1 && (M % 32) != 0) return fail(SWB_ERR_ARG, "n_members must be 1 or a multiple of 32");
+    if (M > 8192) return fail(SWB_ERR_ARG, "n_members > 8192: split the ensemble over several solvers");
+    swb_solver *s = new swb_solver();
+    s->net = nw; s->M = M; s->launches = 0; s->last_ms = 0.f; s->have_inflows = false;
+    memset(&s->inflows, 0, sizeof(s->inflows));
+    State &st = s->st;
+    memset(&st, 0, sizeof(st));
+    st.M = M;
+    const int nN = nw->net.nN, nL = nw->net.nL, nP = nw->net.nP;
+    for (const FieldInfo &f : field_table()) {
+        size_t n = field_items(f, nN, nL, nP) * (size_t)M;
+        void *p = f.is_u8 ? (void *)dev_zero<unsigned char>(s->allocs, n) : (void *)dev_zero<double>(s->allocs, n);
+        *(void **)((char *)&st + f.offset) = p;
+    }
+    st.dt = dev_zero<double>(s->allocs, M);
+    st.var_step = dev_zero<double>(s->allocs, M);
+    st.sim_time = dev_zero<double>(s->allocs, M);
+    std::vector<double> ev(M, nw->net.opt.evap_rate), hc(M, nw->net.opt.hydcon_factor);
+    st.evap_rate = dev_copy<double>(s->allocs, ev.data(), M);
+    st.hydcon = dev_copy<double>(s->allocs, hc.data(), M);
+    st.iters = dev_zero<int>(s->allocs, M);
+    st.tot_iters = dev_zero<long long>(s->allocs, M);
+    st.tot_steps = dev_zero<long long>(s->allocs, M);
+    st.non_conv = dev_zero<long long>(s->allocs, M);
+    st.crit_node = dev_zero<int>(s->allocs, M);
+    st.crit_link = dev_zero<int>(s->allocs, M);
+    st.tmin_bits = dev_zero<unsigned long long>(s->allocs, M);
+    st.alive = dev_zero<int>(s->allocs, (size_t)(SWB_MAX_TRIALS_CAP + 1) * M);
+    st.not_conv = dev_zero<int>(s->allocs, (size_t)SWB_MAX_TRIALS_CAP * M);
+    st.done = dev_zero<int>(s->allocs, M);
+    st.mb_reacted = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
+    st.mb_seepage = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
+    st.mb_final_storage = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
+    // conduit / link settings default to fully open (Link.setting = 1.0, link.c:142)
+    std::vector<double> ones((size_t)nL * M, 1.0);
+    backend::upload(st.l_setting, ones.data(), sizeof(double) * ones.size());
+    backend::upload(st.l_target_setting, ones.data(), sizeof(double) * ones.size());
+    *out = s;
+    return SWB_OK;
+}
+
+void swb_solver_destroy(swb_solver *s)
+{
+    if (!s) return;
+    for (void *p : s->allocs) backend::free_(p);
+    delete s;
+}
+int swb_solver_members(const swb_solver *s) { return s ? s->M : 0; }
+
+// host [member][item(,p)]  <->  device [(p,) item][member]
+static int field_xfer(swb_solver *s, int field, int m0, int nm, double *buf, const double *cbuf, bool set,
+                      bool broadcast)
+{
+    if (!s || (!buf && !cbuf)) return fail(SWB_ERR_ARG, "null argument");
+    const FieldInfo *f = find_field(field);
+    if (!f) return fail(SWB_ERR_ARG, "unknown field id");
+    const int M = s->M, nN = s->net->net.nN, nL = s->net->net.nL, nP = s->net->net.nP;
+    if (broadcast) { m0 = 0; nm = M; }
+    if (m0 < 0 || nm < 1 || m0 + nm > M) return fail(SWB_ERR_ARG, "member range out of bounds");
+    const size_t items = field_items(*f, nN, nL, nP);
+    const size_t base = (f->kind == 'n') ? nN : (f->kind == 'l') ? nL : items;   // objects per plane
+    const int planes = (int)(items / (base ? base : 1));
+    void *dev = *(void **)((char *)&s->st + f->offset);
+    const size_t total = items * (size_t)M;
+    std::vector<double> h(total);
+    std::vector<unsigned char> h8;
+    auto pull = [&]() {
+        if (f->is_u8) { h8.resize(total); backend::download(h8.data(), dev, total);
+                        for (size_t i = 0; i < total; i++) h[i] = h8[i]; }
+        else backend::download(h.data(), dev, sizeof(double) * total);
+    };
+    if (!set) {
+        pull();
+        for (int mm = 0; mm < nm; mm++)
+            for (size_t it = 0; it < base; it++)
+                for (int p = 0; p < planes; p++)
+                    buf[(size_t)mm * items + it * planes + p] = h[((size_t)p * base + it) * M + (m0 + mm)];
+        return SWB_OK;
+    }
+    if (nm != M) pull();
+    for (int mm = 0; mm < nm; mm++)
+        for (size_t it = 0; it < base; it++)
+            for (int p = 0; p < planes; p++)
+                h[((size_t)p * base + it) * M + (m0 + mm)] =
+                    cbuf[(broadcast ? 0 : (size_t)mm * items) + it * planes + p];
+    if (f->is_u8) { h8.resize(total); for (size_t i = 0; i < total; i++) h8[i] = (unsigned char)h[i];
+                    backend::upload(dev, h8.data(), total); }
+    else backend::upload(dev, h.data(), sizeof(double) * total);
+    return SWB_OK;
+}
+
+int swb_set_field(swb_solver *s, int field, int m0, int nm, const double *buf)
+{ return field_xfer(s, field, m0, nm, nullptr, buf, true, false); }
+int swb_get_field(swb_solver *s, int field, int m0, int nm, double *buf)
+{ return field_xfer(s, field, m0, nm, buf, nullptr, false, false); }
+int swb_broadcast_field(swb_solver *s, int field, const double *buf)
+{ return field_xfer(s, field, 0, 0, nullptr, buf, true, true); }
+
+int swb_set_climate(swb_solver *s, double evap_rate, double hydcon_factor)
+{
+    if (!s) return fail(SWB_ERR_ARG, "null solver");
+    std::vector<double> ev(s->M, evap_rate), hc(s->M, hydcon_factor);
+    backend::upload(s->st.evap_rate, ev.data(), sizeof(double) * s->M);
+    backend::upload(s->st.hydcon, hc.data(), sizeof(double) * s->M);
+    return SWB_OK;
+}
+
+int swb_qual_init(swb_solver *s, const double *init_concen)
+{
+    if (!s) return fail(SWB_ERR_ARG, "null solver");
+    const int M = s->M, nN = s->net->net.nN, nL = s->net->net.nL, nP = s->net->net.nP;
+    if (nP == 0) return SWB_OK;
+    std::vector<double> nd((size_t)nN * M), ld((size_t)nL * M);
+    backend::download(nd.data(), s->st.n_depth, sizeof(double) * nd.size());
+    backend::download(ld.data(), s->st.l_depth, sizeof(double) * ld.size());
+    std::vector<double> nq((size_t)nP * nN * M), lq((size_t)nP * nL * M);
+    for (int p = 0; p < nP; p++) {
+        double c0 = init_concen ? init_concen[p] : 0.0;
+        for (size_t i = 0; i < nd.size(); i++) nq[(size_t)p * nN * M + i] = nd[i] > SWB_ZERO_DEPTH ? c0 : 0.0;
+        for (size_t i = 0; i < ld.size(); i++) lq[(size_t)p * nL * M + i] = ld[i] > SWB_ZERO_DEPTH ? c0 : 0.0;
+    }
+    backend::upload(s->st.n_qual, nq.data(), sizeof(double) * nq.size());
+    backend::upload(s->st.n_old_qual, nq.data(), sizeof(double) * nq.size());
+    backend::upload(s->st.l_qual, lq.data(), sizeof(double) * lq.size());
+    backend::upload(s->st.l_old_qual, lq.data(), sizeof(double) * lq.size());
+    return SWB_OK;
+}
+
+static int run(swb_solver *s, int phases, int n_steps, double t_end, double fixed_step)
+{
+    RunArgs a;
+    memset(&a, 0, sizeof(a));
+    a.phases = phases; a.n_steps = n_steps; a.t_end = t_end; a.fixed_step = fixed_step;
+    a.inflows = s->inflows;
+    std::string err;
+    float ms = 0.f;
+    if (!backend::launch(s->net->net, s->st, a, s->net->device, &ms, err)) return fail(SWB_ERR_CUDA, err);
+    s->launches++;
+    s->last_ms = ms;
+    return SWB_OK;
+}
+
+static int put_dt(swb_solver *s, const double *dt)
+{
+    if (!s || !dt) return fail(SWB_ERR_ARG, "null argument");
+    backend::upload(s->st.dt, dt, sizeof(double) * s->M);
+    return SWB_OK;
+}
+
+int swb_old_state_swap(swb_solver *s, const double *dt, int with_quality)
+{
+    int rc = put_dt(s, dt);
+    if (rc) return rc;
+    return run(s, PH_SWAP | (with_quality ? PH_QSWAP : 0), 1, 0.0, s->net->net.opt.route_step);
+}
+
+int swb_dynwave_execute(swb_solver *s, const double *dt, int *iters)
+{
+    int rc = put_dt(s, dt);
+    if (rc) return rc;
+    rc = run(s, PH_DYNWAVE, 1, 0.0, s->net->net.opt.route_step);
+    if (rc) return rc;
+    if (iters) backend::download(iters, s->st.iters, sizeof(int) * s->M);
+    return SWB_OK;
+}
+
+int swb_qualrout_execute(swb_solver *s, const double *dt)
+{
+    int rc = put_dt(s, dt);
+    if (rc) return rc;
+    return run(s, PH_QUALITY, 1, 0.0, s->net->net.opt.route_step);
+}
+
+int swb_get_routing_step(swb_solver *s, double fixed_step, double *dt_out)
+{
+    if (!s || !dt_out) return fail(SWB_ERR_ARG, "null argument");
+    int rc = run(s, PH_NEXTDT, 1, 0.0, fixed_step);
+    if (rc) return rc;
+    backend::download(dt_out, s->st.var_step, sizeof(double) * s->M);
+    return SWB_OK;
+}
+
+int swb_set_inflows(swb_solver *s, const swb_inflow_desc *d)
+{
+    if (!s || !d) return fail(SWB_ERR_ARG, "null argument");
+    const int nN = s->net->net.nN, nP = s->net->net.nP, n = d->n_inflow_nodes;
+    std::vector<int> slot(nN, -1);
+    for (int k = 0; k < n; k++) {
+        if (d->node[k] < 0 || d->node[k] >= nN) return fail(SWB_ERR_ARG, "inflow node out of range");
+        slot[d->node[k]] = k;
+    }
+    Inflows &f = s->inflows;
+    f.n = n; f.start_day = d->start_day; f.start_secs = d->start_secs;
+    f.node = dev_copy<int>(s->allocs, d->node, n);
+    f.ts_start = dev_copy<int>(s->allocs, d->ts_start, n + 1);
+    f.ts_t = dev_copy<double>(s->allocs, d->ts_t, d->n_ts_pts);
+    f.ts_q = dev_copy<double>(s->allocs, d->ts_q, d->n_ts_pts);
+    f.sfactor = dev_copy<double>(s->allocs, d->sfactor, n);
+    f.baseline = dev_copy<double>(s->allocs, d->baseline, n);
+    std::vector<double> zc((size_t)n * (nP ? nP : 1), 0.0);
+    f.concen = dev_copy<double>(s->allocs, d->concen ? d->concen : zc.data(), (size_t)n * nP);
+    std::vector<double> one(s->M, 1.0), zero(s->M, 0.0);
+    f.member_scale = dev_copy<double>(s->allocs, d->member_scale ? d->member_scale : one.data(), s->M);
+    f.member_shift = dev_copy<double>(s->allocs, d->member_shift ? d->member_shift : zero.data(), s->M);
+    f.node_slot = dev_copy<int>(s->allocs, slot.data(), nN);
+    s->have_inflows = true;
+    return SWB_OK;
+}
+
+int swb_run_steps(swb_solver *s, int n_steps, double t_end)
+{
+    if (!s || n_steps < 1) return fail(SWB_ERR_ARG, "bad arguments");
+    if (!s->have_inflows) return fail(SWB_ERR_ARG, "swb_set_inflows has not been called");
+    const Net &n = s->net->net;
+    int phases = PH_ADVANCE | PH_SWAP | PH_INFLOWS | PH_DYNWAVE | PH_NEXTDT;
+    if (n.nP > 0 && !n.opt.ignore_quality) phases |= PH_QSWAP | PH_QUALITY;
+    return run(s, phases, n_steps, t_end, n.opt.route_step);
+}
+
+int swb_get_stats(swb_solver *s, int m0, int nm, swb_member_stats *out)
+{
+    if (!s || !out || m0 < 0 || nm < 1 || m0 + nm > s->M) return fail(SWB_ERR_ARG, "bad arguments");
+    const int M = s->M;
+    std::vector<double> t(M), dt(M), vs(M);
+    std::vector<long long> st(M), it(M), nc(M);
+    std::vector<int> cn(M), cl(M);
+    backend::download(t.data(), s->st.sim_time, sizeof(double) * M);
+    backend::download(dt.data(), s->st.dt, sizeof(double) * M);
+    backend::download(vs.data(), s->st.var_step, sizeof(double) * M);
+    backend::download(st.data(), s->st.tot_steps, sizeof(long long) * M);
+    backend::download(it.data(), s->st.tot_iters, sizeof(long long) * M);
+    backend::download(nc.data(), s->st.non_conv, sizeof(long long) * M);
+    backend::download(cn.data(), s->st.crit_node, sizeof(int) * M);
+    backend::download(cl.data(), s->st.crit_link, sizeof(int) * M);
+    for (int k = 0; k < nm; k++) {
+        int m = m0 + k;
+        out[k].sim_time = t[m]; out[k].last_dt = dt[m]; out[k].next_dt = vs[m];
+        out[k].steps = st[m]; out[k].iterations = it[m]; out[k].non_converged = nc[m];
+        out[k].crit_node = cn[m]; out[k].crit_link = cl[m];
+    }
+    return SWB_OK;
+}
+
+long long swb_conduit_updates(swb_solver *s)
+{
+    if (!s) return 0;
+    std::vector<long long> it(s->M);
+    backend::download(it.data(), s->st.tot_iters, sizeof(long long) * s->M);
+    long long sum = 0;
+    for (long long v : it) sum += v;
+    return sum * (long long)s->net->net.nTrue;
+}
+
+long long swb_launch_count(const swb_solver *s) { return s ? s->launches : 0; }
+double swb_last_kernel_ms(const swb_solver *s) { return s ? (double)s->last_ms : 0.0; }
+int swb_sync(swb_solver *s)
+{
+    (void)s;
+    std::string err;
+    if (!backend::sync(err)) return fail(SWB_ERR_CUDA, err);
+    return SWB_OK;
+}
+
+} // extern "C"
+#endif

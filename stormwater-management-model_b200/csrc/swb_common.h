@@ -34,4 +34,27 @@
 #define SWB_MAX(x, y) (((x) >= (y)) ? (x) : (y))
 #define SWB_SGN(x)    (((x) < 0) ? (-1) : (1))
 
+#define SWB_MAX_POLLUT 8       // pollutants carried per member (register accumulators)
+
+#include <string.h>
+namespace swb {
+// order-preserving integer image of a non-negative double (for integer atomicMin)
+SWB_HD inline unsigned long long dbits(double v)
+{
+#if defined(__CUDA_ARCH__)
+    return (unsigned long long)__double_as_longlong(v);
+#else
+    unsigned long long u; memcpy(&u, &v, sizeof(u)); return u;
+#endif
+}
+SWB_HD inline double dfrombits(unsigned long long u)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double v; memcpy(&v, &u, sizeof(v)); return v;
+#endif
+}
+}
+
 #endif

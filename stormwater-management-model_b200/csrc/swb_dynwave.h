@@ -1,0 +1,734 @@
+// swb_dynwave.h -- per-(object, member) device functions of the dynamic-wave step.
+//
+//   K1  conduit_flow        <- dwflow_findConduitFlow + findSurfArea + getFlowClass + getWidth /
+//                              getSlotWidth / getArea / getHydRad + checkNormalFlow +
+//                              findLocalLosses (dwflow.c:57-686), link_getFroude (link.c:847),
+//                              conduit_getLossRate (link.c:1334), link_setFlapGate (link.c:643),
+//                              link_getYnorm / link_getYcrit (link.c:770-804)
+//   K3  node_gather         <- initNodeStates + updateNodeFlows (dynwave.c:297-331, 528-589) as a
+//                              fixed-order CSR gather (no atomics, reference summation order)
+//   K4  outfall_depth       <- link_setOutfallDepth / node_setOutletDepth / outfall_setOutletDepth
+//                              (link.c:728-766, node.c:532-558, 1413-1492)
+//   K5  node_set_depth      <- setNodeDepth + getFloodedDepth (dynwave.c:636-795)
+//   K7  link_step/node_step <- getLinkStep / getNodeStep (dynwave.c:836-921)
+//
+// Every function is a pure function of (static Net, State, object index, member index): the
+// persistent kernel in swb_kernels.cu and the host emulation in tests/emul call exactly these.
+#ifndef SWB_DYNWAVE_H
+#define SWB_DYNWAVE_H
+
+#include "swb_state.h"
+#include "swb_xsect.h"
+
+namespace swb {
+
+SWB_HD inline Xs load_xs(const Net &n, int j)
+{
+    Xs x;
+    x.type = n.xs_type[j];
+    x.yFull = n.xs_yfull[j]; x.wMax = n.xs_wmax[j]; x.ywMax = n.xs_ywmax[j];
+    x.aFull = n.xs_afull[j]; x.rFull = n.xs_rfull[j]; x.sFull = n.xs_sfull[j];
+    x.sMax = n.xs_smax[j];   x.yBot = n.xs_ybot[j];   x.aBot = n.xs_abot[j];
+    x.sBot = n.xs_sbot[j];   x.rBot = n.xs_rbot[j];
+    x.ntbl = 0; x.atbl = x.rtbl = x.wtbl = nullptr;
+    int t = n.xs_table[j];
+    if (t >= 0) {
+        x.ntbl = n.shape_tbl_n[t];
+        x.atbl = n.shape_area_tbl + (size_t)t * n.shapeTblLen;
+        x.rtbl = n.shape_hrad_tbl + (size_t)t * n.shapeTblLen;
+        x.wtbl = n.shape_width_tbl + (size_t)t * n.shapeTblLen;
+    }
+    return x;
+}
+
+// ---- dwflow.c:575-633 ---------------------------------------------------------------------------
+SWB_HD inline double dw_slot_width(const Net &n, const Xs &x, bool isOpen, double y)
+{
+    double yNorm = y / x.yFull;
+    if (n.opt.surcharge_method != SWB_SLOT || isOpen || yNorm < n.crownCutoff) return 0.0;
+    if (yNorm > 1.78) return 0.01 * x.wMax;
+    return x.wMax * 0.5423 * exp(-pow(yNorm, 2.4));
+}
+SWB_HD inline double dw_width(const Net &n, const Xs &x, bool isOpen, double y, const double *T)
+{
+    double wSlot = dw_slot_width(n, x, isOpen, y);
+    if (wSlot > 0.0) return wSlot;
+    if (y / x.yFull >= n.crownCutoff && !isOpen) y = n.crownCutoff * x.yFull;
+    return xs_w_of_y(x, y, T);
+}
+SWB_HD inline double dw_area(const Xs &x, double y, double wSlot, const double *T)
+{
+    if (y >= x.yFull) return x.aFull + (y - x.yFull) * wSlot;
+    return xs_a_of_y(x, y, T);
+}
+SWB_HD inline double dw_hyd_rad(const Xs &x, double y, const double *T)
+{
+    if (y >= x.yFull) return x.rFull;
+    return xs_r_of_y(x, y, T);
+}
+
+// ---- link.c:847-871 (conduits only) -------------------------------------------------------------
+SWB_HD inline double link_froude(const Xs &x, bool isOpen, double v, double y, const double *T)
+{
+    if (y <= SWB_FUDGE) return 0.0;
+    if (!isOpen && x.yFull - y <= SWB_FUDGE) return 0.0;
+    y = xs_a_of_y(x, y, T) / xs_w_of_y(x, y, T);
+    return fabs(v) / sqrt(SWB_GRAVITY * y);
+}
+
+// ---- link.c:770-804 -----------------------------------------------------------------------------
+SWB_HD inline double link_ynorm(const Net &n, int j, const Xs &x, double q, const double *T)
+{
+    if (!(n.link_flags[j] & LF_TRUE_CONDUIT)) return 0.0;
+    q = fabs(q);
+    if (q > n.cond_q_max[j]) q = n.cond_q_max[j];
+    if (q <= 0.0) return 0.0;
+    double s = q / n.cond_beta[j];
+    double a = xs_a_of_s(x, s, T);
+    return xs_y_of_a(x, a, T);
+}
+
+// ---- link.c:643-670 with the node tests folded into link_flags ----------------------------------
+SWB_HD inline bool link_flap_closed(int flags, int direction, double q)
+{
+    if (flags & LF_HAS_FLAP) { if (q * (double)direction < 0.0) return true; }
+    if (q < 0.0 && (flags & LF_N2_OUT_FLAP)) return true;
+    if (q > 0.0 && (flags & LF_N1_OUT_FLAP)) return true;
+    return false;
+}
+
+// ---- link.c:1334-1399 (DW branch) ---------------------------------------------------------------
+SWB_HD inline double conduit_loss_rate(const Net &n, const State &s, int j, int m, const Xs &x,
+                                       bool isOpen, double dt, double evapRate, double hydcon,
+                                       double &evapLoss, double &seepLoss, const double *T)
+{
+    size_t ix = SWB_IX(j, m, s.M);
+    double depth = 0.5 * (s.l_old_depth[ix] + s.l_depth[ix]);
+    double evapLossRate = 0.0, seepLossRate = 0.0, totalLossRate = 0.0;
+    if (depth > SWB_FUDGE) {
+        double length = n.cond_length[j];
+        if (isOpen && evapRate > 0.0) {
+            double topWidth = xs_w_of_y(x, depth, T);
+            evapLossRate = topWidth * length * evapRate;
+        }
+        double seepRate = n.link_seep_rate[j];
+        if (seepRate > 0.0) {
+            double width;
+            if (x.type == XS_RECT_CLOSED) width = x.wMax;
+            else {
+                if (depth >= x.ywMax) depth = x.ywMax;
+                width = xs_w_of_y(x, depth, T);
+            }
+            seepLossRate = seepRate * width * length;
+            seepLossRate *= hydcon;
+        }
+        totalLossRate = evapLossRate + seepLossRate;
+        double q = s.l_volume[ix] / dt;
+        if (totalLossRate > q) {
+            evapLossRate = evapLossRate * q / totalLossRate;
+            seepLossRate = seepLossRate * q / totalLossRate;
+            totalLossRate = q;
+        }
+    }
+    evapLoss = evapLossRate;
+    seepLoss = seepLossRate;
+    return totalLossRate;
+}
+
+// ---- dwflow.c:297-413 ---------------------------------------------------------------------------
+struct FlowClassOut { int cls; double yC, yN, fasnh; };
+
+SWB_HD inline FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int flags, double q,
+                                         double h1, double h2, double y1, double y2,
+                                         double depth1, double depth2, double yMidGuess,
+                                         const double *T)
+{
+    FlowClassOut o;
+    o.cls = SWB_SUBCRITICAL; o.fasnh = 1.0; o.yC = yMidGuess; o.yN = yMidGuess;
+    double z1 = n.link_offset1[j], z2 = n.link_offset2[j];
+    if (flags & LF_N1_OUTFALL) z1 = SWB_MAX(0.0, (z1 - depth1));
+    if (flags & LF_N2_OUTFALL) z2 = SWB_MAX(0.0, (z2 - depth2));
+
+    if (y1 > SWB_FUDGE && y2 > SWB_FUDGE) {
+        if (q < 0.0) {
+            if (z1 > 0.0) {
+                o.yN = link_ynorm(n, j, x, fabs(q), T);
+                o.yC = xs_ycrit(x, fabs(q), T);
+                double ycMin = SWB_MIN(o.yN, o.yC);
+                if (y1 < ycMin) o.cls = SWB_UP_CRITICAL;
+            }
+        } else {
+            if (z2 > 0.0) {
+                o.yN = link_ynorm(n, j, x, fabs(q), T);
+                o.yC = xs_ycrit(x, fabs(q), T);
+                double ycMin = SWB_MIN(o.yN, o.yC);
+                double ycMax = SWB_MAX(o.yN, o.yC);
+                if (y2 < ycMin) o.cls = SWB_DN_CRITICAL;
+                else if (y2 < ycMax) {
+                    if (ycMax - ycMin < SWB_FUDGE) o.fasnh = 0.0;
+                    else o.fasnh = (ycMax - y2) / (ycMax - ycMin);
+                }
+            }
+        }
+    }
+    else if (y1 <= SWB_FUDGE && y2 <= SWB_FUDGE) o.cls = SWB_DRY;
+    else if (y2 > SWB_FUDGE) {
+        if (h2 < n.link_z1[j]) o.cls = SWB_UP_DRY;
+        else if (z1 > 0.0) {
+            o.yN = link_ynorm(n, j, x, fabs(q), T);
+            o.yC = xs_ycrit(x, fabs(q), T);
+            o.cls = SWB_UP_CRITICAL;
+        }
+    }
+    else {
+        if (h1 < n.link_z2[j]) o.cls = SWB_DN_DRY;
+        else if (z2 > 0.0) {
+            o.yN = link_ynorm(n, j, x, fabs(q), T);
+            o.yC = xs_ycrit(x, fabs(q), T);
+            o.cls = SWB_DN_CRITICAL;
+        }
+    }
+    return o;
+}
+
+// ---- K1: dwflow.c:57-293 (with findSurfArea :417-550, checkNormalFlow :637-686) ------------------
+SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int steps, double dt,
+                                const double *T)
+{
+    const int M = s.M;
+    const size_t ix = SWB_IX(j, m, M);
+    const int flags = n.link_flags[j];
+    const Xs x = load_xs(n, j);
+    const bool isOpen = (flags & LF_OPEN_SHAPE) != 0;
+    const int n1 = n.link_node1[j], n2 = n.link_node2[j];
+    const double barrels = (double)n.cond_barrels[j];
+    const bool slot = (n.opt.surcharge_method == SWB_SLOT);
+
+    bool isClosed = (s.l_setting[ix] == 0);
+    double qOld = s.l_old_flow[ix] / barrels;
+    double qLast = s.c_q1[ix];
+    double evapLoss = 0.0, seepLoss = 0.0;
+
+    const double depth1 = s.n_depth[SWB_IX(n1, m, M)], depth2 = s.n_depth[SWB_IX(n2, m, M)];
+    const double inv1 = n.node_invert[n1], inv2 = n.node_invert[n2];
+    double z1 = n.link_z1[j], z2 = n.link_z2[j];
+    double h1 = depth1 + inv1, h2 = depth2 + inv2;
+    h1 = SWB_MAX(h1, z1);
+    h2 = SWB_MAX(h2, z2);
+    double y1 = h1 - z1, y2 = h2 - z2;
+    y1 = SWB_MAX(y1, SWB_FUDGE);
+    y2 = SWB_MAX(y2, SWB_FUDGE);
+    if (!slot) { y1 = SWB_MIN(y1, x.yFull); y2 = SWB_MIN(y2, x.yFull); }
+
+    double aOld = s.c_a2[ix];
+    aOld = SWB_MAX(aOld, SWB_FUDGE);
+    const double length = n.cond_mod_length[j];
+    const double trueLength = n.cond_length[j];
+
+    // --- findSurfArea (dwflow.c:417-550) on the previous iteration's flow
+    int flowClass;
+    double surfArea1 = 0.0, surfArea2 = 0.0;
+    {
+        double fd1 = y1, fd2 = y2, fdMid, width1, width2, widthMid;
+        double normalDepth = (fd1 + fd2) / 2.0, criticalDepth = normalDepth, fasnh = 1.0;
+        if (fd1 >= x.yFull && fd2 >= x.yFull) flowClass = SWB_SUBCRITICAL;
+        else {
+            FlowClassOut fc = dw_flow_class(n, j, x, flags, qLast, h1, h2, y1, y2, depth1, depth2,
+                                            normalDepth, T);
+            flowClass = fc.cls; criticalDepth = fc.yC; normalDepth = fc.yN; fasnh = fc.fasnh;
+        }
+        switch (flowClass) {
+          case SWB_SUBCRITICAL:
+            fdMid = 0.5 * (fd1 + fd2);
+            if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
+            width1 = dw_width(n, x, isOpen, fd1, T);
+            width2 = dw_width(n, x, isOpen, fd2, T);
+            widthMid = dw_width(n, x, isOpen, fdMid, T);
+            surfArea1 = (width1 + widthMid) * length / 4.;
+            surfArea2 = (widthMid + width2) * length / 4. * fasnh;
+            break;
+          case SWB_UP_CRITICAL:
+            fd1 = criticalDepth;
+            if (normalDepth < criticalDepth) fd1 = normalDepth;
+            fd1 = SWB_MAX(fd1, SWB_FUDGE);
+            h1 = z1 + fd1;
+            fdMid = 0.5 * (fd1 + fd2);
+            if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
+            width2 = dw_width(n, x, isOpen, fd2, T);
+            widthMid = dw_width(n, x, isOpen, fdMid, T);
+            surfArea2 = (widthMid + width2) * length * 0.5;
+            break;
+          case SWB_DN_CRITICAL:
+            fd2 = criticalDepth;
+            if (normalDepth < criticalDepth) fd2 = normalDepth;
+            fd2 = SWB_MAX(fd2, SWB_FUDGE);
+            h2 = z2 + fd2;
+            width1 = dw_width(n, x, isOpen, fd1, T);
+            fdMid = 0.5 * (fd1 + fd2);
+            if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
+            widthMid = dw_width(n, x, isOpen, fdMid, T);
+            surfArea1 = (width1 + widthMid) * length * 0.5;
+            break;
+          case SWB_UP_DRY:
+            fd1 = SWB_FUDGE;
+            fdMid = 0.5 * (fd1 + fd2);
+            if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
+            width1 = dw_width(n, x, isOpen, fd1, T);
+            width2 = dw_width(n, x, isOpen, fd2, T);
+            widthMid = dw_width(n, x, isOpen, fdMid, T);
+            surfArea2 = (widthMid + width2) * length / 4.;
+            if (n.link_offset1[j] <= 0.0) surfArea1 = (width1 + widthMid) * length / 4.;
+            break;
+          case SWB_DN_DRY:
+            fd2 = SWB_FUDGE;
+            fdMid = 0.5 * (fd1 + fd2);
+            if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
+            width1 = dw_width(n, x, isOpen, fd1, T);
+            width2 = dw_width(n, x, isOpen, fd2, T);
+            widthMid = dw_width(n, x, isOpen, fdMid, T);
+            surfArea1 = (widthMid + width1) * length / 4.;
+            if (n.link_offset2[j] <= 0.0) surfArea2 = (width2 + widthMid) * length / 4.;
+            break;
+          case SWB_DRY:
+            surfArea1 = SWB_FUDGE * length / 2.0;
+            surfArea2 = surfArea1;
+            break;
+        }
+        y1 = fd1; y2 = fd2;
+    }
+    s.l_surf_area1[ix] = surfArea1;
+    s.l_surf_area2[ix] = surfArea2;
+
+    // --- areas and hydraulic radii (dwflow.c:142-153)
+    double wSlot = dw_slot_width(n, x, isOpen, y1);
+    double a1 = dw_area(x, y1, wSlot, T);
+    double r1 = dw_hyd_rad(x, y1, T);
+    wSlot = dw_slot_width(n, x, isOpen, y2);
+    double a2 = dw_area(x, y2, wSlot, T);
+    double yMid = 0.5 * (y1 + y2);
+    wSlot = dw_slot_width(n, x, isOpen, yMid);
+    double aMid = dw_area(x, yMid, wSlot, T);
+    double rMid = dw_hyd_rad(x, yMid, T);
+
+    bool isFull = (y1 >= x.yFull && y2 >= x.yFull);
+
+    // --- dry / closed exit (dwflow.c:165-180)
+    if (flowClass == SWB_DRY || flowClass == SWB_UP_DRY || flowClass == SWB_DN_DRY || isClosed ||
+        aMid <= SWB_FUDGE) {
+        double a1s = 0.5 * (a1 + a2);
+        s.c_a1[ix] = a1s;
+        s.c_q1[ix] = 0.0;
+        s.c_q2[ix] = 0.0;
+        s.l_dqdh[ix] = SWB_GRAVITY * dt * aMid / length * barrels;
+        s.l_froude[ix] = 0.0;
+        s.l_depth[ix] = SWB_MIN(yMid, x.yFull);
+        s.l_volume[ix] = a1s * trueLength * barrels;
+        s.l_flow[ix] = 0.0;
+        s.l_flow_class[ix] = (unsigned char)flowClass;
+        s.c_evap_loss[ix] = 0.0;
+        s.c_seep_loss[ix] = 0.0;
+        return;
+    }
+
+    // --- velocity, Froude number, inertial damping (dwflow.c:183-208)
+    double v = qLast / aMid;
+    if (fabs(v) > SWB_MAXVELOCITY) v = SWB_MAXVELOCITY * SWB_SGN(qLast);
+    double froude = link_froude(x, isOpen, v, yMid, T);
+    if (flowClass == SWB_SUBCRITICAL && froude > 1.0) flowClass = SWB_SUPCRITICAL;
+    double sigma;
+    if      (froude <= 0.5) sigma = 1.0;
+    else if (froude >= 1.0) sigma = 0.0;
+    else    sigma = 2.0 * (1.0 - froude);
+    double rho = 1.0;
+    if (!isFull && qLast > 0.0 && h1 >= h2) rho = sigma;
+    double aWtd = a1 + (aMid - a1) * rho;
+    double rWtd = r1 + (rMid - r1) * rho;
+    if      (n.opt.inert_damping == SWB_NO_DAMPING)   sigma = 1.0;
+    else if (n.opt.inert_damping == SWB_FULL_DAMPING) sigma = 0.0;
+    if (isFull && !isOpen) sigma = 0.0;
+
+    // --- momentum terms (dwflow.c:210-236)
+    double dq1 = dt * n.cond_rough_factor[j] / pow(rWtd, 1.33333) * fabs(v);
+    double dq2 = dt * SWB_GRAVITY * aWtd * (h2 - h1) / length;
+    double dq3 = 0.0, dq4 = 0.0;
+    if (sigma > 0.0) {
+        dq3 = 2.0 * v * (aMid - aOld) * sigma;
+        dq4 = dt * v * v * (a2 - a1) / length * sigma;
+    }
+    double dq5 = 0.0;
+    if (n.cond_has_losses[j]) {
+        double losses = 0.0, qa = fabs(qLast);
+        if (a1 > SWB_FUDGE)   losses += n.link_closs_in[j]  * (qa / a1);
+        if (a2 > SWB_FUDGE)   losses += n.link_closs_out[j] * (qa / a2);
+        if (aMid > SWB_FUDGE) losses += n.link_closs_avg[j] * (qa / aMid);
+        dq5 = losses / 2.0 / length * dt;
+    }
+    double dq6 = 0.0;
+    if (flags & LF_HAS_LOSSRATE) {
+        double lossRate = conduit_loss_rate(n, s, j, m, x, isOpen, dt, s.evap_rate[m], s.hydcon[m],
+                                            evapLoss, seepLoss, T);
+        dq6 = lossRate * 2.5 * dt * v / trueLength;
+    }
+
+    double denom = 1.0 + dq1 + dq5;
+    double q = (qOld - dq2 + dq3 + dq4 + dq6) / denom;
+    double dqdh = 1.0 / denom * SWB_GRAVITY * dt * aWtd / length * barrels;
+
+    // --- flow limitations (dwflow.c:245-259; culverts are rejected at network creation)
+    unsigned char normalFlow = 0;
+    if (q > 0.0) {
+        if (n.opt.normal_flow_ltd != SWB_NF_NEITHER && y1 < x.yFull &&
+            (flowClass == SWB_SUBCRITICAL || flowClass == SWB_SUPCRITICAL)) {
+            // checkNormalFlow (dwflow.c:637-686)
+            bool check = false;
+            bool hasOutfall = (flags & (LF_N1_OUTFALL | LF_N2_OUTFALL)) != 0;
+            int nfl = n.opt.normal_flow_ltd;
+            if (nfl == SWB_NF_SLOPE || nfl == SWB_NF_BOTH || hasOutfall) { if (y1 < y2) check = true; }
+            if (!check && (nfl == SWB_NF_FROUDE || nfl == SWB_NF_BOTH) && !hasOutfall) {
+                if (y1 > SWB_FUDGE && y2 > SWB_FUDGE) {
+                    double f1 = link_froude(x, isOpen, q / a1, y1, T);
+                    if (f1 >= 1.0) check = true;
+                }
+            }
+            if (check) {
+                double qNorm = n.cond_beta[j] * a1 * pow(r1, 2. / 3.);
+                if (qNorm < q) { normalFlow = 1; q = qNorm; }
+            }
+        }
+    }
+
+    // --- under-relaxation, limits, flap gates, dry nodes (dwflow.c:261-281)
+    if (steps > 0) {
+        q = (1.0 - SWB_OMEGA) * qLast + SWB_OMEGA * q;
+        if (q * qLast < 0.0) q = 0.001 * SWB_SGN(q);
+    }
+    double qLimit = n.link_q_limit[j];
+    if (qLimit > 0.0) { if (fabs(q) > qLimit) q = SWB_SGN(q) * qLimit; }
+    if (link_flap_closed(flags, n.link_direction[j], q)) q = 0.0;
+    if (q >  SWB_FUDGE && depth1 <= SWB_FUDGE) q =  SWB_FUDGE;
+    if (q < -SWB_FUDGE && depth2 <= SWB_FUDGE) q = -SWB_FUDGE;
+
+    // --- save (dwflow.c:283-292)
+    s.c_a1[ix] = aMid;
+    s.c_q1[ix] = q;
+    s.c_q2[ix] = q;
+    s.l_depth[ix] = SWB_MIN(yMid, x.yFull);
+    double aAvg = (a1 + a2) / 2.0;
+    unsigned char fullState = 0;
+    if (a1 >= x.aFull) fullState = (a2 >= x.aFull) ? SWB_ALL_FULL : SWB_UP_FULL;
+    else if (a2 >= x.aFull) fullState = SWB_DN_FULL;
+    s.c_full_state[ix] = fullState;
+    s.l_volume[ix] = aAvg * trueLength * barrels;
+    s.l_flow[ix] = q * barrels;
+    s.l_dqdh[ix] = dqdh;
+    s.l_froude[ix] = froude;
+    s.l_flow_class[ix] = (unsigned char)flowClass;
+    s.l_normal_flow[ix] = normalFlow;
+    s.l_inlet_control[ix] = 0;
+    s.c_evap_loss[ix] = evapLoss;
+    s.c_seep_loss[ix] = seepLoss;
+}
+
+// ---- node.c:362-396, 562-585, 930-1018 -----------------------------------------------------------
+SWB_HD inline double curve_lookup_ex(const Net &n, int c, double x)          // table.c:467-500
+{
+    int i0 = n.curve_start[c], i1 = n.curve_start[c + 1];
+    if (i1 <= i0) return 0.0;
+    double x1 = n.curve_x[i0], y1 = n.curve_y[i0], x2, y2, sl = 0.0;
+    if (x <= x1) { if (x1 > 0.0) return x / x1 * y1; else return y1; }
+    for (int i = i0 + 1; i < i1; i++) {
+        x2 = n.curve_x[i]; y2 = n.curve_y[i];
+        if (x2 != x1) sl = (y2 - y1) / (x2 - x1);
+        if (x <= x2) {
+            double dx = x2 - x1;
+            if (fabs(dx) < 1.0e-20) return (y1 + y2) / 2.;
+            return y1 + (x - x1) * (y2 - y1) / dx;
+        }
+        x1 = x2; y1 = y2;
+    }
+    if (sl < 0.0) sl = 0.0;
+    return y1 + sl * (x - x1);
+}
+
+SWB_HD inline double tbl_interp(double x, double x1, double y1, double x2, double y2)  // table.c:51
+{
+    double dx = x2 - x1;
+    if (fabs(dx) < 1.0e-20) return (y1 + y2) / 2.;
+    return y1 + (x - x1) * (y2 - y1) / dx;
+}
+
+SWB_HD inline double curve_storage_volume(const Net &n, int c, double x)    // table.c:590-648
+{
+    int i0 = n.curve_start[c], i1 = n.curve_start[c + 1];
+    if (i1 <= i0) return 0.0;
+    double a, a1, x1, v = 0.0, dx = 0.0, dy = 0.0, sl;
+    x1 = n.curve_x[i0]; a1 = n.curve_y[i0];
+    if (x <= x1) {
+        if (x1 < 1.e-6) return 0.0;
+        return (a1 / x1) * x * x / 2.0;
+    }
+    for (int i = i0 + 1; i < i1; i++) {
+        double ex = n.curve_x[i], ey = n.curve_y[i];
+        if (ex >= x) {
+            a = tbl_interp(x, x1, a1, ex, ey);
+            return v + (a1 + a) / 2.0 * (x - x1);
+        }
+        dx = ex - x1; dy = ey - a1;
+        v = v + (a1 + ey) / 2.0 * dx;
+        x1 = ex; a1 = ey;
+    }
+    if (dx > 1.0e-6) {
+        sl = dy / dx;
+        a = a1 + sl * (x - x1);
+        if (a < 0.0) v = v - a1 * a1 / sl / 2.0;
+        else v = v + (a1 + a) / 2.0 * (x - x1);
+    }
+    return v;
+}
+
+SWB_HD inline double storage_surf_area(const Net &n, int i, double d)
+{
+    double area = 0.0;
+    const double ucfL = n.opt.ucf_length;
+    switch (n.storage_shape[i]) {
+      case 0: { int c = n.storage_curve[i]; if (c >= 0) area = curve_lookup_ex(n, c, d * ucfL); break; }
+      case 1: area = n.storage_a0[i] + n.storage_a1[i] * pow(d * ucfL, n.storage_a2[i]); break;
+      case 2: case 3: case 4: case 5:
+        d *= ucfL;
+        area = n.storage_a0[i] + d * (n.storage_a1[i] + d * n.storage_a2[i]);
+        break;
+      default: return 0.0;
+    }
+    return area / ucfL / ucfL;
+}
+
+SWB_HD inline double storage_volume(const Net &n, int i, double d)
+{
+    if (d == 0.0) return 0.0;
+    if (d >= n.node_full_depth[i] && n.node_full_volume[i] > 0.0) return n.node_full_volume[i];
+    const double ucfL = n.opt.ucf_length, ucfV = n.opt.ucf_volume;
+    switch (n.storage_shape[i]) {
+      case 0: { int c = n.storage_curve[i];
+                if (c >= 0) return curve_storage_volume(n, c, d * ucfL) / ucfV;
+                return 0.0; }
+      case 1: { d *= ucfL;
+                double nn = n.storage_a2[i] + 1.0;
+                double v = (n.storage_a0[i] * d) + n.storage_a1[i] / nn * pow(d, nn);
+                return v / ucfV; }
+      case 2: case 3: case 4: case 5: {
+                d *= ucfL;
+                double v = d * (n.storage_a0[i] + d * (n.storage_a1[i] / 2.0 + d * n.storage_a2[i] / 3.0));
+                return v / ucfV; }
+      default: return 0.0;
+    }
+}
+
+SWB_HD inline double node_surf_area(const Net &n, int i, double d)
+{
+    return n.node_type[i] == SWB_STORAGE ? storage_surf_area(n, i, d) : 0.0;
+}
+SWB_HD inline double node_ponded_area(const Net &n, int i, double d)        // node.c:562-585
+{
+    if (d <= n.node_full_depth[i] || n.node_ponded_area[i] == 0.0) return node_surf_area(n, i, d);
+    double a = n.node_ponded_area[i];
+    if (a <= 0.0) a = node_surf_area(n, i, n.node_full_depth[i]);
+    return a;
+}
+SWB_HD inline double node_volume(const Net &n, int i, double d)             // node.c:345-358
+{
+    if (n.node_type[i] == SWB_STORAGE) return storage_volume(n, i, d);
+    if (n.node_full_depth[i] > 0.0) return n.node_full_volume[i] * (d / n.node_full_depth[i]);
+    return 0.0;
+}
+
+// ---- K3: initNodeStates + updateNodeFlows over the node's incidence list ------------------------
+// Accumulates in the reference's order: lateral flow / losses first, then the incident link ends in
+// CSR order [first, last).  Called once for the true-conduit segment and, for networks with
+// regulators, link by link from the ordered pass.
+struct NodeAcc { double inflow, outflow, surfArea, sumdqdh; };
+
+SWB_HD inline NodeAcc node_init_acc(const Net &n, const State &s, int i, int m)
+{
+    NodeAcc a;
+    size_t ix = SWB_IX(i, m, s.M);
+    double depth = s.n_depth[ix];
+    a.surfArea = n.opt.allow_ponding ? node_ponded_area(n, i, depth) : node_surf_area(n, i, depth);
+    a.inflow = 0.0;
+    a.outflow = s.n_losses[ix];
+    double lat = s.n_latflow[ix];
+    if (lat >= 0.0) a.inflow += lat; else a.outflow -= lat;
+    a.sumdqdh = 0.0;
+    return a;
+}
+
+// contribution of link j (end = 0: node is node1 / upstream, 1: node2) -- dynwave.c:528-589
+SWB_HD inline void node_add_link_end(const Net &n, const State &s, int j, int end, int m, NodeAcc &a)
+{
+    size_t ix = SWB_IX(j, m, s.M);
+    int flags = n.link_flags[j];
+    double q = s.l_flow[ix];
+    if (q >= 0.0) { if (end == 0) a.outflow += q; else a.inflow += q; }
+    else          { if (end == 0) a.inflow -= q;  else a.outflow -= q; }
+    int barrels = 1;
+    if (n.link_type[j] == SWB_CONDUIT) {
+        barrels = n.cond_barrels[j];
+        if (flags & LF_HAS_LOSSRATE) {
+            double lossRate = (s.c_evap_loss[ix] + s.c_seep_loss[ix]) * barrels;
+            if (lossRate > 0.0) {
+                bool o1 = (flags & LF_N1_OUTFALL) != 0, o2 = (flags & LF_N2_OUTFALL) != 0;
+                if (!o1 && !o2) lossRate /= 2.0;
+                if (end == 0 ? !o1 : !o2) a.outflow += lossRate;
+            }
+        }
+    }
+    a.surfArea += (end == 0 ? s.l_surf_area1[ix] : s.l_surf_area2[ix]) * barrels;
+    double dqdh = s.l_dqdh[ix];
+    if (end == 0) a.sumdqdh += dqdh;
+    else if (n.link_type[j] == SWB_PUMP) { if (n.pump_type[j] != 3 /*TYPE4_PUMP*/) a.sumdqdh += dqdh; }
+    else a.sumdqdh += dqdh;
+}
+
+// ---- K4: outfall boundary depth (link.c:728-766, node.c:1413-1492) ------------------------------
+SWB_HD inline void outfall_depth(const Net &n, const State &s, int i, int m, const double *T)
+{
+    int j = n.outfall_link[i];
+    if (j < 0) return;
+    size_t ixl = SWB_IX(j, m, s.M), ixn = SWB_IX(i, m, s.M);
+    double z = (n.link_node2[j] == i) ? n.link_offset2[j] : n.link_offset1[j];
+    double yNorm = 0.0, yCrit = 0.0;
+    if (n.link_type[j] == SWB_CONDUIT) {
+        Xs x = load_xs(n, j);
+        double q = fabs(s.l_flow[ixl] / n.cond_barrels[j]);
+        yNorm = link_ynorm(n, j, x, q, T);
+        yCrit = xs_ycrit(x, q, T);
+    }
+    double yNew;
+    switch (n.outfall_type[i]) {
+      case SWB_FREE_OUTFALL:
+        if (z > 0.0) yNew = 0.0; else yNew = SWB_MIN(yNorm, yCrit);
+        break;
+      case SWB_NORMAL_OUTFALL:
+        if (z > 0.0) yNew = 0.0; else yNew = yNorm;
+        break;
+      default: {
+        double stage = s.n_stage[ixn];
+        double inv = n.node_invert[i];
+        yCrit = SWB_MIN(yCrit, yNorm);
+        if (yCrit + z + inv < stage) yNew = stage - inv;
+        else if (z > 0.0) {
+            if (stage < inv + z) yNew = SWB_MAX(0.0, (stage - inv));
+            else yNew = z + yCrit;
+        }
+        else yNew = yCrit;
+      }
+    }
+    s.n_depth[ixn] = yNew;
+}
+
+// ---- K5: setNodeDepth + getFloodedDepth (dynwave.c:636-795); returns the converged flag ---------
+SWB_HD inline bool node_set_depth(const Net &n, const State &s, int i, int m, int steps, double dt,
+                                  const NodeAcc &acc)
+{
+    const size_t ix = SWB_IX(i, m, s.M);
+    const double fullDepth = n.node_full_depth[i];
+    const bool canPond = (n.opt.allow_ponding && n.node_ponded_area[i] > 0.0);
+    const double yLast = s.n_depth[ix];
+    const bool isPonded = (canPond && yLast > fullDepth);
+    const double yCrown = n.node_crown_elev[i] - n.node_invert[i];
+    const double yOld = s.n_old_depth[ix];
+    double overflow = 0.0, newVolume;
+    double surfArea = acc.surfArea;
+    surfArea = SWB_MAX(surfArea, n.opt.min_surf_area);
+    double dQ = acc.inflow - acc.outflow;
+    double dV = 0.5 * (s.n_old_net_inflow[ix] + dQ) * dt;
+    bool isSurcharged = false;
+    double yNew, dy;
+
+    if (n.opt.surcharge_method == SWB_EXTRAN) {
+        if (isPonded) isSurcharged = false;
+        else if (n.node_type[i] == SWB_STORAGE)
+            isSurcharged = (n.node_sur_depth[i] > 0.0 && yLast > fullDepth);
+        else isSurcharged = (yCrown > 0.0 && yLast > yCrown);
+    }
+    if (!isSurcharged) {
+        dy = dV / surfArea;
+        yNew = yOld + dy;
+        if (!isPonded) s.n_old_surf_area[ix] = surfArea;
+        if (steps > 0) yNew = (1.0 - SWB_OMEGA) * yLast + SWB_OMEGA * yNew;
+        if (isPonded && yNew < fullDepth) yNew = fullDepth - SWB_FUDGE;
+    } else {
+        double corr = 1.0;
+        if (n.node_degree[i] < 0) corr = 0.6;
+        double denom = acc.sumdqdh;
+        if (yLast < 1.25 * yCrown) {
+            double f = (yLast - yCrown) / yCrown;
+            denom += (s.n_old_surf_area[ix] / dt - acc.sumdqdh) * exp(-15.0 * f);
+        }
+        if (denom == 0.0) dy = 0.0;
+        else dy = corr * dQ / denom;
+        yNew = yLast + dy;
+        if (yNew < yCrown) yNew = yCrown - SWB_FUDGE;
+        if (canPond && yNew > fullDepth) yNew = fullDepth + SWB_FUDGE;
+    }
+    if (yNew < 0) yNew = 0.0;
+    double yMax = fullDepth;
+    if (!canPond) yMax += n.node_sur_depth[i];
+    if (yNew > yMax) {
+        // getFloodedDepth (dynwave.c:766-795)
+        double fullVolume = n.node_full_volume[i];
+        if (!canPond) {
+            overflow = dV / dt;
+            newVolume = fullVolume;
+            yNew = yMax;
+        } else {
+            double oldVolume = s.n_old_volume[ix];
+            newVolume = SWB_MAX((oldVolume + dV), fullVolume);
+            overflow = (newVolume - SWB_MAX(oldVolume, fullVolume)) / dt;
+        }
+        if (overflow < SWB_FUDGE) overflow = 0.0;
+    }
+    else newVolume = node_volume(n, i, yNew);
+
+    s.n_dydt[ix] = fabs(yNew - yOld) / dt;
+    s.n_depth[ix] = yNew;
+    s.n_volume[ix] = newVolume;
+    s.n_overflow[ix] = overflow;
+    s.n_inflow[ix] = acc.inflow;
+    s.n_outflow[ix] = acc.outflow;
+    bool conv = !(fabs(yLast - yNew) > n.opt.head_tol);
+    s.n_converged[ix] = conv ? 1 : 0;
+    return conv;
+}
+
+// ---- K7: Courant / depth-change step candidates (dynwave.c:836-921) ------------------------------
+// return the candidate step of one object, or a negative value when the object is skipped
+SWB_HD inline double link_step(const Net &n, const State &s, int j, int m)
+{
+    if (n.link_type[j] != SWB_CONDUIT) return -1.0;
+    size_t ix = SWB_IX(j, m, s.M);
+    double barrels = (double)n.cond_barrels[j];
+    double q = fabs(s.l_flow[ix]) / barrels;
+    double froude = s.l_froude[ix];
+    if (q <= SWB_FUDGE || s.c_a1[ix] <= SWB_FUDGE || froude <= 0.01) return -1.0;
+    double t = s.l_volume[ix] / barrels / q;
+    t = t * n.cond_mod_length[j] / n.cond_length[j];
+    t = t * froude / (1.0 + froude) * n.opt.courant_factor;
+    return t;
+}
+SWB_HD inline double node_step(const Net &n, const State &s, int i, int m)
+{
+    if (n.node_type[i] == SWB_OUTFALL) return -1.0;
+    size_t ix = SWB_IX(i, m, s.M);
+    double depth = s.n_depth[ix];
+    double yCrown = n.node_crown_elev[i] - n.node_invert[i];
+    if (depth <= SWB_FUDGE) return -1.0;
+    if (depth + SWB_FUDGE >= yCrown) return -1.0;
+    double maxDepth = yCrown * 0.25;
+    if (maxDepth < SWB_FUDGE) return -1.0;
+    double dYdT = s.n_dydt[ix];
+    if (dYdT < SWB_FUDGE) return -1.0;
+    return maxDepth / dYdT;
+}
+
+} // namespace swb
+#endif

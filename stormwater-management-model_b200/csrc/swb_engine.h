@@ -1,0 +1,348 @@
+// swb_engine.h -- K9: the persistent routing-step driver.
+//
+// ONE cooperative launch runs `n_steps` complete routing steps for all M lockstep members: step
+// prologue, the Picard loop of dynwave_execute (dynwave.c:224-262) with its data-dependent trip
+// count, capacity flags, quality routing and the Courant search for the next step.  Phases are
+// separated by grid-wide barriers; there is no host round trip per iteration or per step.
+//
+// Work mapping: the launch has G threads with G % M == 0, so thread t always works on member
+// m = t % M and walks objects  t / M, t / M + G / M, ...  A warp is 32 consecutive members of one
+// object (see swb_state.h).  Convergence is tracked per member: not_conv[k][m] is raised by any
+// node of member m that misses the head tolerance in trial k; a member leaves the loop after
+// trial k >= 1 with not_conv[k][m] == 0, exactly like `if (Steps > 1 && converged) break`.
+//
+// The body is a template over an execution context so that tests/emul can run the very same
+// control flow (including every barrier) on host threads.  Ctx provides:
+//     int tid, G, lane, block_size;   const double *T (shape tables);
+//     void grid_sync();  bool block_or(bool);
+//     void atomic_min_u64(unsigned long long*, unsigned long long);
+//     void atomic_add_f64(double*, double);
+#ifndef SWB_ENGINE_H
+#define SWB_ENGINE_H
+
+#include "swb_dynwave.h"
+#include "swb_qual.h"
+#include "swb_regulator.h"
+
+#ifdef __CUDACC__
+#define SWB_ENGINE __device__ __forceinline__
+#else
+#define SWB_ENGINE inline
+#endif
+
+namespace swb {
+
+enum {                         // RunArgs.phases
+    PH_SWAP    = 1,            // old <- new, node_initFlows, overflow reset (routing.c:399-409)
+    PH_INFLOWS = 2,            // evaluate lateral inflows + quality preload on the device
+    PH_DYNWAVE = 4,            // dynwave_execute
+    PH_QUALITY = 8,            // qualrout_execute
+    PH_NEXTDT  = 16,           // dynwave_getRoutingStep -> var_step
+    PH_ADVANCE = 32,           // ensemble clock: pick dt from var_step / t_end, advance sim_time
+    PH_QSWAP   = 64            // quality old <- new, new = 0 (routing.c:312-336)
+};
+
+struct Inflows {               // device image of swb_inflow_desc
+    int n;                     // inflow nodes
+    const int    *node, *ts_start;
+    const double *ts_t, *ts_q, *sfactor, *baseline, *concen;
+    const double *member_scale, *member_shift;
+    const int    *node_slot;   // per node: index into the inflow list or -1
+    double start_day, start_secs;
+};
+
+struct RunArgs {
+    int    phases;
+    int    n_steps;
+    double t_end;              // PH_ADVANCE: members stop at this simulated time (s)
+    double fixed_step;         // RouteStep for PH_NEXTDT / PH_ADVANCE
+    Inflows inflows;
+};
+
+#define SWB_FLOW_TOL 0.00001   // consts.h: FLOW_TOL, routing.c:455
+
+// hydrograph value at time t (s) for inflow slot k: linear between breakpoints, 0 outside
+// (table_tseriesLookup with extend = FALSE, table.c:745-806)
+SWB_HD inline double inflow_series(const Inflows &f, int k, double t)
+{
+    int i0 = f.ts_start[k], i1 = f.ts_start[k + 1];
+    if (i1 <= i0) return 0.0;
+    if (t < f.ts_t[i0] || t > f.ts_t[i1 - 1]) return 0.0;
+    for (int i = i0 + 1; i < i1; i++) {
+        if (t <= f.ts_t[i]) return tbl_interp(t, f.ts_t[i - 1], f.ts_q[i - 1], f.ts_t[i], f.ts_q[i]);
+    }
+    return 0.0;
+}
+
+template <class Ctx>
+SWB_ENGINE void engine_run(const Net &net, const State &st, const RunArgs &args, Ctx &ctx)
+{
+    const int M = st.M, nN = net.nN, nL = net.nL, nP = net.nP;
+    const int m = ctx.tid % M;
+    const int first = ctx.tid / M, stride = ctx.G / M;
+    const bool owner = (first == 0);             // the one thread that owns member m's scalars
+    const double *T = ctx.T;
+    const int maxTrials = net.opt.max_trials < SWB_MAX_TRIALS_CAP ? net.opt.max_trials
+                                                                  : SWB_MAX_TRIALS_CAP;
+    const bool withQual = (nP > 0) && !net.opt.ignore_quality;
+
+    for (int step = 0; step < args.n_steps; step++) {
+        // ================= step prologue =======================================================
+        if (args.phases & PH_ADVANCE) {
+            // execRouting (swmm5.c:528-546): step = variable step, shortened to end at t_end
+            if (owner) {
+                double t = st.sim_time[m];
+                int done = (t >= args.t_end) ? 1 : 0;
+                double dt = st.var_step[m];
+                if (net.opt.courant_factor == 0.0) dt = args.fixed_step;
+                else if (dt == 0.0) {      // first call of dynwave_getRoutingStep (dynwave.c:209-218)
+                    dt = floor(1000.0 * net.opt.min_route_step) / 1000.0;
+                    st.var_step[m] = dt;
+                }
+                // time is kept in milliseconds like NewRoutingTime (routing.c:301)
+                double tms = 1000.0 * t, nextms = tms + 1000.0 * dt, endms = 1000.0 * args.t_end;
+                if (!done && nextms > endms) {
+                    dt = (endms - tms) / 1000.0;
+                    dt = SWB_MAX(dt, 1. / 1000.0);
+                }
+                st.dt[m] = dt;
+                st.done[m] = done;
+            }
+            ctx.grid_sync();
+        }
+        const bool active = !((args.phases & PH_ADVANCE) && st.done[m]);
+        const double dt = st.dt[m];
+
+        if (active && (args.phases & (PH_SWAP | PH_INFLOWS | PH_QSWAP | PH_DYNWAVE))) {
+            // getDateTime(NewRoutingTime): 1 ms after the routing time (swmm5.c:1551), in days
+            const double tNow = args.inflows.start_day +
+                (args.inflows.start_secs + (1000.0 * st.sim_time[m] + 1.0) / 1000.0) / 86400.0;
+            for (int i = first; i < nN; i += stride) {
+                size_t ix = SWB_IX(i, m, M);
+                if (args.phases & PH_QSWAP)
+                    for (int p = 0; p < nP; p++) {
+                        size_t iq = SWB_IXP(p, i, nN, m, M);
+                        st.n_old_qual[iq] = st.n_qual[iq];
+                        st.n_qual[iq] = 0.0;
+                    }
+                if (args.phases & PH_INFLOWS) {
+                    // addExternalInflows (routing.c:435-490)
+                    double q = 0.0;
+                    int k = args.inflows.node_slot[i];
+                    if (k >= 0) {
+                        double tsv = inflow_series(args.inflows, k, tNow - args.inflows.member_shift[m])
+                                     * (args.inflows.sfactor[k] * args.inflows.member_scale[m]);
+                        q = tsv + args.inflows.baseline[k];
+                        if (fabs(q) < SWB_FLOW_TOL) q = 0.0;
+                        if (q >= 0.0)
+                            for (int p = 0; p < nP; p++)
+                                st.n_qual[SWB_IXP(p, i, nN, m, M)] += args.inflows.concen[k * nP + p] * q;
+                    }
+                    st.n_latflow[ix] = q;
+                    st.n_losses[ix] = 0.0;
+                }
+                if (args.phases & PH_SWAP) {
+                    // node_setOldHydState, node_initFlows, flowrout.c:153-162
+                    double newVolume = st.n_volume[ix];
+                    st.n_old_depth[ix] = st.n_depth[ix];
+                    st.n_old_volume[ix] = newVolume;
+                    st.n_old_net_inflow[ix] = st.n_inflow[ix] - st.n_outflow[ix];
+                    st.n_inflow[ix] = st.n_latflow[ix];
+                    st.n_outflow[ix] = st.n_losses[ix];
+                    double ov = 0.0, fullVolume = net.node_full_volume[i];
+                    if (net.node_type[i] != SWB_STORAGE && newVolume > fullVolume)
+                        ov = (newVolume - fullVolume) / dt;
+                    st.n_overflow[ix] = ov;
+                }
+                if (args.phases & PH_DYNWAVE) {        // initRoutingStep (dynwave.c:276-293)
+                    st.n_converged[ix] = 0;
+                    st.n_dydt[ix] = 0.0;
+                }
+            }
+            for (int j = first; j < nL; j += stride) {
+                size_t ix = SWB_IX(j, m, M);
+                if (args.phases & PH_QSWAP)
+                    for (int p = 0; p < nP; p++) {
+                        size_t iq = SWB_IXP(p, j, nL, m, M);
+                        st.l_old_qual[iq] = st.l_qual[iq];
+                        st.l_qual[iq] = 0.0;
+                    }
+                if (args.phases & PH_SWAP) {            // link_setOldHydState (link.c:564-583)
+                    st.l_old_depth[ix] = st.l_depth[ix];
+                    st.l_old_flow[ix] = st.l_flow[ix];
+                    st.l_old_volume[ix] = st.l_volume[ix];
+                }
+                if (args.phases & PH_DYNWAVE) {
+                    st.l_bypassed[ix] = 0;
+                    if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) {
+                        st.l_surf_area1[ix] = 0.0;
+                        st.l_surf_area2[ix] = 0.0;
+                    }
+                    if (net.link_type[j] == SWB_CONDUIT) st.c_a2[ix] = st.c_a1[ix];
+                }
+            }
+        }
+        if (owner && (args.phases & PH_DYNWAVE))
+            for (int k = 0; k < maxTrials; k++) st.not_conv[k * M + m] = 0;
+        ctx.grid_sync();
+
+        // ================= dynwave_execute: Picard iterations ==================================
+        if (args.phases & PH_DYNWAVE) {
+            bool alive = active;
+            int itersDone = 0;
+            for (int k = 0; k < maxTrials; k++) {
+                // ---- findLinkFlows, pass (i): true conduits (dynwave.c:387-395)
+                if (alive) {
+                    for (int j = first; j < nL; j += stride) {
+                        if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) continue;
+                        if (k >= 2) {              // findBypassedLinks of the previous trial (:335)
+                            bool byp = st.n_converged[SWB_IX(net.link_node1[j], m, M)] &&
+                                       st.n_converged[SWB_IX(net.link_node2[j], m, M)];
+                            st.l_bypassed[SWB_IX(j, m, M)] = byp ? 1 : 0;
+                            if (byp) continue;
+                        }
+                        conduit_flow(net, st, j, m, k, dt, T);
+                    }
+                }
+                ctx.grid_sync();
+                // ---- networks with regulators / dummy links: ordered pass (A.4)
+                if (net.nNonConduit > 0) {
+                    if (alive)
+                        for (int i = first; i < nN; i += stride) {
+                            NodeAcc acc = node_init_acc(net, st, i, m);
+                            for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++) {
+                                int j = net.adj[e] >> 1;
+                                if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) break;
+                                node_add_link_end(net, st, j, net.adj[e] & 1, m, acc);
+                            }
+                            size_t ix = SWB_IX(i, m, M);
+                            st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;
+                            st.n_new_surf_area[ix] = acc.surfArea; st.n_sumdqdh[ix] = acc.sumdqdh;
+                        }
+                    ctx.grid_sync();
+                    if (alive && owner) regulator_pass(net, st, m, k, dt, T);
+                    ctx.grid_sync();
+                }
+                // ---- findNodeDepths (dynwave.c:593-632)
+                if (alive) {
+                    bool anyNotConv = false;
+                    for (int i = first; i < nN; i += stride) {
+                        NodeAcc acc;
+                        size_t ix = SWB_IX(i, m, M);
+                        if (net.nNonConduit > 0) {
+                            acc.inflow = st.n_inflow[ix]; acc.outflow = st.n_outflow[ix];
+                            acc.surfArea = st.n_new_surf_area[ix]; acc.sumdqdh = st.n_sumdqdh[ix];
+                        } else {
+                            acc = node_init_acc(net, st, i, m);
+                            for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++)
+                                node_add_link_end(net, st, net.adj[e] >> 1, net.adj[e] & 1, m, acc);
+                        }
+                        if (net.node_type[i] == SWB_OUTFALL) {
+                            st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;
+                            outfall_depth(net, st, i, m, T);
+                        } else {
+                            if (!node_set_depth(net, st, i, m, k, dt, acc)) anyNotConv = true;
+                        }
+                    }
+                    if (anyNotConv) st.not_conv[k * M + m] = 1;
+                    itersDone = k + 1;
+                }
+                ctx.grid_sync();
+                // ---- loop control: Steps++ ; if (Steps > 1 && converged) break (:248-251)
+                if (alive && k >= 1 && st.not_conv[k * M + m] == 0) alive = false;
+                bool any = false;
+                if (k + 1 < maxTrials)
+                    for (int mm = ctx.lane; mm < M; mm += ctx.block_size) {
+                        bool a = !((args.phases & PH_ADVANCE) && st.done[mm]);
+                        for (int kk = 1; kk <= k && a; kk++) a = (st.not_conv[kk * M + mm] != 0);
+                        any = any || a;
+                    }
+                if (!ctx.block_or(any)) break;
+            }
+            // ---- updateConvergenceStats, findLimitedLinks (dynwave.c:257-260, 349-378)
+            if (active) {
+                if (owner) {
+                    st.iters[m] = itersDone;
+                    st.tot_iters[m] += itersDone;
+                    st.tot_steps[m] += 1;
+                    if (st.not_conv[(itersDone - 1) * M + m]) st.non_conv[m] += 1;
+                }
+                for (int j = first; j < nL; j += stride) {
+                    if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) continue;
+                    size_t ix = SWB_IX(j, m, M);
+                    unsigned char lim = 0;
+                    if (st.c_a1[ix] >= net.xs_afull[j]) {
+                        int n1 = net.link_node1[j], n2 = net.link_node2[j];
+                        double h1 = st.n_depth[SWB_IX(n1, m, M)] + net.node_invert[n1];
+                        double h2 = st.n_depth[SWB_IX(n2, m, M)] + net.node_invert[n2];
+                        // Conduit.length is the user's length (dynwave.c:374), not the true length
+                        if ((h1 - h2) > fabs(net.cond_slope[j]) * net.cond_user_length[j]) lim = 1;
+                    }
+                    st.c_cap_limited[ix] = lim;
+                }
+            }
+        }
+
+        // ================= qualrout_execute (qualrout.c:100-142) ===============================
+        if (withQual && (args.phases & PH_QUALITY)) {
+            QualAcc acc[SWB_MAX_POLLUT];
+            for (int p = 0; p < nP; p++) { acc[p].reacted = acc[p].seepage = acc[p].finalStorage = 0.0; }
+            if (active)
+                for (int i = first; i < nN; i += stride)
+                    for (int p = 0; p < nP; p++) qual_node(net, st, i, m, p, dt, acc[p]);
+            ctx.grid_sync();
+            if (active) {
+                for (int j = first; j < nL; j += stride) qual_link(net, st, j, m, dt, acc);
+                for (int p = 0; p < nP; p++) {
+                    if (acc[p].reacted != 0.0) ctx.atomic_add_f64(&st.mb_reacted[p * M + m], acc[p].reacted * dt);
+                    if (acc[p].seepage != 0.0) ctx.atomic_add_f64(&st.mb_seepage[p * M + m], acc[p].seepage * dt);
+                    if (acc[p].finalStorage != 0.0) ctx.atomic_add_f64(&st.mb_final_storage[p * M + m], acc[p].finalStorage);
+                }
+            }
+        }
+
+        // ================= dynwave_getRoutingStep (dynwave.c:195-220, 799-921) =================
+        if (args.phases & PH_NEXTDT) {
+            if (owner) {
+                double t0 = args.fixed_step;
+                st.tmin_bits[m] = (unsigned long long)dbits(t0);
+                st.crit_link[m] = -1; st.crit_node[m] = -1;
+            }
+            ctx.grid_sync();
+            const bool variable = !(net.opt.courant_factor == 0.0 || args.fixed_step < SWB_MINTIMESTEP);
+            if (active && variable && st.var_step[m] != 0.0) {
+                double tmin = args.fixed_step;
+                for (int j = first; j < nL; j += stride) {
+                    double t = link_step(net, st, j, m);
+                    if (t >= 0.0 && t < tmin) tmin = t;
+                }
+                for (int i = first; i < nN; i += stride) {
+                    double t = node_step(net, st, i, m);
+                    if (t >= 0.0 && t < tmin) tmin = t;
+                }
+                if (tmin < args.fixed_step) ctx.atomic_min_u64(&st.tmin_bits[m], dbits(tmin));
+            }
+            ctx.grid_sync();
+            if (owner && active) {
+                if (!variable) st.var_step[m] = args.fixed_step;
+                else {
+                    double vs;
+                    if (st.var_step[m] == 0.0) vs = net.opt.min_route_step;
+                    else {
+                        vs = dfrombits(st.tmin_bits[m]);
+                        if (vs < net.opt.min_route_step) vs = net.opt.min_route_step;
+                    }
+                    st.var_step[m] = floor(1000.0 * vs) / 1000.0;
+                }
+            }
+        }
+        if ((args.phases & PH_ADVANCE) && owner && active) {
+            // NewRoutingTime += 1000 * routingStep (routing.c:301-302), kept in ms
+            st.sim_time[m] = (1000.0 * st.sim_time[m] + 1000.0 * dt) / 1000.0;
+        }
+        if (step + 1 < args.n_steps) ctx.grid_sync();
+    }
+}
+
+} // namespace swb
+#endif

@@ -1,0 +1,150 @@
+// swb_host.h -- host-side preparation shared by the CUDA library (swb_api.cu) and the CPU test
+// emulation (tests/emul): validation of a swb_network_desc, the derived static arrays (link flags,
+// end-node elevations, CSR incidence in the reference's summation order) and the field table that
+// maps swb_field ids onto State members.
+#ifndef SWB_HOST_H
+#define SWB_HOST_H
+
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+#include "swb_state.h"
+#include "swb_xsect.h"
+
+namespace swb {
+
+struct Derived {
+    std::vector<int> link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link;
+    std::vector<double> link_z1, link_z2, xs_tables;
+    int nTrue = 0, nNonConduit = 0;
+};
+
+inline size_t desc_count(const swb_network_desc &d, char kind0, char kind1)
+{
+    switch (kind0) {
+      case 'N': return d.n_nodes;
+      case 'L': return d.n_links;
+      case 'P': return d.n_pollut;
+      case 'C': return kind1 == '1' ? d.n_curves + 1 : (kind1 == 'P' ? d.n_curve_pts : d.n_curves);
+      case 'T': return kind1 == 'T' ? (size_t)d.n_shape_tbls * d.shape_tbl_len : d.n_shape_tbls;
+    }
+    return 0;
+}
+
+// returns "" when the descriptor is acceptable, else the reason
+inline std::string validate_desc(const swb_network_desc &d, const swb_options &o)
+{
+    if (d.n_nodes <= 0 || d.n_links < 0) return "empty network";
+    if (d.n_pollut > SWB_MAX_POLLUT) return "more than SWB_MAX_POLLUT pollutants";
+    if (o.max_trials < 1) return "max_trials < 1";
+#define X(T, name, kind) if (desc_count(d, #kind[0], #kind[1]) > 0 && d.name == nullptr) return "null array: " #name;
+    SWB_DESC_ARRAYS(X)
+#undef X
+    for (int j = 0; j < d.n_links; j++) {
+        int a = d.link_node1[j], b = d.link_node2[j];
+        if (a < 0 || a >= d.n_nodes || b < 0 || b >= d.n_nodes) return "link end node out of range";
+        if (d.link_type[j] == SWB_CONDUIT) {
+            if (d.xs_culvert[j] > 0) return "culvert-coded conduit (culvert.c) not supported yet";
+            if (d.xs_type[j] == XS_FORCE_MAIN) return "FORCE_MAIN conduit (forcmain.c) not supported yet";
+            if (d.xs_type[j] == XS_DUMMY &&
+                (d.node_type[a] == SWB_STORAGE || d.node_type[a] == SWB_DIVIDER))
+                return "dummy conduit out of a storage / divider node";
+            if (d.cond_barrels[j] < 1) return "conduit with < 1 barrel";
+        }
+        if (d.link_type[j] == SWB_WEIR && d.weir_type[j] == 4) return "ROADWAY weir (roadway.c) not supported yet";
+        int t = d.xs_table[j];
+        if (t >= d.n_shape_tbls) return "xs_table out of range";
+    }
+    return "";
+}
+
+inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
+{
+    const int nN = d.n_nodes, nL = d.n_links;
+    r.link_flags.assign(nL, 0); r.link_z1.assign(nL, 0.0); r.link_z2.assign(nL, 0.0);
+    r.outfall_link.assign(nN, -1);
+    r.nc_links.clear(); r.nTrue = 0;
+    for (int j = 0; j < nL; j++) {
+        int a = d.link_node1[j], b = d.link_node2[j], f = 0;
+        bool trueConduit = (d.link_type[j] == SWB_CONDUIT && d.xs_type[j] != XS_DUMMY);
+        if (trueConduit) { f |= LF_TRUE_CONDUIT; r.nTrue++; } else r.nc_links.push_back(j);
+        if (d.link_has_flap[j]) f |= LF_HAS_FLAP;
+        if (d.node_type[a] == SWB_OUTFALL) { f |= LF_N1_OUTFALL; if (d.outfall_flap[a]) f |= LF_N1_OUT_FLAP; }
+        if (d.node_type[b] == SWB_OUTFALL) { f |= LF_N2_OUTFALL; if (d.outfall_flap[b]) f |= LF_N2_OUT_FLAP; }
+        if (d.node_type[a] == SWB_STORAGE) f |= LF_N1_STORAGE;
+        if (d.node_type[b] == SWB_STORAGE) f |= LF_N2_STORAGE;
+        bool open = xs_is_open(d.xs_type[j]);
+        if (open) f |= LF_OPEN_SHAPE;
+        if (trueConduit && (d.link_seep_rate[j] > 0.0 || open)) f |= LF_HAS_LOSSRATE;
+        r.link_flags[j] = f;
+        r.link_z1[j] = d.node_invert[a] + d.link_offset1[j];
+        r.link_z2[j] = d.node_invert[b] + d.link_offset2[j];
+        // link_setOutfallDepth (link.c:743-753) tests node2 first; a later link overrides an
+        // earlier one exactly as the reference's loop over all links does
+        if (d.node_type[b] == SWB_OUTFALL) r.outfall_link[b] = j;
+        else if (d.node_type[a] == SWB_OUTFALL) r.outfall_link[a] = j;
+    }
+    r.nNonConduit = (int)r.nc_links.size();
+    // CSR incidence.  adjq: ascending link index.  adj: true conduits first, then the rest.
+    std::vector<std::vector<int>> inc(nN);
+    for (int j = 0; j < nL; j++) {
+        inc[d.link_node1[j]].push_back((j << 1) | 0);
+        inc[d.link_node2[j]].push_back((j << 1) | 1);
+    }
+    r.adj_start.assign(nN + 1, 0); r.adjq_start.assign(nN + 1, 0);
+    r.adj.clear(); r.adjq.clear();
+    for (int i = 0; i < nN; i++) {
+        r.adjq_start[i] = (int)r.adjq.size();
+        r.adj_start[i] = (int)r.adj.size();
+        for (int e : inc[i]) r.adjq.push_back(e);
+        for (int e : inc[i]) if (r.link_flags[e >> 1] & LF_TRUE_CONDUIT) r.adj.push_back(e);
+        for (int e : inc[i]) if (!(r.link_flags[e >> 1] & LF_TRUE_CONDUIT)) r.adj.push_back(e);
+    }
+    r.adjq_start[nN] = (int)r.adjq.size();
+    r.adj_start[nN] = (int)r.adj.size();
+    static const double tab[] = { SWB_XS_TABLE_DATA };
+    r.xs_tables.assign(tab, tab + XT_TOTAL);
+    (void)o;
+}
+
+inline void fill_net_scalars(Net &n, const swb_network_desc &d, const swb_options &o, const Derived &r)
+{
+    n.nN = d.n_nodes; n.nL = d.n_links; n.nP = d.n_pollut; n.nCurves = d.n_curves;
+    n.nShapeTbl = d.n_shape_tbls; n.shapeTblLen = d.shape_tbl_len;
+    n.nTrue = r.nTrue; n.nNonConduit = r.nNonConduit; n.nOutfallLinks = 0;
+    n.opt = o;
+    n.crownCutoff = (o.surcharge_method == SWB_SLOT) ? 0.985257 : 0.96;   // dynwave.c:64-65,159
+}
+
+// ---- field table ---------------------------------------------------------------------------------
+struct FieldInfo { int id; char kind; bool is_u8; size_t offset; };   // offset of the member in State
+
+inline const std::vector<FieldInfo> &field_table()
+{
+    static std::vector<FieldInfo> t;
+    if (t.empty()) {
+#define X(T, name, id, kind) t.push_back(FieldInfo{id, #kind[0] == 'N' ? (#kind[1] == 'P' ? 'n' : 'N') \
+                                                        : (#kind[1] == 'P' ? 'l' : 'L'), \
+                                          sizeof(T) == 1, offsetof(State, name)});
+        SWB_STATE_FIELDS(X)
+#undef X
+    }
+    return t;
+}
+inline const FieldInfo *find_field(int id)
+{
+    for (const FieldInfo &f : field_table()) if (f.id == id) return &f;
+    return nullptr;
+}
+// items per member of a field ('N' nodes, 'L' links, 'n'/'l' x pollutants)
+inline size_t field_items(const FieldInfo &f, int nN, int nL, int nP)
+{
+    switch (f.kind) {
+      case 'N': return nN;  case 'L': return nL;
+      case 'n': return (size_t)nN * nP;  default: return (size_t)nL * nP;
+    }
+}
+
+} // namespace swb
+#endif

@@ -1,0 +1,139 @@
+// swb_qual.h -- K8: completely-mixed water-quality routing, per (object, member).
+//
+//   qual_node  <- findLinkMassFlow gathered per node + findNodeQual / findStorageQual + updateHRT
+//                 (qualrout.c:179-249, 398-494)
+//   qual_link  <- findLinkQual + the link's totalLoad update (qualrout.c:253-353, 214)
+//   getMixedQual / getReactedQual (qualrout.c:146-174, 498-518)
+//
+// The reference scatters link loads into Node.newQual in ascending link order (qualrout.c:112);
+// the gather below walks the node's incidence list in the same ascending link order, so each
+// node's floating-point sum is identical.  Treatment (treatmnt.c) stays on the host.
+#ifndef SWB_QUAL_H
+#define SWB_QUAL_H
+
+#include "swb_state.h"
+
+namespace swb {
+
+struct QualAcc { double reacted, seepage, finalStorage; };   // massbal.c:517-555 contributions
+
+SWB_HD inline double qual_mixed(double c, double v1, double wIn, double qIn, double tStep)
+{
+    if (qIn <= SWB_ZERO) return c;
+    double vIn = qIn * tStep;
+    double cIn = wIn * tStep / vIn;
+    double cMax = SWB_MAX(c, cIn);
+    c = (c * v1 + wIn * tStep) / (v1 + vIn);
+    c = SWB_MIN(c, cMax);
+    c = SWB_MAX(c, 0.0);
+    return c;
+}
+
+SWB_HD inline double qual_reacted(double kDecay, double c, double v1, double tStep, double &reacted)
+{
+    if (kDecay == 0.0) return c;
+    double c2 = c * (1.0 - kDecay * tStep);
+    c2 = SWB_MAX(0.0, c2);
+    double lossRate = (c - c2) * v1 / tStep;
+    reacted += lossRate;
+    return c2;
+}
+
+// node i, pollutant p.  n_qual holds the external mass-rate preload on entry (routing.c:488 ...),
+// the new concentration on exit.
+SWB_HD inline void qual_node(const Net &n, const State &s, int i, int m, int p, double tStep,
+                             QualAcc &acc)
+{
+    const int M = s.M;
+    const size_t ix = SWB_IX(i, m, M), ixq = SWB_IXP(p, i, n.nN, m, M);
+    // --- link mass flows into this node, ascending link index (qualrout.c:112, 179-217)
+    double w = s.n_qual[ixq];
+    for (int k = n.adjq_start[i]; k < n.adjq_start[i + 1]; k++) {
+        int e = n.adjq[k], j = e >> 1, end = e & 1;
+        double q = s.l_flow[SWB_IX(j, m, M)];
+        bool into = (q < 0.0) ? (end == 0) : (end == 1);
+        if (!into) continue;
+        w += fabs(q) * s.l_old_qual[SWB_IXP(p, j, n.nL, m, M)];
+    }
+    double qIn = s.n_inflow[ix];                       // Node.qualInflow = Node.inflow (:118)
+    double oldVolume = s.n_old_volume[ix];
+    bool isStorage = (n.node_type[i] == SWB_STORAGE);
+    double c2;
+    if (isStorage || oldVolume > SWB_ZERO_VOLUME) {
+        // findStorageQual (qualrout.c:398-474)
+        double v1 = oldVolume, qExfil = 0.0, vEvap = 0.0, fEvap = 1.0;
+        if (isStorage) {
+            if (p == 0) {                              // updateHRT once per node (:478-494)
+                double hrt = s.n_hrt[ix];
+                if (v1 < SWB_ZERO) hrt = 0.0;
+                else hrt = (hrt + tStep) * v1 / (v1 + qIn * tStep);
+                s.n_hrt[ix] = SWB_MAX(hrt, 0.0);
+            }
+            qExfil = s.n_exfil_loss[ix] / tStep;
+            vEvap = s.n_evap_loss[ix];
+            if (vEvap > 0.0 && v1 > SWB_ZERO_VOLUME) fEvap += vEvap / v1;
+        }
+        double c1 = s.n_old_qual[ixq];
+        acc.seepage += qExfil * c1;
+        c1 *= fEvap;
+        c1 = qual_reacted(n.pollut_kdecay[p], c1, v1, tStep, acc.reacted);
+        c2 = qual_mixed(c1, v1, w, qIn, tStep);
+        double newVolume = s.n_volume[ix];
+        if ((newVolume <= SWB_ZERO_VOLUME || s.n_depth[ix] <= SWB_ZERO_DEPTH) && qIn <= SWB_ZERO) {
+            acc.finalStorage += c2 * newVolume;
+            c2 = 0.0;
+        }
+    } else {
+        // findNodeQual (qualrout.c:221-249)
+        if (qIn > SWB_ZERO) c2 = w / qIn;
+        else if (s.n_depth[ix] > SWB_ZERO_DEPTH) c2 = s.n_old_qual[ixq];
+        else c2 = 0.0;
+    }
+    s.n_qual[ixq] = c2;
+}
+
+// link j, all pollutants (the hydraulic part is shared between pollutants)
+SWB_HD inline void qual_link(const Net &n, const State &s, int j, int m, double tStep, QualAcc *acc)
+{
+    const int M = s.M, nP = n.nP;
+    const size_t ix = SWB_IX(j, m, M);
+    const double newFlow = s.l_flow[ix];
+    // totalLoad (qualrout.c:210-214): w = |q| * oldQual
+    double qAbs = fabs(newFlow);
+    int up = n.link_node1[j];
+    if (newFlow < 0.0) up = n.link_node2[j];
+    if (!(n.link_flags[j] & LF_TRUE_CONDUIT)) {
+        for (int p = 0; p < nP; p++) {
+            size_t iq = SWB_IXP(p, j, n.nL, m, M);
+            s.l_total_load[iq] += qAbs * s.l_old_qual[iq] * tStep;
+            s.l_qual[iq] = s.n_qual[SWB_IXP(p, up, n.nN, m, M)];
+        }
+        return;
+    }
+    double barrels = (double)n.cond_barrels[j];
+    double qIn = fabs(s.c_q1[ix]) * barrels;
+    double qSeep = s.c_seep_loss[ix] * barrels;
+    double vEvap = s.c_evap_loss[ix] * barrels * tStep;
+    double v1 = s.l_old_volume[ix], v2 = s.l_volume[ix];
+    double vLosses = qSeep * tStep + vEvap;
+    double fEvap = 1.0;
+    if (vEvap > 0.0 && v1 > SWB_ZERO_VOLUME) fEvap += vEvap / v1;
+    qIn = qIn + (v2 + vLosses - v1) / tStep;
+    qIn = SWB_MAX(qIn, 0.0);
+    bool empty = (v2 < SWB_ZERO_VOLUME || s.l_depth[ix] <= SWB_ZERO_DEPTH);
+    for (int p = 0; p < nP; p++) {
+        size_t iq = SWB_IXP(p, j, n.nL, m, M);
+        double c1 = s.l_old_qual[iq];
+        s.l_total_load[iq] += qAbs * c1 * tStep;
+        acc[p].seepage += qSeep * c1;
+        c1 *= fEvap;
+        double c2 = qual_reacted(n.pollut_kdecay[p], c1, v1, tStep, acc[p].reacted);
+        double wIn = s.n_qual[SWB_IXP(p, up, n.nN, m, M)] * qIn;
+        c2 = qual_mixed(c2, v1, wIn, qIn, tStep);
+        if (empty) { acc[p].finalStorage += c2 * v2; c2 = 0.0; }
+        s.l_qual[iq] = c2;
+    }
+}
+
+} // namespace swb
+#endif

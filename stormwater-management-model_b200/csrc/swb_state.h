@@ -1,0 +1,140 @@
+// swb_state.h -- HBM layout of the static network (Net) and of the lockstep ensemble state (State).
+//
+// Layout rules (DESIGN.md "Data layout in HBM"):
+//   * static geometry is structure-of-arrays indexed by node / link, shared by every member and
+//     small enough (about 2.2 MB for the 10k-node grid) to stay L2-resident;
+//   * dynamic state is structure-of-arrays with the MEMBER index fastest: element (item, m) of a
+//     field lives at field[item * M + m].  A warp therefore works on 32 members of ONE link or
+//     node: every dynamic load/store is a fully coalesced 256-byte transaction, every static load
+//     is a warp-uniform broadcast, and shape / link-type branches never diverge.  With M == 1 the
+//     same indexing degenerates to the reference's plain per-object arrays.
+#ifndef SWB_STATE_H
+#define SWB_STATE_H
+
+#include "swb_common.h"
+#include "../../include/swmm_b200.h"
+
+namespace swb {
+
+// ---- descriptor arrays mirrored on the device, name for name (X(type, name, count-kind)) --------
+// count-kind: N nodes, L links, C curves, C1 curves+1, CP curve points, T shape tables,
+//             TT shape tables x table length, P pollutants
+#define SWB_DESC_ARRAYS(X) \
+    X(int, node_type, N) X(int, node_degree, N) X(double, node_invert, N) \
+    X(double, node_full_depth, N) X(double, node_sur_depth, N) X(double, node_ponded_area, N) \
+    X(double, node_full_volume, N) X(double, node_crown_elev, N) X(int, outfall_type, N) \
+    X(int, outfall_flap, N) X(int, storage_shape, N) X(int, storage_curve, N) \
+    X(double, storage_a0, N) X(double, storage_a1, N) X(double, storage_a2, N) \
+    X(int, link_type, L) X(int, link_node1, L) X(int, link_node2, L) X(int, link_direction, L) \
+    X(int, link_has_flap, L) X(double, link_offset1, L) X(double, link_offset2, L) \
+    X(double, link_q_limit, L) X(double, link_q_full, L) X(double, link_closs_in, L) \
+    X(double, link_closs_out, L) X(double, link_closs_avg, L) X(double, link_seep_rate, L) \
+    X(int, xs_type, L) X(int, xs_culvert, L) X(int, xs_table, L) X(double, xs_yfull, L) \
+    X(double, xs_wmax, L) X(double, xs_ywmax, L) X(double, xs_afull, L) X(double, xs_rfull, L) \
+    X(double, xs_sfull, L) X(double, xs_smax, L) X(double, xs_ybot, L) X(double, xs_abot, L) \
+    X(double, xs_sbot, L) X(double, xs_rbot, L) X(int, cond_barrels, L) X(int, cond_has_losses, L) \
+    X(double, cond_length, L) X(double, cond_user_length, L) X(double, cond_mod_length, L) X(double, cond_rough_factor, L) \
+    X(double, cond_slope, L) X(double, cond_beta, L) X(double, cond_q_max, L) X(int, pump_type, L) \
+    X(int, pump_curve, L) X(double, pump_xmin, L) X(double, pump_xmax, L) X(int, orif_type, L) \
+    X(double, orif_cdisch, L) X(double, orif_length, L) X(int, weir_type, L) \
+    X(int, weir_can_surcharge, L) X(int, weir_cd_curve, L) X(double, weir_cdisch1, L) \
+    X(double, weir_cdisch2, L) X(double, weir_end_con, L) X(double, weir_slope, L) \
+    X(double, weir_length, L) X(int, outlet_curve, L) X(int, outlet_curve_type, L) \
+    X(double, outlet_qcoeff, L) X(double, outlet_qexpon, L) X(int, curve_start, C1) \
+    X(int, curve_type, C) X(double, curve_x, CP) X(double, curve_y, CP) X(int, shape_tbl_n, T) \
+    X(double, shape_area_tbl, TT) X(double, shape_hrad_tbl, TT) X(double, shape_width_tbl, TT) \
+    X(double, pollut_kdecay, P)
+
+// link_flags bits (static, derived once on the host)
+enum {
+    LF_TRUE_CONDUIT = 1,     // type == CONDUIT && xsect != DUMMY (dynwave.c:416-419)
+    LF_HAS_FLAP     = 2,     // Link.hasFlapGate
+    LF_N1_OUTFALL   = 4,   LF_N2_OUTFALL = 8,
+    LF_N1_OUT_FLAP  = 16,  LF_N2_OUT_FLAP = 32,   // end node is an outfall with a flap gate
+    LF_N1_STORAGE   = 64,  LF_N2_STORAGE = 128,
+    LF_OPEN_SHAPE   = 256,   // xsect_isOpen
+    LF_HAS_LOSSRATE = 512    // seepRate > 0 or open shape (evaporation possible)
+};
+
+struct Net {
+    int nN, nL, nP, nCurves, nShapeTbl, shapeTblLen;
+    int nTrue;               // true conduits
+    int nNonConduit;         // links handled by the ordered regulator pass
+    int nOutfallLinks;
+    swb_options opt;
+    double crownCutoff;      // dynwave.c:159-160
+#define X(T, name, kind) const T *name;
+    SWB_DESC_ARRAYS(X)
+#undef X
+    // derived
+    const int    *link_flags;
+    const double *link_z1, *link_z2;       // Node[n].invertElev + Link.offset (dwflow.c:110-111)
+    const int    *adj_start;               // nN+1: CSR node -> incident link ends
+    const int    *adj;                     // (link << 1) | end, ordered true conduits first, then
+                                           // other links, each ascending by link index (A.3)
+    const int    *adjq_start, *adjq;       // same incidence ordered by plain link index (quality)
+    const int    *nc_links;                // non-true-conduit links in ascending index order
+    const int    *outfall_link;            // per node: its (single) link, or -1
+    const double *xs_tables;               // XT_TOTAL doubles (global copy of the shape tables)
+};
+
+// ---- dynamic fields: X(ctype, member name, field id, kind) ; kind N = per node, L = per link,
+//      NP / LP = per node / link x pollutant -----------------------------------------------------
+#define SWB_STATE_FIELDS(X) \
+    X(double, n_depth, SWB_NODE_NEW_DEPTH, N) X(double, n_old_depth, SWB_NODE_OLD_DEPTH, N) \
+    X(double, n_volume, SWB_NODE_NEW_VOLUME, N) X(double, n_old_volume, SWB_NODE_OLD_VOLUME, N) \
+    X(double, n_latflow, SWB_NODE_NEW_LATFLOW, N) X(double, n_losses, SWB_NODE_LOSSES, N) \
+    X(double, n_inflow, SWB_NODE_INFLOW, N) X(double, n_outflow, SWB_NODE_OUTFLOW, N) \
+    X(double, n_overflow, SWB_NODE_OVERFLOW, N) X(double, n_old_net_inflow, SWB_NODE_OLD_NET_INFLOW, N) \
+    X(double, n_new_surf_area, SWB_NODE_NEW_SURF_AREA, N) X(double, n_old_surf_area, SWB_NODE_OLD_SURF_AREA, N) \
+    X(double, n_sumdqdh, SWB_NODE_SUMDQDH, N) X(double, n_dydt, SWB_NODE_DYDT, N) \
+    X(unsigned char, n_converged, SWB_NODE_CONVERGED, N) X(double, n_stage, SWB_NODE_OUTFALL_STAGE, N) \
+    X(double, n_evap_loss, SWB_NODE_STORAGE_EVAP_LOSS, N) X(double, n_exfil_loss, SWB_NODE_STORAGE_EXFIL_LOSS, N) \
+    X(double, n_hrt, SWB_NODE_HRT, N) X(double, n_qual, SWB_NODE_NEW_QUAL, NP) \
+    X(double, n_old_qual, SWB_NODE_OLD_QUAL, NP) \
+    X(double, l_flow, SWB_LINK_NEW_FLOW, L) X(double, l_old_flow, SWB_LINK_OLD_FLOW, L) \
+    X(double, l_depth, SWB_LINK_NEW_DEPTH, L) X(double, l_old_depth, SWB_LINK_OLD_DEPTH, L) \
+    X(double, l_volume, SWB_LINK_NEW_VOLUME, L) X(double, l_old_volume, SWB_LINK_OLD_VOLUME, L) \
+    X(double, l_setting, SWB_LINK_SETTING, L) X(double, l_target_setting, SWB_LINK_TARGET_SETTING, L) \
+    X(double, l_dqdh, SWB_LINK_DQDH, L) X(double, l_froude, SWB_LINK_FROUDE, L) \
+    X(unsigned char, l_flow_class, SWB_LINK_FLOW_CLASS, L) X(double, l_surf_area1, SWB_LINK_SURF_AREA1, L) \
+    X(double, l_surf_area2, SWB_LINK_SURF_AREA2, L) X(unsigned char, l_bypassed, SWB_LINK_BYPASSED, L) \
+    X(unsigned char, l_normal_flow, SWB_LINK_NORMAL_FLOW, L) X(unsigned char, l_inlet_control, SWB_LINK_INLET_CONTROL, L) \
+    X(double, c_a1, SWB_COND_A1, L) X(double, c_a2, SWB_COND_A2, L) X(double, c_q1, SWB_COND_Q1, L) \
+    X(double, c_q2, SWB_COND_Q2, L) X(unsigned char, c_full_state, SWB_COND_FULL_STATE, L) \
+    X(unsigned char, c_cap_limited, SWB_COND_CAPACITY_LIMITED, L) X(double, c_evap_loss, SWB_COND_EVAP_LOSS, L) \
+    X(double, c_seep_loss, SWB_COND_SEEP_LOSS, L) X(double, o_corif, SWB_ORIF_CORIF, L) \
+    X(double, o_cweir, SWB_ORIF_CWEIR, L) X(double, o_hcrit, SWB_ORIF_HCRIT, L) \
+    X(double, r_surf_area, SWB_REG_SURF_AREA, L) X(double, w_csurcharge, SWB_WEIR_CSURCHARGE, L) \
+    X(double, l_qual, SWB_LINK_NEW_QUAL, LP) X(double, l_old_qual, SWB_LINK_OLD_QUAL, LP) \
+    X(double, l_total_load, SWB_LINK_TOTAL_LOAD, LP)
+
+#define SWB_MAX_TRIALS_CAP 32     // alive / notConv bookkeeping rows (MaxTrials is 8 by default)
+
+struct State {
+    int M;                       // members
+#define X(T, name, id, kind) T *name;
+    SWB_STATE_FIELDS(X)
+#undef X
+    // per member
+    double *dt;                  // routing step being taken
+    double *var_step;            // VariableStep (dynwave.c:84); 0 before the first step
+    double *sim_time;            // elapsed simulated seconds
+    double *evap_rate, *hydcon;  // per-member climate scalars
+    int    *iters;               // iterations used by the last dynwave_execute
+    long long *tot_iters, *tot_steps, *non_conv;
+    int    *crit_node, *crit_link;
+    unsigned long long *tmin_bits;  // Courant search scratch (ordered bits of a positive double)
+    int    *alive;               // [SWB_MAX_TRIALS_CAP + 1][M] member still iterating at trial k
+    int    *not_conv;            // [SWB_MAX_TRIALS_CAP][M] some node failed the head tolerance
+    int    *done;                // member has reached t_end
+    // mass-balance accumulators per member x pollutant (massbal.c:517-555)
+    double *mb_reacted, *mb_seepage, *mb_final_storage;
+};
+
+// pollutant-plane index: field[(p * nItems + item) * M + m]
+#define SWB_IX(item, m, M)            ((size_t)(item) * (size_t)(M) + (size_t)(m))
+#define SWB_IXP(p, item, n, m, M)     (((size_t)(p) * (size_t)(n) + (size_t)(item)) * (size_t)(M) + (size_t)(m))
+
+} // namespace swb
+#endif

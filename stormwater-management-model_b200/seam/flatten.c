@@ -128,7 +128,7 @@ int swb_flatten_network(swb_flat *f)
                *sf = DARR(nL), *sm = DARR(nL), *yb = DARR(nL), *ab = DARR(nL), *sb = DARR(nL),
                *rb = DARR(nL);
         int *bar = IARR(nL), *hl = IARR(nL);
-        double *len = DARR(nL), *ml = DARR(nL), *rgh = DARR(nL), *slp = DARR(nL), *beta = DARR(nL),
+        double *len = DARR(nL), *ulen = DARR(nL), *ml = DARR(nL), *rgh = DARR(nL), *slp = DARR(nL), *beta = DARR(nL),
                *qmax = DARR(nL);
         int *pt = IARR(nL), *pc = IARR(nL), *ot = IARR(nL), *wt = IARR(nL), *wcs = IARR(nL),
             *wcc = IARR(nL), *olc = IARR(nL), *olt = IARR(nL);
@@ -175,6 +175,7 @@ int swb_flatten_network(swb_flat *f)
               case CONDUIT:
                 bar[j] = Conduit[k].barrels; hl[j] = Conduit[k].hasLosses;
                 len[j] = link_getLength(j);              /* true length (link.c:808,1195) */
+                ulen[j] = Conduit[k].length;
                 ml[j] = Conduit[k].modLength; rgh[j] = Conduit[k].roughFactor;
                 slp[j] = Conduit[k].slope; beta[j] = Conduit[k].beta; qmax[j] = Conduit[k].qMax;
                 if (x->culvertCode > 0) rc = SWB_ERR_UNSUPP;          /* culvert.c: phase 2 */
@@ -205,7 +206,7 @@ int swb_flatten_network(swb_flat *f)
         d->link_seep_rate = sr; d->xs_type = xt; d->xs_culvert = xc; d->xs_table = xtab;
         d->xs_yfull = yf; d->xs_wmax = wm; d->xs_ywmax = yw; d->xs_afull = af; d->xs_rfull = rf;
         d->xs_sfull = sf; d->xs_smax = sm; d->xs_ybot = yb; d->xs_abot = ab; d->xs_sbot = sb;
-        d->xs_rbot = rb; d->cond_barrels = bar; d->cond_has_losses = hl; d->cond_length = len;
+        d->xs_rbot = rb; d->cond_barrels = bar; d->cond_has_losses = hl; d->cond_length = len; d->cond_user_length = ulen;
         d->cond_mod_length = ml; d->cond_rough_factor = rgh; d->cond_slope = slp;
         d->cond_beta = beta; d->cond_q_max = qmax; d->pump_type = pt; d->pump_curve = pc;
         d->pump_xmin = pmin; d->pump_xmax = pmax; d->orif_type = ot; d->orif_cdisch = ocd;

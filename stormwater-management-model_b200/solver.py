@@ -1,0 +1,234 @@
+"""Host side of the C-ABI: thin ctypes wrapper over libswmm_b200.so (include/swmm_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no device is present every call
+raises.  (tests/emul builds a host emulation of the same ABI for the CPU-only test suite; it is
+loaded only when a test passes its path explicitly.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB = os.path.join(_PKG, "csrc", "libswmm_b200.so")
+
+_P_D = C.POINTER(C.c_double)
+_P_I = C.POINTER(C.c_int)
+
+
+class SwbError(RuntimeError):
+    pass
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    path = path or CUDA_LIB
+    if not os.path.exists(path):
+        raise SwbError(f"{path} not found: build the CUDA extension first "
+                       f"(python -c 'import __graft_entry__ as g; g.build()')")
+    lib = C.CDLL(path)
+    lib.swb_last_error.restype = C.c_char_p
+    lib.swb_network_create.argtypes = [C.POINTER(abi.NetworkDesc), C.POINTER(abi.Options), C.c_int,
+                                       C.POINTER(C.c_void_p)]
+    lib.swb_network_destroy.argtypes = [C.c_void_p]
+    lib.swb_solver_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.swb_solver_destroy.argtypes = [C.c_void_p]
+    lib.swb_set_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _P_D]
+    lib.swb_get_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _P_D]
+    lib.swb_broadcast_field.argtypes = [C.c_void_p, C.c_int, _P_D]
+    lib.swb_set_climate.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lib.swb_qual_init.argtypes = [C.c_void_p, _P_D]
+    lib.swb_old_state_swap.argtypes = [C.c_void_p, _P_D, C.c_int]
+    lib.swb_dynwave_execute.argtypes = [C.c_void_p, _P_D, _P_I]
+    lib.swb_qualrout_execute.argtypes = [C.c_void_p, _P_D]
+    lib.swb_get_routing_step.argtypes = [C.c_void_p, C.c_double, _P_D]
+    lib.swb_set_inflows.argtypes = [C.c_void_p, C.POINTER(abi.InflowDesc)]
+    lib.swb_run_steps.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    lib.swb_get_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.MemberStats)]
+    lib.swb_conduit_updates.argtypes = [C.c_void_p]
+    lib.swb_conduit_updates.restype = C.c_longlong
+    lib.swb_launch_count.argtypes = [C.c_void_p]
+    lib.swb_launch_count.restype = C.c_longlong
+    lib.swb_last_kernel_ms.argtypes = [C.c_void_p]
+    lib.swb_last_kernel_ms.restype = C.c_double
+    lib.swb_sync.argtypes = [C.c_void_p]
+    return lib
+
+
+class Solver:
+    """M lockstep members of one flat network on one GPU."""
+
+    def __init__(self, net: abi.Network, n_members: int = 1, device: int = 0, lib_path: str | None = None):
+        self.lib = load_library(lib_path)
+        self.net = net
+        self.M = n_members
+        self._desc, self._opt = net.to_c()        # keep alive
+        self._hnet = C.c_void_p()
+        self._chk(self.lib.swb_network_create(C.byref(self._desc), C.byref(self._opt), device,
+                                              C.byref(self._hnet)))
+        self._h = C.c_void_p()
+        self._chk(self.lib.swb_solver_create(self._hnet, n_members, C.byref(self._h)))
+        self._keep = []
+
+    def _chk(self, rc: int):
+        if rc:
+            raise SwbError(f"swb error {rc}: {self.lib.swb_last_error().decode()}")
+
+    def close(self):
+        if self._h:
+            self.lib.swb_solver_destroy(self._h)
+            self._h = C.c_void_p()
+        if self._hnet:
+            self.lib.swb_network_destroy(self._hnet)
+            self._hnet = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- fields ------------------------------------------------------------------------------
+    def _fid(self, f):
+        return abi.FIELD[f] if isinstance(f, str) else int(f)
+
+    def _items(self, fid: int) -> int:
+        n = self.net.n_nodes if abi.is_node_field(fid) else self.net.n_links
+        return n * abi.field_width(fid, self.net.n_pollut)
+
+    def set_field(self, field, values, member0: int = 0):
+        fid = self._fid(field)
+        a = np.ascontiguousarray(values, dtype=np.float64)
+        items = self._items(fid)
+        if items == 0:
+            return
+        nm = a.size // items
+        assert nm * items == a.size, (field, a.size, items)
+        self._chk(self.lib.swb_set_field(self._h, fid, member0, nm, a.ctypes.data_as(_P_D)))
+
+    def broadcast_field(self, field, values):
+        fid = self._fid(field)
+        a = np.ascontiguousarray(values, dtype=np.float64)
+        if self._items(fid) == 0:
+            return
+        assert a.size == self._items(fid), (field, a.size, self._items(fid))
+        self._chk(self.lib.swb_broadcast_field(self._h, fid, a.ctypes.data_as(_P_D)))
+
+    def get_field(self, field, member0: int = 0, n_members: int | None = None) -> np.ndarray:
+        fid = self._fid(field)
+        nm = self.M - member0 if n_members is None else n_members
+        items = self._items(fid)
+        out = np.zeros((nm, items), dtype=np.float64)
+        if items:
+            self._chk(self.lib.swb_get_field(self._h, fid, member0, nm, out.ctypes.data_as(_P_D)))
+        return out
+
+    # ---- the reference's per-step calls ---------------------------------------------------------
+    def _dt(self, dt):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, dtype=np.float64), (self.M,)))
+        return a, a.ctypes.data_as(_P_D)
+
+    def old_state_swap(self, dt, with_quality: bool = False):
+        a, p = self._dt(dt)
+        self._chk(self.lib.swb_old_state_swap(self._h, p, int(with_quality)))
+
+    def dynwave_execute(self, dt) -> np.ndarray:
+        a, p = self._dt(dt)
+        it = np.zeros(self.M, dtype=np.int32)
+        self._chk(self.lib.swb_dynwave_execute(self._h, p, it.ctypes.data_as(_P_I)))
+        return it
+
+    def qualrout_execute(self, dt):
+        a, p = self._dt(dt)
+        self._chk(self.lib.swb_qualrout_execute(self._h, p))
+
+    def get_routing_step(self, fixed_step: float) -> np.ndarray:
+        out = np.zeros(self.M, dtype=np.float64)
+        self._chk(self.lib.swb_get_routing_step(self._h, fixed_step, out.ctypes.data_as(_P_D)))
+        return out
+
+    def qual_init(self, init_concen):
+        a = np.ascontiguousarray(init_concen, dtype=np.float64)
+        self._chk(self.lib.swb_qual_init(self._h, a.ctypes.data_as(_P_D)))
+
+    def set_climate(self, evap_rate: float, hydcon_factor: float = 1.0):
+        self._chk(self.lib.swb_set_climate(self._h, evap_rate, hydcon_factor))
+
+    # ---- ensemble driver ----------------------------------------------------------------------
+    def set_inflows(self, node, ts_start, ts_t, ts_q, sfactor, baseline, concen=None,
+                    member_scale=None, member_shift=None, start_day=0.0, start_secs=0.0):
+        d = abi.InflowDesc()
+        arrs = {
+            "node": np.ascontiguousarray(node, dtype=np.int32),
+            "ts_start": np.ascontiguousarray(ts_start, dtype=np.int32),
+            "ts_t": np.ascontiguousarray(ts_t, dtype=np.float64),
+            "ts_q": np.ascontiguousarray(ts_q, dtype=np.float64),
+            "sfactor": np.ascontiguousarray(sfactor, dtype=np.float64),
+            "baseline": np.ascontiguousarray(baseline, dtype=np.float64),
+        }
+        n = arrs["node"].size
+        if concen is not None:
+            arrs["concen"] = np.ascontiguousarray(concen, dtype=np.float64)
+            assert arrs["concen"].size == n * self.net.n_pollut
+        if member_scale is not None:
+            arrs["member_scale"] = np.ascontiguousarray(member_scale, dtype=np.float64)
+            assert arrs["member_scale"].size == self.M
+        if member_shift is not None:
+            arrs["member_shift"] = np.ascontiguousarray(member_shift, dtype=np.float64)
+            assert arrs["member_shift"].size == self.M
+        d.n_inflow_nodes = n
+        d.n_ts_pts = arrs["ts_t"].size
+        d.start_day = float(start_day)
+        d.start_secs = float(start_secs)
+        for name, base in abi.INFLOW_ARRAYS:
+            if name in arrs:
+                ct = C.c_int if base == "int" else C.c_double
+                setattr(d, name, arrs[name].ctypes.data_as(C.POINTER(ct)))
+        self._keep.append(arrs)
+        self._chk(self.lib.swb_set_inflows(self._h, C.byref(d)))
+
+    def run_steps(self, n_steps: int, t_end: float):
+        self._chk(self.lib.swb_run_steps(self._h, n_steps, t_end))
+
+    def stats(self, member0: int = 0, n_members: int | None = None):
+        nm = self.M - member0 if n_members is None else n_members
+        arr = (abi.MemberStats * nm)()
+        self._chk(self.lib.swb_get_stats(self._h, member0, nm, arr))
+        return arr
+
+    def conduit_updates(self) -> int:
+        return int(self.lib.swb_conduit_updates(self._h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.swb_launch_count(self._h))
+
+    def last_kernel_ms(self) -> float:
+        return float(self.lib.swb_last_kernel_ms(self._h))
+
+    def sync(self):
+        self._chk(self.lib.swb_sync(self._h))
+
+    # ---- convenience ---------------------------------------------------------------------------
+    STATE_FIELDS = [
+        "SWB_NODE_NEW_DEPTH", "SWB_NODE_OLD_DEPTH", "SWB_NODE_NEW_VOLUME", "SWB_NODE_OLD_VOLUME",
+        "SWB_NODE_NEW_LATFLOW", "SWB_NODE_LOSSES", "SWB_NODE_INFLOW", "SWB_NODE_OUTFLOW",
+        "SWB_NODE_OVERFLOW", "SWB_NODE_OLD_NET_INFLOW", "SWB_NODE_OUTFALL_STAGE",
+        "SWB_NODE_STORAGE_EVAP_LOSS", "SWB_NODE_STORAGE_EXFIL_LOSS", "SWB_NODE_HRT",
+        "SWB_NODE_NEW_QUAL", "SWB_NODE_OLD_QUAL",
+        "SWB_LINK_NEW_FLOW", "SWB_LINK_OLD_FLOW", "SWB_LINK_NEW_DEPTH", "SWB_LINK_OLD_DEPTH",
+        "SWB_LINK_NEW_VOLUME", "SWB_LINK_OLD_VOLUME", "SWB_LINK_SETTING", "SWB_LINK_TARGET_SETTING",
+        "SWB_LINK_DQDH", "SWB_LINK_FROUDE", "SWB_LINK_FLOW_CLASS", "SWB_LINK_SURF_AREA1",
+        "SWB_LINK_SURF_AREA2", "SWB_LINK_NORMAL_FLOW", "SWB_LINK_INLET_CONTROL", "SWB_COND_A1",
+        "SWB_COND_A2", "SWB_COND_Q1", "SWB_COND_Q2", "SWB_COND_FULL_STATE",
+        "SWB_COND_CAPACITY_LIMITED", "SWB_COND_EVAP_LOSS", "SWB_COND_SEEP_LOSS", "SWB_ORIF_CORIF",
+        "SWB_ORIF_CWEIR", "SWB_ORIF_HCRIT", "SWB_REG_SURF_AREA", "SWB_WEIR_CSURCHARGE",
+        "SWB_LINK_NEW_QUAL", "SWB_LINK_OLD_QUAL", "SWB_LINK_TOTAL_LOAD",
+    ]
+
+    def load_state(self, state: dict):
+        """Broadcast a single-member state image (field name -> array) to every member."""
+        for k, v in state.items():
+            self.broadcast_field(k, v)

@@ -1,0 +1,63 @@
+// CPU emulation of the device engine -- TEST SCAFFOLDING, never part of libswmm_b200.so.
+// Instantiates csrc/swb_api_impl.h with a host-memory backend whose "launch" runs the identical
+// engine_run<> template on G host threads with a real barrier for every grid-wide sync, so the
+// CPU-only suite exercises the kernels' arithmetic AND their control flow (barrier placement,
+// per-member convergence bookkeeping) against the reference.
+#include <barrier>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include "swb_state.h"
+#include "swb_engine.h"
+
+namespace swb { namespace backend {
+static bool init(int, std::string &) { return true; }
+static void *alloc(size_t b) { return std::malloc(b ? b : 8); }
+static void free_(void *p) { std::free(p); }
+static void upload(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
+static void download(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
+static void zero(void *d, size_t b) { std::memset(d, 0, b); }
+static bool sync(std::string &) { return true; }
+static int device_count() { return 1; }
+
+struct EmulCtx {
+    int tid, G, lane, block_size;
+    const double *T;
+    std::barrier<> *bar;
+    void grid_sync() { bar->arrive_and_wait(); }
+    bool block_or(bool b) { return b; }
+    void atomic_min_u64(unsigned long long *p, unsigned long long v)
+    {
+        unsigned long long cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+        while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    }
+    void atomic_add_f64(double *p, double v)
+    {
+        unsigned long long *u = (unsigned long long *)p, cur = __atomic_load_n(u, __ATOMIC_RELAXED), nxt;
+        do { double d; std::memcpy(&d, &cur, 8); d += v; std::memcpy(&nxt, &d, 8); }
+        while (!__atomic_compare_exchange_n(u, &cur, nxt, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    }
+};
+
+static bool launch(const Net &net, const State &st, const RunArgs &args, int, float *ms, std::string &)
+{
+    const int M = st.M;
+    int k = 1;
+    if (M < 4) k = 4 / M;
+    const int G = M * k;
+    std::barrier<> bar(G);
+    std::vector<std::thread> th;
+    for (int t = 0; t < G; t++)
+        th.emplace_back([&, t]() {
+            EmulCtx c{t, G, 0, 1, net.xs_tables, &bar};
+            engine_run(net, st, args, c);
+        });
+    for (auto &x : th) x.join();
+    *ms = 0.f;
+    return true;
+}
+} }
+
+#include "swb_api_impl.h"

@@ -237,6 +237,12 @@ int  swb_get_stats(swb_solver *s, int member0, int n_members, swb_member_stats *
 /* conduit-updates performed so far: sum over members of iterations x true conduits */
 long long swb_conduit_updates(swb_solver *s);
 
+/* Known-answer hook for the geometry library (K1b): evaluates one xsect function on the device for
+ * n arguments.  fn: 0 AofY 1 WofY 2 RofY 3 YofA 4 RofA 5 SofA 6 AofS 7 dSdA 8 Ycrit (xsect.c:714-1319);
+ * params = {yFull,wMax,ywMax,aFull,rFull,sFull,sMax,yBot,aBot,sBot,rBot} (objects.h:581-599). */
+int  swb_xsect_eval(int device, int fn, int xs_type, const double *params, int n, const double *args,
+                    double *out);
+
 /* launch bookkeeping for bench.py ("gpu_launches") and device timing of the last call */
 long long swb_launch_count(const swb_solver *s);
 double    swb_last_kernel_ms(const swb_solver *s);

@@ -29,7 +29,8 @@ def _abi():
 
 def available(lib: str = "libswmm5.so") -> bool:
     return os.path.exists(os.path.join(REFDIR, lib)) and \
-        os.path.exists(os.path.join(REFDIR, "librefhook.so"))
+        os.path.exists(os.path.join(REFDIR, "librefhook.so")) and \
+        os.path.exists(os.path.join(REFDIR, "librefcount.so"))
 
 
 class RefEngine:
@@ -38,9 +39,17 @@ class RefEngine:
     def __init__(self, lib: str = "libswmm5.so"):
         self.abi = _abi()
         mode = C.RTLD_GLOBAL
+        # the counter interposer must enter the global scope BEFORE the engine (see refcount.c)
+        self.count = C.CDLL(os.path.join(REFDIR, "librefcount.so"), mode=mode)
+        self.count.refcount_get.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                            C.POINTER(C.c_double)]
         self.lib = C.CDLL(os.path.join(REFDIR, lib), mode=mode)
         self.hook = C.CDLL(os.path.join(REFDIR, "librefhook.so"), mode=mode)
         L = self.lib
+        self.count.refcount_bind.argtypes = [C.c_void_p] * 4
+        self.count.refcount_bind(*[C.cast(getattr(L, n), C.c_void_p) for n in
+                                   ("dynwave_execute", "dynwave_getRoutingStep", "qualrout_execute",
+                                    "routing_execute")])
         L.swmm_getValue.restype = C.c_double
         L.swmm_getValue.argtypes = [C.c_int, C.c_int]
         L.swmm_step.argtypes = [C.POINTER(C.c_double)]
@@ -143,6 +152,20 @@ class RefEngine:
 
     def total_duration_s(self) -> float:
         return self.hook.refhook_total_duration() / 1000.0
+
+    def last_iterations(self) -> int:
+        """Return value of the most recent dynwave_execute call (Picard iterations of that step)."""
+        return self.count.refcount_last_iterations()
+
+    def seam_totals(self) -> dict:
+        st, it = C.c_longlong(), C.c_longlong()
+        t = (C.c_double * 4)()
+        self.count.refcount_get(C.byref(st), C.byref(it), t)
+        return {"steps": st.value, "iterations": it.value, "t_dynwave_execute": t[0],
+                "t_get_routing_step": t[1], "t_qualrout_execute": t[2], "t_routing_execute": t[3]}
+
+    def reset_seam_totals(self):
+        self.count.refcount_reset()
 
     def routing_time_ms(self) -> float:
         return self.hook.refhook_new_routing_time()

@@ -1,0 +1,164 @@
+// swb_api.cu -- libswmm_b200.so: CUDA (sm_100a) backend of the C-ABI in include/swmm_b200.h.
+//
+// One cooperative, persistent kernel (swb_route_kernel) executes whole routing steps: every CTA
+// stages the 12 KB of normalised cross-section tables into shared memory once, then runs the
+// phase sequence of swb_engine.h with cooperative-groups grid barriers between phases.  The grid
+// is sized to the machine (resident CTAs x SM count, trimmed so that threads % members == 0 and
+// never larger than the work), not to the problem.
+//
+// There is no host fallback in this file: every entry point fails with SWB_ERR_CUDA when no
+// device is usable.
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <string>
+#include "swb_state.h"
+#include "swb_engine.h"
+
+namespace cg = cooperative_groups;
+using namespace swb;
+
+#define SWB_BLOCK 256
+
+struct CudaCtx {
+    int tid, G, lane, block_size;
+    const double *T;
+    __device__ __forceinline__ void grid_sync() { cg::this_grid().sync(); }
+    __device__ __forceinline__ bool block_or(bool b) { return __syncthreads_or(b ? 1 : 0) != 0; }
+    __device__ __forceinline__ void atomic_min_u64(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
+    __device__ __forceinline__ void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
+};
+
+__global__ void __launch_bounds__(SWB_BLOCK)
+swb_route_kernel(const Net net, const State st, const RunArgs args)
+{
+    __shared__ double tab[XT_TOTAL];
+    for (int i = threadIdx.x; i < XT_TOTAL; i += blockDim.x) tab[i] = net.xs_tables[i];
+    __syncthreads();
+    CudaCtx ctx;
+    ctx.tid = blockIdx.x * blockDim.x + threadIdx.x;
+    ctx.G = gridDim.x * blockDim.x;
+    ctx.lane = threadIdx.x;
+    ctx.block_size = blockDim.x;
+    ctx.T = tab;
+    engine_run(net, st, args, ctx);
+}
+
+__global__ void swb_xsect_kernel(int fn, Xs x, int n, const double *tables, const double *args, double *out)
+{
+    __shared__ double tab[XT_TOTAL];
+    for (int i = threadIdx.x; i < XT_TOTAL; i += blockDim.x) tab[i] = tables[i];
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = xs_eval(fn, x, args[i], tab);
+}
+
+namespace swb { namespace backend {
+
+static std::string cuda_err(const char *what, cudaError_t e)
+{
+    return std::string(what) + ": " + cudaGetErrorString(e);
+}
+
+static int g_device = -1, g_sms = 0, g_blocks_per_sm = 0;
+static cudaEvent_t g_ev0, g_ev1;
+
+static int device_count()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static bool init(int device, std::string &err)
+{
+    int n = device_count();
+    if (n <= 0) { err = "no CUDA device available (libswmm_b200 has no CPU path)"; return false; }
+    if (device < 0 || device >= n) { err = "CUDA device ordinal out of range"; return false; }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { err = cuda_err("cudaSetDevice", e); return false; }
+    if (g_device != device) {
+        cudaDeviceProp p;
+        e = cudaGetDeviceProperties(&p, device);
+        if (e != cudaSuccess) { err = cuda_err("cudaGetDeviceProperties", e); return false; }
+        if (!p.cooperativeLaunch) { err = "device does not support cooperative launch"; return false; }
+        g_sms = p.multiProcessorCount;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_blocks_per_sm, swb_route_kernel, SWB_BLOCK, 0);
+        if (e != cudaSuccess || g_blocks_per_sm < 1) { err = cuda_err("occupancy query", e); return false; }
+        if (g_device < 0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+        g_device = device;
+    }
+    return true;
+}
+
+static void *alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr;
+    return p;
+}
+static void free_(void *p) { cudaFree(p); }
+static void upload(void *d, const void *s, size_t b) { if (b) cudaMemcpy(d, s, b, cudaMemcpyHostToDevice); }
+static void download(void *d, const void *s, size_t b) { if (b) cudaMemcpy(d, s, b, cudaMemcpyDeviceToHost); }
+static void zero(void *d, size_t b) { if (b) cudaMemset(d, 0, b); }
+
+static bool sync(std::string &err)
+{
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { err = cuda_err("cudaDeviceSynchronize", e); return false; }
+    return true;
+}
+
+static bool xsect_eval(int device, int fn, const Xs &x, int n, const double *args, double *out, std::string &err)
+{
+    if (!init(device, err)) return false;
+    static const double tab[] = { SWB_XS_TABLE_DATA };
+    double *dT = (double *)alloc(sizeof(tab)), *dA = (double *)alloc(sizeof(double) * n),
+           *dO = (double *)alloc(sizeof(double) * n);
+    upload(dT, tab, sizeof(tab));
+    upload(dA, args, sizeof(double) * n);
+    if (n > 0) swb_xsect_kernel<<<(n + 127) / 128, 128>>>(fn, x, n, dT, dA, dO);
+    cudaError_t e = cudaDeviceSynchronize();
+    download(out, dO, sizeof(double) * n);
+    free_(dT); free_(dA); free_(dO);
+    if (e != cudaSuccess) { err = cuda_err("swb_xsect_kernel", e); return false; }
+    return true;
+}
+
+// CTAs to launch: all that can be co-resident, but (i) threads % M == 0 so a thread keeps one
+// member, (ii) no more threads than (objects x members), (iii) at least one CTA per 256 members.
+static int pick_blocks(int M, int maxItems)
+{
+    long long maxBlocks = (long long)g_sms * g_blocks_per_sm;
+    long long work = ((long long)maxItems * M + SWB_BLOCK - 1) / SWB_BLOCK;
+    long long blocks = std::max(1LL, std::min(maxBlocks, work));
+    int g = M, b = SWB_BLOCK;                 // gcd(M, SWB_BLOCK)
+    while (b) { int t = g % b; g = b; b = t; }
+    long long unit = M / g;                   // blocks must be a multiple of this
+    blocks = (blocks / unit) * unit;
+    if (blocks < unit) blocks = unit;
+    return (int)blocks;
+}
+
+static bool launch(const Net &net, const State &st, const RunArgs &args, int device, float *ms, std::string &err)
+{
+    if (!init(device, err)) return false;
+    int blocks = pick_blocks(st.M, std::max(net.nN, net.nL));
+    if ((long long)blocks > (long long)g_sms * g_blocks_per_sm) {
+        err = "ensemble too wide for one cooperative launch on this device";
+        return false;
+    }
+    void *kargs[] = { (void *)&net, (void *)&st, (void *)&args };
+    cudaEventRecord(g_ev0, 0);
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)swb_route_kernel, dim3(blocks), dim3(SWB_BLOCK), kargs, 0, 0);
+    if (e != cudaSuccess) { err = cuda_err("cudaLaunchCooperativeKernel", e); return false; }
+    cudaEventRecord(g_ev1, 0);
+    e = cudaEventSynchronize(g_ev1);
+    if (e != cudaSuccess) { err = cuda_err("swb_route_kernel", e); return false; }
+    cudaEventElapsedTime(ms, g_ev0, g_ev1);
+    return true;
+}
+
+} }
+
+#include "swb_api_impl.h"

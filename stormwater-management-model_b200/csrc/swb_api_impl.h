@@ -11,6 +11,7 @@
 //     void  zero(void *dst, size_t bytes);
 //     bool  launch(const Net &, const State &, const RunArgs &, int device, float *ms, std::string &err);
 //     bool  sync(std::string &err);         int device_count();
+//     bool  xsect_eval(int device, int fn, const Xs &x, int n, const double *args, double *out, std::string &err);
 //   } }
 #ifndef SWB_API_IMPL_H
 #define SWB_API_IMPL_H
@@ -361,6 +362,18 @@ long long swb_conduit_updates(swb_solver *s)
     long long sum = 0;
     for (long long v : it) sum += v;
     return sum * (long long)s->net->net.nTrue;
+}
+
+int swb_xsect_eval(int device, int fn, int xs_type, const double *p, int n, const double *args, double *out)
+{
+    if (!p || !args || !out || n < 0 || fn < 0 || fn > 8) return fail(SWB_ERR_ARG, "bad arguments");
+    Xs x;
+    x.type = xs_type; x.ntbl = 0; x.atbl = x.rtbl = x.wtbl = nullptr;
+    x.yFull = p[0]; x.wMax = p[1]; x.ywMax = p[2]; x.aFull = p[3]; x.rFull = p[4]; x.sFull = p[5];
+    x.sMax = p[6]; x.yBot = p[7]; x.aBot = p[8]; x.sBot = p[9]; x.rBot = p[10];
+    std::string err;
+    if (!backend::xsect_eval(device, fn, x, n, args, out, err)) return fail(SWB_ERR_CUDA, err);
+    return SWB_OK;
 }
 
 long long swb_launch_count(const swb_solver *s) { return s ? s->launches : 0; }

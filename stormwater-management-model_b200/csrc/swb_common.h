@@ -8,8 +8,8 @@
 #define SWB_COMMON_H
 
 #ifdef __CUDACC__
-#define SWB_HD __host__ __device__ __forceinline__
-#define SWB_D  __device__ __forceinline__
+#define SWB_HD __host__ __device__
+#define SWB_D  __device__
 #else
 #define SWB_HD
 #define SWB_D

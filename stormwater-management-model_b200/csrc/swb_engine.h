@@ -25,9 +25,9 @@
 #include "swb_regulator.h"
 
 #ifdef __CUDACC__
-#define SWB_ENGINE __device__ __forceinline__
+#define SWB_ENGINE __device__
 #else
-#define SWB_ENGINE inline
+#define SWB_ENGINE
 #endif
 
 namespace swb {
@@ -75,7 +75,7 @@ SWB_HD inline double inflow_series(const Inflows &f, int k, double t)
 }
 
 template <class Ctx>
-SWB_ENGINE void engine_run(const Net &net, const State &st, const RunArgs &args, Ctx &ctx)
+SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs &args, Ctx &ctx)
 {
     const int M = st.M, nN = net.nN, nL = net.nL, nP = net.nP;
     const int m = ctx.tid % M;

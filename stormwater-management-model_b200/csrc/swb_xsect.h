@@ -881,5 +881,21 @@ SWB_HD inline double xs_ycrit(const Xs &x, double q, const double *T)
     return SWB_MIN(y, x.yFull);
 }
 
+// known-answer dispatcher used by swb_xsect_eval
+SWB_HD inline double xs_eval(int fn, const Xs &x, double arg, const double *T)
+{
+    switch (fn) {
+      case 0: return xs_a_of_y(x, arg, T);
+      case 1: return xs_w_of_y(x, arg, T);
+      case 2: return xs_r_of_y(x, arg, T);
+      case 3: return xs_y_of_a(x, arg, T);
+      case 4: return xs_r_of_a(x, arg, T);
+      case 5: return xs_s_of_a(x, arg, T);
+      case 6: return xs_a_of_s(x, arg, T);
+      case 7: return xs_dsda(x, arg, T);
+      default: return xs_ycrit(x, arg, T);
+    }
+}
+
 } // namespace swb
 #endif

@@ -55,7 +55,25 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_last_kernel_ms.argtypes = [C.c_void_p]
     lib.swb_last_kernel_ms.restype = C.c_double
     lib.swb_sync.argtypes = [C.c_void_p]
+    lib.swb_xsect_eval.argtypes = [C.c_int, C.c_int, C.c_int, _P_D, C.c_int, _P_D, _P_D]
     return lib
+
+
+XS_FN = {"AofY": 0, "WofY": 1, "RofY": 2, "YofA": 3, "RofA": 4, "SofA": 5, "AofS": 6, "dSdA": 7,
+         "Ycrit": 8}
+
+
+def xsect_eval(fn: str, xs_type: int, params, args, device: int = 0, lib_path: str | None = None):
+    """Evaluate one geometry function on the device (known-answer hook, swb_xsect_eval)."""
+    lib = load_library(lib_path)
+    p = np.ascontiguousarray(params, dtype=np.float64)
+    a = np.ascontiguousarray(args, dtype=np.float64)
+    out = np.zeros_like(a)
+    rc = lib.swb_xsect_eval(device, XS_FN[fn], int(xs_type), p.ctypes.data_as(_P_D), a.size,
+                            a.ctypes.data_as(_P_D), out.ctypes.data_as(_P_D))
+    if rc:
+        raise SwbError(f"swb error {rc}: {lib.swb_last_error().decode()}")
+    return out
 
 
 class Solver:

@@ -4,6 +4,7 @@
 // CPU-only suite exercises the kernels' arithmetic AND their control flow (barrier placement,
 // per-member convergence bookkeeping) against the reference.
 #include <barrier>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -21,6 +22,12 @@ static void download(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 static void zero(void *d, size_t b) { std::memset(d, 0, b); }
 static bool sync(std::string &) { return true; }
 static int device_count() { return 1; }
+static bool xsect_eval(int, int fn, const Xs &x, int n, const double *args, double *out, std::string &)
+{
+    static const double tab[] = { SWB_XS_TABLE_DATA };
+    for (int i = 0; i < n; i++) out[i] = xs_eval(fn, x, args[i], tab);
+    return true;
+}
 
 struct EmulCtx {
     int tid, G, lane, block_size;
@@ -47,6 +54,7 @@ static bool launch(const Net &net, const State &st, const RunArgs &args, int, fl
     int k = 1;
     if (M < 4) k = 4 / M;
     const int G = M * k;
+    auto t0 = std::chrono::steady_clock::now();
     std::barrier<> bar(G);
     std::vector<std::thread> th;
     for (int t = 0; t < G; t++)
@@ -55,7 +63,7 @@ static bool launch(const Net &net, const State &st, const RunArgs &args, int, fl
             engine_run(net, st, args, c);
         });
     for (auto &x : th) x.join();
-    *ms = 0.f;
+    *ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return true;
 }
 } }

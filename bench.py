@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--grid", type=int, default=100)
     ap.add_argument("--hours", type=float, default=6.0)
     ap.add_argument("--surcharge", default="SLOT")
-    ap.add_argument("--spinup", type=float, default=3600.0, help="simulated seconds before timing")
+    ap.add_argument("--spinup", type=float, default=6000.0, help="simulated seconds before timing")
     ap.add_argument("--routing-steps", type=int, default=10, help="routing steps per bench step / launch")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=60)

@@ -30,7 +30,8 @@ struct CudaCtx {
 };
 
 __global__ void __launch_bounds__(SWB_BLOCK)
-swb_route_kernel(const Net net, const State st, const RunArgs args)
+swb_route_kernel(const __grid_constant__ Net net, const __grid_constant__ State st,
+                 const __grid_constant__ RunArgs args)
 {
     __shared__ double tab[XT_TOTAL];
     for (int i = threadIdx.x; i < XT_TOTAL; i += blockDim.x) tab[i] = net.xs_tables[i];

@@ -7,12 +7,21 @@
 #ifndef SWB_COMMON_H
 #define SWB_COMMON_H
 
+// Inlining policy: every SWB_HD function is force-inlined on the device so that a call with a
+// compile-time shape constant folds its switch away and keeps the cross section in registers;
+// the few SWB_NI wrappers are real calls, used where the shape is only known at run time
+// (generic conduit path, regulators, outfall boundary) to keep the code footprint bounded.
+//   SWB_FI  small hot functions of the specialised conduit path (force-inlined)
+//   SWB_HD  everything else (the compiler decides)
+//   SWB_NI  real calls
 #ifdef __CUDACC__
-#define SWB_HD __host__ __device__
-#define SWB_D  __device__
+#define SWB_FI __host__ __device__ __forceinline__
+#define SWB_HD __host__ __device__ inline
+#define SWB_NI __host__ __device__ __noinline__ inline
 #else
-#define SWB_HD
-#define SWB_D
+#define SWB_FI inline
+#define SWB_HD inline
+#define SWB_NI __attribute__((noinline)) inline
 #endif
 
 // consts.h:31-50 and the module constants of dynwave.c:60-66, dwflow.c:37, qualrout.c:40-41.
@@ -39,7 +48,7 @@
 #include <string.h>
 namespace swb {
 // order-preserving integer image of a non-negative double (for integer atomicMin)
-SWB_HD inline unsigned long long dbits(double v)
+SWB_HD unsigned long long dbits(double v)
 {
 #if defined(__CUDA_ARCH__)
     return (unsigned long long)__double_as_longlong(v);
@@ -47,7 +56,7 @@ SWB_HD inline unsigned long long dbits(double v)
     unsigned long long u; memcpy(&u, &v, sizeof(u)); return u;
 #endif
 }
-SWB_HD inline double dfrombits(unsigned long long u)
+SWB_HD double dfrombits(unsigned long long u)
 {
 #if defined(__CUDA_ARCH__)
     return __longlong_as_double((long long)u);

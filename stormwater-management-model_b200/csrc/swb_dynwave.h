@@ -22,7 +22,7 @@
 
 namespace swb {
 
-SWB_HD inline Xs load_xs(const Net &n, int j)
+SWB_FI Xs load_xs(const Net &n, int j)
 {
     Xs x;
     x.type = n.xs_type[j];
@@ -42,54 +42,58 @@ SWB_HD inline Xs load_xs(const Net &n, int j)
 }
 
 // ---- dwflow.c:575-633 ---------------------------------------------------------------------------
-SWB_HD inline double dw_slot_width(const Net &n, const Xs &x, bool isOpen, double y)
+SWB_FI double dw_slot_width(const Net &n, const Xs &x, bool isOpen, double y)
 {
     double yNorm = y / x.yFull;
     if (n.opt.surcharge_method != SWB_SLOT || isOpen || yNorm < n.crownCutoff) return 0.0;
     if (yNorm > 1.78) return 0.01 * x.wMax;
     return x.wMax * 0.5423 * exp(-pow(yNorm, 2.4));
 }
-SWB_HD inline double dw_width(const Net &n, const Xs &x, bool isOpen, double y, const double *T)
+template <int S>
+SWB_FI double dw_width(const Net &n, const Xs &x, bool isOpen, double y, const double *T)
 {
     double wSlot = dw_slot_width(n, x, isOpen, y);
     if (wSlot > 0.0) return wSlot;
     if (y / x.yFull >= n.crownCutoff && !isOpen) y = n.crownCutoff * x.yFull;
-    return xs_w_of_y(x, y, T);
+    return xw<S>(x, y, T);
 }
-SWB_HD inline double dw_area(const Xs &x, double y, double wSlot, const double *T)
+template <int S>
+SWB_FI double dw_area(const Xs &x, double y, double wSlot, const double *T)
 {
     if (y >= x.yFull) return x.aFull + (y - x.yFull) * wSlot;
-    return xs_a_of_y(x, y, T);
+    return xa<S>(x, y, T);
 }
-SWB_HD inline double dw_hyd_rad(const Xs &x, double y, const double *T)
+template <int S>
+SWB_FI double dw_hyd_rad(const Xs &x, double y, const double *T)
 {
     if (y >= x.yFull) return x.rFull;
-    return xs_r_of_y(x, y, T);
+    return xr<S>(x, y, T);
 }
 
 // ---- link.c:847-871 (conduits only) -------------------------------------------------------------
-SWB_HD inline double link_froude(const Xs &x, bool isOpen, double v, double y, const double *T)
+template <int S>
+SWB_FI double link_froude(const Xs &x, bool isOpen, double v, double y, const double *T)
 {
     if (y <= SWB_FUDGE) return 0.0;
     if (!isOpen && x.yFull - y <= SWB_FUDGE) return 0.0;
-    y = xs_a_of_y(x, y, T) / xs_w_of_y(x, y, T);
+    y = xa<S>(x, y, T) / xw<S>(x, y, T);
     return fabs(v) / sqrt(SWB_GRAVITY * y);
 }
 
 // ---- link.c:770-804 -----------------------------------------------------------------------------
-SWB_HD inline double link_ynorm(const Net &n, int j, const Xs &x, double q, const double *T)
+SWB_NI double link_ynorm(const Net &n, int j, const Xs &x, double q, const double *T)
 {
     if (!(n.link_flags[j] & LF_TRUE_CONDUIT)) return 0.0;
     q = fabs(q);
     if (q > n.cond_q_max[j]) q = n.cond_q_max[j];
     if (q <= 0.0) return 0.0;
     double s = q / n.cond_beta[j];
-    double a = xs_a_of_s(x, s, T);
-    return xs_y_of_a(x, a, T);
+    double a = xs_a_of_s_ni(x, s, T);
+    return xs_y_of_a_ni(x, a, T);
 }
 
 // ---- link.c:643-670 with the node tests folded into link_flags ----------------------------------
-SWB_HD inline bool link_flap_closed(int flags, int direction, double q)
+SWB_FI bool link_flap_closed(int flags, int direction, double q)
 {
     if (flags & LF_HAS_FLAP) { if (q * (double)direction < 0.0) return true; }
     if (q < 0.0 && (flags & LF_N2_OUT_FLAP)) return true;
@@ -98,7 +102,8 @@ SWB_HD inline bool link_flap_closed(int flags, int direction, double q)
 }
 
 // ---- link.c:1334-1399 (DW branch) ---------------------------------------------------------------
-SWB_HD inline double conduit_loss_rate(const Net &n, const State &s, int j, int m, const Xs &x,
+template <int S>
+SWB_FI double conduit_loss_rate(const Net &n, const State &s, int j, int m, const Xs &x,
                                        bool isOpen, double dt, double evapRate, double hydcon,
                                        double &evapLoss, double &seepLoss, const double *T)
 {
@@ -108,7 +113,7 @@ SWB_HD inline double conduit_loss_rate(const Net &n, const State &s, int j, int 
     if (depth > SWB_FUDGE) {
         double length = n.cond_length[j];
         if (isOpen && evapRate > 0.0) {
-            double topWidth = xs_w_of_y(x, depth, T);
+            double topWidth = xw<S>(x, depth, T);
             evapLossRate = topWidth * length * evapRate;
         }
         double seepRate = n.link_seep_rate[j];
@@ -117,7 +122,7 @@ SWB_HD inline double conduit_loss_rate(const Net &n, const State &s, int j, int 
             if (x.type == XS_RECT_CLOSED) width = x.wMax;
             else {
                 if (depth >= x.ywMax) depth = x.ywMax;
-                width = xs_w_of_y(x, depth, T);
+                width = xw<S>(x, depth, T);
             }
             seepLossRate = seepRate * width * length;
             seepLossRate *= hydcon;
@@ -138,7 +143,7 @@ SWB_HD inline double conduit_loss_rate(const Net &n, const State &s, int j, int 
 // ---- dwflow.c:297-413 ---------------------------------------------------------------------------
 struct FlowClassOut { int cls; double yC, yN, fasnh; };
 
-SWB_HD inline FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int flags, double q,
+SWB_FI FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int flags, double q,
                                          double h1, double h2, double y1, double y2,
                                          double depth1, double depth2, double yMidGuess,
                                          const double *T)
@@ -153,14 +158,14 @@ SWB_HD inline FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int f
         if (q < 0.0) {
             if (z1 > 0.0) {
                 o.yN = link_ynorm(n, j, x, fabs(q), T);
-                o.yC = xs_ycrit(x, fabs(q), T);
+                o.yC = xs_ycrit_ni(x, fabs(q), T);
                 double ycMin = SWB_MIN(o.yN, o.yC);
                 if (y1 < ycMin) o.cls = SWB_UP_CRITICAL;
             }
         } else {
             if (z2 > 0.0) {
                 o.yN = link_ynorm(n, j, x, fabs(q), T);
-                o.yC = xs_ycrit(x, fabs(q), T);
+                o.yC = xs_ycrit_ni(x, fabs(q), T);
                 double ycMin = SWB_MIN(o.yN, o.yC);
                 double ycMax = SWB_MAX(o.yN, o.yC);
                 if (y2 < ycMin) o.cls = SWB_DN_CRITICAL;
@@ -176,7 +181,7 @@ SWB_HD inline FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int f
         if (h2 < n.link_z1[j]) o.cls = SWB_UP_DRY;
         else if (z1 > 0.0) {
             o.yN = link_ynorm(n, j, x, fabs(q), T);
-            o.yC = xs_ycrit(x, fabs(q), T);
+            o.yC = xs_ycrit_ni(x, fabs(q), T);
             o.cls = SWB_UP_CRITICAL;
         }
     }
@@ -184,7 +189,7 @@ SWB_HD inline FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int f
         if (h1 < n.link_z2[j]) o.cls = SWB_DN_DRY;
         else if (z2 > 0.0) {
             o.yN = link_ynorm(n, j, x, fabs(q), T);
-            o.yC = xs_ycrit(x, fabs(q), T);
+            o.yC = xs_ycrit_ni(x, fabs(q), T);
             o.cls = SWB_DN_CRITICAL;
         }
     }
@@ -192,13 +197,15 @@ SWB_HD inline FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int f
 }
 
 // ---- K1: dwflow.c:57-293 (with findSurfArea :417-550, checkNormalFlow :637-686) ------------------
-SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int steps, double dt,
-                                const double *T)
+template <int S>
+SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, double dt,
+                         const double *T)
 {
     const int M = s.M;
     const size_t ix = SWB_IX(j, m, M);
     const int flags = n.link_flags[j];
-    const Xs x = load_xs(n, j);
+    Xs x = load_xs(n, j);
+    if constexpr (S >= 0) x.type = S;        // compile-time shape: every geometry switch folds
     const bool isOpen = (flags & LF_OPEN_SHAPE) != 0;
     const int n1 = n.link_node1[j], n2 = n.link_node2[j];
     const double barrels = (double)n.cond_barrels[j];
@@ -241,9 +248,9 @@ SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int 
           case SWB_SUBCRITICAL:
             fdMid = 0.5 * (fd1 + fd2);
             if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
-            width1 = dw_width(n, x, isOpen, fd1, T);
-            width2 = dw_width(n, x, isOpen, fd2, T);
-            widthMid = dw_width(n, x, isOpen, fdMid, T);
+            width1 = dw_width<S>(n, x, isOpen, fd1, T);
+            width2 = dw_width<S>(n, x, isOpen, fd2, T);
+            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
             surfArea1 = (width1 + widthMid) * length / 4.;
             surfArea2 = (widthMid + width2) * length / 4. * fasnh;
             break;
@@ -254,8 +261,8 @@ SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int 
             h1 = z1 + fd1;
             fdMid = 0.5 * (fd1 + fd2);
             if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
-            width2 = dw_width(n, x, isOpen, fd2, T);
-            widthMid = dw_width(n, x, isOpen, fdMid, T);
+            width2 = dw_width<S>(n, x, isOpen, fd2, T);
+            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
             surfArea2 = (widthMid + width2) * length * 0.5;
             break;
           case SWB_DN_CRITICAL:
@@ -263,19 +270,19 @@ SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int 
             if (normalDepth < criticalDepth) fd2 = normalDepth;
             fd2 = SWB_MAX(fd2, SWB_FUDGE);
             h2 = z2 + fd2;
-            width1 = dw_width(n, x, isOpen, fd1, T);
+            width1 = dw_width<S>(n, x, isOpen, fd1, T);
             fdMid = 0.5 * (fd1 + fd2);
             if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
-            widthMid = dw_width(n, x, isOpen, fdMid, T);
+            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
             surfArea1 = (width1 + widthMid) * length * 0.5;
             break;
           case SWB_UP_DRY:
             fd1 = SWB_FUDGE;
             fdMid = 0.5 * (fd1 + fd2);
             if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
-            width1 = dw_width(n, x, isOpen, fd1, T);
-            width2 = dw_width(n, x, isOpen, fd2, T);
-            widthMid = dw_width(n, x, isOpen, fdMid, T);
+            width1 = dw_width<S>(n, x, isOpen, fd1, T);
+            width2 = dw_width<S>(n, x, isOpen, fd2, T);
+            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
             surfArea2 = (widthMid + width2) * length / 4.;
             if (n.link_offset1[j] <= 0.0) surfArea1 = (width1 + widthMid) * length / 4.;
             break;
@@ -283,9 +290,9 @@ SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int 
             fd2 = SWB_FUDGE;
             fdMid = 0.5 * (fd1 + fd2);
             if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
-            width1 = dw_width(n, x, isOpen, fd1, T);
-            width2 = dw_width(n, x, isOpen, fd2, T);
-            widthMid = dw_width(n, x, isOpen, fdMid, T);
+            width1 = dw_width<S>(n, x, isOpen, fd1, T);
+            width2 = dw_width<S>(n, x, isOpen, fd2, T);
+            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
             surfArea1 = (widthMid + width1) * length / 4.;
             if (n.link_offset2[j] <= 0.0) surfArea2 = (width2 + widthMid) * length / 4.;
             break;
@@ -301,14 +308,14 @@ SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int 
 
     // --- areas and hydraulic radii (dwflow.c:142-153)
     double wSlot = dw_slot_width(n, x, isOpen, y1);
-    double a1 = dw_area(x, y1, wSlot, T);
-    double r1 = dw_hyd_rad(x, y1, T);
+    double a1 = dw_area<S>(x, y1, wSlot, T);
+    double r1 = dw_hyd_rad<S>(x, y1, T);
     wSlot = dw_slot_width(n, x, isOpen, y2);
-    double a2 = dw_area(x, y2, wSlot, T);
+    double a2 = dw_area<S>(x, y2, wSlot, T);
     double yMid = 0.5 * (y1 + y2);
     wSlot = dw_slot_width(n, x, isOpen, yMid);
-    double aMid = dw_area(x, yMid, wSlot, T);
-    double rMid = dw_hyd_rad(x, yMid, T);
+    double aMid = dw_area<S>(x, yMid, wSlot, T);
+    double rMid = dw_hyd_rad<S>(x, yMid, T);
 
     bool isFull = (y1 >= x.yFull && y2 >= x.yFull);
 
@@ -318,22 +325,20 @@ SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int 
         double a1s = 0.5 * (a1 + a2);
         s.c_a1[ix] = a1s;
         s.c_q1[ix] = 0.0;
-        s.c_q2[ix] = 0.0;
         s.l_dqdh[ix] = SWB_GRAVITY * dt * aMid / length * barrels;
         s.l_froude[ix] = 0.0;
         s.l_depth[ix] = SWB_MIN(yMid, x.yFull);
         s.l_volume[ix] = a1s * trueLength * barrels;
         s.l_flow[ix] = 0.0;
         s.l_flow_class[ix] = (unsigned char)flowClass;
-        s.c_evap_loss[ix] = 0.0;
-        s.c_seep_loss[ix] = 0.0;
+        if (flags & LF_HAS_LOSSRATE) { s.c_evap_loss[ix] = 0.0; s.c_seep_loss[ix] = 0.0; }
         return;
     }
 
     // --- velocity, Froude number, inertial damping (dwflow.c:183-208)
     double v = qLast / aMid;
     if (fabs(v) > SWB_MAXVELOCITY) v = SWB_MAXVELOCITY * SWB_SGN(qLast);
-    double froude = link_froude(x, isOpen, v, yMid, T);
+    double froude = link_froude<S>(x, isOpen, v, yMid, T);
     if (flowClass == SWB_SUBCRITICAL && froude > 1.0) flowClass = SWB_SUPCRITICAL;
     double sigma;
     if      (froude <= 0.5) sigma = 1.0;
@@ -365,7 +370,7 @@ SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int 
     }
     double dq6 = 0.0;
     if (flags & LF_HAS_LOSSRATE) {
-        double lossRate = conduit_loss_rate(n, s, j, m, x, isOpen, dt, s.evap_rate[m], s.hydcon[m],
+        double lossRate = conduit_loss_rate<S>(n, s, j, m, x, isOpen, dt, s.evap_rate[m], s.hydcon[m],
                                             evapLoss, seepLoss, T);
         dq6 = lossRate * 2.5 * dt * v / trueLength;
     }
@@ -386,7 +391,7 @@ SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int 
             if (nfl == SWB_NF_SLOPE || nfl == SWB_NF_BOTH || hasOutfall) { if (y1 < y2) check = true; }
             if (!check && (nfl == SWB_NF_FROUDE || nfl == SWB_NF_BOTH) && !hasOutfall) {
                 if (y1 > SWB_FUDGE && y2 > SWB_FUDGE) {
-                    double f1 = link_froude(x, isOpen, q / a1, y1, T);
+                    double f1 = link_froude<S>(x, isOpen, q / a1, y1, T);
                     if (f1 >= 1.0) check = true;
                 }
             }
@@ -410,8 +415,7 @@ SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int 
 
     // --- save (dwflow.c:283-292)
     s.c_a1[ix] = aMid;
-    s.c_q1[ix] = q;
-    s.c_q2[ix] = q;
+    s.c_q1[ix] = q;                       // Conduit.q2 == q1 under dynamic wave (dwflow.c:285-286)
     s.l_depth[ix] = SWB_MIN(yMid, x.yFull);
     double aAvg = (a1 + a2) / 2.0;
     unsigned char fullState = 0;
@@ -423,14 +427,29 @@ SWB_HD inline void conduit_flow(const Net &n, const State &s, int j, int m, int 
     s.l_dqdh[ix] = dqdh;
     s.l_froude[ix] = froude;
     s.l_flow_class[ix] = (unsigned char)flowClass;
-    s.l_normal_flow[ix] = normalFlow;
-    s.l_inlet_control[ix] = 0;
-    s.c_evap_loss[ix] = evapLoss;
-    s.c_seep_loss[ix] = seepLoss;
+    s.l_normal_flow[ix] = normalFlow;     // inletControl stays 0: culverts are rejected up front
+    if (flags & LF_HAS_LOSSRATE) { s.c_evap_loss[ix] = evapLoss; s.c_seep_loss[ix] = seepLoss; }
+}
+
+// Real (non-inlined) entry points: one compact function per specialised shape plus the generic one.
+// A warp holds one link, so the dispatch in conduit_update is warp-uniform.
+SWB_NI void conduit_flow_circular(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
+{ conduit_flow<XS_CIRCULAR>(n, s, j, m, steps, dt, T); }
+SWB_NI void conduit_flow_rect_closed(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
+{ conduit_flow<XS_RECT_CLOSED>(n, s, j, m, steps, dt, T); }
+SWB_NI void conduit_flow_generic(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
+{ conduit_flow<-1>(n, s, j, m, steps, dt, T); }
+SWB_FI void conduit_update(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
+{
+    switch (n.xs_type[j]) {
+      case XS_CIRCULAR:    conduit_flow_circular(n, s, j, m, steps, dt, T); break;
+      case XS_RECT_CLOSED: conduit_flow_rect_closed(n, s, j, m, steps, dt, T); break;
+      default:             conduit_flow_generic(n, s, j, m, steps, dt, T);
+    }
 }
 
 // ---- node.c:362-396, 562-585, 930-1018 -----------------------------------------------------------
-SWB_HD inline double curve_lookup_ex(const Net &n, int c, double x)          // table.c:467-500
+SWB_HD double curve_lookup_ex(const Net &n, int c, double x)          // table.c:467-500
 {
     int i0 = n.curve_start[c], i1 = n.curve_start[c + 1];
     if (i1 <= i0) return 0.0;
@@ -450,14 +469,14 @@ SWB_HD inline double curve_lookup_ex(const Net &n, int c, double x)          // 
     return y1 + sl * (x - x1);
 }
 
-SWB_HD inline double tbl_interp(double x, double x1, double y1, double x2, double y2)  // table.c:51
+SWB_HD double tbl_interp(double x, double x1, double y1, double x2, double y2)  // table.c:51
 {
     double dx = x2 - x1;
     if (fabs(dx) < 1.0e-20) return (y1 + y2) / 2.;
     return y1 + (x - x1) * (y2 - y1) / dx;
 }
 
-SWB_HD inline double curve_storage_volume(const Net &n, int c, double x)    // table.c:590-648
+SWB_HD double curve_storage_volume(const Net &n, int c, double x)    // table.c:590-648
 {
     int i0 = n.curve_start[c], i1 = n.curve_start[c + 1];
     if (i1 <= i0) return 0.0;
@@ -486,7 +505,7 @@ SWB_HD inline double curve_storage_volume(const Net &n, int c, double x)    // t
     return v;
 }
 
-SWB_HD inline double storage_surf_area(const Net &n, int i, double d)
+SWB_HD double storage_surf_area(const Net &n, int i, double d)
 {
     double area = 0.0;
     const double ucfL = n.opt.ucf_length;
@@ -502,7 +521,7 @@ SWB_HD inline double storage_surf_area(const Net &n, int i, double d)
     return area / ucfL / ucfL;
 }
 
-SWB_HD inline double storage_volume(const Net &n, int i, double d)
+SWB_HD double storage_volume(const Net &n, int i, double d)
 {
     if (d == 0.0) return 0.0;
     if (d >= n.node_full_depth[i] && n.node_full_volume[i] > 0.0) return n.node_full_volume[i];
@@ -523,18 +542,18 @@ SWB_HD inline double storage_volume(const Net &n, int i, double d)
     }
 }
 
-SWB_HD inline double node_surf_area(const Net &n, int i, double d)
+SWB_FI double node_surf_area(const Net &n, int i, double d)
 {
     return n.node_type[i] == SWB_STORAGE ? storage_surf_area(n, i, d) : 0.0;
 }
-SWB_HD inline double node_ponded_area(const Net &n, int i, double d)        // node.c:562-585
+SWB_FI double node_ponded_area(const Net &n, int i, double d)        // node.c:562-585
 {
     if (d <= n.node_full_depth[i] || n.node_ponded_area[i] == 0.0) return node_surf_area(n, i, d);
     double a = n.node_ponded_area[i];
     if (a <= 0.0) a = node_surf_area(n, i, n.node_full_depth[i]);
     return a;
 }
-SWB_HD inline double node_volume(const Net &n, int i, double d)             // node.c:345-358
+SWB_FI double node_volume(const Net &n, int i, double d)             // node.c:345-358
 {
     if (n.node_type[i] == SWB_STORAGE) return storage_volume(n, i, d);
     if (n.node_full_depth[i] > 0.0) return n.node_full_volume[i] * (d / n.node_full_depth[i]);
@@ -547,7 +566,7 @@ SWB_HD inline double node_volume(const Net &n, int i, double d)             // n
 // regulators, link by link from the ordered pass.
 struct NodeAcc { double inflow, outflow, surfArea, sumdqdh; };
 
-SWB_HD inline NodeAcc node_init_acc(const Net &n, const State &s, int i, int m)
+SWB_FI NodeAcc node_init_acc(const Net &n, const State &s, int i, int m)
 {
     NodeAcc a;
     size_t ix = SWB_IX(i, m, s.M);
@@ -562,7 +581,7 @@ SWB_HD inline NodeAcc node_init_acc(const Net &n, const State &s, int i, int m)
 }
 
 // contribution of link j (end = 0: node is node1 / upstream, 1: node2) -- dynwave.c:528-589
-SWB_HD inline void node_add_link_end(const Net &n, const State &s, int j, int end, int m, NodeAcc &a)
+SWB_FI void node_add_link_end(const Net &n, const State &s, int j, int end, int m, NodeAcc &a)
 {
     size_t ix = SWB_IX(j, m, s.M);
     int flags = n.link_flags[j];
@@ -589,7 +608,7 @@ SWB_HD inline void node_add_link_end(const Net &n, const State &s, int j, int en
 }
 
 // ---- K4: outfall boundary depth (link.c:728-766, node.c:1413-1492) ------------------------------
-SWB_HD inline void outfall_depth(const Net &n, const State &s, int i, int m, const double *T)
+SWB_NI void outfall_depth(const Net &n, const State &s, int i, int m, const double *T)
 {
     int j = n.outfall_link[i];
     if (j < 0) return;
@@ -600,7 +619,7 @@ SWB_HD inline void outfall_depth(const Net &n, const State &s, int i, int m, con
         Xs x = load_xs(n, j);
         double q = fabs(s.l_flow[ixl] / n.cond_barrels[j]);
         yNorm = link_ynorm(n, j, x, q, T);
-        yCrit = xs_ycrit(x, q, T);
+        yCrit = xs_ycrit_ni(x, q, T);
     }
     double yNew;
     switch (n.outfall_type[i]) {
@@ -626,7 +645,7 @@ SWB_HD inline void outfall_depth(const Net &n, const State &s, int i, int m, con
 }
 
 // ---- K5: setNodeDepth + getFloodedDepth (dynwave.c:636-795); returns the converged flag ---------
-SWB_HD inline bool node_set_depth(const Net &n, const State &s, int i, int m, int steps, double dt,
+SWB_FI bool node_set_depth(const Net &n, const State &s, int i, int m, int steps, double dt,
                                   const NodeAcc &acc)
 {
     const size_t ix = SWB_IX(i, m, s.M);
@@ -702,7 +721,7 @@ SWB_HD inline bool node_set_depth(const Net &n, const State &s, int i, int m, in
 
 // ---- K7: Courant / depth-change step candidates (dynwave.c:836-921) ------------------------------
 // return the candidate step of one object, or a negative value when the object is skipped
-SWB_HD inline double link_step(const Net &n, const State &s, int j, int m)
+SWB_FI double link_step(const Net &n, const State &s, int j, int m)
 {
     if (n.link_type[j] != SWB_CONDUIT) return -1.0;
     size_t ix = SWB_IX(j, m, s.M);
@@ -715,7 +734,7 @@ SWB_HD inline double link_step(const Net &n, const State &s, int j, int m)
     t = t * froude / (1.0 + froude) * n.opt.courant_factor;
     return t;
 }
-SWB_HD inline double node_step(const Net &n, const State &s, int i, int m)
+SWB_FI double node_step(const Net &n, const State &s, int i, int m)
 {
     if (n.node_type[i] == SWB_OUTFALL) return -1.0;
     size_t ix = SWB_IX(i, m, s.M);

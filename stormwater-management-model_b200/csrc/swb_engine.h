@@ -63,7 +63,7 @@ struct RunArgs {
 
 // hydrograph value at time t (s) for inflow slot k: linear between breakpoints, 0 outside
 // (table_tseriesLookup with extend = FALSE, table.c:745-806)
-SWB_HD inline double inflow_series(const Inflows &f, int k, double t)
+SWB_HD double inflow_series(const Inflows &f, int k, double t)
 {
     int i0 = f.ts_start[k], i1 = f.ts_start[k + 1];
     if (i1 <= i0) return 0.0;
@@ -72,6 +72,14 @@ SWB_HD inline double inflow_series(const Inflows &f, int k, double t)
         if (t <= f.ts_t[i]) return tbl_interp(t, f.ts_t[i - 1], f.ts_q[i - 1], f.ts_t[i], f.ts_q[i]);
     }
     return 0.0;
+}
+
+template <class Ctx>
+SWB_ENGINE inline void qual_acc_flush(Ctx &ctx, const State &st, int p, int m, int M, double dt, const QualAcc &a)
+{
+    if (a.reacted != 0.0) ctx.atomic_add_f64(&st.mb_reacted[p * M + m], a.reacted * dt);
+    if (a.seepage != 0.0) ctx.atomic_add_f64(&st.mb_seepage[p * M + m], a.seepage * dt);
+    if (a.finalStorage != 0.0) ctx.atomic_add_f64(&st.mb_final_storage[p * M + m], a.finalStorage);
 }
 
 template <class Ctx>
@@ -201,7 +209,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                             st.l_bypassed[SWB_IX(j, m, M)] = byp ? 1 : 0;
                             if (byp) continue;
                         }
-                        conduit_flow(net, st, j, m, k, dt, T);
+                        conduit_update(net, st, j, m, k, dt, T);
                     }
                 }
                 ctx.grid_sync();
@@ -285,20 +293,20 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
 
         // ================= qualrout_execute (qualrout.c:100-142) ===============================
         if (withQual && (args.phases & PH_QUALITY)) {
-            QualAcc acc[SWB_MAX_POLLUT];
-            for (int p = 0; p < nP; p++) { acc[p].reacted = acc[p].seepage = acc[p].finalStorage = 0.0; }
+            // pollutant-major loops keep the three mass-balance partial sums in registers
             if (active)
-                for (int i = first; i < nN; i += stride)
-                    for (int p = 0; p < nP; p++) qual_node(net, st, i, m, p, dt, acc[p]);
-            ctx.grid_sync();
-            if (active) {
-                for (int j = first; j < nL; j += stride) qual_link(net, st, j, m, dt, acc);
                 for (int p = 0; p < nP; p++) {
-                    if (acc[p].reacted != 0.0) ctx.atomic_add_f64(&st.mb_reacted[p * M + m], acc[p].reacted * dt);
-                    if (acc[p].seepage != 0.0) ctx.atomic_add_f64(&st.mb_seepage[p * M + m], acc[p].seepage * dt);
-                    if (acc[p].finalStorage != 0.0) ctx.atomic_add_f64(&st.mb_final_storage[p * M + m], acc[p].finalStorage);
+                    QualAcc acc = {0.0, 0.0, 0.0};
+                    for (int i = first; i < nN; i += stride) qual_node(net, st, i, m, p, dt, acc);
+                    qual_acc_flush(ctx, st, p, m, M, dt, acc);
                 }
-            }
+            ctx.grid_sync();
+            if (active)
+                for (int p = 0; p < nP; p++) {
+                    QualAcc acc = {0.0, 0.0, 0.0};
+                    for (int j = first; j < nL; j += stride) qual_link(net, st, j, m, p, dt, acc);
+                    qual_acc_flush(ctx, st, p, m, M, dt, acc);
+                }
         }
 
         // ================= dynwave_getRoutingStep (dynwave.c:195-220, 799-921) =================

@@ -134,6 +134,7 @@ inline const std::vector<FieldInfo> &field_table()
 }
 inline const FieldInfo *find_field(int id)
 {
+    if (id == SWB_COND_Q2) id = SWB_COND_Q1;     // q2 == q1 under dynamic wave: one array
     for (const FieldInfo &f : field_table()) if (f.id == id) return &f;
     return nullptr;
 }

@@ -17,7 +17,7 @@ namespace swb {
 
 struct QualAcc { double reacted, seepage, finalStorage; };   // massbal.c:517-555 contributions
 
-SWB_HD inline double qual_mixed(double c, double v1, double wIn, double qIn, double tStep)
+SWB_FI double qual_mixed(double c, double v1, double wIn, double qIn, double tStep)
 {
     if (qIn <= SWB_ZERO) return c;
     double vIn = qIn * tStep;
@@ -29,7 +29,7 @@ SWB_HD inline double qual_mixed(double c, double v1, double wIn, double qIn, dou
     return c;
 }
 
-SWB_HD inline double qual_reacted(double kDecay, double c, double v1, double tStep, double &reacted)
+SWB_FI double qual_reacted(double kDecay, double c, double v1, double tStep, double &reacted)
 {
     if (kDecay == 0.0) return c;
     double c2 = c * (1.0 - kDecay * tStep);
@@ -41,7 +41,7 @@ SWB_HD inline double qual_reacted(double kDecay, double c, double v1, double tSt
 
 // node i, pollutant p.  n_qual holds the external mass-rate preload on entry (routing.c:488 ...),
 // the new concentration on exit.
-SWB_HD inline void qual_node(const Net &n, const State &s, int i, int m, int p, double tStep,
+SWB_FI void qual_node(const Net &n, const State &s, int i, int m, int p, double tStep,
                              QualAcc &acc)
 {
     const int M = s.M;
@@ -92,47 +92,41 @@ SWB_HD inline void qual_node(const Net &n, const State &s, int i, int m, int p, 
     s.n_qual[ixq] = c2;
 }
 
-// link j, all pollutants (the hydraulic part is shared between pollutants)
-SWB_HD inline void qual_link(const Net &n, const State &s, int j, int m, double tStep, QualAcc *acc)
+// link j, pollutant p
+SWB_FI void qual_link(const Net &n, const State &s, int j, int m, int p, double tStep, QualAcc &acc)
 {
-    const int M = s.M, nP = n.nP;
-    const size_t ix = SWB_IX(j, m, M);
+    const int M = s.M;
+    const size_t ix = SWB_IX(j, m, M), iq = SWB_IXP(p, j, n.nL, m, M);
     const double newFlow = s.l_flow[ix];
-    // totalLoad (qualrout.c:210-214): w = |q| * oldQual
-    double qAbs = fabs(newFlow);
+    double qAbs = fabs(newFlow);                       // totalLoad (qualrout.c:210-214)
     int up = n.link_node1[j];
     if (newFlow < 0.0) up = n.link_node2[j];
+    double c1 = s.l_old_qual[iq];
+    s.l_total_load[iq] += qAbs * c1 * tStep;
     if (!(n.link_flags[j] & LF_TRUE_CONDUIT)) {
-        for (int p = 0; p < nP; p++) {
-            size_t iq = SWB_IXP(p, j, n.nL, m, M);
-            s.l_total_load[iq] += qAbs * s.l_old_qual[iq] * tStep;
-            s.l_qual[iq] = s.n_qual[SWB_IXP(p, up, n.nN, m, M)];
-        }
+        s.l_qual[iq] = s.n_qual[SWB_IXP(p, up, n.nN, m, M)];
         return;
     }
     double barrels = (double)n.cond_barrels[j];
     double qIn = fabs(s.c_q1[ix]) * barrels;
-    double qSeep = s.c_seep_loss[ix] * barrels;
-    double vEvap = s.c_evap_loss[ix] * barrels * tStep;
+    double qSeep = 0.0, vEvap = 0.0;
+    if (n.link_flags[j] & LF_HAS_LOSSRATE) {
+        qSeep = s.c_seep_loss[ix] * barrels;
+        vEvap = s.c_evap_loss[ix] * barrels * tStep;
+    }
     double v1 = s.l_old_volume[ix], v2 = s.l_volume[ix];
     double vLosses = qSeep * tStep + vEvap;
     double fEvap = 1.0;
     if (vEvap > 0.0 && v1 > SWB_ZERO_VOLUME) fEvap += vEvap / v1;
     qIn = qIn + (v2 + vLosses - v1) / tStep;
     qIn = SWB_MAX(qIn, 0.0);
-    bool empty = (v2 < SWB_ZERO_VOLUME || s.l_depth[ix] <= SWB_ZERO_DEPTH);
-    for (int p = 0; p < nP; p++) {
-        size_t iq = SWB_IXP(p, j, n.nL, m, M);
-        double c1 = s.l_old_qual[iq];
-        s.l_total_load[iq] += qAbs * c1 * tStep;
-        acc[p].seepage += qSeep * c1;
-        c1 *= fEvap;
-        double c2 = qual_reacted(n.pollut_kdecay[p], c1, v1, tStep, acc[p].reacted);
-        double wIn = s.n_qual[SWB_IXP(p, up, n.nN, m, M)] * qIn;
-        c2 = qual_mixed(c2, v1, wIn, qIn, tStep);
-        if (empty) { acc[p].finalStorage += c2 * v2; c2 = 0.0; }
-        s.l_qual[iq] = c2;
-    }
+    acc.seepage += qSeep * c1;
+    c1 *= fEvap;
+    double c2 = qual_reacted(n.pollut_kdecay[p], c1, v1, tStep, acc.reacted);
+    double wIn = s.n_qual[SWB_IXP(p, up, n.nN, m, M)] * qIn;
+    c2 = qual_mixed(c2, v1, wIn, qIn, tStep);
+    if (v2 < SWB_ZERO_VOLUME || s.l_depth[ix] <= SWB_ZERO_DEPTH) { acc.finalStorage += c2 * v2; c2 = 0.0; }
+    s.l_qual[iq] = c2;
 }
 
 } // namespace swb

@@ -18,7 +18,7 @@
 
 namespace swb {
 
-SWB_HD inline double curve_lookup(const Net &n, int c, double x)             // table.c:395-426
+SWB_HD double curve_lookup(const Net &n, int c, double x)             // table.c:395-426
 {
     int i0 = n.curve_start[c], i1 = n.curve_start[c + 1];
     if (i1 <= i0) return 0.0;
@@ -31,7 +31,7 @@ SWB_HD inline double curve_lookup(const Net &n, int c, double x)             // 
     }
     return y1;
 }
-SWB_HD inline double curve_slope(const Net &n, int c, double x)              // table.c:430-460
+SWB_HD double curve_slope(const Net &n, int c, double x)              // table.c:430-460
 {
     int i0 = n.curve_start[c], i1 = n.curve_start[c + 1];
     if (i1 <= i0) return 0.0;
@@ -45,7 +45,7 @@ SWB_HD inline double curve_slope(const Net &n, int c, double x)              // 
     if (dx == 0.0) return 0.0;
     return (y2 - y1) / dx;
 }
-SWB_HD inline double curve_interval_lookup(const Net &n, int c, double x)    // table.c:504-522
+SWB_HD double curve_interval_lookup(const Net &n, int c, double x)    // table.c:504-522
 {
     int i0 = n.curve_start[c], i1 = n.curve_start[c + 1];
     if (i1 <= i0) return 0.0;
@@ -61,7 +61,7 @@ struct RegCtx {             // one link of one member, gathered once
 };
 
 // ---- pump_getInflow (link.c:1548-1634) -----------------------------------------------------------
-SWB_HD inline double pump_inflow(const Net &n, const State &s, const RegCtx &r)
+SWB_HD double pump_inflow(const Net &n, const State &s, const RegCtx &r)
 {
     const int j = r.j;
     const double ucfL = n.opt.ucf_length, ucfV = n.opt.ucf_volume, ucfQ = n.opt.ucf_flow;
@@ -107,7 +107,7 @@ SWB_HD inline double pump_inflow(const Net &n, const State &s, const RegCtx &r)
 }
 
 // ---- orifice_getFlow (link.c:1938-2004), one level of the flap-gate recursion unrolled ------------
-SWB_HD inline double orifice_flow_core(const State &s, size_t ix, double head, double f)
+SWB_HD double orifice_flow_core(const State &s, size_t ix, double head, double f)
 {
     double q;
     if (head == 0.0 || f <= 0.0) { s.l_dqdh[ix] = 0.0; return 0.0; }
@@ -120,13 +120,13 @@ SWB_HD inline double orifice_flow_core(const State &s, size_t ix, double head, d
     }
     return q;
 }
-SWB_HD inline double orifice_flow(const Net &n, const State &s, const RegCtx &r, const Xs &x,
+SWB_HD double orifice_flow(const Net &n, const State &s, const RegCtx &r, const Xs &x,
                                   double head, double f, bool hasFlapGate, const double *T)
 {
     if (head == 0.0 || f <= 0.0) { s.l_dqdh[r.ix] = 0.0; return 0.0; }
     double q = orifice_flow_core(s, r.ix, head, f);
     if (hasFlapGate) {
-        double area = xs_a_of_y(x, s.l_setting[r.ix] * x.yFull, T);
+        double area = xs_a_of_y_ni(x, s.l_setting[r.ix] * x.yFull, T);
         double veloc = q / area;
         double hLoss = (4.0 / SWB_GRAVITY) * veloc * veloc * exp(-1.15 * veloc / sqrt(head));
         if (f < 1.0) { f = f - hLoss / s.o_hcrit[r.ix]; if (f < 0.0) f = 0.0; }
@@ -137,7 +137,7 @@ SWB_HD inline double orifice_flow(const Net &n, const State &s, const RegCtx &r,
 }
 
 // ---- orifice_getInflow (link.c:1812-1934) ---------------------------------------------------------
-SWB_HD inline double orifice_inflow(const Net &n, const State &s, const RegCtx &r, const double *T)
+SWB_HD double orifice_inflow(const Net &n, const State &s, const RegCtx &r, const double *T)
 {
     const int j = r.j;
     const Xs x = load_xs(n, j);
@@ -177,10 +177,10 @@ SWB_HD inline double orifice_inflow(const Net &n, const State &s, const RegCtx &
     if (n.orif_type[j] == 0 /*SIDE_ORIFICE*/) {
         double d = y1 * f;
         s.l_depth[r.ix] = d;
-        s.r_surf_area[r.ix] = xs_w_of_y(x, d, T) * n.orif_length[j];
+        s.r_surf_area[r.ix] = xs_w_of_y_ni(x, d, T) * n.orif_length[j];
     } else {
         s.l_depth[r.ix] = y1;
-        s.r_surf_area[r.ix] = xs_a_of_y(x, y1, T);
+        s.r_surf_area[r.ix] = xs_a_of_y_ni(x, y1, T);
     }
     double q = dir * orifice_flow(n, s, r, x, head, f, (r.flags & LF_HAS_FLAP) != 0, T);
     if (f < 1.0 && h2 > hcrest) {
@@ -191,14 +191,14 @@ SWB_HD inline double orifice_inflow(const Net &n, const State &s, const RegCtx &
 }
 
 // ---- weirs (link.c:2198-2517) ---------------------------------------------------------------------
-SWB_HD inline double weir_open_area(const State &s, const RegCtx &r, const Xs &x, double y, const double *T)
+SWB_HD double weir_open_area(const State &s, const RegCtx &r, const Xs &x, double y, const double *T)
 {
     double z = (1.0 - s.l_setting[r.ix]) * x.yFull;
     double zy = z + y;
     zy = SWB_MIN(zy, x.yFull);
-    return xs_a_of_y(x, zy, T) - xs_a_of_y(x, z, T);
+    return xs_a_of_y_ni(x, zy, T) - xs_a_of_y_ni(x, z, T);
 }
-SWB_HD inline double weir_dqdh(int wtype, double dir, double h, double q1, double q2)
+SWB_HD double weir_dqdh(int wtype, double dir, double h, double q1, double q2)
 {
     if (fabs(h) < SWB_FUDGE) return 0.0;
     double q1h = fabs(q1 / h), q2h = fabs(q2 / h);
@@ -210,7 +210,7 @@ SWB_HD inline double weir_dqdh(int wtype, double dir, double h, double q1, doubl
     }
     return 0.0;
 }
-SWB_HD inline void weir_flow_core(const Net &n, const State &s, const RegCtx &r, const Xs &x,
+SWB_HD void weir_flow_core(const Net &n, const State &s, const RegCtx &r, const Xs &x,
                                   double head, double dir, double &q1, double &q2, const double *T)
 {
     const int j = r.j;
@@ -243,14 +243,14 @@ SWB_HD inline void weir_flow_core(const Net &n, const State &s, const RegCtx &r,
         break;
       case 3: {
         double y = (1.0 - setting) * x.yFull;
-        length = xs_w_of_y(x, y, T) * ucfL;
+        length = xs_w_of_y_ni(x, y, T) * ucfL;
         q1 = cDisch1 * length * pow(h, 1.5);
         q2 = n.weir_cdisch2[j] * n.weir_slope[j] * pow(h, 2.5);
         break; }
     }
     if (n.opt.unit_system == 1) { q1 /= SWB_M3_PER_FT3; q2 /= SWB_M3_PER_FT3; }
 }
-SWB_HD inline void weir_flow(const Net &n, const State &s, const RegCtx &r, const Xs &x, double head,
+SWB_HD void weir_flow(const Net &n, const State &s, const RegCtx &r, const Xs &x, double head,
                              double dir, bool hasFlapGate, double &q1, double &q2, const double *T)
 {
     q1 = 0.0; q2 = 0.0;
@@ -272,7 +272,7 @@ SWB_HD inline void weir_flow(const Net &n, const State &s, const RegCtx &r, cons
     }
     s.l_dqdh[r.ix] = weir_dqdh(n.weir_type[r.j], dir, head, q1, q2);
 }
-SWB_HD inline double weir_inflow(const Net &n, const State &s, const RegCtx &r, const double *T)
+SWB_HD double weir_inflow(const Net &n, const State &s, const RegCtx &r, const double *T)
 {
     const int j = r.j;
     const Xs x = load_xs(n, j);
@@ -294,7 +294,7 @@ SWB_HD inline double weir_inflow(const Net &n, const State &s, const RegCtx &r, 
     if (hcrest > h2) cls = (dir == 1.0) ? SWB_DN_CRITICAL : SWB_UP_CRITICAL;
     s.l_flow_class[r.ix] = (unsigned char)cls;
     y = x.yFull - (hcrown - SWB_MIN(h1, hcrown));
-    s.r_surf_area[r.ix] = xs_w_of_y(x, y, T) * n.weir_length[j];
+    s.r_surf_area[r.ix] = xs_w_of_y_ni(x, y, T) * n.weir_length[j];
     bool hasFlap = (r.flags & LF_HAS_FLAP) != 0;
     if (h1 >= hcrown) {
         if (n.weir_can_surcharge[j]) {
@@ -332,7 +332,7 @@ SWB_HD inline double weir_inflow(const Net &n, const State &s, const RegCtx &r, 
 }
 
 // ---- outlet_getInflow / getFlow (link.c:2608-2692) -------------------------------------------------
-SWB_HD inline double outlet_inflow(const Net &n, const State &s, const RegCtx &r)
+SWB_HD double outlet_inflow(const Net &n, const State &s, const RegCtx &r)
 {
     const int j = r.j;
     double h1 = r.depth1 + r.inv1, h2 = r.depth2 + r.inv2, head, y1;
@@ -357,7 +357,7 @@ SWB_HD inline double outlet_inflow(const Net &n, const State &s, const RegCtx &r
 }
 
 // ---- node_getMaxOutflow (node.c:418-434) ------------------------------------------------------------
-SWB_HD inline double node_max_outflow(const Net &n, const State &s, int i, size_t ixn, double q, double dt)
+SWB_HD double node_max_outflow(const Net &n, const State &s, int i, size_t ixn, double q, double dt)
 {
     if (n.node_full_volume[i] > 0.0) {
         double qMax = s.n_inflow[ixn] + s.n_old_volume[ixn] / dt;
@@ -367,7 +367,7 @@ SWB_HD inline double node_max_outflow(const Net &n, const State &s, int i, size_
 }
 
 // ---- findNonConduitFlow + updateNodeFlows for one member, ascending link order ----------------------
-SWB_HD inline void regulator_pass(const Net &n, const State &s, int m, int steps, double dt, const double *T)
+SWB_NI void regulator_pass(const Net &n, const State &s, int m, int steps, double dt, const double *T)
 {
     const int M = s.M;
     for (int k = 0; k < n.nNonConduit; k++) {

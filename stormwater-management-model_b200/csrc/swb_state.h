@@ -101,7 +101,7 @@ struct Net {
     X(double, l_surf_area2, SWB_LINK_SURF_AREA2, L) X(unsigned char, l_bypassed, SWB_LINK_BYPASSED, L) \
     X(unsigned char, l_normal_flow, SWB_LINK_NORMAL_FLOW, L) X(unsigned char, l_inlet_control, SWB_LINK_INLET_CONTROL, L) \
     X(double, c_a1, SWB_COND_A1, L) X(double, c_a2, SWB_COND_A2, L) X(double, c_q1, SWB_COND_Q1, L) \
-    X(double, c_q2, SWB_COND_Q2, L) X(unsigned char, c_full_state, SWB_COND_FULL_STATE, L) \
+    X(unsigned char, c_full_state, SWB_COND_FULL_STATE, L) \
     X(unsigned char, c_cap_limited, SWB_COND_CAPACITY_LIMITED, L) X(double, c_evap_loss, SWB_COND_EVAP_LOSS, L) \
     X(double, c_seep_loss, SWB_COND_SEEP_LOSS, L) X(double, o_corif, SWB_ORIF_CORIF, L) \
     X(double, o_cweir, SWB_ORIF_CWEIR, L) X(double, o_hcrit, SWB_ORIF_HCRIT, L) \

@@ -37,7 +37,7 @@ struct Xs {                 // objects.h:581-599, plus resolved per-object table
 };
 
 // ratio of area at max. flow to full area (xsect.c:55-81); >= 1 means an open shape
-SWB_HD inline double xs_amax_ratio(int type)
+SWB_FI double xs_amax_ratio(int type)
 {
     switch (type) {
       case XS_CIRCULAR: case XS_FILLED_CIRCULAR: case XS_FORCE_MAIN: return 0.9756;
@@ -50,11 +50,11 @@ SWB_HD inline double xs_amax_ratio(int type)
       default: return 1.0;
     }
 }
-SWB_HD inline bool xs_is_open(int type) { return xs_amax_ratio(type) >= 1.0; }
+SWB_FI bool xs_is_open(int type) { return xs_amax_ratio(type) >= 1.0; }
 
 // ---- table primitives -----------------------------------------------------------------------
 // xsect.c:1474-1507
-SWB_HD inline double xs_lookup(double x, const double *tb, int n)
+SWB_FI double xs_lookup(double x, const double *tb, int n)
 {
     double delta = 1.0 / ((double)n - 1);
     int i = (int)(x / delta);
@@ -72,7 +72,7 @@ SWB_HD inline double xs_lookup(double x, const double *tb, int n)
 }
 
 // xsect.c:1571-1608
-SWB_HD inline int xs_locate(double y, const double *tb, int jLast)
+SWB_HD int xs_locate(double y, const double *tb, int jLast)
 {
     int j1 = 0, j2 = jLast;
     if (y <= tb[0]) return 0;
@@ -85,7 +85,7 @@ SWB_HD inline int xs_locate(double y, const double *tb, int jLast)
 }
 
 // xsect.c:1511-1567
-SWB_HD inline double xs_inv_lookup(double y, const double *tb, int nItems)
+SWB_HD double xs_inv_lookup(double y, const double *tb, int nItems)
 {
     double dx = 1.0 / (double)((double)nItems - 1);
     int n = nItems, i;
@@ -107,9 +107,9 @@ SWB_HD inline double xs_inv_lookup(double y, const double *tb, int nItems)
 }
 
 // ---- circular specials (xsect.c:2531-2618) ---------------------------------------------------
-SWB_HD inline double xs_sign(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
+SWB_HD double xs_sign(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
 
-SWB_HD inline double circ_theta_of_alpha(double alpha)
+SWB_HD double circ_theta_of_alpha(double alpha)
 {
     double theta, theta1, ap, d;
     if (alpha > 0.04) theta = 1.2 + 5.08 * (alpha - 0.04) / 0.96;
@@ -125,7 +125,7 @@ SWB_HD inline double circ_theta_of_alpha(double alpha)
     return theta1;
 }
 
-SWB_HD inline double circ_theta_of_psi(double psi)
+SWB_HD double circ_theta_of_psi(double psi)
 {
     double theta, theta1, ap, tt, tt23, t3, d;
     if      (psi > 0.90)  theta = 4.17 + 1.12 * (psi - 0.90) / 0.176;
@@ -147,7 +147,7 @@ SWB_HD inline double circ_theta_of_psi(double psi)
     return theta1;
 }
 
-SWB_HD inline double circ_y_norm(double alpha)            // getYcircular
+SWB_HD double circ_y_norm(double alpha)            // getYcircular
 {
     if (alpha >= 1.0) return 1.0;
     if (alpha <= 0.0) return 0.0;
@@ -159,7 +159,7 @@ SWB_HD inline double circ_y_norm(double alpha)            // getYcircular
     return (1.0 - cos(theta / 2.)) / 2.0;
 }
 
-SWB_HD inline double circ_s_norm(double alpha)            // getScircular
+SWB_HD double circ_s_norm(double alpha)            // getScircular
 {
     if (alpha >= 1.0) return 1.0;
     if (alpha <= 0.0) return 0.0;
@@ -171,7 +171,7 @@ SWB_HD inline double circ_s_norm(double alpha)            // getScircular
     return pow((theta - sin(theta)), 5. / 3.) / (2.0 * SWB_PI) / pow(theta, 2. / 3.);
 }
 
-SWB_HD inline double circ_a_norm(double psi)              // getAcircular
+SWB_HD double circ_a_norm(double psi)              // getAcircular
 {
     if (psi >= 1.0) return 1.0;
     if (psi <= 0.0) return 0.0;
@@ -184,7 +184,7 @@ SWB_HD inline double circ_a_norm(double psi)              // getAcircular
 }
 
 // xsect.c:2367-2376 (yFull, aFull passed so FILLED_CIRCULAR can use shifted values)
-SWB_HD inline double circ_y_of_a(double yFull, double aFull, double a, const double *T)
+SWB_HD double circ_y_of_a(double yFull, double aFull, double a, const double *T)
 {
     double alpha = a / aFull;
     if (alpha < 0.04) return yFull * circ_y_norm(alpha);
@@ -192,9 +192,9 @@ SWB_HD inline double circ_y_of_a(double yFull, double aFull, double a, const dou
 }
 
 // ---- forward declarations ----------------------------------------------------------------------
-SWB_HD inline double xs_a_of_y(const Xs &x, double y, const double *T);
-SWB_HD inline double xs_w_of_y(const Xs &x, double y, const double *T);
-SWB_HD inline double xs_y_of_a(const Xs &x, double a, const double *T);
+SWB_FI double xs_a_of_y(const Xs &x, double y, const double *T);
+SWB_FI double xs_w_of_y(const Xs &x, double y, const double *T);
+SWB_HD double xs_y_of_a(const Xs &x, double a, const double *T);
 // The reference's getRofY / getRofA / getSofA call one another through their default branches
 // (xsect.c:1094,1113,1137,768).  No shape ever goes round the cycle, so it is unrolled here into
 // an acyclic chain r_of_y -> r_of_a -> s_of_a -> r_of_a_direct -> r_of_y_direct that the device
@@ -205,7 +205,7 @@ SWB_HD inline double xs_y_of_a(const Xs &x, double a, const double *T);
 #define SWB_RECT_TRIANG_ALFMAX 0.98
 #define SWB_RECT_ROUND_ALFMAX  0.98
 
-SWB_HD inline double rect_closed_r_of_a(const Xs &x, double a)
+SWB_FI double rect_closed_r_of_a(const Xs &x, double a)
 {
     if (a <= 0.0) return 0.0;
     double p = x.wMax + 2. * a / x.wMax;
@@ -215,12 +215,12 @@ SWB_HD inline double rect_closed_r_of_a(const Xs &x, double a)
 }
 
 // ---- RECT_TRIANG (xsect.c:1836-1931) -----------------------------------------------------------
-SWB_HD inline double rect_triang_y_of_a(const Xs &x, double a)
+SWB_HD double rect_triang_y_of_a(const Xs &x, double a)
 {
     if (a <= x.aBot) return sqrt(a / x.sBot);
     return x.yBot + (a - x.aBot) / x.wMax;
 }
-SWB_HD inline double rect_triang_r_of_a(const Xs &x, double a)
+SWB_HD double rect_triang_r_of_a(const Xs &x, double a)
 {
     if (a <= 0.0) return 0.0;
     double y = rect_triang_y_of_a(x, a);
@@ -230,7 +230,7 @@ SWB_HD inline double rect_triang_r_of_a(const Xs &x, double a)
     if (alf > 0.0) p += alf / (1.0 - SWB_RECT_TRIANG_ALFMAX) * x.wMax;
     return a / p;
 }
-SWB_HD inline double rect_triang_r_of_y(const Xs &x, double y)
+SWB_HD double rect_triang_r_of_y(const Xs &x, double y)
 {
     if (y <= x.yBot) return y * x.sBot / (2. * x.rBot);
     double a = x.aBot + (y - x.yBot) * x.wMax;
@@ -241,14 +241,14 @@ SWB_HD inline double rect_triang_r_of_y(const Xs &x, double y)
 }
 
 // ---- RECT_ROUND (xsect.c:1938-2072) ------------------------------------------------------------
-SWB_HD inline double rect_round_y_of_a(const Xs &x, double a, const double *T)
+SWB_HD double rect_round_y_of_a(const Xs &x, double a, const double *T)
 {
     if (a > x.aBot) return x.yBot + (a - x.aBot) / x.wMax;
     double alpha = a / (SWB_PI * x.rBot * x.rBot);
     if (alpha < 0.04) return (2.0 * x.rBot) * circ_y_norm(alpha);
     return (2.0 * x.rBot) * xs_lookup(alpha, T + XT_Y_CIRC, XN_Y_CIRC);
 }
-SWB_HD inline double rect_round_r_of_a(const Xs &x, double a, const double *T)
+SWB_HD double rect_round_r_of_a(const Xs &x, double a, const double *T)
 {
     double y1, theta1, p, arg;
     if (a <= 0.0) return 0.0;
@@ -265,7 +265,7 @@ SWB_HD inline double rect_round_r_of_a(const Xs &x, double a, const double *T)
     p = x.rBot * theta1;
     return a / p;
 }
-SWB_HD inline double rect_round_a_of_y(const Xs &x, double y)
+SWB_HD double rect_round_a_of_y(const Xs &x, double y)
 {
     if (y > x.yBot) return x.aBot + (y - x.yBot) * x.wMax;
     double theta1 = 2.0 * acos(1.0 - y / x.rBot);
@@ -273,7 +273,7 @@ SWB_HD inline double rect_round_a_of_y(const Xs &x, double y)
 }
 
 // ---- MOD_BASKET (xsect.c:2082-2173) ------------------------------------------------------------
-SWB_HD inline double mod_basket_y_of_a(const Xs &x, double a, const double *T)
+SWB_HD double mod_basket_y_of_a(const Xs &x, double a, const double *T)
 {
     if (a <= x.aFull - x.aBot) return a / x.wMax;
     double alpha = (x.aFull - a) / (SWB_PI * x.rBot * x.rBot), y1;
@@ -282,7 +282,7 @@ SWB_HD inline double mod_basket_y_of_a(const Xs &x, double a, const double *T)
     y1 = 2.0 * x.rBot * y1;
     return x.yFull - y1;
 }
-SWB_HD inline double mod_basket_r_of_a(const Xs &x, double a, const double *T)
+SWB_HD double mod_basket_r_of_a(const Xs &x, double a, const double *T)
 {
     if (a <= x.aFull - x.aBot) return a / (x.wMax + 2.0 * a / x.wMax);
     double y1 = x.yFull - mod_basket_y_of_a(x, a, T);
@@ -294,21 +294,21 @@ SWB_HD inline double mod_basket_r_of_a(const Xs &x, double a, const double *T)
 }
 
 // ---- TRAPEZOIDAL / TRIANGULAR / PARABOLIC / POWERFUNC (xsect.c:2184-2357) ----------------------
-SWB_HD inline double trapez_y_of_a(const Xs &x, double a)
+SWB_HD double trapez_y_of_a(const Xs &x, double a)
 {
     if (x.sBot == 0.0) return a / x.yBot;
     return (sqrt(x.yBot * x.yBot + 4. * x.sBot * a) - x.yBot) / (2. * x.sBot);
 }
-SWB_HD inline double trapez_a_of_y(const Xs &x, double y) { return (x.yBot + x.sBot * y) * y; }
-SWB_HD inline double parab_p_of_y(const Xs &x, double y)
+SWB_HD double trapez_a_of_y(const Xs &x, double y) { return (x.yBot + x.sBot * y) * y; }
+SWB_HD double parab_p_of_y(const Xs &x, double y)
 {
     double xx = 2. * sqrt(y) / x.rBot;
     double t = sqrt(1.0 + xx * xx);
     return 0.5 * x.rBot * x.rBot * (xx * t + log(xx + t));
 }
-SWB_HD inline double parab_a_of_y(const Xs &x, double y) { return (4. / 3. * x.rBot * y * sqrt(y)); }
-SWB_HD inline double parab_y_of_a(const Xs &x, double a) { return pow((3. / 4.) * a / x.rBot, 2. / 3.); }
-SWB_HD inline double powerfunc_p_of_y(const Xs &x, double y)
+SWB_HD double parab_a_of_y(const Xs &x, double y) { return (4. / 3. * x.rBot * y * sqrt(y)); }
+SWB_HD double parab_y_of_a(const Xs &x, double a) { return pow((3. / 4.) * a / x.rBot, 2. / 3.); }
+SWB_HD double powerfunc_p_of_y(const Xs &x, double y)
 {
     double dy1 = 0.02 * x.yFull;
     double h = (x.sBot + 1.0) * x.rBot / 2.0;
@@ -325,11 +325,11 @@ SWB_HD inline double powerfunc_p_of_y(const Xs &x, double y)
     } while (y2 < y);
     return 2.0 * p;
 }
-SWB_HD inline double powerfunc_a_of_y(const Xs &x, double y) { return x.rBot * pow(y, x.sBot + 1.0); }
-SWB_HD inline double powerfunc_y_of_a(const Xs &x, double a) { return pow(a / x.rBot, 1.0 / (x.sBot + 1.0)); }
+SWB_HD double powerfunc_a_of_y(const Xs &x, double y) { return x.rBot * pow(y, x.sBot + 1.0); }
+SWB_HD double powerfunc_y_of_a(const Xs &x, double a) { return pow(a / x.rBot, 1.0 / (x.sBot + 1.0)); }
 
 // ---- FILLED_CIRCULAR (xsect.c:2462-2524) on shifted local values -------------------------------
-SWB_HD inline double filled_circ_r_of_y(const Xs &x, double y, const double *T)
+SWB_HD double filled_circ_r_of_y(const Xs &x, double y, const double *T)
 {
     double yF = x.yFull + x.yBot, aF = x.aFull + x.aBot;
     y += x.yBot;
@@ -345,7 +345,7 @@ SWB_HD inline double filled_circ_r_of_y(const Xs &x, double y, const double *T)
 // ---- per-shape table descriptor for the "tabulated" families -----------------------------------
 struct XsTabs { short aO, aN, rO, rN, yO, yN, sO, sN, wO, wN; };
 #define SWB_T(NAME) (short)XT_##NAME, (short)XN_##NAME
-SWB_HD inline XsTabs xs_tabs(int type)
+SWB_FI XsTabs xs_tabs(int type)
 {
     switch (type) {
       case XS_EGGSHAPED:      return XsTabs{SWB_T(A_EGG), SWB_T(R_EGG), SWB_T(Y_EGG), SWB_T(S_EGG), SWB_T(W_EGG)};
@@ -363,7 +363,7 @@ SWB_HD inline XsTabs xs_tabs(int type)
 }
 
 // ---- A(y)  (xsect.c:857-939) -------------------------------------------------------------------
-SWB_HD inline double xs_a_of_y(const Xs &x, double y, const double *T)
+SWB_FI double xs_a_of_y(const Xs &x, double y, const double *T)
 {
     double yNorm = y / x.yFull;
     if (y <= 0.0) return 0.0;
@@ -408,7 +408,7 @@ SWB_HD inline double xs_a_of_y(const Xs &x, double y, const double *T)
 }
 
 // ---- W(y)  (xsect.c:943-1027) ------------------------------------------------------------------
-SWB_HD inline double xs_w_of_y(const Xs &x, double y, const double *T)
+SWB_FI double xs_w_of_y(const Xs &x, double y, const double *T)
 {
     double yNorm = y / x.yFull;
     switch (x.type) {
@@ -450,7 +450,7 @@ SWB_HD inline double xs_w_of_y(const Xs &x, double y, const double *T)
 }
 
 // ---- R(y)  (xsect.c:1031-1096) -----------------------------------------------------------------
-SWB_HD inline double xs_r_of_y_direct(const Xs &x, double y, const double *T)
+SWB_FI double xs_r_of_y_direct(const Xs &x, double y, const double *T)
 {
     double yNorm = y / x.yFull;
     switch (x.type) {
@@ -488,7 +488,7 @@ SWB_HD inline double xs_r_of_y_direct(const Xs &x, double y, const double *T)
 }
 
 // ---- Y(a)  (xsect.c:776-853) -------------------------------------------------------------------
-SWB_HD inline double xs_y_of_a(const Xs &x, double a, const double *T)
+SWB_HD double xs_y_of_a(const Xs &x, double a, const double *T)
 {
     double alpha = a / x.aFull;
     switch (x.type) {
@@ -523,7 +523,7 @@ SWB_HD inline double xs_y_of_a(const Xs &x, double a, const double *T)
 }
 
 // ---- R(a)  (xsect.c:1100-1142) -----------------------------------------------------------------
-SWB_HD inline double xs_r_of_a_direct(const Xs &x, double a, const double *T)
+SWB_FI double xs_r_of_a_direct(const Xs &x, double a, const double *T)
 {
     if (a <= 0.0) return 0.0;
     switch (x.type) {
@@ -544,7 +544,7 @@ SWB_HD inline double xs_r_of_a_direct(const Xs &x, double a, const double *T)
 }
 
 // ---- S(a)  (xsect.c:714-772) -------------------------------------------------------------------
-SWB_HD inline double xs_s_of_a(const Xs &x, double a, const double *T)
+SWB_HD double xs_s_of_a(const Xs &x, double a, const double *T)
 {
     double alpha = a / x.aFull;
     switch (x.type) {
@@ -592,7 +592,7 @@ SWB_HD inline double xs_s_of_a(const Xs &x, double a, const double *T)
 }
 
 // shapes whose R(A) is derived from the section factor (default branch of xsect.c:1137-1141)
-SWB_HD inline bool xs_r_of_a_via_s(int type)
+SWB_FI bool xs_r_of_a_via_s(int type)
 {
     switch (type) {
       case XS_DUMMY: case XS_CIRCULAR: case XS_FORCE_MAIN: case XS_EGGSHAPED: case XS_HORSESHOE:
@@ -601,7 +601,7 @@ SWB_HD inline bool xs_r_of_a_via_s(int type)
       default: return false;
     }
 }
-SWB_HD inline double xs_r_of_a(const Xs &x, double a, const double *T)
+SWB_FI double xs_r_of_a(const Xs &x, double a, const double *T)
 {
     if (a <= 0.0) return 0.0;
     if (xs_r_of_a_via_s(x.type)) {
@@ -613,7 +613,7 @@ SWB_HD inline double xs_r_of_a(const Xs &x, double a, const double *T)
     return xs_r_of_a_direct(x, a, T);
 }
 // shapes whose R(Y) is R(A(Y)) (default branch of xsect.c:1094)
-SWB_HD inline double xs_r_of_y(const Xs &x, double y, const double *T)
+SWB_FI double xs_r_of_y(const Xs &x, double y, const double *T)
 {
     switch (x.type) {
       case XS_DUMMY: case XS_RECT_CLOSED: case XS_RECT_OPEN: case XS_MOD_BASKET: case XS_GOTHIC:
@@ -624,7 +624,7 @@ SWB_HD inline double xs_r_of_y(const Xs &x, double y, const double *T)
 }
 
 // ---- dS/dA (xsect.c:1194-1253, 1424-1470) ------------------------------------------------------
-SWB_HD inline double xs_generic_dsda(const Xs &x, double a, const double *T)
+SWB_HD double xs_generic_dsda(const Xs &x, double a, const double *T)
 {
     double alpha = a / x.aFull;
     double alpha1 = alpha - 0.001;
@@ -634,7 +634,7 @@ SWB_HD inline double xs_generic_dsda(const Xs &x, double a, const double *T)
     double a2 = alpha2 * x.aFull;
     return (xs_s_of_a(x, a2, T) - xs_s_of_a(x, a1, T)) / (a2 - a1);
 }
-SWB_HD inline double xs_tabular_dsda(const Xs &x, double a, const double *tb, int n)
+SWB_HD double xs_tabular_dsda(const Xs &x, double a, const double *tb, int n)
 {
     double alpha = a / x.aFull;
     double delta = 1.0 / ((double)n - 1);
@@ -643,7 +643,7 @@ SWB_HD inline double xs_tabular_dsda(const Xs &x, double a, const double *tb, in
     double dSdA = (tb[i + 1] - tb[i]) / delta;
     return dSdA * x.sFull / x.aFull;
 }
-SWB_HD inline double xs_dsda(const Xs &x, double a, const double *T)
+SWB_HD double xs_dsda(const Xs &x, double a, const double *T)
 {
     switch (x.type) {
       case XS_FORCE_MAIN:
@@ -722,13 +722,13 @@ SWB_HD inline double xs_dsda(const Xs &x, double a, const double *T)
 }
 
 // ---- A(s): normal-depth side (xsect.c:1146-1190, 1359-1400; findroot.c:20-88) -----------------
-SWB_HD inline double xs_amax(const Xs &x)
+SWB_HD double xs_amax(const Xs &x)
 {
     if (x.type == XS_IRREGULAR || x.type == XS_CUSTOM) return x.aBot;
     return xs_amax_ratio(x.type) * x.aFull;
 }
 
-SWB_HD inline double xs_generic_a_of_s(const Xs &x, double s, const double *T)
+SWB_HD double xs_generic_a_of_s(const Xs &x, double s, const double *T)
 {
     if (s <= 0.0) return 0.0;
     double a1, a2;
@@ -761,7 +761,7 @@ SWB_HD inline double xs_generic_a_of_s(const Xs &x, double s, const double *T)
     return xx;
 }
 
-SWB_HD inline double xs_a_of_s(const Xs &x, double s, const double *T)
+SWB_HD double xs_a_of_s(const Xs &x, double s, const double *T)
 {
     double psi = s / x.sFull;
     if (s <= 0.0) return 0.0;
@@ -786,7 +786,7 @@ SWB_HD inline double xs_a_of_s(const Xs &x, double s, const double *T)
 }
 
 // ---- critical depth (xsect.c:1257-1319, 1612-1748; findroot.c:91-138) --------------------------
-SWB_HD inline double xs_qcrit_residual(const Xs &x, double yc, double qTarget, const double *T)
+SWB_HD double xs_qcrit_residual(const Xs &x, double yc, double qTarget, const double *T)
 {
     double a = xs_a_of_y(x, yc, T);
     double w = xs_w_of_y(x, yc, T);
@@ -795,7 +795,7 @@ SWB_HD inline double xs_qcrit_residual(const Xs &x, double yc, double qTarget, c
     return qc;
 }
 
-SWB_HD inline double xs_ycrit_enum(const Xs &x, double q, double y0, const double *T)
+SWB_HD double xs_ycrit_enum(const Xs &x, double q, double y0, const double *T)
 {
     double dy = x.yFull / 25.;
     int i1 = (int)(y0 / dy);
@@ -818,7 +818,7 @@ SWB_HD inline double xs_ycrit_enum(const Xs &x, double q, double y0, const doubl
     return yc;
 }
 
-SWB_HD inline double xs_ycrit_ridder(const Xs &x, double q, double y0, const double *T)
+SWB_HD double xs_ycrit_ridder(const Xs &x, double q, double y0, const double *T)
 {
     double y1 = 0.0, y2 = 0.99 * x.yFull;
     double q2 = xs_qcrit_residual(x, y2, 0.0, T);
@@ -856,7 +856,7 @@ SWB_HD inline double xs_ycrit_ridder(const Xs &x, double q, double y0, const dou
     return -1.e20;
 }
 
-SWB_HD inline double xs_ycrit(const Xs &x, double q, const double *T)
+SWB_HD double xs_ycrit(const Xs &x, double q, const double *T)
 {
     double q2g = (q * q) / SWB_GRAVITY;
     double y, r;
@@ -881,8 +881,24 @@ SWB_HD inline double xs_ycrit(const Xs &x, double q, const double *T)
     return SWB_MIN(y, x.yFull);
 }
 
+// ---- run-time-shape entry points: real calls (one copy of each big switch in the binary) ---------
+SWB_NI double xs_a_of_y_ni(const Xs &x, double y, const double *T) { return xs_a_of_y(x, y, T); }
+SWB_NI double xs_w_of_y_ni(const Xs &x, double y, const double *T) { return xs_w_of_y(x, y, T); }
+SWB_NI double xs_r_of_y_ni(const Xs &x, double y, const double *T) { return xs_r_of_y(x, y, T); }
+SWB_NI double xs_y_of_a_ni(const Xs &x, double a, const double *T) { return xs_y_of_a(x, a, T); }
+SWB_NI double xs_a_of_s_ni(const Xs &x, double s, const double *T) { return xs_a_of_s(x, s, T); }
+SWB_NI double xs_ycrit_ni(const Xs &x, double q, const double *T) { return xs_ycrit(x, q, T); }
+
+// S >= 0: shape known at compile time (inlined, switch folded); S < 0: run-time shape (call)
+template <int S> SWB_FI double xa(const Xs &x, double y, const double *T)
+{ if constexpr (S >= 0) return xs_a_of_y(x, y, T); else return xs_a_of_y_ni(x, y, T); }
+template <int S> SWB_FI double xw(const Xs &x, double y, const double *T)
+{ if constexpr (S >= 0) return xs_w_of_y(x, y, T); else return xs_w_of_y_ni(x, y, T); }
+template <int S> SWB_FI double xr(const Xs &x, double y, const double *T)
+{ if constexpr (S >= 0) return xs_r_of_y(x, y, T); else return xs_r_of_y_ni(x, y, T); }
+
 // known-answer dispatcher used by swb_xsect_eval
-SWB_HD inline double xs_eval(int fn, const Xs &x, double arg, const double *T)
+SWB_HD double xs_eval(int fn, const Xs &x, double arg, const double *T)
 {
     switch (fn) {
       case 0: return xs_a_of_y(x, arg, T);

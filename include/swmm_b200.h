@@ -234,6 +234,10 @@ int  swb_set_inflows(swb_solver *s, const swb_inflow_desc *inflows);
  * swmm5.c:541-546). */
 int  swb_run_steps(swb_solver *s, int n_steps, double t_end);
 int  swb_get_stats(swb_solver *s, int member0, int n_members, swb_member_stats *out);
+/* cumulative quality mass-balance terms per member and pollutant, [member][pollutant]:
+ * reacted and seepage in mass (sum of rate x dt, massbal.c:517-540), final_storage in mass (:545) */
+int  swb_get_massbal(swb_solver *s, int member0, int n_members, double *reacted, double *seepage,
+                     double *final_storage);
 /* conduit-updates performed so far: sum over members of iterations x true conduits */
 long long swb_conduit_updates(swb_solver *s);
 

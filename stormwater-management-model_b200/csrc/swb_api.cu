@@ -18,7 +18,12 @@
 namespace cg = cooperative_groups;
 using namespace swb;
 
+#ifndef SWB_BLOCK
 #define SWB_BLOCK 256
+#endif
+#ifndef SWB_MIN_BLOCKS
+#define SWB_MIN_BLOCKS 1
+#endif
 
 struct CudaCtx {
     int tid, G, lane, block_size;
@@ -29,7 +34,7 @@ struct CudaCtx {
     __device__ __forceinline__ void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
 };
 
-__global__ void __launch_bounds__(SWB_BLOCK)
+__global__ void __launch_bounds__(SWB_BLOCK, SWB_MIN_BLOCKS)
 swb_route_kernel(const __grid_constant__ Net net, const __grid_constant__ State st,
                  const __grid_constant__ RunArgs args)
 {

@@ -354,6 +354,22 @@ int swb_get_stats(swb_solver *s, int m0, int nm, swb_member_stats *out)
     return SWB_OK;
 }
 
+int swb_get_massbal(swb_solver *s, int m0, int nm, double *reacted, double *seepage, double *final_storage)
+{
+    if (!s || m0 < 0 || nm < 1 || m0 + nm > s->M) return fail(SWB_ERR_ARG, "bad arguments");
+    const int M = s->M, nP = s->net->net.nP;
+    std::vector<double> h((size_t)(nP ? nP : 1) * M);
+    double *dst[3] = { reacted, seepage, final_storage };
+    const double *src[3] = { s->st.mb_reacted, s->st.mb_seepage, s->st.mb_final_storage };
+    for (int k = 0; k < 3; k++) {
+        if (!dst[k]) continue;
+        backend::download(h.data(), src[k], sizeof(double) * h.size());
+        for (int mm = 0; mm < nm; mm++)
+            for (int p = 0; p < nP; p++) dst[k][mm * nP + p] = h[(size_t)p * M + m0 + mm];
+    }
+    return SWB_OK;
+}
+
 long long swb_conduit_updates(swb_solver *s)
 {
     if (!s) return 0;

@@ -59,6 +59,15 @@ struct RunArgs {
     Inflows inflows;
 };
 
+// Object loop of one thread: round k covers objects [k*stride, (k+1)*stride) and the thread takes
+// slot (first + k) % stride of it.  The rotation matters: with a fixed slot a periodic pattern in
+// the object order (e.g. alternating circular / rectangular conduits with an even stride) would
+// hand all expensive objects to the same warps and every grid barrier would wait for them.
+#define SWB_FOR_ITEMS(idx, n) \
+    for (int _base = 0, _r = first, idx = first; _base < (n); \
+         _base += stride, _r = (_r + 1 == stride ? 0 : _r + 1), idx = _base + _r) \
+        if (idx < (n))
+
 #define SWB_FLOW_TOL 0.00001   // consts.h: FLOW_TOL, routing.c:455
 
 // hydrograph value at time t (s) for inflow slot k: linear between breakpoints, 0 outside
@@ -125,7 +134,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             // getDateTime(NewRoutingTime): 1 ms after the routing time (swmm5.c:1551), in days
             const double tNow = args.inflows.start_day +
                 (args.inflows.start_secs + (1000.0 * st.sim_time[m] + 1.0) / 1000.0) / 86400.0;
-            for (int i = first; i < nN; i += stride) {
+            SWB_FOR_ITEMS(i, nN) {
                 size_t ix = SWB_IX(i, m, M);
                 if (args.phases & PH_QSWAP)
                     for (int p = 0; p < nP; p++) {
@@ -167,7 +176,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     st.n_dydt[ix] = 0.0;
                 }
             }
-            for (int j = first; j < nL; j += stride) {
+            SWB_FOR_ITEMS(j, nL) {
                 size_t ix = SWB_IX(j, m, M);
                 if (args.phases & PH_QSWAP)
                     for (int p = 0; p < nP; p++) {
@@ -201,7 +210,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             for (int k = 0; k < maxTrials; k++) {
                 // ---- findLinkFlows, pass (i): true conduits (dynwave.c:387-395)
                 if (alive) {
-                    for (int j = first; j < nL; j += stride) {
+                    SWB_FOR_ITEMS(j, nL) {
                         if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) continue;
                         if (k >= 2) {              // findBypassedLinks of the previous trial (:335)
                             bool byp = st.n_converged[SWB_IX(net.link_node1[j], m, M)] &&
@@ -216,7 +225,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 // ---- networks with regulators / dummy links: ordered pass (A.4)
                 if (net.nNonConduit > 0) {
                     if (alive)
-                        for (int i = first; i < nN; i += stride) {
+                        SWB_FOR_ITEMS(i, nN) {
                             NodeAcc acc = node_init_acc(net, st, i, m);
                             for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++) {
                                 int j = net.adj[e] >> 1;
@@ -234,7 +243,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 // ---- findNodeDepths (dynwave.c:593-632)
                 if (alive) {
                     bool anyNotConv = false;
-                    for (int i = first; i < nN; i += stride) {
+                    SWB_FOR_ITEMS(i, nN) {
                         NodeAcc acc;
                         size_t ix = SWB_IX(i, m, M);
                         if (net.nNonConduit > 0) {
@@ -275,7 +284,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     st.tot_steps[m] += 1;
                     if (st.not_conv[(itersDone - 1) * M + m]) st.non_conv[m] += 1;
                 }
-                for (int j = first; j < nL; j += stride) {
+                SWB_FOR_ITEMS(j, nL) {
                     if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) continue;
                     size_t ix = SWB_IX(j, m, M);
                     unsigned char lim = 0;
@@ -297,14 +306,14 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             if (active)
                 for (int p = 0; p < nP; p++) {
                     QualAcc acc = {0.0, 0.0, 0.0};
-                    for (int i = first; i < nN; i += stride) qual_node(net, st, i, m, p, dt, acc);
+                    SWB_FOR_ITEMS(i, nN) qual_node(net, st, i, m, p, dt, acc);
                     qual_acc_flush(ctx, st, p, m, M, dt, acc);
                 }
             ctx.grid_sync();
             if (active)
                 for (int p = 0; p < nP; p++) {
                     QualAcc acc = {0.0, 0.0, 0.0};
-                    for (int j = first; j < nL; j += stride) qual_link(net, st, j, m, p, dt, acc);
+                    SWB_FOR_ITEMS(j, nL) qual_link(net, st, j, m, p, dt, acc);
                     qual_acc_flush(ctx, st, p, m, M, dt, acc);
                 }
         }
@@ -320,11 +329,11 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             const bool variable = !(net.opt.courant_factor == 0.0 || args.fixed_step < SWB_MINTIMESTEP);
             if (active && variable && st.var_step[m] != 0.0) {
                 double tmin = args.fixed_step;
-                for (int j = first; j < nL; j += stride) {
+                SWB_FOR_ITEMS(j, nL) {
                     double t = link_step(net, st, j, m);
                     if (t >= 0.0 && t < tmin) tmin = t;
                 }
-                for (int i = first; i < nN; i += stride) {
+                SWB_FOR_ITEMS(i, nN) {
                     double t = node_step(net, st, i, m);
                     if (t >= 0.0 && t < tmin) tmin = t;
                 }

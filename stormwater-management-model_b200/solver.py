@@ -48,6 +48,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_set_inflows.argtypes = [C.c_void_p, C.POINTER(abi.InflowDesc)]
     lib.swb_run_steps.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.swb_get_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.MemberStats)]
+    lib.swb_get_massbal.argtypes = [C.c_void_p, C.c_int, C.c_int, _P_D, _P_D, _P_D]
     lib.swb_conduit_updates.argtypes = [C.c_void_p]
     lib.swb_conduit_updates.restype = C.c_longlong
     lib.swb_launch_count.argtypes = [C.c_void_p]
@@ -216,6 +217,13 @@ class Solver:
         arr = (abi.MemberStats * nm)()
         self._chk(self.lib.swb_get_stats(self._h, member0, nm, arr))
         return arr
+
+    def massbal(self):
+        nP = max(self.net.n_pollut, 1)
+        r, sp, f = (np.zeros((self.M, nP)) for _ in range(3))
+        self._chk(self.lib.swb_get_massbal(self._h, 0, self.M, r.ctypes.data_as(_P_D),
+                                           sp.ctypes.data_as(_P_D), f.ctypes.data_as(_P_D)))
+        return {"reacted": r, "seepage": sp, "final_storage": f}
 
     def conduit_updates(self) -> int:
         return int(self.lib.swb_conduit_updates(self._h))

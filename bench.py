@@ -208,10 +208,10 @@ def run_ours(args):
                              (4.8e-3 * args.members * (n_true / 19801.0)),
                 "timing": "CUDA events around each cooperative launch (library stream), max over ranks",
             },
-            "e2e": {"value": e2e_cu / e2e_s, "unit": "conduit-updates/s",
+            "e2e": {"value": e2e_cu / max(e2e_s, 1e-9), "unit": "conduit-updates/s",
                     "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                    "steps": e2e["steps"], "what": "per routing step: host lateral inflows + quality loads "
-                    "-> device, swap / dynwave / quality / next-step calls, depths + flows + dt -> host"},
+                    "steps": e2e["steps"], "what": "swb_step_host per routing step: pinned host lateral inflows + quality loads -> device, "
+                    "swap / dynwave / quality / Courant search in one launch, depths + flows + next dt + iterations -> host"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -231,40 +231,38 @@ def run_ours(args):
 
 
 def measure_e2e(s, case, args, n_true: int) -> dict:
-    """The seam's per-step sequence for all members with HOST buffers on both sides."""
+    """Whole routing steps through swb_step_host: lateral inflows and quality loads come from
+    pinned HOST buffers every step, node depths / link flows / next step / iteration counts go
+    back to pinned host buffers every step; wall clock around the calls."""
     net = case.net
     nP = net.n_pollut
     M = s.M
-    steps = max(2, min(args.e2e_steps, args.steps * args.routing_steps))
-    fixed = net.options["route_step"]
-    # host-side inputs for the next step: reuse the device-evaluated inflows of the last step as
-    # the host engine's "newLatFlow" (values do not matter for the cost, shapes and copies do)
-    lat = s.get_field("SWB_NODE_NEW_LATFLOW")
-    conc = np.zeros((net.n_nodes, max(nP, 1)))
+    steps = args.e2e_steps
+    if steps <= 0:
+        return {"seconds": 1.0, "cu": 0, "steps": 0, "h2d": 0, "d2h": 0}
+    # the step's inputs, as the host engine would hand them over (values: the inflows the device
+    # evaluated for its last step; they are re-sent from the host every step)
+    lat = s.host_array((M, net.n_nodes))
+    lat[:] = s.get_field("SWB_NODE_NEW_LATFLOW")
+    load = None
     if nP:
+        conc = np.zeros((net.n_nodes, nP))
         conc[case.inflows["node"]] = case.inflows["concen"].reshape(-1, nP)
+        load = s.host_array((M, net.n_nodes, nP))
+        load[:] = np.maximum(lat, 0.0)[:, :, None] * conc[None]
+    depth = s.host_array((M, net.n_nodes))
+    flow = s.host_array((M, net.n_links))
+    next_dt = s.host_array((M,))
+    iters = s.host_array((M,), dtype=np.int32)
+    s.step_host(lat, qual_load=load, node_depth=depth, link_flow=flow, next_dt=next_dt, iters=iters)  # warm
     cu0 = s.conduit_updates()
-    h2d = d2h = 0
     t0 = time.perf_counter()
     for _ in range(steps):
-        dt = s.get_routing_step(fixed)                              # D2H M doubles
-        s.old_state_swap(dt, with_quality=nP > 0)
-        s.set_field("SWB_NODE_NEW_LATFLOW", lat)                    # H2D
-        h2d += lat.nbytes + dt.nbytes
-        if nP:
-            pre = (np.maximum(lat, 0.0)[:, :, None] * conc[None, :, :nP])
-            s.set_field("SWB_NODE_NEW_QUAL", pre)
-            h2d += pre.nbytes
-        it = s.dynwave_execute(dt)                                  # D2H M ints
-        if nP:
-            s.qualrout_execute(dt)
-        depth = s.get_field("SWB_NODE_NEW_DEPTH")                   # D2H
-        flow = s.get_field("SWB_LINK_NEW_FLOW")
-        d2h += depth.nbytes + flow.nbytes + dt.nbytes + it.nbytes
-    s.sync()
+        s.step_host(lat, qual_load=load, node_depth=depth, link_flow=flow, next_dt=next_dt, iters=iters)
     sec = time.perf_counter() - t0
-    return {"seconds": sec, "cu": s.conduit_updates() - cu0, "steps": steps,
-            "h2d": h2d // steps, "d2h": d2h // steps}
+    h2d = lat.nbytes + (load.nbytes if load is not None else 0)
+    d2h = depth.nbytes + flow.nbytes + next_dt.nbytes + iters.nbytes
+    return {"seconds": sec, "cu": s.conduit_updates() - cu0, "steps": steps, "h2d": h2d, "d2h": d2h}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -387,7 +385,7 @@ def main():
     ap.add_argument("--surcharge", default="SLOT")
     ap.add_argument("--spinup", type=float, default=6000.0, help="simulated seconds before timing")
     ap.add_argument("--routing-steps", type=int, default=10, help="routing steps per bench step / launch")
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-steps", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -202,6 +202,28 @@ int  swb_qualrout_execute(swb_solver *s, const double *dt);
 int  swb_get_routing_step(swb_solver *s, double fixed_step, double *dt_out);
 
 /*
+ * One routing step of all members with HOST buffers on both sides: the ensemble form of what the
+ * seam does per step (routing.c:399-409 swap, lateral inflows and quality loads from the host
+ * engine, dynwave_execute, qualrout_execute, dynwave_getRoutingStep).  Host arrays use the host
+ * layout [member][item(,pollutant)]; copies are asynchronous on the solver's stream and overlap
+ * the device-side transposes; buffers from swb_host_alloc are pinned (any host pointer works,
+ * pageable memory just copies slower).
+ */
+typedef struct swb_step_io {
+    const double *dt;           /* [M] routing step to take; NULL = the device's variable step   */
+    const double *latflow;      /* [M][n_nodes] Node.newLatFlow (required)                        */
+    const double *node_losses;  /* [M][n_nodes] Node.losses, or NULL (zero)                       */
+    const double *qual_load;    /* [M][n_nodes][n_pollut] external mass-rate preload, or NULL     */
+    double *node_depth;         /* out [M][n_nodes] Node.newDepth, or NULL                        */
+    double *link_flow;          /* out [M][n_links] Link.newFlow, or NULL                         */
+    double *next_dt;            /* out [M] next variable step, or NULL                            */
+    int    *iters;              /* out [M] Picard iterations used, or NULL                        */
+} swb_step_io;
+void *swb_host_alloc(unsigned long long bytes);
+void  swb_host_free(void *p);
+int   swb_step_host(swb_solver *s, const swb_step_io *io);
+
+/*
  * Ensemble driver ("runoff once, route many"): lateral inflows are evaluated on the device from
  * per-node hydrographs shared by all members and a per-member (scale, time shift) pair:
  *   latflow[m][node] = baseline[node] + scale[m] * sfactor[node] * TS_node(date_m - shift[m])

@@ -70,6 +70,7 @@ _DESC_FIELDS = _parse_struct(_TEXT, "swb_network_desc")
 _OPT_FIELDS = _parse_struct(_TEXT, "swb_options")
 _INFLOW_FIELDS = _parse_struct(_TEXT, "swb_inflow_desc")
 _STATS_FIELDS = _parse_struct(_TEXT, "swb_member_stats")
+_STEPIO_FIELDS = _parse_struct(_TEXT, "swb_step_io")
 FIELD = _parse_enum(_TEXT, "swb_field")
 FIELD_NAME = {v: k for k, v in FIELD.items()}
 
@@ -84,6 +85,10 @@ class Options(C.Structure):
 
 class InflowDesc(C.Structure):
     _fields_ = [(n, t) for (n, t, _, _) in _INFLOW_FIELDS]
+
+
+class StepIO(C.Structure):
+    _fields_ = [(n, t) for (n, t, _, _) in _STEPIO_FIELDS]
 
 
 class MemberStats(C.Structure):

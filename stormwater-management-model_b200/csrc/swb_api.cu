@@ -22,7 +22,7 @@ using namespace swb;
 #define SWB_BLOCK 256
 #endif
 #ifndef SWB_MIN_BLOCKS
-#define SWB_MIN_BLOCKS 1
+#define SWB_MIN_BLOCKS 2     // 128 registers/thread, 16 resident warps per SM
 #endif
 
 struct CudaCtx {
@@ -57,6 +57,41 @@ __global__ void swb_xsect_kernel(int fn, Xs x, int n, const double *tables, cons
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = xs_eval(fn, x, args[i], tab);
+}
+
+// host layout [m][item][p]  ->  device layout [(p * items + item)][m]   (32 x 32 shared-memory tiles)
+__global__ void swb_transpose_in_kernel(double *dst, const double *src, int M, int items, int planes)
+{
+    __shared__ double tile[32][33];
+    const int cols = items * planes;                  // src is M rows x cols
+    int c0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int m = m0 + r, c = c0 + threadIdx.x;
+        if (m < M && c < cols) tile[r][threadIdx.x] = src[(size_t)m * cols + c];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int c = c0 + r, m = m0 + threadIdx.x;
+        if (m < M && c < cols) {
+            int item = c / planes, p = c - item * planes;
+            dst[((size_t)p * items + item) * M + m] = tile[threadIdx.x][r];
+        }
+    }
+}
+// device layout [item][m] -> host layout [m][item]
+__global__ void swb_transpose_out_kernel(double *dst, const double *src, int M, int items)
+{
+    __shared__ double tile[32][33];
+    int i0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int i = i0 + r, m = m0 + threadIdx.x;
+        if (i < items && m < M) tile[r][threadIdx.x] = src[(size_t)i * M + m];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int m = m0 + r, i = i0 + threadIdx.x;
+        if (i < items && m < M) dst[(size_t)m * items + i] = tile[threadIdx.x][r];
+    }
 }
 
 namespace swb { namespace backend {
@@ -107,6 +142,26 @@ static void free_(void *p) { cudaFree(p); }
 static void upload(void *d, const void *s, size_t b) { if (b) cudaMemcpy(d, s, b, cudaMemcpyHostToDevice); }
 static void download(void *d, const void *s, size_t b) { if (b) cudaMemcpy(d, s, b, cudaMemcpyDeviceToHost); }
 static void zero(void *d, size_t b) { if (b) cudaMemset(d, 0, b); }
+
+static void *host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr;
+    return p;
+}
+static void host_free(void *p) { if (p) cudaFreeHost(p); }
+static void h2d_async(void *d, const void *s, size_t b) { if (b) cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, 0); }
+static void d2h_async(void *d, const void *s, size_t b) { if (b) cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, 0); }
+static void transpose_in(double *dev, const double *stage, int M, int items, int planes)
+{
+    dim3 grid((items * planes + 31) / 32, (M + 31) / 32), block(32, 8);
+    swb_transpose_in_kernel<<<grid, block>>>(dev, stage, M, items, planes);
+}
+static void transpose_out(double *stage, const double *dev, int M, int items)
+{
+    dim3 grid((items + 31) / 32, (M + 31) / 32), block(32, 8);
+    swb_transpose_out_kernel<<<grid, block>>>(stage, dev, M, items);
+}
 
 static bool sync(std::string &err)
 {

@@ -11,6 +11,10 @@
 //     void  zero(void *dst, size_t bytes);
 //     bool  launch(const Net &, const State &, const RunArgs &, int device, float *ms, std::string &err);
 //     bool  sync(std::string &err);         int device_count();
+//     void *host_alloc(size_t);  void host_free(void *);
+//     void  h2d_async(void *dst, const void *src, size_t bytes);  void d2h_async(...);
+//     void  transpose_in(double *dev, const double *stage, int M, int items, int planes);   [m][item][p] -> [(p,item)][m]
+//     void  transpose_out(double *stage, const double *dev, int M, int items);
 //     bool  xsect_eval(int device, int fn, const Xs &x, int n, const double *args, double *out, std::string &err);
 //   } }
 #ifndef SWB_API_IMPL_H
@@ -45,6 +49,8 @@ struct swb_solver {
     long long launches;
     float last_ms;
     std::vector<double> h_dt;
+    // swb_step_host staging (device): host-layout landing zones and device-layout images
+    double *stg_lat, *stg_loss, *stg_qual, *img_lat, *img_loss, *img_qual, *stg_depth, *stg_flow;
 };
 
 template <class T>
@@ -115,6 +121,8 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     if (M > 8192) return fail(SWB_ERR_ARG, "n_members > 8192: split the ensemble over several solvers");
     swb_solver *s = new swb_solver();
     s->net = nw; s->M = M; s->launches = 0; s->last_ms = 0.f; s->have_inflows = false;
+    s->stg_lat = s->stg_loss = s->stg_qual = s->img_lat = s->img_loss = s->img_qual = nullptr;
+    s->stg_depth = s->stg_flow = nullptr;
     memset(&s->inflows, 0, sizeof(s->inflows));
     State &st = s->st;
     memset(&st, 0, sizeof(st));
@@ -239,10 +247,13 @@ int swb_qual_init(swb_solver *s, const double *init_concen)
     return SWB_OK;
 }
 
-static int run(swb_solver *s, int phases, int n_steps, double t_end, double fixed_step)
+static int run(swb_solver *s, int phases, int n_steps, double t_end, double fixed_step,
+               const double *host_lat = nullptr, const double *host_losses = nullptr,
+               const double *host_qual = nullptr)
 {
     RunArgs a;
     memset(&a, 0, sizeof(a));
+    a.host_lat = host_lat; a.host_losses = host_losses; a.host_qual = host_qual;
     a.phases = phases; a.n_steps = n_steps; a.t_end = t_end; a.fixed_step = fixed_step;
     a.inflows = s->inflows;
     std::string err;
@@ -290,6 +301,61 @@ int swb_get_routing_step(swb_solver *s, double fixed_step, double *dt_out)
     int rc = run(s, PH_NEXTDT, 1, 0.0, fixed_step);
     if (rc) return rc;
     backend::download(dt_out, s->st.var_step, sizeof(double) * s->M);
+    return SWB_OK;
+}
+
+void *swb_host_alloc(unsigned long long bytes) { return backend::host_alloc((size_t)bytes); }
+void swb_host_free(void *p) { backend::host_free(p); }
+
+int swb_step_host(swb_solver *s, const swb_step_io *io)
+{
+    if (!s || !io || !io->latflow) return fail(SWB_ERR_ARG, "null argument");
+    const Net &n = s->net->net;
+    const int M = s->M, nN = n.nN, nL = n.nL, nP = n.nP;
+    const size_t nb = sizeof(double) * (size_t)nN * M, lb = sizeof(double) * (size_t)nL * M;
+    const bool withQual = nP > 0 && !n.opt.ignore_quality;
+    if (!s->stg_lat) {
+        s->stg_lat = (double *)dev_zero<double>(s->allocs, (size_t)nN * M);
+        s->img_lat = (double *)dev_zero<double>(s->allocs, (size_t)nN * M);
+        s->stg_loss = (double *)dev_zero<double>(s->allocs, (size_t)nN * M);
+        s->img_loss = (double *)dev_zero<double>(s->allocs, (size_t)nN * M);
+        s->stg_qual = (double *)dev_zero<double>(s->allocs, (size_t)nN * M * (nP ? nP : 1));
+        s->img_qual = (double *)dev_zero<double>(s->allocs, (size_t)nN * M * (nP ? nP : 1));
+        s->stg_depth = (double *)dev_zero<double>(s->allocs, (size_t)nN * M);
+        s->stg_flow = (double *)dev_zero<double>(s->allocs, (size_t)nL * M);
+    }
+    backend::h2d_async(s->stg_lat, io->latflow, nb);
+    backend::transpose_in(s->img_lat, s->stg_lat, M, nN, 1);
+    if (io->node_losses) {
+        backend::h2d_async(s->stg_loss, io->node_losses, nb);
+        backend::transpose_in(s->img_loss, s->stg_loss, M, nN, 1);
+    }
+    const bool haveQ = withQual && io->qual_load;
+    if (haveQ) {
+        backend::h2d_async(s->stg_qual, io->qual_load, nb * nP);
+        backend::transpose_in(s->img_qual, s->stg_qual, M, nN, nP);
+    }
+    int phases = PH_SWAP | PH_HOSTIN | PH_DYNWAVE | PH_NEXTDT;
+    if (withQual) phases |= PH_QSWAP | PH_QUALITY;
+    double t_end = 0.0;
+    if (io->dt) {
+        backend::h2d_async(s->st.dt, io->dt, sizeof(double) * M);
+        // a host-chosen step means dynwave_getRoutingStep has been called before (dynwave.c:209):
+        // the Courant search that follows this step must not take the first-call shortcut
+        backend::h2d_async(s->st.var_step, io->dt, sizeof(double) * M);
+    }
+    else { phases |= PH_ADVANCE; t_end = 1.0e300; }
+    int rc = run(s, phases, 1, t_end, n.opt.route_step, s->img_lat, io->node_losses ? s->img_loss : nullptr,
+                 haveQ ? s->img_qual : nullptr);
+    if (rc) return rc;
+    if (io->node_depth) { backend::transpose_out(s->stg_depth, s->st.n_depth, M, nN);
+                          backend::d2h_async(io->node_depth, s->stg_depth, nb); }
+    if (io->link_flow)  { backend::transpose_out(s->stg_flow, s->st.l_flow, M, nL);
+                          backend::d2h_async(io->link_flow, s->stg_flow, lb); }
+    if (io->next_dt) backend::d2h_async(io->next_dt, s->st.var_step, sizeof(double) * M);
+    if (io->iters)   backend::d2h_async(io->iters, s->st.iters, sizeof(int) * M);
+    std::string err;
+    if (!backend::sync(err)) return fail(SWB_ERR_CUDA, err);
     return SWB_OK;
 }
 

@@ -39,7 +39,8 @@ enum {                         // RunArgs.phases
     PH_QUALITY = 8,            // qualrout_execute
     PH_NEXTDT  = 16,           // dynwave_getRoutingStep -> var_step
     PH_ADVANCE = 32,           // ensemble clock: pick dt from var_step / t_end, advance sim_time
-    PH_QSWAP   = 64            // quality old <- new, new = 0 (routing.c:312-336)
+    PH_QSWAP   = 64,           // quality old <- new, new = 0 (routing.c:312-336)
+    PH_HOSTIN  = 128           // lateral inflows / losses / quality loads from host-fed staging
 };
 
 struct Inflows {               // device image of swb_inflow_desc
@@ -57,6 +58,7 @@ struct RunArgs {
     double t_end;              // PH_ADVANCE: members stop at this simulated time (s)
     double fixed_step;         // RouteStep for PH_NEXTDT / PH_ADVANCE
     Inflows inflows;
+    const double *host_lat, *host_losses, *host_qual;   // PH_HOSTIN staging, device layout
 };
 
 // Object loop of one thread: round k covers objects [k*stride, (k+1)*stride) and the thread takes
@@ -130,7 +132,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
         const bool active = !((args.phases & PH_ADVANCE) && st.done[m]);
         const double dt = st.dt[m];
 
-        if (active && (args.phases & (PH_SWAP | PH_INFLOWS | PH_QSWAP | PH_DYNWAVE))) {
+        if (active && (args.phases & (PH_SWAP | PH_INFLOWS | PH_QSWAP | PH_DYNWAVE | PH_HOSTIN))) {
             // getDateTime(NewRoutingTime): 1 ms after the routing time (swmm5.c:1551), in days
             const double tNow = args.inflows.start_day +
                 (args.inflows.start_secs + (1000.0 * st.sim_time[m] + 1.0) / 1000.0) / 86400.0;
@@ -157,6 +159,16 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     }
                     st.n_latflow[ix] = q;
                     st.n_losses[ix] = 0.0;
+                }
+                if (args.phases & PH_HOSTIN) {
+                    double q = args.host_lat[ix];
+                    st.n_latflow[ix] = q;
+                    st.n_losses[ix] = args.host_losses ? args.host_losses[ix] : 0.0;
+                    if (args.host_qual)
+                        for (int p = 0; p < nP; p++) {
+                            size_t iq = SWB_IXP(p, i, nN, m, M);
+                            st.n_qual[iq] += args.host_qual[iq];
+                        }
                 }
                 if (args.phases & PH_SWAP) {
                     // node_setOldHydState, node_initFlows, flowrout.c:153-162

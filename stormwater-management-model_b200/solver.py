@@ -56,6 +56,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_last_kernel_ms.argtypes = [C.c_void_p]
     lib.swb_last_kernel_ms.restype = C.c_double
     lib.swb_sync.argtypes = [C.c_void_p]
+    lib.swb_host_alloc.argtypes = [C.c_ulonglong]
+    lib.swb_host_alloc.restype = C.c_void_p
+    lib.swb_host_free.argtypes = [C.c_void_p]
+    lib.swb_step_host.argtypes = [C.c_void_p, C.POINTER(abi.StepIO)]
     lib.swb_xsect_eval.argtypes = [C.c_int, C.c_int, C.c_int, _P_D, C.c_int, _P_D, _P_D]
     return lib
 
@@ -91,12 +95,16 @@ class Solver:
         self._h = C.c_void_p()
         self._chk(self.lib.swb_solver_create(self._hnet, n_members, C.byref(self._h)))
         self._keep = []
+        self._pinned = []
 
     def _chk(self, rc: int):
         if rc:
             raise SwbError(f"swb error {rc}: {self.lib.swb_last_error().decode()}")
 
     def close(self):
+        for p in getattr(self, "_pinned", []):
+            self.lib.swb_host_free(p)
+        self._pinned = []
         if self._h:
             self.lib.swb_solver_destroy(self._h)
             self._h = C.c_void_p()
@@ -236,6 +244,39 @@ class Solver:
 
     def sync(self):
         self._chk(self.lib.swb_sync(self._h))
+
+    # ---- host-buffer step (ensemble form of the seam's per-step exchange) -----------------------
+    def host_array(self, shape, dtype=np.float64) -> np.ndarray:
+        """numpy array over pinned host memory (swb_host_alloc); freed with the solver."""
+        n = int(np.prod(shape))
+        nbytes = max(n * np.dtype(dtype).itemsize, 8)
+        ptr = self.lib.swb_host_alloc(nbytes)
+        if not ptr:
+            raise SwbError("swb_host_alloc failed")
+        self._pinned.append(ptr)
+        buf = (C.c_char * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def step_host(self, latflow, dt=None, node_losses=None, qual_load=None, node_depth=None,
+                  link_flow=None, next_dt=None, iters=None):
+        io = abi.StepIO()
+        keep = []
+
+        def ptr(a, ct):
+            if a is None:
+                return None
+            assert a.flags["C_CONTIGUOUS"]
+            keep.append(a)
+            return a.ctypes.data_as(C.POINTER(ct))
+        io.dt = ptr(dt, C.c_double)
+        io.latflow = ptr(latflow, C.c_double)
+        io.node_losses = ptr(node_losses, C.c_double)
+        io.qual_load = ptr(qual_load, C.c_double)
+        io.node_depth = ptr(node_depth, C.c_double)
+        io.link_flow = ptr(link_flow, C.c_double)
+        io.next_dt = ptr(next_dt, C.c_double)
+        io.iters = ptr(iters, C.c_int)
+        self._chk(self.lib.swb_step_host(self._h, C.byref(io)))
 
     # ---- convenience ---------------------------------------------------------------------------
     STATE_FIELDS = [

@@ -22,6 +22,22 @@ static void download(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 static void zero(void *d, size_t b) { std::memset(d, 0, b); }
 static bool sync(std::string &) { return true; }
 static int device_count() { return 1; }
+static void *host_alloc(size_t b) { return std::malloc(b ? b : 8); }
+static void host_free(void *p) { std::free(p); }
+static void h2d_async(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
+static void d2h_async(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
+static void transpose_in(double *dev, const double *stage, int M, int items, int planes)
+{
+    for (int m = 0; m < M; m++)
+        for (int i = 0; i < items; i++)
+            for (int p = 0; p < planes; p++)
+                dev[((size_t)p * items + i) * M + m] = stage[((size_t)m * items + i) * planes + p];
+}
+static void transpose_out(double *stage, const double *dev, int M, int items)
+{
+    for (int m = 0; m < M; m++)
+        for (int i = 0; i < items; i++) stage[(size_t)m * items + i] = dev[(size_t)i * M + m];
+}
 static bool xsect_eval(int, int fn, const Xs &x, int n, const double *args, double *out, std::string &)
 {
     static const double tab[] = { SWB_XS_TABLE_DATA };

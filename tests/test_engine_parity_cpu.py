@@ -82,3 +82,42 @@ def test_seam_style_calls_match_ensemble_driver(emul_lib):
         assert it[0] == g["series_iters"][step]
         for f in ("SWB_NODE_NEW_DEPTH", "SWB_LINK_NEW_FLOW", "SWB_NODE_NEW_QUAL", "SWB_LINK_NEW_QUAL"):
             assert np.array_equal(a.get_field(f), b.get_field(f)), (step, f)
+
+
+def test_step_host_equals_device_driver(emul_lib):
+    """swb_step_host (host lateral inflows / quality loads in, depths / flows / next dt out, device
+    transposes) reproduces swb_run_steps step for step, for several members at once."""
+    from swmm_b200 import solver
+    net, g = pc.load_golden("c2_grid12_slot")
+    nP = net.n_pollut
+    M = 32
+
+    def fresh():
+        s = solver.Solver(net, M, lib_path=emul_lib)
+        s.load_state({k[3:]: g[k] for k in g if k.startswith("s0_")})
+        s.set_inflows(node=g["inf_node"], ts_start=g["inf_ts_start"], ts_t=g["inf_ts_t"],
+                      ts_q=g["inf_ts_q"], sfactor=g["inf_sfactor"], baseline=g["inf_baseline"],
+                      concen=g["inf_concen"] if nP else None,
+                      member_scale=np.linspace(0.5, 1.5, M),
+                      start_day=float(g["inf_start"][0]), start_secs=float(g["inf_start"][1]))
+        return s
+    a, b = fresh(), fresh()
+    lat = b.host_array((M, net.n_nodes))
+    load = b.host_array((M, net.n_nodes, nP))
+    depth = b.host_array((M, net.n_nodes))
+    flow = b.host_array((M, net.n_links))
+    next_dt = b.host_array((M,))
+    iters = b.host_array((M,), dtype=np.int32)
+    conc = np.zeros((net.n_nodes, nP))
+    conc[g["inf_node"]] = g["inf_concen"].reshape(-1, nP)
+    for step in range(60):
+        a.run_steps(1, 1e9)
+        lat[:] = a.get_field("SWB_NODE_NEW_LATFLOW")
+        load[:] = np.maximum(lat, 0.0)[:, :, None] * conc[None]
+        b.step_host(lat, qual_load=load, node_depth=depth, link_flow=flow, next_dt=next_dt, iters=iters)
+        assert np.array_equal(depth, a.get_field("SWB_NODE_NEW_DEPTH")), step
+        assert np.array_equal(flow, a.get_field("SWB_LINK_NEW_FLOW")), step
+        assert np.array_equal(b.get_field("SWB_NODE_NEW_QUAL"), a.get_field("SWB_NODE_NEW_QUAL")), step
+        sa = a.stats()
+        assert all(next_dt[k] == sa[k].next_dt for k in range(M))
+    assert len(set(np.round(depth[:, 5], 12))) > 1      # members really differ

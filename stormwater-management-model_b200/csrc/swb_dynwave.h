@@ -42,12 +42,13 @@ SWB_FI Xs load_xs(const Net &n, int j)
 }
 
 // ---- dwflow.c:575-633 ---------------------------------------------------------------------------
+SWB_NI double dw_sjoberg(double yNorm) { return exp(-pow(yNorm, 2.4)); }   // one copy of pow + exp
 SWB_FI double dw_slot_width(const Net &n, const Xs &x, bool isOpen, double y)
 {
     double yNorm = y / x.yFull;
     if (n.opt.surcharge_method != SWB_SLOT || isOpen || yNorm < n.crownCutoff) return 0.0;
     if (yNorm > 1.78) return 0.01 * x.wMax;
-    return x.wMax * 0.5423 * exp(-pow(yNorm, 2.4));
+    return x.wMax * 0.5423 * dw_sjoberg(yNorm);
 }
 template <int S>
 SWB_FI double dw_width(const Net &n, const Xs &x, bool isOpen, double y, const double *T)
@@ -244,62 +245,54 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
                                             normalDepth, T);
             flowClass = fc.cls; criticalDepth = fc.yC; normalDepth = fc.yN; fasnh = fc.fasnh;
         }
+        // depths per class (dwflow.c:465-545); the widths are pure functions of depth, so they are
+        // evaluated once below instead of once per case (identical values, 3 call sites not 15)
         switch (flowClass) {
-          case SWB_SUBCRITICAL:
-            fdMid = 0.5 * (fd1 + fd2);
-            if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
-            width1 = dw_width<S>(n, x, isOpen, fd1, T);
-            width2 = dw_width<S>(n, x, isOpen, fd2, T);
-            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
-            surfArea1 = (width1 + widthMid) * length / 4.;
-            surfArea2 = (widthMid + width2) * length / 4. * fasnh;
-            break;
           case SWB_UP_CRITICAL:
             fd1 = criticalDepth;
             if (normalDepth < criticalDepth) fd1 = normalDepth;
             fd1 = SWB_MAX(fd1, SWB_FUDGE);
             h1 = z1 + fd1;
-            fdMid = 0.5 * (fd1 + fd2);
-            if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
-            width2 = dw_width<S>(n, x, isOpen, fd2, T);
-            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
-            surfArea2 = (widthMid + width2) * length * 0.5;
             break;
           case SWB_DN_CRITICAL:
             fd2 = criticalDepth;
             if (normalDepth < criticalDepth) fd2 = normalDepth;
             fd2 = SWB_MAX(fd2, SWB_FUDGE);
             h2 = z2 + fd2;
-            width1 = dw_width<S>(n, x, isOpen, fd1, T);
-            fdMid = 0.5 * (fd1 + fd2);
-            if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
-            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
-            surfArea1 = (width1 + widthMid) * length * 0.5;
             break;
-          case SWB_UP_DRY:
-            fd1 = SWB_FUDGE;
-            fdMid = 0.5 * (fd1 + fd2);
-            if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
-            width1 = dw_width<S>(n, x, isOpen, fd1, T);
-            width2 = dw_width<S>(n, x, isOpen, fd2, T);
-            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
-            surfArea2 = (widthMid + width2) * length / 4.;
-            if (n.link_offset1[j] <= 0.0) surfArea1 = (width1 + widthMid) * length / 4.;
-            break;
-          case SWB_DN_DRY:
-            fd2 = SWB_FUDGE;
-            fdMid = 0.5 * (fd1 + fd2);
-            if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
-            width1 = dw_width<S>(n, x, isOpen, fd1, T);
-            width2 = dw_width<S>(n, x, isOpen, fd2, T);
-            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
-            surfArea1 = (widthMid + width1) * length / 4.;
-            if (n.link_offset2[j] <= 0.0) surfArea2 = (width2 + widthMid) * length / 4.;
-            break;
-          case SWB_DRY:
+          case SWB_UP_DRY: fd1 = SWB_FUDGE; break;
+          case SWB_DN_DRY: fd2 = SWB_FUDGE; break;
+          default: break;
+        }
+        if (flowClass == SWB_DRY) {
             surfArea1 = SWB_FUDGE * length / 2.0;
             surfArea2 = surfArea1;
-            break;
+        } else {
+            fdMid = 0.5 * (fd1 + fd2);
+            if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
+            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
+            width1 = (flowClass == SWB_UP_CRITICAL) ? 0.0 : dw_width<S>(n, x, isOpen, fd1, T);
+            width2 = (flowClass == SWB_DN_CRITICAL) ? 0.0 : dw_width<S>(n, x, isOpen, fd2, T);
+            switch (flowClass) {
+              case SWB_SUBCRITICAL:
+                surfArea1 = (width1 + widthMid) * length / 4.;
+                surfArea2 = (widthMid + width2) * length / 4. * fasnh;
+                break;
+              case SWB_UP_CRITICAL:
+                surfArea2 = (widthMid + width2) * length * 0.5;
+                break;
+              case SWB_DN_CRITICAL:
+                surfArea1 = (width1 + widthMid) * length * 0.5;
+                break;
+              case SWB_UP_DRY:
+                surfArea2 = (widthMid + width2) * length / 4.;
+                if (n.link_offset1[j] <= 0.0) surfArea1 = (width1 + widthMid) * length / 4.;
+                break;
+              case SWB_DN_DRY:
+                surfArea1 = (widthMid + width1) * length / 4.;
+                if (n.link_offset2[j] <= 0.0) surfArea2 = (width2 + widthMid) * length / 4.;
+                break;
+            }
         }
         y1 = fd1; y2 = fd2;
     }

@@ -25,9 +25,36 @@ using namespace swb;
 #define SWB_MIN_BLOCKS 2     // 128 registers/thread, 16 resident warps per SM
 #endif
 
+#define SWB_MAX_MEMBERS 8192
+
 struct CudaCtx {
     int tid, G, lane, block_size;
     const double *T;
+    int *alive_list;            // shared memory, SWB_MAX_MEMBERS entries
+    int *scan;                  // shared memory, 1 + warps entries
+    // Ordered stream compaction of the members for which alive(m) holds; every CTA computes the
+    // same list (ballot + popc within warps, warp totals through shared memory).
+    template <class Pred>
+    __device__ __forceinline__ int compact_members(int M, Pred alive)
+    {
+        const int lane_id = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        if (threadIdx.x == 0) scan[0] = 0;
+        __syncthreads();
+        for (int m0 = 0; m0 < M; m0 += blockDim.x) {
+            int mm = m0 + threadIdx.x;
+            bool flag = (mm < M) && alive(mm);
+            unsigned b = __ballot_sync(0xffffffffu, flag);
+            if (lane_id == 0) scan[1 + wid] = __popc(b);
+            __syncthreads();
+            int off = scan[0];
+            for (int w = 0; w < wid; w++) off += scan[1 + w];
+            if (flag) alive_list[off + __popc(b & ((1u << lane_id) - 1u))] = mm;
+            __syncthreads();
+            if (threadIdx.x == 0) { int t = scan[0]; for (int w = 0; w < nw; w++) t += scan[1 + w]; scan[0] = t; }
+            __syncthreads();
+        }
+        return scan[0];
+    }
     __device__ __forceinline__ void grid_sync() { cg::this_grid().sync(); }
     __device__ __forceinline__ bool block_or(bool b) { return __syncthreads_or(b ? 1 : 0) != 0; }
     __device__ __forceinline__ void atomic_min_u64(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
@@ -39,9 +66,13 @@ swb_route_kernel(const __grid_constant__ Net net, const __grid_constant__ State 
                  const __grid_constant__ RunArgs args)
 {
     __shared__ double tab[XT_TOTAL];
+    __shared__ int s_alive[SWB_MAX_MEMBERS];
+    __shared__ int s_scan[1 + SWB_BLOCK / 32];
     for (int i = threadIdx.x; i < XT_TOTAL; i += blockDim.x) tab[i] = net.xs_tables[i];
     __syncthreads();
     CudaCtx ctx;
+    ctx.alive_list = s_alive;
+    ctx.scan = s_scan;
     ctx.tid = blockIdx.x * blockDim.x + threadIdx.x;
     ctx.G = gridDim.x * blockDim.x;
     ctx.lane = threadIdx.x;

@@ -42,7 +42,7 @@ SWB_FI Xs load_xs(const Net &n, int j)
 }
 
 // ---- dwflow.c:575-633 ---------------------------------------------------------------------------
-SWB_NI double dw_sjoberg(double yNorm) { return exp(-pow(yNorm, 2.4)); }   // one copy of pow + exp
+SWB_FI double dw_sjoberg(double yNorm) { return exp(-pow(yNorm, 2.4)); }
 SWB_FI double dw_slot_width(const Net &n, const Xs &x, bool isOpen, double y)
 {
     double yNorm = y / x.yFull;

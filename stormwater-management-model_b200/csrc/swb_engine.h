@@ -15,6 +15,7 @@
 // control flow (including every barrier) on host threads.  Ctx provides:
 //     int tid, G, lane, block_size;   const double *T (shape tables);
 //     void grid_sync();  bool block_or(bool);
+//     int *alive_list;  int compact_members(int M, Pred alive);   // ordered list, same in every CTA
 //     void atomic_min_u64(unsigned long long*, unsigned long long);
 //     void atomic_add_f64(double*, double);
 #ifndef SWB_ENGINE_H
@@ -83,6 +84,53 @@ SWB_HD double inflow_series(const Inflows &f, int k, double t)
         if (t <= f.ts_t[i]) return tbl_interp(t, f.ts_t[i - 1], f.ts_q[i - 1], f.ts_t[i], f.ts_q[i]);
     }
     return 0.0;
+}
+
+// ---- per-(object, member) bodies of the Picard phases --------------------------------------------
+SWB_FI void picard_link(const Net &net, const State &st, int j, int m, int k, double dt, const double *T)
+{
+    if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) return;
+    if (k >= 2) {                      // findBypassedLinks of the previous trial (dynwave.c:335-345)
+        const int M = st.M;
+        bool byp = st.n_converged[SWB_IX(net.link_node1[j], m, M)] &&
+                   st.n_converged[SWB_IX(net.link_node2[j], m, M)];
+        st.l_bypassed[SWB_IX(j, m, M)] = byp ? 1 : 0;
+        if (byp) return;
+    }
+    conduit_update(net, st, j, m, k, dt, T);
+}
+// node sums over the true conduits only, stored for the ordered regulator pass
+SWB_FI void picard_node_presum(const Net &net, const State &st, int i, int m)
+{
+    NodeAcc acc = node_init_acc(net, st, i, m);
+    for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++) {
+        int j = net.adj[e] >> 1;
+        if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) break;
+        node_add_link_end(net, st, j, net.adj[e] & 1, m, acc);
+    }
+    size_t ix = SWB_IX(i, m, st.M);
+    st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;
+    st.n_new_surf_area[ix] = acc.surfArea; st.n_sumdqdh[ix] = acc.sumdqdh;
+}
+// gather + outfall boundary / node depth update; returns the node's converged flag
+SWB_FI bool picard_node(const Net &net, const State &st, int i, int m, int k, double dt, const double *T)
+{
+    NodeAcc acc;
+    size_t ix = SWB_IX(i, m, st.M);
+    if (net.nNonConduit > 0) {
+        acc.inflow = st.n_inflow[ix]; acc.outflow = st.n_outflow[ix];
+        acc.surfArea = st.n_new_surf_area[ix]; acc.sumdqdh = st.n_sumdqdh[ix];
+    } else {
+        acc = node_init_acc(net, st, i, m);
+        for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++)
+            node_add_link_end(net, st, net.adj[e] >> 1, net.adj[e] & 1, m, acc);
+    }
+    if (net.node_type[i] == SWB_OUTFALL) {
+        st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;
+        outfall_depth(net, st, i, m, T);
+        return true;
+    }
+    return node_set_depth(net, st, i, m, k, dt, acc);
 }
 
 template <class Ctx>
@@ -216,81 +264,78 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
         ctx.grid_sync();
 
         // ================= dynwave_execute: Picard iterations ==================================
+        // Trials 0 and 1 run for every active member with the fixed thread -> member mapping.
+        // From trial 2 on only the members that have not converged yet keep iterating
+        // (dynwave.c:249-251); they are COMPACTED into a list so that warps stay full: work item w
+        // is (object w / nAlive, member list[w % nAlive]).  Without this a few slow members would
+        // keep every warp busy at a handful of active lanes.
         if (args.phases & PH_DYNWAVE) {
-            bool alive = active;
-            int itersDone = 0;
+            int nAlive = M;
             for (int k = 0; k < maxTrials; k++) {
+                const bool compact = (k >= 2);
                 // ---- findLinkFlows, pass (i): true conduits (dynwave.c:387-395)
-                if (alive) {
-                    SWB_FOR_ITEMS(j, nL) {
-                        if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) continue;
-                        if (k >= 2) {              // findBypassedLinks of the previous trial (:335)
-                            bool byp = st.n_converged[SWB_IX(net.link_node1[j], m, M)] &&
-                                       st.n_converged[SWB_IX(net.link_node2[j], m, M)];
-                            st.l_bypassed[SWB_IX(j, m, M)] = byp ? 1 : 0;
-                            if (byp) continue;
-                        }
-                        conduit_update(net, st, j, m, k, dt, T);
+                if (!compact) {
+                    if (active) SWB_FOR_ITEMS(j, nL) picard_link(net, st, j, m, k, st.dt[m], T);
+                } else {
+                    const long long W = (long long)nL * nAlive;
+                    for (long long w = ctx.tid; w < W; w += ctx.G) {
+                        int j = (int)(w / nAlive), mm = ctx.alive_list[(int)(w - (long long)j * nAlive)];
+                        picard_link(net, st, j, mm, k, st.dt[mm], T);
                     }
                 }
                 ctx.grid_sync();
                 // ---- networks with regulators / dummy links: ordered pass (A.4)
                 if (net.nNonConduit > 0) {
-                    if (alive)
-                        SWB_FOR_ITEMS(i, nN) {
-                            NodeAcc acc = node_init_acc(net, st, i, m);
-                            for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++) {
-                                int j = net.adj[e] >> 1;
-                                if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) break;
-                                node_add_link_end(net, st, j, net.adj[e] & 1, m, acc);
-                            }
-                            size_t ix = SWB_IX(i, m, M);
-                            st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;
-                            st.n_new_surf_area[ix] = acc.surfArea; st.n_sumdqdh[ix] = acc.sumdqdh;
+                    if (!compact) {
+                        if (active) SWB_FOR_ITEMS(i, nN) picard_node_presum(net, st, i, m);
+                    } else {
+                        const long long W = (long long)nN * nAlive;
+                        for (long long w = ctx.tid; w < W; w += ctx.G) {
+                            int i = (int)(w / nAlive);
+                            picard_node_presum(net, st, i, ctx.alive_list[(int)(w - (long long)i * nAlive)]);
                         }
+                    }
                     ctx.grid_sync();
-                    if (alive && owner) regulator_pass(net, st, m, k, dt, T);
+                    if (!compact) { if (active && owner) regulator_pass(net, st, m, k, st.dt[m], T); }
+                    else if (ctx.tid < nAlive) {
+                        int mm = ctx.alive_list[ctx.tid];
+                        regulator_pass(net, st, mm, k, st.dt[mm], T);
+                    }
                     ctx.grid_sync();
                 }
                 // ---- findNodeDepths (dynwave.c:593-632)
-                if (alive) {
-                    bool anyNotConv = false;
-                    SWB_FOR_ITEMS(i, nN) {
-                        NodeAcc acc;
-                        size_t ix = SWB_IX(i, m, M);
-                        if (net.nNonConduit > 0) {
-                            acc.inflow = st.n_inflow[ix]; acc.outflow = st.n_outflow[ix];
-                            acc.surfArea = st.n_new_surf_area[ix]; acc.sumdqdh = st.n_sumdqdh[ix];
-                        } else {
-                            acc = node_init_acc(net, st, i, m);
-                            for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++)
-                                node_add_link_end(net, st, net.adj[e] >> 1, net.adj[e] & 1, m, acc);
-                        }
-                        if (net.node_type[i] == SWB_OUTFALL) {
-                            st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;
-                            outfall_depth(net, st, i, m, T);
-                        } else {
-                            if (!node_set_depth(net, st, i, m, k, dt, acc)) anyNotConv = true;
-                        }
+                if (!compact) {
+                    if (active) {
+                        bool anyNotConv = false;
+                        SWB_FOR_ITEMS(i, nN) if (!picard_node(net, st, i, m, k, st.dt[m], T)) anyNotConv = true;
+                        if (anyNotConv) st.not_conv[k * M + m] = 1;
                     }
-                    if (anyNotConv) st.not_conv[k * M + m] = 1;
-                    itersDone = k + 1;
+                } else {
+                    const long long W = (long long)nN * nAlive;
+                    for (long long w = ctx.tid; w < W; w += ctx.G) {
+                        int i = (int)(w / nAlive), mm = ctx.alive_list[(int)(w - (long long)i * nAlive)];
+                        if (!picard_node(net, st, i, mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
+                    }
                 }
                 ctx.grid_sync();
-                // ---- loop control: Steps++ ; if (Steps > 1 && converged) break (:248-251)
-                if (alive && k >= 1 && st.not_conv[k * M + m] == 0) alive = false;
-                bool any = false;
-                if (k + 1 < maxTrials)
-                    for (int mm = ctx.lane; mm < M; mm += ctx.block_size) {
-                        bool a = !((args.phases & PH_ADVANCE) && st.done[mm]);
-                        for (int kk = 1; kk <= k && a; kk++) a = (st.not_conv[kk * M + mm] != 0);
-                        any = any || a;
-                    }
-                if (!ctx.block_or(any)) break;
+                // ---- loop control: Steps++ ; if (Steps > 1 && converged) break (:248-251).
+                // Every CTA rebuilds the same ordered list of members that go on to trial k + 1.
+                if (k + 1 >= maxTrials) break;
+                nAlive = ctx.compact_members(M, [&](int mm) {
+                    bool a = !((args.phases & PH_ADVANCE) && st.done[mm]);
+                    for (int kk = 1; kk <= k && a; kk++) a = (st.not_conv[kk * M + mm] != 0);
+                    return a;
+                });
+                if (nAlive == 0) break;
             }
             // ---- updateConvergenceStats, findLimitedLinks (dynwave.c:257-260, 349-378)
             if (active) {
                 if (owner) {
+                    // iterations used: first trial k >= 1 that ended converged, else MaxTrials
+                    int itersDone = maxTrials;
+                    for (int kk = 1; kk < maxTrials; kk++)
+                        if (st.not_conv[kk * M + m] == 0) { itersDone = kk + 1; break; }
+                    if (maxTrials == 1) itersDone = 1;
                     st.iters[m] = itersDone;
                     st.tot_iters[m] += itersDone;
                     st.tot_steps[m] += 1;

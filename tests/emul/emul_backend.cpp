@@ -49,6 +49,16 @@ struct EmulCtx {
     int tid, G, lane, block_size;
     const double *T;
     std::barrier<> *bar;
+    int *alive_list;
+    std::vector<int> own_list;
+    template <class Pred> int compact_members(int M, Pred alive)
+    {
+        own_list.resize(M);
+        alive_list = own_list.data();
+        int n = 0;
+        for (int mm = 0; mm < M; mm++) if (alive(mm)) alive_list[n++] = mm;
+        return n;
+    }
     void grid_sync() { bar->arrive_and_wait(); }
     bool block_or(bool b) { return b; }
     void atomic_min_u64(unsigned long long *p, unsigned long long v)
@@ -75,7 +85,7 @@ static bool launch(const Net &net, const State &st, const RunArgs &args, int, fl
     std::vector<std::thread> th;
     for (int t = 0; t < G; t++)
         th.emplace_back([&, t]() {
-            EmulCtx c{t, G, 0, 1, net.xs_tables, &bar};
+            EmulCtx c{t, G, 0, 1, net.xs_tables, &bar, nullptr, {}};
             engine_run(net, st, args, c);
         });
     for (auto &x : th) x.join();

@@ -63,3 +63,12 @@ def test_cuda_multi_step_launch_equals_single_steps(cuda_lib):
         assert np.array_equal(a.get_field(f), b.get_field(f)), f
     assert a.stats()[0].iterations == b.stats()[0].iterations
     assert a.launch_count() == 1 and b.launch_count() == 250
+
+
+def test_cuda_ragged_ensemble_members_equal_single_runs(cuda_lib):
+    """Different members need different Picard trip counts; with the alive-member compaction each
+    must still equal its own single-member run bit for bit (same device arithmetic)."""
+    from test_engine_parity_cpu import _ensemble_vs_single
+    scales = np.linspace(0.2, 3.0, 64)
+    iters = _ensemble_vs_single(None, "c2_grid12_extran", 64, 900, scales, [0, 21, 40, 63])
+    print("iterations per member: min", min(iters), "max", max(iters))

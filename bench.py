@@ -155,6 +155,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     cu0, l0 = s.conduit_updates(), s.launch_count()
+    s.phase_times(reset=True)
     sim_before = float(np.sum([x.sim_time for x in s.stats(0, s.M)]))
     kern_ms = []
     t0 = time.perf_counter()
@@ -165,6 +166,7 @@ def run_ours(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     cu = s.conduit_updates() - cu0
+    phases = s.phase_times()
     launches = s.launch_count() - l0
     dev_s = sum(kern_ms) / 1000.0
     sim_hours = (float(np.sum([x.sim_time for x in s.stats(0, s.M)])) - sim_before) / 3600.0
@@ -217,7 +219,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_conduit_update": BYTES_PER_CU,
-                         "kernel": "swb_route_kernel", "kernel_ms_avg": float(np.mean(kern_ms))},
+                         "kernel": "swb_route_kernel", "kernel_ms_avg": float(np.mean(kern_ms)),
+                         "phase_ms": {k: round(v, 3) for k, v in phases.items()}},
             "sim_hours_per_wall_s": sim_hours / max(dev_s, 1e-9),
             "wall_s_timed_region": wall,
         }

@@ -56,6 +56,8 @@ struct CudaCtx {
         return scan[0];
     }
     __device__ __forceinline__ void grid_sync() { cg::this_grid().sync(); }
+    __device__ __forceinline__ unsigned long long now_ns()
+    { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
     __device__ __forceinline__ bool block_or(bool b) { return __syncthreads_or(b ? 1 : 0) != 0; }
     __device__ __forceinline__ void atomic_min_u64(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
     __device__ __forceinline__ void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }

@@ -152,6 +152,7 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     st.mb_reacted = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
     st.mb_seepage = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
     st.mb_final_storage = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
+    st.phase_ns = dev_zero<unsigned long long>(s->allocs, SWB_N_PHASES);
     // conduit / link settings default to fully open (Link.setting = 1.0, link.c:142)
     std::vector<double> ones((size_t)nL * M, 1.0);
     backend::upload(st.l_setting, ones.data(), sizeof(double) * ones.size());
@@ -455,6 +456,16 @@ int swb_xsect_eval(int device, int fn, int xs_type, const double *p, int n, cons
     x.sMax = p[6]; x.yBot = p[7]; x.aBot = p[8]; x.sBot = p[9]; x.rBot = p[10];
     std::string err;
     if (!backend::xsect_eval(device, fn, x, n, args, out, err)) return fail(SWB_ERR_CUDA, err);
+    return SWB_OK;
+}
+
+int swb_get_phase_times(swb_solver *s, double *ms, int n, int reset)
+{
+    if (!s || !ms || n < 1) return fail(SWB_ERR_ARG, "bad arguments");
+    unsigned long long h[SWB_N_PHASES];
+    backend::download(h, s->st.phase_ns, sizeof(h));
+    for (int i = 0; i < n; i++) ms[i] = i < SWB_N_PHASES ? (double)h[i] * 1.0e-6 : 0.0;
+    if (reset) backend::zero(s->st.phase_ns, sizeof(h));
     return SWB_OK;
 }
 

@@ -14,7 +14,7 @@
 // The body is a template over an execution context so that tests/emul can run the very same
 // control flow (including every barrier) on host threads.  Ctx provides:
 //     int tid, G, lane, block_size;   const double *T (shape tables);
-//     void grid_sync();  bool block_or(bool);
+//     void grid_sync();  bool block_or(bool);  unsigned long long now_ns();
 //     int *alive_list;  int compact_members(int M, Pred alive);   // ordered list, same in every CTA
 //     void atomic_min_u64(unsigned long long*, unsigned long long);
 //     void atomic_add_f64(double*, double);
@@ -70,6 +70,9 @@ struct RunArgs {
     for (int _base = 0, _r = first, idx = first; _base < (n); \
          _base += stride, _r = (_r + 1 == stride ? 0 : _r + 1), idx = _base + _r) \
         if (idx < (n))
+
+#define SWB_TICK(phase) do { if (ctx.tid == 0) { unsigned long long _t = ctx.now_ns(); \
+        st.phase_ns[phase] += _t - tmark; tmark = _t; } } while (0)
 
 #define SWB_FLOW_TOL 0.00001   // consts.h: FLOW_TOL, routing.c:455
 
@@ -152,6 +155,8 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
     const int maxTrials = net.opt.max_trials < SWB_MAX_TRIALS_CAP ? net.opt.max_trials
                                                                   : SWB_MAX_TRIALS_CAP;
     const bool withQual = (nP > 0) && !net.opt.ignore_quality;
+
+    unsigned long long tmark = (ctx.tid == 0) ? ctx.now_ns() : 0ull;
 
     for (int step = 0; step < args.n_steps; step++) {
         // ================= step prologue =======================================================
@@ -262,6 +267,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
         if (owner && (args.phases & PH_DYNWAVE))
             for (int k = 0; k < maxTrials; k++) st.not_conv[k * M + m] = 0;
         ctx.grid_sync();
+        SWB_TICK(TP_PROLOGUE);
 
         // ================= dynwave_execute: Picard iterations ==================================
         // Trials 0 and 1 run for every active member with the fixed thread -> member mapping.
@@ -284,6 +290,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     }
                 }
                 ctx.grid_sync();
+                SWB_TICK(TP_LINKS);
                 // ---- networks with regulators / dummy links: ordered pass (A.4)
                 if (net.nNonConduit > 0) {
                     if (!compact) {
@@ -302,6 +309,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                         regulator_pass(net, st, mm, k, st.dt[mm], T);
                     }
                     ctx.grid_sync();
+                    SWB_TICK(TP_REGULATORS);
                 }
                 // ---- findNodeDepths (dynwave.c:593-632)
                 if (!compact) {
@@ -318,6 +326,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     }
                 }
                 ctx.grid_sync();
+                SWB_TICK(TP_NODES);
                 // ---- loop control: Steps++ ; if (Steps > 1 && converged) break (:248-251).
                 // Every CTA rebuilds the same ordered list of members that go on to trial k + 1.
                 if (k + 1 >= maxTrials) break;
@@ -326,6 +335,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     for (int kk = 1; kk <= k && a; kk++) a = (st.not_conv[kk * M + mm] != 0);
                     return a;
                 });
+                SWB_TICK(TP_CONTROL);
                 if (nAlive == 0) break;
             }
             // ---- updateConvergenceStats, findLimitedLinks (dynwave.c:257-260, 349-378)
@@ -357,6 +367,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             }
         }
 
+        SWB_TICK(TP_EPILOGUE);
         // ================= qualrout_execute (qualrout.c:100-142) ===============================
         if (withQual && (args.phases & PH_QUALITY)) {
             // pollutant-major loops keep the three mass-balance partial sums in registers
@@ -367,6 +378,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     qual_acc_flush(ctx, st, p, m, M, dt, acc);
                 }
             ctx.grid_sync();
+            SWB_TICK(TP_QUAL_NODES);
             if (active)
                 for (int p = 0; p < nP; p++) {
                     QualAcc acc = {0.0, 0.0, 0.0};
@@ -375,6 +387,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 }
         }
 
+        SWB_TICK(TP_QUAL_LINKS);
         // ================= dynwave_getRoutingStep (dynwave.c:195-220, 799-921) =================
         if (args.phases & PH_NEXTDT) {
             if (owner) {
@@ -415,6 +428,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             st.sim_time[m] = (1000.0 * st.sim_time[m] + 1000.0 * dt) / 1000.0;
         }
         if (step + 1 < args.n_steps) ctx.grid_sync();
+        SWB_TICK(TP_NEXTDT);
     }
 }
 

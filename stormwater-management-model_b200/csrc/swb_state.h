@@ -109,6 +109,8 @@ struct Net {
     X(double, l_qual, SWB_LINK_NEW_QUAL, LP) X(double, l_old_qual, SWB_LINK_OLD_QUAL, LP) \
     X(double, l_total_load, SWB_LINK_TOTAL_LOAD, LP)
 
+enum { TP_PROLOGUE = 0, TP_LINKS, TP_REGULATORS, TP_NODES, TP_CONTROL, TP_EPILOGUE, TP_QUAL_NODES,
+       TP_QUAL_LINKS, TP_NEXTDT, SWB_N_PHASES = 12 };
 #define SWB_MAX_TRIALS_CAP 32     // alive / notConv bookkeeping rows (MaxTrials is 8 by default)
 
 struct State {
@@ -130,6 +132,8 @@ struct State {
     int    *done;                // member has reached t_end
     // mass-balance accumulators per member x pollutant (massbal.c:517-555)
     double *mb_reacted, *mb_seepage, *mb_final_storage;
+    // device-side phase timers (ns, accumulated by thread 0 between grid barriers)
+    unsigned long long *phase_ns;    // [SWB_N_PHASES]
 };
 
 // pollutant-plane index: field[(p * nItems + item) * M + m]

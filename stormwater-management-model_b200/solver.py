@@ -56,6 +56,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_last_kernel_ms.argtypes = [C.c_void_p]
     lib.swb_last_kernel_ms.restype = C.c_double
     lib.swb_sync.argtypes = [C.c_void_p]
+    lib.swb_get_phase_times.argtypes = [C.c_void_p, _P_D, C.c_int, C.c_int]
     lib.swb_host_alloc.argtypes = [C.c_ulonglong]
     lib.swb_host_alloc.restype = C.c_void_p
     lib.swb_host_free.argtypes = [C.c_void_p]
@@ -232,6 +233,14 @@ class Solver:
         self._chk(self.lib.swb_get_massbal(self._h, 0, self.M, r.ctypes.data_as(_P_D),
                                            sp.ctypes.data_as(_P_D), f.ctypes.data_as(_P_D)))
         return {"reacted": r, "seepage": sp, "final_storage": f}
+
+    PHASES = ["prologue", "links", "regulators", "nodes", "control", "epilogue", "qual_nodes",
+              "qual_links", "next_dt"]
+
+    def phase_times(self, reset: bool = True) -> dict:
+        ms = np.zeros(len(self.PHASES))
+        self._chk(self.lib.swb_get_phase_times(self._h, ms.ctypes.data_as(_P_D), ms.size, int(reset)))
+        return dict(zip(self.PHASES, ms.tolist()))
 
     def conduit_updates(self) -> int:
         return int(self.lib.swb_conduit_updates(self._h))

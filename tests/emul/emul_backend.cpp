@@ -60,6 +60,9 @@ struct EmulCtx {
         return n;
     }
     void grid_sync() { bar->arrive_and_wait(); }
+    unsigned long long now_ns()
+    { return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+          std::chrono::steady_clock::now().time_since_epoch()).count(); }
     bool block_or(bool b) { return b; }
     void atomic_min_u64(unsigned long long *p, unsigned long long v)
     {

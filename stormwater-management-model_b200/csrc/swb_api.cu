@@ -30,6 +30,13 @@ using namespace swb;
 struct CudaCtx {
     int tid, G, lane, block_size;
     const double *T;
+    int warp_size, warp_lane;
+    __device__ __forceinline__ unsigned long long next_ticket(unsigned long long *p)
+    {
+        unsigned long long t = 0;
+        if (warp_lane == 0) t = atomicAdd(p, 1ull);
+        return __shfl_sync(0xffffffffu, t, 0);
+    }
     int *alive_list;            // shared memory, SWB_MAX_MEMBERS entries
     int *scan;                  // shared memory, 1 + warps entries
     // Ordered stream compaction of the members for which alive(m) holds; every CTA computes the
@@ -74,6 +81,8 @@ swb_route_kernel(const __grid_constant__ Net net, const __grid_constant__ State 
     __syncthreads();
     CudaCtx ctx;
     ctx.alive_list = s_alive;
+    ctx.warp_size = 32;
+    ctx.warp_lane = threadIdx.x & 31;
     ctx.scan = s_scan;
     ctx.tid = blockIdx.x * blockDim.x + threadIdx.x;
     ctx.G = gridDim.x * blockDim.x;

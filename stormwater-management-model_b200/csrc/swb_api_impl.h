@@ -153,6 +153,7 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     st.mb_seepage = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
     st.mb_final_storage = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
     st.phase_ns = dev_zero<unsigned long long>(s->allocs, SWB_N_PHASES);
+    st.tickets = dev_zero<unsigned long long>(s->allocs, 3 * SWB_MAX_TRIALS_CAP);
     // conduit / link settings default to fully open (Link.setting = 1.0, link.c:142)
     std::vector<double> ones((size_t)nL * M, 1.0);
     backend::upload(st.l_setting, ones.data(), sizeof(double) * ones.size());

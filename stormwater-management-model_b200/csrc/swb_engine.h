@@ -16,6 +16,7 @@
 //     int tid, G, lane, block_size;   const double *T (shape tables);
 //     void grid_sync();  bool block_or(bool);  unsigned long long now_ns();
 //     int *alive_list;  int compact_members(int M, Pred alive);   // ordered list, same in every CTA
+//     int warp_size, warp_lane;  unsigned long long next_ticket(unsigned long long *);  // warp-uniform
 //     void atomic_min_u64(unsigned long long*, unsigned long long);
 //     void atomic_add_f64(double*, double);
 #ifndef SWB_ENGINE_H
@@ -134,6 +135,24 @@ SWB_FI bool picard_node(const Net &net, const State &st, int i, int m, int k, do
         return true;
     }
     return node_set_depth(net, st, i, m, k, dt, acc);
+}
+
+// Dynamic tile loop: tile t = (object t / nChunks, chunk t % nChunks of the member list); a warp
+// draws tickets until the phase is exhausted.  ctx.warp_size is 32 on the device, 1 in the host
+// emulation.
+template <class Ctx, class Body>
+SWB_ENGINE inline void for_tiles(Ctx &ctx, int nItems, int nAlive, unsigned long long *ticket, Body body)
+{
+    const int W = ctx.warp_size;
+    const int nChunks = (nAlive + W - 1) / W;
+    const long long total = (long long)nItems * nChunks;
+    for (;;) {
+        long long t = (long long)ctx.next_ticket(ticket);
+        if (t >= total) break;
+        int item = (int)(t / nChunks);
+        int slot = (int)(t - (long long)item * nChunks) * W + ctx.warp_lane;
+        if (slot < nAlive) body(item, ctx.alive_list[slot]);
+    }
 }
 
 template <class Ctx>
@@ -266,45 +285,32 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
         }
         if (owner && (args.phases & PH_DYNWAVE))
             for (int k = 0; k < maxTrials; k++) st.not_conv[k * M + m] = 0;
+        for (int c = ctx.tid; c < 3 * SWB_MAX_TRIALS_CAP; c += ctx.G) st.tickets[c] = 0ull;
         ctx.grid_sync();
         SWB_TICK(TP_PROLOGUE);
 
         // ================= dynwave_execute: Picard iterations ==================================
-        // Trials 0 and 1 run for every active member with the fixed thread -> member mapping.
-        // From trial 2 on only the members that have not converged yet keep iterating
-        // (dynwave.c:249-251); they are COMPACTED into a list so that warps stay full: work item w
-        // is (object w / nAlive, member list[w % nAlive]).  Without this a few slow members would
-        // keep every warp busy at a handful of active lanes.
+        // The members that still iterate are kept as an ordered list (all active members for
+        // trials 0 and 1, then only those that have not converged, dynwave.c:249-251).  Work is cut
+        // into TILES = (object, 32 consecutive list entries) and handed to warps through an atomic
+        // ticket counter per phase: warps stay full when only a few members keep iterating, and a
+        // warp that drew cheap tiles (dry or bypassed conduits) simply draws more instead of
+        // waiting at the barrier for the warps that drew surcharged ones.
         if (args.phases & PH_DYNWAVE) {
-            int nAlive = M;
-            for (int k = 0; k < maxTrials; k++) {
-                const bool compact = (k >= 2);
+            int nAlive = ctx.compact_members(M, [&](int mm) { return !((args.phases & PH_ADVANCE) && st.done[mm]); });
+            for (int k = 0; k < maxTrials && nAlive > 0; k++) {
+                unsigned long long *tickets = st.tickets + 3 * k;
                 // ---- findLinkFlows, pass (i): true conduits (dynwave.c:387-395)
-                if (!compact) {
-                    if (active) SWB_FOR_ITEMS(j, nL) picard_link(net, st, j, m, k, st.dt[m], T);
-                } else {
-                    const long long W = (long long)nL * nAlive;
-                    for (long long w = ctx.tid; w < W; w += ctx.G) {
-                        int j = (int)(w / nAlive), mm = ctx.alive_list[(int)(w - (long long)j * nAlive)];
-                        picard_link(net, st, j, mm, k, st.dt[mm], T);
-                    }
-                }
+                for_tiles(ctx, nL, nAlive, tickets + 0, [&](int j, int mm) {
+                    picard_link(net, st, j, mm, k, st.dt[mm], T);
+                });
                 ctx.grid_sync();
                 SWB_TICK(TP_LINKS);
                 // ---- networks with regulators / dummy links: ordered pass (A.4)
                 if (net.nNonConduit > 0) {
-                    if (!compact) {
-                        if (active) SWB_FOR_ITEMS(i, nN) picard_node_presum(net, st, i, m);
-                    } else {
-                        const long long W = (long long)nN * nAlive;
-                        for (long long w = ctx.tid; w < W; w += ctx.G) {
-                            int i = (int)(w / nAlive);
-                            picard_node_presum(net, st, i, ctx.alive_list[(int)(w - (long long)i * nAlive)]);
-                        }
-                    }
+                    for_tiles(ctx, nN, nAlive, tickets + 1, [&](int i, int mm) { picard_node_presum(net, st, i, mm); });
                     ctx.grid_sync();
-                    if (!compact) { if (active && owner) regulator_pass(net, st, m, k, st.dt[m], T); }
-                    else if (ctx.tid < nAlive) {
+                    if (ctx.tid < nAlive) {
                         int mm = ctx.alive_list[ctx.tid];
                         regulator_pass(net, st, mm, k, st.dt[mm], T);
                     }
@@ -312,31 +318,21 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     SWB_TICK(TP_REGULATORS);
                 }
                 // ---- findNodeDepths (dynwave.c:593-632)
-                if (!compact) {
-                    if (active) {
-                        bool anyNotConv = false;
-                        SWB_FOR_ITEMS(i, nN) if (!picard_node(net, st, i, m, k, st.dt[m], T)) anyNotConv = true;
-                        if (anyNotConv) st.not_conv[k * M + m] = 1;
-                    }
-                } else {
-                    const long long W = (long long)nN * nAlive;
-                    for (long long w = ctx.tid; w < W; w += ctx.G) {
-                        int i = (int)(w / nAlive), mm = ctx.alive_list[(int)(w - (long long)i * nAlive)];
-                        if (!picard_node(net, st, i, mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
-                    }
-                }
+                for_tiles(ctx, nN, nAlive, tickets + 2, [&](int i, int mm) {
+                    if (!picard_node(net, st, i, mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
+                });
                 ctx.grid_sync();
                 SWB_TICK(TP_NODES);
                 // ---- loop control: Steps++ ; if (Steps > 1 && converged) break (:248-251).
                 // Every CTA rebuilds the same ordered list of members that go on to trial k + 1.
                 if (k + 1 >= maxTrials) break;
-                nAlive = ctx.compact_members(M, [&](int mm) {
-                    bool a = !((args.phases & PH_ADVANCE) && st.done[mm]);
-                    for (int kk = 1; kk <= k && a; kk++) a = (st.not_conv[kk * M + mm] != 0);
-                    return a;
-                });
+                if (k >= 1)
+                    nAlive = ctx.compact_members(M, [&](int mm) {
+                        bool a = !((args.phases & PH_ADVANCE) && st.done[mm]);
+                        for (int kk = 1; kk <= k && a; kk++) a = (st.not_conv[kk * M + mm] != 0);
+                        return a;
+                    });
                 SWB_TICK(TP_CONTROL);
-                if (nAlive == 0) break;
             }
             // ---- updateConvergenceStats, findLimitedLinks (dynwave.c:257-260, 349-378)
             if (active) {

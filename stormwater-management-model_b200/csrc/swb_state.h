@@ -134,6 +134,7 @@ struct State {
     double *mb_reacted, *mb_seepage, *mb_final_storage;
     // device-side phase timers (ns, accumulated by thread 0 between grid barriers)
     unsigned long long *phase_ns;    // [SWB_N_PHASES]
+    unsigned long long *tickets;     // [3 * SWB_MAX_TRIALS_CAP] work-distribution counters of one step
 };
 
 // pollutant-plane index: field[(p * nItems + item) * M + m]

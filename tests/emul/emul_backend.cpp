@@ -51,6 +51,8 @@ struct EmulCtx {
     std::barrier<> *bar;
     int *alive_list;
     std::vector<int> own_list;
+    int warp_size = 1, warp_lane = 0;
+    unsigned long long next_ticket(unsigned long long *p) { return __atomic_fetch_add(p, 1ull, __ATOMIC_RELAXED); }
     template <class Pred> int compact_members(int M, Pred alive)
     {
         own_list.resize(M);
@@ -88,7 +90,7 @@ static bool launch(const Net &net, const State &st, const RunArgs &args, int, fl
     std::vector<std::thread> th;
     for (int t = 0; t < G; t++)
         th.emplace_back([&, t]() {
-            EmulCtx c{t, G, 0, 1, net.xs_tables, &bar, nullptr, {}};
+            EmulCtx c{t, G, 0, 1, net.xs_tables, &bar, nullptr, {}, 1, 0};
             engine_run(net, st, args, c);
         });
     for (auto &x : th) x.join();

@@ -101,6 +101,7 @@ int swb_network_create(const swb_network_desc *d, const swb_options *o, int devi
     nw->net.adjq_start = dev_copy<int>(nw->allocs, r.adjq_start.data(), r.adjq_start.size());
     nw->net.adjq = dev_copy<int>(nw->allocs, r.adjq.data(), r.adjq.size());
     nw->net.nc_links = dev_copy<int>(nw->allocs, r.nc_links.data(), r.nc_links.size());
+    nw->net.link_order = dev_copy<int>(nw->allocs, r.link_order.data(), r.link_order.size());
     nw->net.outfall_link = dev_copy<int>(nw->allocs, r.outfall_link.data(), r.outfall_link.size());
     nw->net.xs_tables = dev_copy<double>(nw->allocs, r.xs_tables.data(), r.xs_tables.size());
     *out = nw;

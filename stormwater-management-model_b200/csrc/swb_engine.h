@@ -144,14 +144,29 @@ template <class Ctx, class Body>
 SWB_ENGINE inline void for_tiles(Ctx &ctx, int nItems, int nAlive, unsigned long long *ticket, Body body)
 {
     const int W = ctx.warp_size;
-    const int nChunks = (nAlive + W - 1) / W;
-    const long long total = (long long)nItems * nChunks;
-    for (;;) {
-        long long t = (long long)ctx.next_ticket(ticket);
-        if (t >= total) break;
-        int item = (int)(t / nChunks);
-        int slot = (int)(t - (long long)item * nChunks) * W + ctx.warp_lane;
-        if (slot < nAlive) body(item, ctx.alive_list[slot]);
+    if (nAlive >= W) {
+        // wide ensembles: a tile is one object x W consecutive list entries
+        const int nChunks = (nAlive + W - 1) / W;
+        const long long total = (long long)nItems * nChunks;
+        for (;;) {
+            long long t = (long long)ctx.next_ticket(ticket);
+            if (t >= total) break;
+            int item = (int)(t / nChunks);
+            int slot = (int)(t - (long long)item * nChunks) * W + ctx.warp_lane;
+            if (slot < nAlive) body(item, ctx.alive_list[slot]);
+        }
+    } else {
+        // few members (a single model has one): a tile is W / nAlive objects x all list entries,
+        // so a lone network still fills every lane with a different object
+        const int perTile = W / nAlive;
+        const long long total = ((long long)nItems + perTile - 1) / perTile;
+        const int sub = ctx.warp_lane / nAlive, slot = ctx.warp_lane - sub * nAlive;
+        for (;;) {
+            long long t = (long long)ctx.next_ticket(ticket);
+            if (t >= total) break;
+            long long item = t * perTile + sub;
+            if (sub < perTile && item < nItems) body((int)item, ctx.alive_list[slot]);
+        }
     }
 }
 
@@ -301,8 +316,8 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             for (int k = 0; k < maxTrials && nAlive > 0; k++) {
                 unsigned long long *tickets = st.tickets + 3 * k;
                 // ---- findLinkFlows, pass (i): true conduits (dynwave.c:387-395)
-                for_tiles(ctx, nL, nAlive, tickets + 0, [&](int j, int mm) {
-                    picard_link(net, st, j, mm, k, st.dt[mm], T);
+                for_tiles(ctx, net.nTrue, nAlive, tickets + 0, [&](int jj, int mm) {
+                    picard_link(net, st, net.link_order[jj], mm, k, st.dt[mm], T);
                 });
                 ctx.grid_sync();
                 SWB_TICK(TP_LINKS);

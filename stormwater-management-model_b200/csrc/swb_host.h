@@ -15,7 +15,7 @@
 namespace swb {
 
 struct Derived {
-    std::vector<int> link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link;
+    std::vector<int> link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link, link_order;
     std::vector<double> link_z1, link_z2, xs_tables;
     int nTrue = 0, nNonConduit = 0;
 };
@@ -86,6 +86,10 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
         else if (d.node_type[a] == SWB_OUTFALL) r.outfall_link[a] = j;
     }
     r.nNonConduit = (int)r.nc_links.size();
+    r.link_order.clear();
+    for (int j = 0; j < nL; j++) if (r.link_flags[j] & LF_TRUE_CONDUIT) r.link_order.push_back(j);
+    std::stable_sort(r.link_order.begin(), r.link_order.end(),
+                     [&](int a, int b) { return d.xs_type[a] < d.xs_type[b]; });
     // CSR incidence.  adjq: ascending link index.  adj: true conduits first, then the rest.
     std::vector<std::vector<int>> inc(nN);
     for (int j = 0; j < nL; j++) {

@@ -73,6 +73,10 @@ struct Net {
     const int    *adj;                     // (link << 1) | end, ordered true conduits first, then
                                            // other links, each ascending by link index (A.3)
     const int    *adjq_start, *adjq;       // same incidence ordered by plain link index (quality)
+    const int    *link_order;              // true conduits grouped by cross-section shape: tickets are
+                                           // drawn in this order, so at any moment every warp of the
+                                           // chip runs the same specialised conduit function (one
+                                           // instruction-cache footprint instead of several)
     const int    *nc_links;                // non-true-conduit links in ascending index order
     const int    *outfall_link;            // per node: its (single) link, or -1
     const double *xs_tables;               // XT_TOTAL doubles (global copy of the shape tables)

@@ -24,6 +24,8 @@ static double (*real_step)(double);
 static void   (*real_qual)(double);
 static void   (*real_route)(int, double);
 
+static void   (*real_crit)(int, int);
+static int g_crit_node = -1, g_crit_link = -1;
 static long long g_steps, g_iters;
 static int g_last_iters;
 static double g_t_exec, g_t_step, g_t_qual, g_t_route;
@@ -59,6 +61,16 @@ void routing_execute(int model, double tStep)
     real_route(model, tStep);
     g_t_route += now() - t0;
 }
+
+/* stats.c:522-532: records which element limited the variable time step */
+void stats_updateCriticalTimeCount(int node, int link)
+{
+    if (!real_crit) real_crit = (void (*)(int, int))dlsym(RTLD_NEXT, "stats_updateCriticalTimeCount");
+    g_crit_node = node; g_crit_link = link;
+    if (real_crit) real_crit(node, link);
+}
+void refcount_bind_crit(void *f) { real_crit = (void (*)(int, int))f; }
+void refcount_last_critical(int *node, int *link) { *node = g_crit_node; *link = g_crit_link; }
 
 /* dlopen use: hand over the engine's own entry points explicitly (RTLD_NEXT only works for
  * LD_PRELOAD / link-order interposition) */

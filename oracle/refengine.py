@@ -50,6 +50,8 @@ class RefEngine:
         self.count.refcount_bind(*[C.cast(getattr(L, n), C.c_void_p) for n in
                                    ("dynwave_execute", "dynwave_getRoutingStep", "qualrout_execute",
                                     "routing_execute")])
+        self.count.refcount_bind_crit.argtypes = [C.c_void_p]
+        self.count.refcount_bind_crit(C.cast(L.stats_updateCriticalTimeCount, C.c_void_p))
         L.swmm_getValue.restype = C.c_double
         L.swmm_getValue.argtypes = [C.c_int, C.c_int]
         L.swmm_step.argtypes = [C.POINTER(C.c_double)]
@@ -156,6 +158,12 @@ class RefEngine:
     def last_iterations(self) -> int:
         """Return value of the most recent dynwave_execute call (Picard iterations of that step)."""
         return self.count.refcount_last_iterations()
+
+    def last_critical(self):
+        """(node, link) passed to the most recent stats_updateCriticalTimeCount (dynwave.c:827)."""
+        n, l = C.c_int(-1), C.c_int(-1)
+        self.count.refcount_last_critical(C.byref(n), C.byref(l))
+        return n.value, l.value
 
     def seam_totals(self) -> dict:
         st, it = C.c_longlong(), C.c_longlong()

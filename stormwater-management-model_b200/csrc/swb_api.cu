@@ -68,6 +68,7 @@ struct CudaCtx {
     __device__ __forceinline__ bool block_or(bool b) { return __syncthreads_or(b ? 1 : 0) != 0; }
     __device__ __forceinline__ void atomic_min_u64(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
     __device__ __forceinline__ void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
+    __device__ __forceinline__ void atomic_min_i32(int *p, int v) { atomicMin(p, v); }
 };
 
 __global__ void __launch_bounds__(SWB_BLOCK, SWB_MIN_BLOCKS)

@@ -146,7 +146,7 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     st.non_conv = dev_zero<long long>(s->allocs, M);
     st.crit_node = dev_zero<int>(s->allocs, M);
     st.crit_link = dev_zero<int>(s->allocs, M);
-    st.tmin_bits = dev_zero<unsigned long long>(s->allocs, M);
+    st.tmin_bits = dev_zero<unsigned long long>(s->allocs, 2 * (size_t)M);
     st.alive = dev_zero<int>(s->allocs, (size_t)(SWB_MAX_TRIALS_CAP + 1) * M);
     st.not_conv = dev_zero<int>(s->allocs, (size_t)SWB_MAX_TRIALS_CAP * M);
     st.done = dev_zero<int>(s->allocs, M);

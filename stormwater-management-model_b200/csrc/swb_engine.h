@@ -18,7 +18,7 @@
 //     int *alive_list;  int compact_members(int M, Pred alive);   // ordered list, same in every CTA
 //     int warp_size, warp_lane;  unsigned long long next_ticket(unsigned long long *);  // warp-uniform
 //     void atomic_min_u64(unsigned long long*, unsigned long long);
-//     void atomic_add_f64(double*, double);
+//     void atomic_add_f64(double*, double);  void atomic_min_i32(int*, int);
 #ifndef SWB_ENGINE_H
 #define SWB_ENGINE_H
 
@@ -400,36 +400,56 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
 
         SWB_TICK(TP_QUAL_LINKS);
         // ================= dynwave_getRoutingStep (dynwave.c:195-220, 799-921) =================
+        // Two-level arg-min with integer atomics only (deterministic): the minimum itself as the
+        // ordered bit image of the positive double, then the smallest object index among the
+        // objects that attain it ("first index wins", like the reference's strict `<` loops).
         if (args.phases & PH_NEXTDT) {
             if (owner) {
-                double t0 = args.fixed_step;
-                st.tmin_bits[m] = (unsigned long long)dbits(t0);
-                st.crit_link[m] = -1; st.crit_node[m] = -1;
+                unsigned long long t0 = dbits(args.fixed_step);
+                st.tmin_bits[m] = t0;                 // links: min(maxStep, link candidates)
+                st.tmin_bits[M + m] = t0;             // nodes
+                st.crit_link[m] = 0x7fffffff; st.crit_node[m] = 0x7fffffff;
             }
             ctx.grid_sync();
             const bool variable = !(net.opt.courant_factor == 0.0 || args.fixed_step < SWB_MINTIMESTEP);
-            if (active && variable && st.var_step[m] != 0.0) {
-                double tmin = args.fixed_step;
+            const bool search = active && variable && st.var_step[m] != 0.0;
+            double tl = args.fixed_step, tn = args.fixed_step;
+            int il = -1, in = -1;
+            if (search) {
                 SWB_FOR_ITEMS(j, nL) {
                     double t = link_step(net, st, j, m);
-                    if (t >= 0.0 && t < tmin) tmin = t;
+                    if (t >= 0.0 && t < tl) { tl = t; il = j; }
                 }
                 SWB_FOR_ITEMS(i, nN) {
                     double t = node_step(net, st, i, m);
-                    if (t >= 0.0 && t < tmin) tmin = t;
+                    if (t >= 0.0 && t < tn) { tn = t; in = i; }
                 }
-                if (tmin < args.fixed_step) ctx.atomic_min_u64(&st.tmin_bits[m], dbits(tmin));
+                if (il >= 0) ctx.atomic_min_u64(&st.tmin_bits[m], dbits(tl));
+                if (in >= 0) ctx.atomic_min_u64(&st.tmin_bits[M + m], dbits(tn));
+            }
+            ctx.grid_sync();
+            if (search) {
+                if (il >= 0 && dbits(tl) == st.tmin_bits[m]) ctx.atomic_min_i32(&st.crit_link[m], il);
+                if (in >= 0 && dbits(tn) == st.tmin_bits[M + m]) ctx.atomic_min_i32(&st.crit_node[m], in);
             }
             ctx.grid_sync();
             if (owner && active) {
                 if (!variable) st.var_step[m] = args.fixed_step;
                 else {
                     double vs;
-                    if (st.var_step[m] == 0.0) vs = net.opt.min_route_step;
+                    int cl = st.crit_link[m], cn = st.crit_node[m];
+                    if (cl == 0x7fffffff) cl = -1;
+                    if (cn == 0x7fffffff) cn = -1;
+                    if (st.var_step[m] == 0.0) { vs = net.opt.min_route_step; cl = cn = -1; }
                     else {
-                        vs = dfrombits(st.tmin_bits[m]);
+                        // getVariableStep (dynwave.c:813-831): a node wins only when strictly below
+                        // the link step, and then the link is dropped
+                        double tLink = dfrombits(st.tmin_bits[m]), tNode = dfrombits(st.tmin_bits[M + m]);
+                        vs = tLink;
+                        if (cn >= 0 && tNode < tLink) { vs = tNode; cl = -1; } else cn = -1;
                         if (vs < net.opt.min_route_step) vs = net.opt.min_route_step;
                     }
+                    st.crit_link[m] = cl; st.crit_node[m] = cn;
                     st.var_step[m] = floor(1000.0 * vs) / 1000.0;
                 }
             }

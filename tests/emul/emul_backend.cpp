@@ -71,6 +71,11 @@ struct EmulCtx {
         unsigned long long cur = __atomic_load_n(p, __ATOMIC_RELAXED);
         while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
     }
+    void atomic_min_i32(int *p, int v)
+    {
+        int cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+        while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    }
     void atomic_add_f64(double *p, double v)
     {
         unsigned long long *u = (unsigned long long *)p, cur = __atomic_load_n(u, __ATOMIC_RELAXED), nxt;

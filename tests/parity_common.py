@@ -127,9 +127,19 @@ def lockstep_vs_reference(inp_text: str, lib_path, max_steps: int | None = None,
         worst = {f: 0.0 for f in SNAP_FIELDS}
         worst_dt = 0.0
         steps = 0
+        crit_checked = crit_bad = 0
+        prev_crit = None
         while True:
             t = e.step()
+            # the reference searched the step it just took on the state BEFORE it: compare with
+            # the arg-min our previous step left behind
+            if prev_crit is not None and steps >= 1:
+                crit_checked += 1
+                if prev_crit != e.last_critical():
+                    crit_bad += 1
             s.run_steps(1, t_end)
+            st0 = s.stats()[0]
+            prev_crit = (st0.crit_node, st0.crit_link)
             steps += 1
             st = s.stats()
             t_ref = e.routing_time_ms() / 1000.0
@@ -146,7 +156,7 @@ def lockstep_vs_reference(inp_text: str, lib_path, max_steps: int | None = None,
                         worst[f] = max(worst[f], rel_err(m[k], r, FLOOR[f]))
             if t == 0 or (max_steps and steps >= max_steps):
                 break
-        out = {"steps": steps, "time_err_s": worst_dt, "iterations": int(st[0].iterations),
+        out = {"steps": steps, "time_err_s": worst_dt, "crit_checked": crit_checked, "crit_mismatch": crit_bad, "iterations": int(st[0].iterations),
                "non_converged": int(st[0].non_converged), "ref_non_converged": e.non_converge_count()}
         out.update({"rel_" + f: v for f, v in worst.items()})
         out["max_rel"] = max(worst.values())

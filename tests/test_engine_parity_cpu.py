@@ -38,6 +38,8 @@ def test_emulated_engine_grid_with_quality_vs_live_reference(emul_lib, have_refe
         r = pc.lockstep_vs_reference(pc.case_inp(f"c2_grid16_{sur}"), emul_lib, max_steps=700, every=25)
         assert r["time_err_s"] == 0.0 and r["max_rel"] == 0.0, (sur, r)
         assert r["non_converged"] == r["ref_non_converged"], (sur, r)
+        # time-step critical element (dynwave.c:813-827): same arg-min as the reference every step
+        assert r["crit_checked"] > 500 and r["crit_mismatch"] == 0, (sur, r)
 
 
 def test_lockstep_members_are_independent(emul_lib):

@@ -31,6 +31,7 @@ def test_cuda_full_grid_with_quality_vs_live_reference(cuda_lib, have_reference)
     print(r)
     assert r["time_err_s"] < 1e-9 and r["max_rel"] <= TOL, r
     assert r["non_converged"] == r["ref_non_converged"], r
+    assert r["crit_mismatch"] == 0, r
 
 
 def test_cuda_lockstep_ensemble_members(cuda_lib):

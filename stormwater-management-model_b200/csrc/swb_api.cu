@@ -69,6 +69,19 @@ struct CudaCtx {
     __device__ __forceinline__ void atomic_min_u64(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
     __device__ __forceinline__ void atomic_add_f64(double *p, double v) { atomicAdd(p, v); }
     __device__ __forceinline__ void atomic_min_i32(int *p, int v) { atomicMin(p, v); }
+    __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
+    {
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+            v = w < v ? w : v;
+        }
+        return v;
+    }
+    __device__ __forceinline__ double warp_sum_f64(double v)
+    {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
 };
 
 __global__ void __launch_bounds__(SWB_BLOCK, SWB_MIN_BLOCKS)

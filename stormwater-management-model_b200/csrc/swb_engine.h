@@ -19,6 +19,7 @@
 //     int warp_size, warp_lane;  unsigned long long next_ticket(unsigned long long *);  // warp-uniform
 //     void atomic_min_u64(unsigned long long*, unsigned long long);
 //     void atomic_add_f64(double*, double);  void atomic_min_i32(int*, int);
+//     unsigned long long warp_min_u64(unsigned long long);  double warp_sum_f64(double);   // full-warp reductions
 #ifndef SWB_ENGINE_H
 #define SWB_ENGINE_H
 
@@ -173,9 +174,14 @@ SWB_ENGINE inline void for_tiles(Ctx &ctx, int nItems, int nAlive, unsigned long
 template <class Ctx>
 SWB_ENGINE inline void qual_acc_flush(Ctx &ctx, const State &st, int p, int m, int M, double dt, const QualAcc &a)
 {
-    if (a.reacted != 0.0) ctx.atomic_add_f64(&st.mb_reacted[p * M + m], a.reacted * dt);
-    if (a.seepage != 0.0) ctx.atomic_add_f64(&st.mb_seepage[p * M + m], a.seepage * dt);
-    if (a.finalStorage != 0.0) ctx.atomic_add_f64(&st.mb_final_storage[p * M + m], a.finalStorage);
+    double r = a.reacted * dt, sp = a.seepage * dt, f = a.finalStorage;
+    if (M == 1) {                      // one member: shuffle-sum the warp, one atomic per warp
+        r = ctx.warp_sum_f64(r); sp = ctx.warp_sum_f64(sp); f = ctx.warp_sum_f64(f);
+        if (ctx.warp_lane != 0) return;
+    }
+    if (r != 0.0) ctx.atomic_add_f64(&st.mb_reacted[p * M + m], r);
+    if (sp != 0.0) ctx.atomic_add_f64(&st.mb_seepage[p * M + m], sp);
+    if (f != 0.0) ctx.atomic_add_f64(&st.mb_final_storage[p * M + m], f);
 }
 
 template <class Ctx>
@@ -424,8 +430,17 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     double t = node_step(net, st, i, m);
                     if (t >= 0.0 && t < tn) { tn = t; in = i; }
                 }
-                if (il >= 0) ctx.atomic_min_u64(&st.tmin_bits[m], dbits(tl));
-                if (in >= 0) ctx.atomic_min_u64(&st.tmin_bits[M + m], dbits(tn));
+                unsigned long long bl = dbits(tl), bn = dbits(tn);
+                if (M == 1) {          // all lanes share the member: shuffle-reduce, one atomic per warp
+                    bl = ctx.warp_min_u64(bl); bn = ctx.warp_min_u64(bn);
+                    if (ctx.warp_lane == 0) {
+                        if (bl < dbits(args.fixed_step)) ctx.atomic_min_u64(&st.tmin_bits[m], bl);
+                        if (bn < dbits(args.fixed_step)) ctx.atomic_min_u64(&st.tmin_bits[M + m], bn);
+                    }
+                } else {
+                    if (il >= 0) ctx.atomic_min_u64(&st.tmin_bits[m], bl);
+                    if (in >= 0) ctx.atomic_min_u64(&st.tmin_bits[M + m], bn);
+                }
             }
             ctx.grid_sync();
             if (search) {

@@ -71,6 +71,8 @@ struct EmulCtx {
         unsigned long long cur = __atomic_load_n(p, __ATOMIC_RELAXED);
         while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
     }
+    unsigned long long warp_min_u64(unsigned long long v) { return v; }
+    double warp_sum_f64(double v) { return v; }
     void atomic_min_i32(int *p, int v)
     {
         int cur = __atomic_load_n(p, __ATOMIC_RELAXED);

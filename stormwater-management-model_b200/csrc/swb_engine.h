@@ -221,6 +221,10 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 st.done[m] = done;
             }
             ctx.grid_sync();
+            // every member has reached t_end: leave the launch (grid-uniform decision)
+            bool anyLeft = false;
+            for (int mm = ctx.lane; mm < M; mm += ctx.block_size) anyLeft = anyLeft || !st.done[mm];
+            if (!ctx.block_or(anyLeft)) break;
         }
         const bool active = !((args.phases & PH_ADVANCE) && st.done[m]);
         const double dt = st.dt[m];

@@ -108,11 +108,7 @@ SWB_FI void picard_link(const Net &net, const State &st, int j, int m, int k, do
 SWB_FI void picard_node_presum(const Net &net, const State &st, int i, int m)
 {
     NodeAcc acc = node_init_acc(net, st, i, m);
-    for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++) {
-        int j = net.adj[e] >> 1;
-        if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) break;
-        node_add_link_end(net, st, j, net.adj[e] & 1, m, acc);
-    }
+    node_gather(net, st, i, m, true, acc);
     size_t ix = SWB_IX(i, m, st.M);
     st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;
     st.n_new_surf_area[ix] = acc.surfArea; st.n_sumdqdh[ix] = acc.sumdqdh;
@@ -127,8 +123,7 @@ SWB_FI bool picard_node(const Net &net, const State &st, int i, int m, int k, do
         acc.surfArea = st.n_new_surf_area[ix]; acc.sumdqdh = st.n_sumdqdh[ix];
     } else {
         acc = node_init_acc(net, st, i, m);
-        for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++)
-            node_add_link_end(net, st, net.adj[e] >> 1, net.adj[e] & 1, m, acc);
+        node_gather(net, st, i, m, false, acc);
     }
     if (net.node_type[i] == SWB_OUTFALL) {
         st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;
@@ -233,78 +228,109 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             // getDateTime(NewRoutingTime): 1 ms after the routing time (swmm5.c:1551), in days
             const double tNow = args.inflows.start_day +
                 (args.inflows.start_secs + (1000.0 * st.sim_time[m] + 1.0) / 1000.0) / 86400.0;
+            // Every body below issues ALL of its loads before its first store: the state arrays may
+            // alias as far as the compiler knows, so a load written after a store cannot be hoisted
+            // above it and each load/store pair would cost a full DRAM round trip.
+            const int ph = args.phases;
             SWB_FOR_ITEMS(i, nN) {
-                size_t ix = SWB_IX(i, m, M);
-                if (args.phases & PH_QSWAP)
-                    for (int p = 0; p < nP; p++) {
+                const size_t ix = SWB_IX(i, m, M);
+                // ---- loads
+                double qv[SWB_MAX_POLLUT], hq[SWB_MAX_POLLUT];
+                const bool touchQual = (ph & (PH_QSWAP | PH_INFLOWS)) || ((ph & PH_HOSTIN) && args.host_qual);
+#pragma unroll
+                for (int p = 0; p < SWB_MAX_POLLUT; p++) {
+                    qv[p] = 0.0; hq[p] = 0.0;
+                    if (p < nP && touchQual) {
                         size_t iq = SWB_IXP(p, i, nN, m, M);
-                        st.n_old_qual[iq] = st.n_qual[iq];
-                        st.n_qual[iq] = 0.0;
+                        qv[p] = st.n_qual[iq];
+                        if ((ph & PH_HOSTIN) && args.host_qual) hq[p] = args.host_qual[iq];
                     }
-                if (args.phases & PH_INFLOWS) {
+                }
+                double depth = 0.0, volume = 0.0, inflow = 0.0, outflow = 0.0, lat = 0.0, losses = 0.0;
+                if (ph & PH_SWAP) {
+                    depth = st.n_depth[ix]; volume = st.n_volume[ix];
+                    inflow = st.n_inflow[ix]; outflow = st.n_outflow[ix];
+                }
+                bool newLat = false;
+                int slot = -1;
+                if (ph & PH_INFLOWS) {
                     // addExternalInflows (routing.c:435-490)
-                    double q = 0.0;
-                    int k = args.inflows.node_slot[i];
-                    if (k >= 0) {
-                        double tsv = inflow_series(args.inflows, k, tNow - args.inflows.member_shift[m])
-                                     * (args.inflows.sfactor[k] * args.inflows.member_scale[m]);
-                        q = tsv + args.inflows.baseline[k];
-                        if (fabs(q) < SWB_FLOW_TOL) q = 0.0;
-                        if (q >= 0.0)
-                            for (int p = 0; p < nP; p++)
-                                st.n_qual[SWB_IXP(p, i, nN, m, M)] += args.inflows.concen[k * nP + p] * q;
+                    slot = args.inflows.node_slot[i];
+                    if (slot >= 0) {
+                        double tsv = inflow_series(args.inflows, slot, tNow - args.inflows.member_shift[m])
+                                     * (args.inflows.sfactor[slot] * args.inflows.member_scale[m]);
+                        lat = tsv + args.inflows.baseline[slot];
+                        if (fabs(lat) < SWB_FLOW_TOL) lat = 0.0;
                     }
-                    st.n_latflow[ix] = q;
-                    st.n_losses[ix] = 0.0;
+                    newLat = true;
                 }
-                if (args.phases & PH_HOSTIN) {
-                    double q = args.host_lat[ix];
-                    st.n_latflow[ix] = q;
-                    st.n_losses[ix] = args.host_losses ? args.host_losses[ix] : 0.0;
-                    if (args.host_qual)
-                        for (int p = 0; p < nP; p++) {
-                            size_t iq = SWB_IXP(p, i, nN, m, M);
-                            st.n_qual[iq] += args.host_qual[iq];
-                        }
+                if (ph & PH_HOSTIN) {
+                    lat = args.host_lat[ix];
+                    losses = args.host_losses ? args.host_losses[ix] : 0.0;
+                    newLat = true;
                 }
-                if (args.phases & PH_SWAP) {
+                if (!newLat && (ph & PH_SWAP)) { lat = st.n_latflow[ix]; losses = st.n_losses[ix]; }
+                // ---- stores
+#pragma unroll
+                for (int p = 0; p < SWB_MAX_POLLUT; p++)
+                    if (p < nP && touchQual) {
+                        size_t iq = SWB_IXP(p, i, nN, m, M);
+                        double c = qv[p];
+                        if (ph & PH_QSWAP) { st.n_old_qual[iq] = c; c = 0.0; }      // routing.c:312-336
+                        if ((ph & PH_INFLOWS) && slot >= 0 && lat >= 0.0) c += args.inflows.concen[slot * nP + p] * lat;
+                        if ((ph & PH_HOSTIN) && args.host_qual) c += hq[p];
+                        st.n_qual[iq] = c;
+                    }
+                if (newLat) { st.n_latflow[ix] = lat; st.n_losses[ix] = losses; }
+                if (ph & PH_SWAP) {
                     // node_setOldHydState, node_initFlows, flowrout.c:153-162
-                    double newVolume = st.n_volume[ix];
-                    st.n_old_depth[ix] = st.n_depth[ix];
-                    st.n_old_volume[ix] = newVolume;
-                    st.n_old_net_inflow[ix] = st.n_inflow[ix] - st.n_outflow[ix];
-                    st.n_inflow[ix] = st.n_latflow[ix];
-                    st.n_outflow[ix] = st.n_losses[ix];
+                    st.n_old_depth[ix] = depth;
+                    st.n_old_volume[ix] = volume;
+                    st.n_old_net_inflow[ix] = inflow - outflow;
+                    st.n_inflow[ix] = lat;
+                    st.n_outflow[ix] = losses;
                     double ov = 0.0, fullVolume = net.node_full_volume[i];
-                    if (net.node_type[i] != SWB_STORAGE && newVolume > fullVolume)
-                        ov = (newVolume - fullVolume) / dt;
+                    if (net.node_type[i] != SWB_STORAGE && volume > fullVolume) ov = (volume - fullVolume) / dt;
                     st.n_overflow[ix] = ov;
                 }
-                if (args.phases & PH_DYNWAVE) {        // initRoutingStep (dynwave.c:276-293)
+                if (ph & PH_DYNWAVE) {                 // initRoutingStep (dynwave.c:276-293)
                     st.n_converged[ix] = 0;
                     st.n_dydt[ix] = 0.0;
                 }
             }
             SWB_FOR_ITEMS(j, nL) {
-                size_t ix = SWB_IX(j, m, M);
-                if (args.phases & PH_QSWAP)
-                    for (int p = 0; p < nP; p++) {
+                const size_t ix = SWB_IX(j, m, M);
+                // ---- loads
+                double qv[SWB_MAX_POLLUT];
+#pragma unroll
+                for (int p = 0; p < SWB_MAX_POLLUT; p++) {
+                    qv[p] = 0.0;
+                    if (p < nP && (ph & PH_QSWAP)) qv[p] = st.l_qual[SWB_IXP(p, j, nL, m, M)];
+                }
+                double depth = 0.0, flow = 0.0, volume = 0.0, a1 = 0.0;
+                const bool isConduit = (net.link_type[j] == SWB_CONDUIT);
+                if (ph & PH_SWAP) { depth = st.l_depth[ix]; flow = st.l_flow[ix]; volume = st.l_volume[ix]; }
+                if ((ph & PH_DYNWAVE) && isConduit) a1 = st.c_a1[ix];
+                // ---- stores
+#pragma unroll
+                for (int p = 0; p < SWB_MAX_POLLUT; p++)
+                    if (p < nP && (ph & PH_QSWAP)) {
                         size_t iq = SWB_IXP(p, j, nL, m, M);
-                        st.l_old_qual[iq] = st.l_qual[iq];
+                        st.l_old_qual[iq] = qv[p];
                         st.l_qual[iq] = 0.0;
                     }
-                if (args.phases & PH_SWAP) {            // link_setOldHydState (link.c:564-583)
-                    st.l_old_depth[ix] = st.l_depth[ix];
-                    st.l_old_flow[ix] = st.l_flow[ix];
-                    st.l_old_volume[ix] = st.l_volume[ix];
+                if (ph & PH_SWAP) {                     // link_setOldHydState (link.c:564-583)
+                    st.l_old_depth[ix] = depth;
+                    st.l_old_flow[ix] = flow;
+                    st.l_old_volume[ix] = volume;
                 }
-                if (args.phases & PH_DYNWAVE) {
+                if (ph & PH_DYNWAVE) {
                     st.l_bypassed[ix] = 0;
                     if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) {
                         st.l_surf_area1[ix] = 0.0;
                         st.l_surf_area2[ix] = 0.0;
                     }
-                    if (net.link_type[j] == SWB_CONDUIT) st.c_a2[ix] = st.c_a1[ix];
+                    if (isConduit) st.c_a2[ix] = a1;    // dynwave.c:292
                 }
             }
         }

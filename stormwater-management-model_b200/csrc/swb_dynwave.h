@@ -600,63 +600,6 @@ SWB_FI void node_add_link_end(const Net &n, const State &s, int j, int end, int 
     else a.sumdqdh += dqdh;
 }
 
-// Gather over the incidence range [e0, e1) with the loads of up to four link ends issued together
-// (memory-level parallelism) and the floating-point accumulation kept strictly in list order, so the
-// sums are the reference's sums.  `conduitsOnly` stops at the first non-conduit entry.
-struct LinkEndVals { double q, sa, dqdh, loss; int j, end; };
-
-SWB_FI void node_gather(const Net &n, const State &s, int i, int m, bool conduitsOnly, NodeAcc &a)
-{
-    const int e1 = n.adj_start[i + 1];
-    int e = n.adj_start[i];
-    while (e < e1) {
-        LinkEndVals v[4];
-        int cnt = 0;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (e + u < e1) {
-                int code = n.adj[e + u], j = code >> 1;
-                if (conduitsOnly && !(n.link_flags[j] & LF_TRUE_CONDUIT)) break;
-                size_t ix = SWB_IX(j, m, s.M);
-                v[u].j = j; v[u].end = code & 1;
-                v[u].q = s.l_flow[ix];
-                v[u].sa = (code & 1) ? s.l_surf_area2[ix] : s.l_surf_area1[ix];
-                v[u].dqdh = s.l_dqdh[ix];
-                v[u].loss = (n.link_flags[j] & LF_HAS_LOSSRATE) ? (s.c_evap_loss[ix] + s.c_seep_loss[ix]) : 0.0;
-                cnt = u + 1;
-            }
-        }
-        if (cnt == 0) break;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (u < cnt) {
-                const int j = v[u].j, end = v[u].end, flags = n.link_flags[j];
-                const double q = v[u].q;
-                if (q >= 0.0) { if (end == 0) a.outflow += q; else a.inflow += q; }
-                else          { if (end == 0) a.inflow -= q;  else a.outflow -= q; }
-                int barrels = 1;
-                if (n.link_type[j] == SWB_CONDUIT) {
-                    barrels = n.cond_barrels[j];
-                    if (flags & LF_HAS_LOSSRATE) {
-                        double lossRate = v[u].loss * barrels;
-                        if (lossRate > 0.0) {
-                            bool o1 = (flags & LF_N1_OUTFALL) != 0, o2 = (flags & LF_N2_OUTFALL) != 0;
-                            if (!o1 && !o2) lossRate /= 2.0;
-                            if (end == 0 ? !o1 : !o2) a.outflow += lossRate;
-                        }
-                    }
-                }
-                a.surfArea += v[u].sa * barrels;
-                if (end == 0) a.sumdqdh += v[u].dqdh;
-                else if (n.link_type[j] == SWB_PUMP) { if (n.pump_type[j] != 3) a.sumdqdh += v[u].dqdh; }
-                else a.sumdqdh += v[u].dqdh;
-            }
-        }
-        if (cnt < 4) break;
-        e += 4;
-    }
-}
-
 // ---- K4: outfall boundary depth (link.c:728-766, node.c:1413-1492) ------------------------------
 SWB_NI void outfall_depth(const Net &n, const State &s, int i, int m, const double *T)
 {

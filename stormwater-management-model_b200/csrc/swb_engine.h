@@ -108,7 +108,11 @@ SWB_FI void picard_link(const Net &net, const State &st, int j, int m, int k, do
 SWB_FI void picard_node_presum(const Net &net, const State &st, int i, int m)
 {
     NodeAcc acc = node_init_acc(net, st, i, m);
-    node_gather(net, st, i, m, true, acc);
+    for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++) {
+        int j = net.adj[e] >> 1;
+        if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) break;
+        node_add_link_end(net, st, j, net.adj[e] & 1, m, acc);
+    }
     size_t ix = SWB_IX(i, m, st.M);
     st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;
     st.n_new_surf_area[ix] = acc.surfArea; st.n_sumdqdh[ix] = acc.sumdqdh;
@@ -123,7 +127,8 @@ SWB_FI bool picard_node(const Net &net, const State &st, int i, int m, int k, do
         acc.surfArea = st.n_new_surf_area[ix]; acc.sumdqdh = st.n_sumdqdh[ix];
     } else {
         acc = node_init_acc(net, st, i, m);
-        node_gather(net, st, i, m, false, acc);
+        for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++)
+            node_add_link_end(net, st, net.adj[e] >> 1, net.adj[e] & 1, m, acc);
     }
     if (net.node_type[i] == SWB_OUTFALL) {
         st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;

@@ -19,10 +19,10 @@ namespace cg = cooperative_groups;
 using namespace swb;
 
 #ifndef SWB_BLOCK
-#define SWB_BLOCK 256
+#define SWB_BLOCK 512
 #endif
 #ifndef SWB_MIN_BLOCKS
-#define SWB_MIN_BLOCKS 2     // 128 registers/thread, 16 resident warps per SM
+#define SWB_MIN_BLOCKS 2     // 64 registers/thread, 32 resident warps per SM: measured best (profiles/README.md)
 #endif
 
 #define SWB_MAX_MEMBERS 8192

@@ -89,7 +89,7 @@ swb_route_kernel(const __grid_constant__ Net net, const __grid_constant__ State 
                  const __grid_constant__ RunArgs args)
 {
     __shared__ double tab[XT_TOTAL];
-    __shared__ int s_alive[SWB_MAX_MEMBERS];
+    extern __shared__ int s_alive[];          // st.M entries (dynamic: keeps the L1 carve-out large)
     __shared__ int s_scan[1 + SWB_BLOCK / 32];
     for (int i = threadIdx.x; i < XT_TOTAL; i += blockDim.x) tab[i] = net.xs_tables[i];
     __syncthreads();
@@ -180,7 +180,8 @@ static bool init(int device, std::string &err)
         if (e != cudaSuccess) { err = cuda_err("cudaGetDeviceProperties", e); return false; }
         if (!p.cooperativeLaunch) { err = "device does not support cooperative launch"; return false; }
         g_sms = p.multiProcessorCount;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_blocks_per_sm, swb_route_kernel, SWB_BLOCK, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_blocks_per_sm, swb_route_kernel, SWB_BLOCK,
+                                                          sizeof(int) * SWB_MAX_MEMBERS);
         if (e != cudaSuccess || g_blocks_per_sm < 1) { err = cuda_err("occupancy query", e); return false; }
         if (g_device < 0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
         g_device = device;
@@ -267,7 +268,8 @@ static bool launch(const Net &net, const State &st, const RunArgs &args, int dev
     }
     void *kargs[] = { (void *)&net, (void *)&st, (void *)&args };
     cudaEventRecord(g_ev0, 0);
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)swb_route_kernel, dim3(blocks), dim3(SWB_BLOCK), kargs, 0, 0);
+    size_t dyn = sizeof(int) * (size_t)((st.M + 31) / 32 * 32);
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)swb_route_kernel, dim3(blocks), dim3(SWB_BLOCK), kargs, dyn, 0);
     if (e != cudaSuccess) { err = cuda_err("cudaLaunchCooperativeKernel", e); return false; }
     cudaEventRecord(g_ev1, 0);
     e = cudaEventSynchronize(g_ev1);

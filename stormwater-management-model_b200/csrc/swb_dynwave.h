@@ -58,6 +58,14 @@ SWB_FI double dw_width(const Net &n, const Xs &x, bool isOpen, double y, const d
     if (y / x.yFull >= n.crownCutoff && !isOpen) y = n.crownCutoff * x.yFull;
     return xw<S>(x, y, T);
 }
+// top width given the slot width already evaluated at the same depth (dwflow.c:592-605)
+template <int S>
+SWB_FI double dw_width_ws(const Net &n, const Xs &x, bool isOpen, double y, double wSlot, const double *T)
+{
+    if (wSlot > 0.0) return wSlot;
+    if (y / x.yFull >= n.crownCutoff && !isOpen) y = n.crownCutoff * x.yFull;
+    return xw<S>(x, y, T);
+}
 template <int S>
 SWB_FI double dw_area(const Xs &x, double y, double wSlot, const double *T)
 {
@@ -236,8 +244,12 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     // --- findSurfArea (dwflow.c:417-550) on the previous iteration's flow
     int flowClass;
     double surfArea1 = 0.0, surfArea2 = 0.0;
+    // Preissmann slot widths at the three depths: each is needed for a top width AND an area
+    // (dwflow.c:143-152, 600), so it is evaluated once (pow + exp) and shared; < 0 = not yet
+    double ws1 = -1.0, ws2 = -1.0, wsM = -1.0, widthMid = 0.0;
+    bool widthMidPlain = false;          // widthMid == W(yMid) with no slot and no crown clamp
     {
-        double fd1 = y1, fd2 = y2, fdMid, width1, width2, widthMid;
+        double fd1 = y1, fd2 = y2, fdMid, width1 = 0.0, width2 = 0.0;
         double normalDepth = (fd1 + fd2) / 2.0, criticalDepth = normalDepth, fasnh = 1.0;
         if (fd1 >= x.yFull && fd2 >= x.yFull) flowClass = SWB_SUBCRITICAL;
         else {
@@ -270,9 +282,17 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
         } else {
             fdMid = 0.5 * (fd1 + fd2);
             if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
-            widthMid = dw_width<S>(n, x, isOpen, fdMid, T);
-            width1 = (flowClass == SWB_UP_CRITICAL) ? 0.0 : dw_width<S>(n, x, isOpen, fd1, T);
-            width2 = (flowClass == SWB_DN_CRITICAL) ? 0.0 : dw_width<S>(n, x, isOpen, fd2, T);
+            wsM = dw_slot_width(n, x, isOpen, fdMid);
+            widthMid = dw_width_ws<S>(n, x, isOpen, fdMid, wsM, T);
+            widthMidPlain = !(wsM > 0.0) && !(fdMid / x.yFull >= n.crownCutoff && !isOpen);
+            if (flowClass != SWB_UP_CRITICAL) {
+                ws1 = dw_slot_width(n, x, isOpen, fd1);
+                width1 = dw_width_ws<S>(n, x, isOpen, fd1, ws1, T);
+            }
+            if (flowClass != SWB_DN_CRITICAL) {
+                ws2 = dw_slot_width(n, x, isOpen, fd2);
+                width2 = dw_width_ws<S>(n, x, isOpen, fd2, ws2, T);
+            }
             switch (flowClass) {
               case SWB_SUBCRITICAL:
                 surfArea1 = (width1 + widthMid) * length / 4.;
@@ -300,14 +320,14 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     s.l_surf_area2[ix] = surfArea2;
 
     // --- areas and hydraulic radii (dwflow.c:142-153)
-    double wSlot = dw_slot_width(n, x, isOpen, y1);
-    double a1 = dw_area<S>(x, y1, wSlot, T);
+    if (ws1 < 0.0) ws1 = dw_slot_width(n, x, isOpen, y1);
+    double a1 = dw_area<S>(x, y1, ws1, T);
     double r1 = dw_hyd_rad<S>(x, y1, T);
-    wSlot = dw_slot_width(n, x, isOpen, y2);
-    double a2 = dw_area<S>(x, y2, wSlot, T);
-    double yMid = 0.5 * (y1 + y2);
-    wSlot = dw_slot_width(n, x, isOpen, yMid);
-    double aMid = dw_area<S>(x, yMid, wSlot, T);
+    if (ws2 < 0.0) ws2 = dw_slot_width(n, x, isOpen, y2);
+    double a2 = dw_area<S>(x, y2, ws2, T);
+    double yMid = 0.5 * (y1 + y2);       // == fdMid whenever widthMid was evaluated (y1, y2 >= FUDGE)
+    if (wsM < 0.0) wsM = dw_slot_width(n, x, isOpen, yMid);
+    double aMid = dw_area<S>(x, yMid, wsM, T);
     double rMid = dw_hyd_rad<S>(x, yMid, T);
 
     bool isFull = (y1 >= x.yFull && y2 >= x.yFull);
@@ -331,7 +351,16 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     // --- velocity, Froude number, inertial damping (dwflow.c:183-208)
     double v = qLast / aMid;
     if (fabs(v) > SWB_MAXVELOCITY) v = SWB_MAXVELOCITY * SWB_SGN(qLast);
-    double froude = link_froude<S>(x, isOpen, v, yMid, T);
+    // link_getFroude (link.c:847-871); A(yMid) and W(yMid) are reused when they are the very values
+    // already computed above (depth below full, no slot, no crown clamp)
+    double froude;
+    if (yMid <= SWB_FUDGE) froude = 0.0;
+    else if (!isOpen && x.yFull - yMid <= SWB_FUDGE) froude = 0.0;
+    else {
+        double aF = (yMid < x.yFull) ? aMid : xa<S>(x, yMid, T);
+        double wF = widthMidPlain ? widthMid : xw<S>(x, yMid, T);
+        froude = fabs(v) / sqrt(SWB_GRAVITY * (aF / wF));
+    }
     if (flowClass == SWB_SUBCRITICAL && froude > 1.0) flowClass = SWB_SUPCRITICAL;
     double sigma;
     if      (froude <= 0.5) sigma = 1.0;

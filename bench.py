@@ -41,6 +41,16 @@ from swmm_b200 import network, scenarios, solver  # noqa: E402
 BYTES_PER_CU = 200.0          # SURVEY.md 8(d), fixed for grading (r = 0.505, k = 3)
 
 
+def measured_traffic():
+    """dram__bytes_read + dram__bytes_write of one swb_route_kernel launch from the committed
+    `ncu --set full` capture of the default bench step (profiles/ncu_traffic_r01.json)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -217,7 +227,11 @@ def run_ours(args):
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": measured_traffic() if (args.members == 512 and args.grid == 100 and rs == 10) else None,
+                         "traffic_unit": "bytes per launch (ncu capture of the default step, profiles/ncu_traffic_r01.json)",
+                         "algorithmic_bytes_per_launch": BYTES_PER_CU * cu / max(args.steps, 1),
+                         "peak_source": peak_src,
                          "bytes_per_conduit_update": BYTES_PER_CU,
                          "kernel": "swb_route_kernel", "kernel_ms_avg": float(np.mean(kern_ms)),
                          "phase_ms": {k: round(v, 3) for k, v in phases.items()}},

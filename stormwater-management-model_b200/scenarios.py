@@ -329,5 +329,169 @@ def c3_mixed_inp() -> str:
     return C3_MIXED_INP
 
 
+# A second mixed-element model that exercises what C3_MIXED_INP does not: pump types 1, 2, 4 and
+# ideal, SIDEFLOW / TRAPEZOIDAL weirs, flap-gated and slowly closing orifices, a TABULAR/HEAD outlet,
+# CYLINDRICAL / CONICAL / PYRAMIDAL storage with evaporation, open channels (trapezoid, rect_open,
+# parabolic, power, triangular), filled circular, horseshoe, arch, gothic, catenary, semi-elliptical,
+# basket-handle, semi-circular, modified basket-handle, rect_round, rect_triangular and horizontal /
+# vertical ellipse sections, an irregular transect, a custom shape, conduit seepage + evaporation,
+# local losses, a flow limit, NORMAL and TIMESERIES outfalls, SI-free CFS units.
+C3B_SHAPES_INP = """[OPTIONS]
+FLOW_UNITS CFS
+FLOW_ROUTING DYNWAVE
+START_DATE 01/01/2020
+START_TIME 00:00:00
+END_DATE 01/01/2020
+END_TIME 12:00:00
+REPORT_STEP 00:10:00
+ROUTING_STEP 5
+VARIABLE_STEP 0.75
+ALLOW_PONDING YES
+SURCHARGE_METHOD SLOT
+THREADS 1
+[EVAPORATION]
+CONSTANT 0.5
+[JUNCTIONS]
+A1 120 10 0 0 200
+A2 118 10 0 0 0
+A3 116 10 0 0 0
+A4 114 10 0 0 0
+A5 112 10 0 0 0
+A6 110 10 0 0 0
+A7 108 10 0 0 0
+A8 106 10 0 0 0
+A9 104 10 0 0 0
+B1 119 10 0 0 0
+B2 117 10 0 0 0
+B3 115 10 0 0 0
+B4 113 10 0 0 0
+B5 111 10 0 0 0
+B6 109 10 0 0 0
+B7 107 10 0 0 0
+B8 105 10 0 0 0
+W1 95 12 0 0 0
+W2 95 12 0 0 0
+W3 95 12 0 0 0
+W4 95 12 0 0 0
+[OUTFALLS]
+OA 100 NORMAL NO
+OB 100 TIMESERIES STG YES
+OC 99 FREE NO
+[STORAGE]
+T1 103 10 1 CYLINDRICAL 30 20 0 0 0.5
+T2 102 10 0.5 CONICAL 20 10 0.5 0 1.0
+T3 101 10 0 PYRAMIDAL 40 20 1 0 0
+[CONDUITS]
+CA1 A1 A2 300 0.013 0 0 0 0
+CA2 A2 A3 300 0.013 0 0 0 0
+CA3 A3 A4 300 0.013 0 0 0 0
+CA4 A4 A5 300 0.013 0 0 0 0
+CA5 A5 A6 300 0.013 0 0 0 0
+CA6 A6 A7 300 0.013 0 0 0 0
+CA7 A7 A8 300 0.013 0 0 0 0
+CA8 A8 A9 300 0.013 0 0 0 0
+CA9 A9 T1 300 0.013 0 1 0 0
+CB1 B1 B2 300 0.02 0 0 0 0
+CB2 B2 B3 300 0.02 0 0 0 0
+CB3 B3 B4 300 0.02 0 0 0 0
+CB4 B4 B5 300 0.02 0 0 0 0
+CB5 B5 B6 300 0.02 0 0 0 0
+CB6 B6 B7 300 0.02 0 0 0 3
+CB7 B7 B8 300 0.03 0 0 0 0
+CB8 B8 T2 300 0.02 0 0.5 0 0
+CX1 A5 B5 200 0.013 0.5 0 0 0
+CX2 T3 OC 300 0.013 0 0 0 0
+CO1 W1 OA 200 0.013 0 0 0 0
+CO2 W3 OB 200 0.013 0 0 0 0
+CP4 W2 W4 200 0.013 0 0 0 0
+[PUMPS]
+P1 T1 W1 PC1 ON 0 0
+P2 T2 W2 PC2 ON 0 0
+P4 W2 W3 PC4 ON 2 0.5
+PI W4 T3 * ON 0 0
+[ORIFICES]
+OR1 T1 T3 SIDE 1 0.65 YES 0
+OR2 T2 T3 BOTTOM 0 0.6 NO 0.2
+[WEIRS]
+WS T1 T2 SIDEFLOW 6 3.0 NO 1 0 NO
+WT T2 T3 TRAPEZOIDAL 5 3.2 YES 0 2.8 YES
+[OUTLETS]
+OL T3 W3 1 TABULAR/HEAD RATE NO
+[XSECTIONS]
+CA1 FILLED_CIRCULAR 3 0.5 0 0 1
+CA2 HORSESHOE 3 0 0 0 1
+CA3 ARCH 3 4.5 0 0 1
+CA4 GOTHIC 3 0 0 0 1
+CA5 CATENARY 3 0 0 0 1
+CA6 SEMIELLIPTICAL 3 0 0 0 1
+CA7 BASKETHANDLE 3 0 0 0 1
+CA8 SEMICIRCULAR 3 0 0 0 1
+CA9 MODBASKETHANDLE 4 3 1.5 0 1
+CB1 TRAPEZOIDAL 4 3 1.5 2 1
+CB2 RECT_OPEN 4 5 0 0 1
+CB3 PARABOLIC 4 8 0 0 1
+CB4 POWER 4 8 1.5 0 1
+CB5 TRIANGULAR 4 8 0 0 1
+CB6 IRREGULAR TR1
+CB7 RECT_ROUND 4 3 2 0 1
+CB8 RECT_TRIANGULAR 4 3 1 0 1
+CX1 HORIZ_ELLIPSE 2.5 4 0 0 1
+CX2 VERT_ELLIPSE 4 2.5 0 0 2
+CO1 CUSTOM 3 SHP 0 0 1
+CO2 EGG 3 0 0 0 1
+CP4 CIRCULAR 2 0 0 0 1
+OR1 CIRCULAR 1.5 0 0 0
+OR2 RECT_CLOSED 1 1.5 0 0
+WS RECT_OPEN 3 8 0 0
+WT TRAPEZOIDAL 3 6 1 1
+[TRANSECTS]
+NC 0.05 0.05 0.03
+X1 TR1 6 10 40 0 0 0 0 0
+GR 6 0 4 10 0 15 0.5 35 4 40 5 45 6 50
+[LOSSES]
+CA2 0.3 0.2 0.1 NO 0
+CB1 0 0 0 NO 0.5
+CB2 0.2 0.2 0 NO 0.2
+CX1 0 0 0 YES 0
+[CURVES]
+PC1 PUMP1 100 2 300 4 600 6 2000 8
+PC2 PUMP2 1 1 2 2 4 3 8 4
+PC4 PUMP4 0 0 1 1 3 3 6 4
+RATE RATING 0 0 1 2 3 5 6 7
+SHP SHAPE 0 0.2 0.25 0.7 0.5 1.0 0.75 0.8 1.0 0.0
+[TIMESERIES]
+QA 0:00 0
+QA 1:00 12
+QA 3:00 25
+QA 6:00 4
+QA 12:00 1
+QB 0:00 0
+QB 2:00 30
+QB 5:00 8
+QB 12:00 2
+STG 0:00 100.5
+STG 6:00 103
+STG 12:00 100.5
+CC 0:00 80
+CC 12:00 80
+[POLLUTANTS]
+TSS MG/L 0 0 0 1.0
+SALT MG/L 0 0 0 0
+[INFLOWS]
+A1 FLOW QA FLOW 1.0 1.0
+A1 TSS CC CONCEN 1.0 1.0
+B1 FLOW QB FLOW 1.0 1.0
+B1 SALT CC CONCEN 1.0 0.5
+A5 FLOW QA FLOW 1.0 0.3
+[REPORT]
+NODES ALL
+LINKS ALL
+"""
+
+
+def c3b_shapes_inp() -> str:
+    return C3B_SHAPES_INP
+
+
 def c5_mega_spec(hours: float = 1.0) -> GridSpec:
     return GridSpec(nx=1000, ny=500, hours=hours, pollutants=False, surcharge="SLOT")

@@ -77,6 +77,8 @@ def case_inp(name: str) -> str:
                                                         pollutants="noq" not in parts))
     if name == "c3_mixed":
         return scenarios.c3_mixed_inp()
+    if name == "c3b_shapes":
+        return scenarios.c3b_shapes_inp()
     raise KeyError(name)
 
 

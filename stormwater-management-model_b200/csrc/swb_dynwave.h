@@ -217,11 +217,10 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     if constexpr (S >= 0) x.type = S;        // compile-time shape: every geometry switch folds
     const bool isOpen = (flags & LF_OPEN_SHAPE) != 0;
     const int n1 = n.link_node1[j], n2 = n.link_node2[j];
-    const double barrels = (double)n.cond_barrels[j];
     const bool slot = (n.opt.surcharge_method == SWB_SLOT);
-
-    bool isClosed = (s.l_setting[ix] == 0);
-    double qOld = s.l_old_flow[ix] / barrels;
+    // Register budget (64 per thread at 32 warps/SM): values that are only needed late (old flow,
+    // old area, barrels, true length, end-node depths for the dry-node test) are loaded late or
+    // re-read instead of being kept live across the geometry evaluation.
     double qLast = s.c_q1[ix];
     double evapLoss = 0.0, seepLoss = 0.0;
 
@@ -236,10 +235,7 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     y2 = SWB_MAX(y2, SWB_FUDGE);
     if (!slot) { y1 = SWB_MIN(y1, x.yFull); y2 = SWB_MIN(y2, x.yFull); }
 
-    double aOld = s.c_a2[ix];
-    aOld = SWB_MAX(aOld, SWB_FUDGE);
     const double length = n.cond_mod_length[j];
-    const double trueLength = n.cond_length[j];
 
     // --- findSurfArea (dwflow.c:417-550) on the previous iteration's flow
     int flowClass;
@@ -333,8 +329,11 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     bool isFull = (y1 >= x.yFull && y2 >= x.yFull);
 
     // --- dry / closed exit (dwflow.c:165-180)
+    const bool isClosed = (s.l_setting[ix] == 0);
+    const double barrels = (double)n.cond_barrels[j];
     if (flowClass == SWB_DRY || flowClass == SWB_UP_DRY || flowClass == SWB_DN_DRY || isClosed ||
         aMid <= SWB_FUDGE) {
+        const double trueLength = n.cond_length[j];
         double a1s = 0.5 * (a1 + a2);
         s.c_a1[ix] = a1s;
         s.c_q1[ix] = 0.0;
@@ -375,6 +374,10 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     if (isFull && !isOpen) sigma = 0.0;
 
     // --- momentum terms (dwflow.c:210-236)
+    const double trueLength = n.cond_length[j];
+    double aOld = s.c_a2[ix];
+    aOld = SWB_MAX(aOld, SWB_FUDGE);
+    const double qOld = s.l_old_flow[ix] / barrels;
     double dq1 = dt * n.cond_rough_factor[j] / pow(rWtd, 1.33333) * fabs(v);
     double dq2 = dt * SWB_GRAVITY * aWtd * (h2 - h1) / length;
     double dq3 = 0.0, dq4 = 0.0;
@@ -413,7 +416,7 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
             if (nfl == SWB_NF_SLOPE || nfl == SWB_NF_BOTH || hasOutfall) { if (y1 < y2) check = true; }
             if (!check && (nfl == SWB_NF_FROUDE || nfl == SWB_NF_BOTH) && !hasOutfall) {
                 if (y1 > SWB_FUDGE && y2 > SWB_FUDGE) {
-                    double f1 = link_froude<S>(x, isOpen, q / a1, y1, T);
+                    double f1 = link_froude<S>(x, isOpen, q / a1, y1, T);   // y1 < yFull here
                     if (f1 >= 1.0) check = true;
                 }
             }
@@ -432,8 +435,8 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     double qLimit = n.link_q_limit[j];
     if (qLimit > 0.0) { if (fabs(q) > qLimit) q = SWB_SGN(q) * qLimit; }
     if (link_flap_closed(flags, n.link_direction[j], q)) q = 0.0;
-    if (q >  SWB_FUDGE && depth1 <= SWB_FUDGE) q =  SWB_FUDGE;
-    if (q < -SWB_FUDGE && depth2 <= SWB_FUDGE) q = -SWB_FUDGE;
+    if (q >  SWB_FUDGE && s.n_depth[SWB_IX(n1, m, M)] <= SWB_FUDGE) q =  SWB_FUDGE;
+    if (q < -SWB_FUDGE && s.n_depth[SWB_IX(n2, m, M)] <= SWB_FUDGE) q = -SWB_FUDGE;
 
     // --- save (dwflow.c:283-292)
     s.c_a1[ix] = aMid;

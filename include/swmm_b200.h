@@ -37,6 +37,8 @@ extern "C" {
 /* enums.h values used in the descriptor (restated so callers need no reference header) */
 enum { SWB_JUNCTION = 0, SWB_OUTFALL = 1, SWB_STORAGE = 2, SWB_DIVIDER = 3 };          /* enums.h:70  */
 enum { SWB_CONDUIT = 0, SWB_PUMP = 1, SWB_ORIFICE = 2, SWB_WEIR = 3, SWB_OUTLET = 4 }; /* enums.h:80  */
+enum { SWB_TRANSVERSE_WEIR = 0, SWB_SIDEFLOW_WEIR, SWB_VNOTCH_WEIR, SWB_TRAPEZOIDAL_WEIR,
+       SWB_ROADWAY_WEIR };                                                               /* enums.h:430 */
 enum { SWB_EXTRAN = 0, SWB_SLOT = 1 };                                                  /* enums.h:369 */
 enum { SWB_NO_DAMPING = 0, SWB_PARTIAL_DAMPING = 1, SWB_FULL_DAMPING = 2 };             /* enums.h:364 */
 enum { SWB_NF_SLOPE = 0, SWB_NF_FROUDE = 1, SWB_NF_BOTH = 2, SWB_NF_NEITHER = 3 };      /* enums.h:358 */
@@ -110,6 +112,8 @@ typedef struct swb_network_desc {
     const double *orif_cdisch, *orif_length;
     const int    *weir_type, *weir_can_surcharge, *weir_cd_curve;
     const double *weir_cdisch1, *weir_cdisch2, *weir_end_con, *weir_slope, *weir_length;
+    const double *weir_road_width;                  /* Weir.roadWidth, ft (ROADWAY weirs)  */
+    const int    *weir_road_surface;                /* Weir.roadSurface: 1 paved, 2 gravel */
     const int    *outlet_curve, *outlet_curve_type; /* Outlet.qCurve, curveType            */
     const double *outlet_qcoeff, *outlet_qexpon;
 

@@ -104,6 +104,9 @@ int swb_network_create(const swb_network_desc *d, const swb_options *o, int devi
     nw->net.link_order = dev_copy<int>(nw->allocs, r.link_order.data(), r.link_order.size());
     nw->net.outfall_link = dev_copy<int>(nw->allocs, r.outfall_link.data(), r.outfall_link.size());
     nw->net.xs_tables = dev_copy<double>(nw->allocs, r.xs_tables.data(), r.xs_tables.size());
+    nw->net.link_kernel = dev_copy<int>(nw->allocs, r.link_kernel.data(), r.link_kernel.size());
+    nw->net.culvert_params = dev_copy<double>(nw->allocs, r.culvert_params.data(), r.culvert_params.size());
+    nw->net.road_tables = dev_copy<double>(nw->allocs, r.road_tables.data(), r.road_tables.size());
     *out = nw;
     return SWB_OK;
 }

@@ -19,6 +19,7 @@
 
 #include "swb_state.h"
 #include "swb_xsect.h"
+#include "swb_culvert.h"
 
 namespace swb {
 
@@ -378,7 +379,10 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     double aOld = s.c_a2[ix];
     aOld = SWB_MAX(aOld, SWB_FUDGE);
     const double qOld = s.l_old_flow[ix] / barrels;
-    double dq1 = dt * n.cond_rough_factor[j] / pow(rWtd, 1.33333) * fabs(v);
+    double dq1;
+    if (S < 0 && x.type == XS_FORCE_MAIN && isFull)
+         dq1 = dt * forcemain_fric_slope(n, x, fabs(v), rMid);
+    else dq1 = dt * n.cond_rough_factor[j] / pow(rWtd, 1.33333) * fabs(v);
     double dq2 = dt * SWB_GRAVITY * aWtd * (h2 - h1) / length;
     double dq3 = 0.0, dq4 = 0.0;
     if (sigma > 0.0) {
@@ -404,10 +408,12 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     double q = (qOld - dq2 + dq3 + dq4 + dq6) / denom;
     double dqdh = 1.0 / denom * SWB_GRAVITY * dt * aWtd / length * barrels;
 
-    // --- flow limitations (dwflow.c:245-259; culverts are rejected at network creation)
-    unsigned char normalFlow = 0;
+    // --- flow limitations (dwflow.c:245-259); culvert-coded links always run the generic instance
+    unsigned char normalFlow = 0, inletControl = 0;
+    const bool hasCulvert = (S < 0) && n.xs_culvert[j] > 0;
     if (q > 0.0) {
-        if (n.opt.normal_flow_ltd != SWB_NF_NEITHER && y1 < x.yFull &&
+        if (hasCulvert && !isFull) q = culvert_inflow(n, x, j, q, h1, dqdh, inletControl, T);
+        else if (n.opt.normal_flow_ltd != SWB_NF_NEITHER && y1 < x.yFull &&
             (flowClass == SWB_SUBCRITICAL || flowClass == SWB_SUPCRITICAL)) {
             // checkNormalFlow (dwflow.c:637-686)
             bool check = false;
@@ -452,7 +458,8 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     s.l_dqdh[ix] = dqdh;
     s.l_froude[ix] = froude;
     s.l_flow_class[ix] = (unsigned char)flowClass;
-    s.l_normal_flow[ix] = normalFlow;     // inletControl stays 0: culverts are rejected up front
+    s.l_normal_flow[ix] = normalFlow;
+    if (hasCulvert) s.l_inlet_control[ix] = inletControl;     // 0 for ever on every other link
     if (flags & LF_HAS_LOSSRATE) { s.c_evap_loss[ix] = evapLoss; s.c_seep_loss[ix] = seepLoss; }
 }
 
@@ -466,9 +473,9 @@ SWB_NI void conduit_flow_generic(const Net &n, const State &s, int j, int m, int
 { conduit_flow<-1>(n, s, j, m, steps, dt, T); }
 SWB_FI void conduit_update(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
 {
-    switch (n.xs_type[j]) {
-      case XS_CIRCULAR:    conduit_flow_circular(n, s, j, m, steps, dt, T); break;
-      case XS_RECT_CLOSED: conduit_flow_rect_closed(n, s, j, m, steps, dt, T); break;
+    switch (n.link_kernel[j]) {
+      case LK_CIRCULAR:    conduit_flow_circular(n, s, j, m, steps, dt, T); break;
+      case LK_RECT_CLOSED: conduit_flow_rect_closed(n, s, j, m, steps, dt, T); break;
       default:             conduit_flow_generic(n, s, j, m, steps, dt, T);
     }
 }

@@ -11,12 +11,14 @@
 #include <vector>
 #include "swb_state.h"
 #include "swb_xsect.h"
+#include "swb_hds5_tables.h"
 
 namespace swb {
 
 struct Derived {
-    std::vector<int> link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link, link_order;
-    std::vector<double> link_z1, link_z2, xs_tables;
+    std::vector<int> link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link, link_order,
+                     link_kernel;
+    std::vector<double> link_z1, link_z2, xs_tables, culvert_params, road_tables;
     int nTrue = 0, nNonConduit = 0;
 };
 
@@ -45,14 +47,12 @@ inline std::string validate_desc(const swb_network_desc &d, const swb_options &o
         int a = d.link_node1[j], b = d.link_node2[j];
         if (a < 0 || a >= d.n_nodes || b < 0 || b >= d.n_nodes) return "link end node out of range";
         if (d.link_type[j] == SWB_CONDUIT) {
-            if (d.xs_culvert[j] > 0) return "culvert-coded conduit (culvert.c) not supported yet";
-            if (d.xs_type[j] == XS_FORCE_MAIN) return "FORCE_MAIN conduit (forcmain.c) not supported yet";
+            if (d.xs_culvert[j] > SWB_MAX_CULVERT_CODE) return "culvert code out of range";
             if (d.xs_type[j] == XS_DUMMY &&
                 (d.node_type[a] == SWB_STORAGE || d.node_type[a] == SWB_DIVIDER))
                 return "dummy conduit out of a storage / divider node";
             if (d.cond_barrels[j] < 1) return "conduit with < 1 barrel";
         }
-        if (d.link_type[j] == SWB_WEIR && d.weir_type[j] == 4) return "ROADWAY weir (roadway.c) not supported yet";
         int t = d.xs_table[j];
         if (t >= d.n_shape_tbls) return "xs_table out of range";
     }
@@ -63,7 +63,7 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
 {
     const int nN = d.n_nodes, nL = d.n_links;
     r.link_flags.assign(nL, 0); r.link_z1.assign(nL, 0.0); r.link_z2.assign(nL, 0.0);
-    r.outfall_link.assign(nN, -1);
+    r.outfall_link.assign(nN, -1); r.link_kernel.assign(nL, LK_GENERIC);
     r.nc_links.clear(); r.nTrue = 0;
     for (int j = 0; j < nL; j++) {
         int a = d.link_node1[j], b = d.link_node2[j], f = 0;
@@ -78,6 +78,12 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
         if (open) f |= LF_OPEN_SHAPE;
         if (trueConduit && (d.link_seep_rate[j] > 0.0 || open)) f |= LF_HAS_LOSSRATE;
         r.link_flags[j] = f;
+        // plain circular / closed rectangular pipes run the specialised conduit functions; culvert
+        // inlets (any shape) and force mains need the extra terms only the generic one carries
+        if (trueConduit && d.xs_culvert[j] <= 0) {
+            if (d.xs_type[j] == XS_CIRCULAR) r.link_kernel[j] = LK_CIRCULAR;
+            else if (d.xs_type[j] == XS_RECT_CLOSED) r.link_kernel[j] = LK_RECT_CLOSED;
+        }
         r.link_z1[j] = d.node_invert[a] + d.link_offset1[j];
         r.link_z2[j] = d.node_invert[b] + d.link_offset2[j];
         // link_setOutfallDepth (link.c:743-753) tests node2 first; a later link overrides an
@@ -89,7 +95,10 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
     r.link_order.clear();
     for (int j = 0; j < nL; j++) if (r.link_flags[j] & LF_TRUE_CONDUIT) r.link_order.push_back(j);
     std::stable_sort(r.link_order.begin(), r.link_order.end(),
-                     [&](int a, int b) { return d.xs_type[a] < d.xs_type[b]; });
+                     [&](int a, int b) {
+                         if (r.link_kernel[a] != r.link_kernel[b]) return r.link_kernel[a] < r.link_kernel[b];
+                         return d.xs_type[a] < d.xs_type[b];
+                     });
     // CSR incidence.  adjq: ascending link index.  adj: true conduits first, then the rest.
     std::vector<std::vector<int>> inc(nN);
     for (int j = 0; j < nL; j++) {
@@ -109,6 +118,10 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
     r.adj_start[nN] = (int)r.adj.size();
     static const double tab[] = { SWB_XS_TABLE_DATA };
     r.xs_tables.assign(tab, tab + XT_TOTAL);
+    static const double cul[] = { SWB_CULVERT_PARAM_DATA };
+    r.culvert_params.assign(cul, cul + 5 * (SWB_MAX_CULVERT_CODE + 1));
+    static const double road[] = { SWB_ROAD_TABLE_DATA };
+    r.road_tables.assign(road, road + 2 * RT_TOTAL);
     (void)o;
 }
 

@@ -15,6 +15,7 @@
 #define SWB_REGULATOR_H
 
 #include "swb_dynwave.h"
+#include "swb_hds5_tables.h"
 
 namespace swb {
 
@@ -272,6 +273,63 @@ SWB_HD void weir_flow(const Net &n, const State &s, const RegCtx &r, const Xs &x
     }
     s.l_dqdh[r.ix] = weir_dqdh(n.weir_type[r.j], dir, head, q1, q2);
 }
+// ---- roadway.c:85-200: flow overtopping a roadway (FHWA HDS-5 weir with variable Cd) ------------
+SWB_HD double road_curve(const double *tb, int first, int np, double x)      // getY (roadway.c:180)
+{
+    const double *p = tb + 2 * first;
+    if (x <= p[0]) return p[1];
+    if (x >= p[2 * (np - 1)]) return p[2 * (np - 1) + 1];
+    for (int i = 1; i < np; i++) {
+        if (x <= p[2 * i]) {
+            double x1 = p[2 * i - 2], dx = p[2 * i] - x1;
+            double y1 = p[2 * i - 1], dy = p[2 * i + 1] - y1;
+            return y1 + (x - x1) * dy / dx;
+        }
+    }
+    return p[2 * (np - 1) + 1];
+}
+SWB_HD double road_cd(const double *tb, double hWr, double ht, double roadWidth, int roadSurf)
+{
+    const bool paved = (roadSurf == 1);
+    double kT = 1.0, cR;
+    if (hWr <= 0.0) return 0.0;
+    double hL = hWr / roadWidth;
+    if (hL <= 0.15)
+        cR = paved ? road_curve(tb, RT_CR_LOW_PAVED, RN_CR_LOW_PAVED, hWr)
+                   : road_curve(tb, RT_CR_LOW_GRAVEL, RN_CR_LOW_GRAVEL, hWr);
+    else
+        cR = paved ? road_curve(tb, RT_CR_HIGH_PAVED, RN_CR_HIGH_PAVED, hL)
+                   : road_curve(tb, RT_CR_HIGH_GRAVEL, RN_CR_HIGH_GRAVEL, hL);
+    if (ht > 0.0) {
+        double htH = ht / hWr;
+        kT = paved ? road_curve(tb, RT_KT_PAVED, RN_KT_PAVED, htH)
+                   : road_curve(tb, RT_KT_GRAVEL, RN_KT_GRAVEL, htH);
+    }
+    return cR * kT;
+}
+SWB_NI double roadway_inflow(const Net &n, const State &s, const RegCtx &r, const Xs &x, double dir,
+                             double hRoad, double h1, double h2)
+{
+    const int j = r.j;
+    double roadWidth = n.weir_road_width[j];
+    int roadSurf = n.weir_road_surface[j];
+    double cD = n.weir_cdisch1[j], q = 0.0, dqdh = 0.0;
+    if (n.opt.unit_system == 1) cD = cD / 0.552;
+    bool useVariableCd = (roadWidth > 0.0 && roadSurf >= 1);
+    double hWr = h1 - hRoad, ht = h2 - hRoad;
+    if (hWr > SWB_FUDGE) {
+        if (useVariableCd) cD = road_cd(n.road_tables, hWr, ht, roadWidth, roadSurf);
+        double length = x.wMax;
+        q = cD * length * pow(hWr, 1.5);
+        dqdh = 1.5 * q / hWr;
+    }
+    s.l_dqdh[r.ix] = dqdh;
+    s.l_depth[r.ix] = SWB_MAX(h1 - hRoad, 0.0);
+    int cls = SWB_SUBCRITICAL;
+    if (hRoad > h2) cls = (dir == 1.0) ? SWB_DN_CRITICAL : SWB_UP_CRITICAL;
+    s.l_flow_class[r.ix] = (unsigned char)cls;
+    return dir * q;
+}
 SWB_HD double weir_inflow(const Net &n, const State &s, const RegCtx &r, const double *T)
 {
     const int j = r.j;
@@ -281,6 +339,7 @@ SWB_HD double weir_inflow(const Net &n, const State &s, const RegCtx &r, const d
     if (dir < 0.0) { head = h1; h1 = h2; h2 = head; }
     double hcrest = r.inv1 + n.link_offset1[j];
     double hcrown = hcrest + x.yFull;
+    if (n.weir_type[j] == SWB_ROADWAY_WEIR) return roadway_inflow(n, s, r, x, dir, hcrest, h1, h2);
     double setting = s.l_setting[r.ix];
     hcrest += (1.0 - setting) * x.yFull;
     head = h1 - hcrest;

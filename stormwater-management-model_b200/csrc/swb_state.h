@@ -39,7 +39,8 @@ namespace swb {
     X(double, orif_cdisch, L) X(double, orif_length, L) X(int, weir_type, L) \
     X(int, weir_can_surcharge, L) X(int, weir_cd_curve, L) X(double, weir_cdisch1, L) \
     X(double, weir_cdisch2, L) X(double, weir_end_con, L) X(double, weir_slope, L) \
-    X(double, weir_length, L) X(int, outlet_curve, L) X(int, outlet_curve_type, L) \
+    X(double, weir_length, L) X(double, weir_road_width, L) X(int, weir_road_surface, L) \
+    X(int, outlet_curve, L) X(int, outlet_curve_type, L) \
     X(double, outlet_qcoeff, L) X(double, outlet_qexpon, L) X(int, curve_start, C1) \
     X(int, curve_type, C) X(double, curve_x, CP) X(double, curve_y, CP) X(int, shape_tbl_n, T) \
     X(double, shape_area_tbl, TT) X(double, shape_hrad_tbl, TT) X(double, shape_width_tbl, TT) \
@@ -55,6 +56,8 @@ enum {
     LF_OPEN_SHAPE   = 256,   // xsect_isOpen
     LF_HAS_LOSSRATE = 512    // seepRate > 0 or open shape (evaporation possible)
 };
+
+enum { LK_CIRCULAR = 0, LK_RECT_CLOSED = 1, LK_GENERIC = 2 };
 
 struct Net {
     int nN, nL, nP, nCurves, nShapeTbl, shapeTblLen;
@@ -79,6 +82,9 @@ struct Net {
                                            // instruction-cache footprint instead of several)
     const int    *nc_links;                // non-true-conduit links in ascending index order
     const int    *outfall_link;            // per node: its (single) link, or -1
+    const int    *link_kernel;             // LK_*: which conduit function a true conduit runs
+    const double *culvert_params;          // [58][5] FHWA inlet-control coefficients (culvert.c:33)
+    const double *road_tables;             // RT_TOTAL (x, y) pairs (roadway.c:42-69)
     const double *xs_tables;               // XT_TOTAL doubles (global copy of the shape tables)
 };
 

@@ -493,5 +493,108 @@ def c3b_shapes_inp() -> str:
     return C3B_SHAPES_INP
 
 
+# Config 3c: SURVEY.md §8 row a28 -- culvert inlet control (four FHWA codes incl. a mitered one and a
+# Form-2 box), three force mains under a pump, and three ROADWAY weirs (paved / gravel / fixed Cd)
+# overtopped by the flood peak and later submerged by an outfall stage wave.
+C3C_CULVERTS_INP = """[OPTIONS]
+FLOW_UNITS CFS
+FLOW_ROUTING DYNWAVE
+START_DATE 01/01/2020
+START_TIME 00:00:00
+END_DATE 01/01/2020
+END_TIME 08:00:00
+REPORT_STEP 00:05:00
+ROUTING_STEP 5
+VARIABLE_STEP 0.75
+ALLOW_PONDING NO
+SURCHARGE_METHOD @SUR@
+FORCE_MAIN_EQUATION @FME@
+THREADS 1
+[JUNCTIONS]
+J1 110 12 0 0 0
+J2 108 14 0 0 0
+J3 106 14 0 0 0
+J4 104 16 0 0 0
+F1 115 1 0 100 0
+F2 112 1 0 100 0
+F3 109 1 0 100 0
+[OUTFALLS]
+O1 102 TIMESERIES STG NO
+[STORAGE]
+S1 95 12 1 FUNCTIONAL 0 0 200 0 0
+[CONDUITS]
+CH1 J1 J2 400 0.03 0 0 0 0
+CU1 J2 J3 80 0.013 0 0 0 0
+CU2 J2 J3 80 0.013 0.5 0 0 0
+CU3 J2 J3 80 0.024 0 0 0 0
+CU4 J2 J3 80 0.024 1 0 0 0
+CH2 J3 J4 400 0.03 0 0 0 0
+CH3 J4 O1 400 0.03 0 0 0 0
+FM1 F1 F2 400 @RGH@ 0 0 0 0
+FM2 F2 F3 400 @RGH@ 0 0 0 0
+FM3 F3 J4 400 @RGH@ 0 3 0 0
+[PUMPS]
+P1 S1 F1 PC2 ON 0 0
+[WEIRS]
+RW1 J2 J3 ROADWAY 7 3.0 NO 0 0 NO 40 PAVED
+RW2 J2 J3 ROADWAY 7.5 3.0 NO 0 0 NO 30 GRAVEL
+RW3 J2 J3 ROADWAY 8 2.8
+[XSECTIONS]
+CH1 TRAPEZOIDAL 12 20 2 2 1
+CH2 TRAPEZOIDAL 14 20 2 2 1
+CH3 TRAPEZOIDAL 16 20 2 2 1
+CU1 CIRCULAR 3 0 0 0 2 1
+CU2 RECT_CLOSED 3 4 0 0 1 12
+CU3 CIRCULAR 3 0 0 0 1 5
+CU4 ARCH 3 4.5 0 0 1 37
+FM1 FORCE_MAIN 1 @FMR@ 0 0 1
+FM2 FORCE_MAIN 1 @FMR@ 0 0 1
+FM3 FORCE_MAIN 1.25 @FMR@ 0 0 1
+RW1 RECT_OPEN 5 100 0 0
+RW2 RECT_OPEN 5 60 0 0
+RW3 RECT_OPEN 5 40 0 0
+[CURVES]
+PC2 PUMP2 1 2 2 4 4 8 8 10
+[TIMESERIES]
+QC 0:00 0
+QC 0:30 40
+QC 1:00 150
+QC 1:30 400
+QC 2:00 1400
+QC 2:30 600
+QC 3:00 100
+QC 4:00 20
+QC 5:00 10
+QC 8:00 5
+QS 0:00 0
+QS 0:20 3
+QS 1:00 9
+QS 2:00 6
+QS 3:00 0.2
+QS 4:00 0.05
+QS 5:00 7
+QS 8:00 1
+STG 0:00 102.5
+STG 4:00 103
+STG 5:00 117
+STG 6:00 117.5
+STG 7:00 104
+STG 8:00 103
+[INFLOWS]
+J1 FLOW QC FLOW 1.0 1.0
+S1 FLOW QS FLOW 1.0 1.0
+[REPORT]
+NODES ALL
+LINKS ALL
+"""
+
+
+def c3c_culverts_inp(eqn: str = "H-W") -> str:
+    """eqn "H-W": Hazen-Williams + SLOT; "D-W": Darcy-Weisbach + EXTRAN (forcmain.c:95-118)."""
+    sur, rough = ("SLOT", "120") if eqn == "H-W" else ("EXTRAN", "0.03")
+    return (C3C_CULVERTS_INP.replace("@SUR@", sur).replace("@FME@", eqn)
+            .replace("@RGH@", "0.012").replace("@FMR@", rough))
+
+
 def c5_mega_spec(hours: float = 1.0) -> GridSpec:
     return GridSpec(nx=1000, ny=500, hours=hours, pollutants=False, surcharge="SLOT")

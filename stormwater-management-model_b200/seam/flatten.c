@@ -131,10 +131,10 @@ int swb_flatten_network(swb_flat *f)
         double *len = DARR(nL), *ulen = DARR(nL), *ml = DARR(nL), *rgh = DARR(nL), *slp = DARR(nL), *beta = DARR(nL),
                *qmax = DARR(nL);
         int *pt = IARR(nL), *pc = IARR(nL), *ot = IARR(nL), *wt = IARR(nL), *wcs = IARR(nL),
-            *wcc = IARR(nL), *olc = IARR(nL), *olt = IARR(nL);
+            *wcc = IARR(nL), *olc = IARR(nL), *olt = IARR(nL), *wrs = IARR(nL);
         double *pmin = DARR(nL), *pmax = DARR(nL), *ocd = DARR(nL), *olen = DARR(nL),
                *wc1 = DARR(nL), *wc2 = DARR(nL), *wec = DARR(nL), *wsl = DARR(nL), *wlen = DARR(nL),
-               *olq = DARR(nL), *ole = DARR(nL);
+               *olq = DARR(nL), *ole = DARR(nL), *wrw = DARR(nL);
         int nT = 0;
         double *at = (double *)d->shape_area_tbl, *ht = (double *)d->shape_hrad_tbl,
                *wtb = (double *)d->shape_width_tbl;
@@ -178,8 +178,6 @@ int swb_flatten_network(swb_flat *f)
                 ulen[j] = Conduit[k].length;
                 ml[j] = Conduit[k].modLength; rgh[j] = Conduit[k].roughFactor;
                 slp[j] = Conduit[k].slope; beta[j] = Conduit[k].beta; qmax[j] = Conduit[k].qMax;
-                if (x->culvertCode > 0) rc = SWB_ERR_UNSUPP;          /* culvert.c: phase 2 */
-                if (x->type == FORCE_MAIN) rc = SWB_ERR_UNSUPP;       /* forcmain.c: phase 2 */
                 break;
               case PUMP:
                 pt[j] = Pump[k].type; pc[j] = Pump[k].pumpCurve;
@@ -192,7 +190,7 @@ int swb_flatten_network(swb_flat *f)
                 wt[j] = Weir[k].type; wcs[j] = Weir[k].canSurcharge; wcc[j] = Weir[k].cdCurve;
                 wc1[j] = Weir[k].cDisch1; wc2[j] = Weir[k].cDisch2; wec[j] = Weir[k].endCon;
                 wsl[j] = Weir[k].slope; wlen[j] = Weir[k].length;
-                if (Weir[k].type == ROADWAY_WEIR) rc = SWB_ERR_UNSUPP;  /* roadway.c: phase 2 */
+                wrw[j] = Weir[k].roadWidth; wrs[j] = Weir[k].roadSurface;
                 break;
               case OUTLET:
                 olc[j] = Outlet[k].qCurve; olt[j] = Outlet[k].curveType;
@@ -212,7 +210,8 @@ int swb_flatten_network(swb_flat *f)
         d->pump_xmin = pmin; d->pump_xmax = pmax; d->orif_type = ot; d->orif_cdisch = ocd;
         d->orif_length = olen; d->weir_type = wt; d->weir_can_surcharge = wcs;
         d->weir_cd_curve = wcc; d->weir_cdisch1 = wc1; d->weir_cdisch2 = wc2; d->weir_end_con = wec;
-        d->weir_slope = wsl; d->weir_length = wlen; d->outlet_curve = olc;
+        d->weir_slope = wsl; d->weir_length = wlen; d->weir_road_width = wrw;
+        d->weir_road_surface = wrs; d->outlet_curve = olc;
         d->outlet_curve_type = olt; d->outlet_qcoeff = olq; d->outlet_qexpon = ole;
     }
 

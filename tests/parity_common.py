@@ -79,6 +79,10 @@ def case_inp(name: str) -> str:
         return scenarios.c3_mixed_inp()
     if name == "c3b_shapes":
         return scenarios.c3b_shapes_inp()
+    if name == "c3c_culverts_hw":
+        return scenarios.c3c_culverts_inp("H-W")
+    if name == "c3c_culverts_dw":
+        return scenarios.c3c_culverts_inp("D-W")
     raise KeyError(name)
 
 

@@ -65,9 +65,12 @@ def test_cuda_library_has_no_cpu_path():
 
 def test_unsupported_elements_are_rejected(emul_lib):
     net, _ = pc.load_golden("c1_tree")
-    net.arrays["xs_culvert"][3] = 5
+    net.arrays["xs_culvert"][3] = 99                 # beyond the 57 FHWA codes (culvert.c:33)
     with pytest.raises(solver.SwbError):
         solver.Solver(net, 1, lib_path=emul_lib)
+    net, _ = pc.load_golden("c1_tree")
+    net.arrays["xs_culvert"][3] = 5                  # a valid culvert code is accepted
+    solver.Solver(net, 1, lib_path=emul_lib).close()
 
 
 def test_member_count_rules(emul_lib):

@@ -153,6 +153,17 @@ SWB_FI double conduit_loss_rate(const Net &n, const State &s, int j, int m, cons
 // ---- dwflow.c:297-413 ---------------------------------------------------------------------------
 struct FlowClassOut { int cls; double yC, yN, fasnh; };
 
+// Normal and critical depth through the out-of-line solvers.  The cross section is taken BY VALUE
+// on purpose: only this copy has its address passed to the opaque callees, so the caller's own Xs
+// never escapes, stays in registers, and its compile-time shape keeps folding every geometry
+// switch after the call (with a shared object the compiler had to reload x.type from the stack and
+// re-instantiated all 26 shapes behind every later lookup).
+SWB_FI void flow_class_depths(const Net &n, int j, Xs xc, double q, const double *T, double &yN, double &yC)
+{
+    yN = link_ynorm(n, j, xc, q, T);
+    yC = xs_ycrit_ni(xc, q, T);
+}
+
 SWB_FI FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int flags, double q,
                                          double h1, double h2, double y1, double y2,
                                          double depth1, double depth2, double yMidGuess,
@@ -167,15 +178,13 @@ SWB_FI FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int flags, d
     if (y1 > SWB_FUDGE && y2 > SWB_FUDGE) {
         if (q < 0.0) {
             if (z1 > 0.0) {
-                o.yN = link_ynorm(n, j, x, fabs(q), T);
-                o.yC = xs_ycrit_ni(x, fabs(q), T);
+                flow_class_depths(n, j, x, fabs(q), T, o.yN, o.yC);
                 double ycMin = SWB_MIN(o.yN, o.yC);
                 if (y1 < ycMin) o.cls = SWB_UP_CRITICAL;
             }
         } else {
             if (z2 > 0.0) {
-                o.yN = link_ynorm(n, j, x, fabs(q), T);
-                o.yC = xs_ycrit_ni(x, fabs(q), T);
+                flow_class_depths(n, j, x, fabs(q), T, o.yN, o.yC);
                 double ycMin = SWB_MIN(o.yN, o.yC);
                 double ycMax = SWB_MAX(o.yN, o.yC);
                 if (y2 < ycMin) o.cls = SWB_DN_CRITICAL;
@@ -190,16 +199,14 @@ SWB_FI FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int flags, d
     else if (y2 > SWB_FUDGE) {
         if (h2 < n.link_z1[j]) o.cls = SWB_UP_DRY;
         else if (z1 > 0.0) {
-            o.yN = link_ynorm(n, j, x, fabs(q), T);
-            o.yC = xs_ycrit_ni(x, fabs(q), T);
+            flow_class_depths(n, j, x, fabs(q), T, o.yN, o.yC);
             o.cls = SWB_UP_CRITICAL;
         }
     }
     else {
         if (h1 < n.link_z2[j]) o.cls = SWB_DN_DRY;
         else if (z2 > 0.0) {
-            o.yN = link_ynorm(n, j, x, fabs(q), T);
-            o.yC = xs_ycrit_ni(x, fabs(q), T);
+            flow_class_depths(n, j, x, fabs(q), T, o.yN, o.yC);
             o.cls = SWB_DN_CRITICAL;
         }
     }

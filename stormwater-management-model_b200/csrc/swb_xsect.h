@@ -192,8 +192,12 @@ SWB_HD double circ_y_of_a(double yFull, double aFull, double a, const double *T)
 }
 
 // ---- forward declarations ----------------------------------------------------------------------
-SWB_FI double xs_a_of_y(const Xs &x, double y, const double *T);
-SWB_FI double xs_w_of_y(const Xs &x, double y, const double *T);
+// S >= 0 names the shape at compile time: `switch (S >= 0 ? S : x.type)` is then resolved by the
+// front end itself (relying on the optimiser to fold a struct member proved unreliable: the member
+// was promoted to a constant only after the last CFG simplification, leaving every shape's code
+// inside the specialised conduit functions).  S < 0 (the default) dispatches at run time.
+template <int S = -1> SWB_FI double xs_a_of_y(const Xs &x, double y, const double *T);
+template <int S = -1> SWB_FI double xs_w_of_y(const Xs &x, double y, const double *T);
 SWB_HD double xs_y_of_a(const Xs &x, double a, const double *T);
 // The reference's getRofY / getRofA / getSofA call one another through their default branches
 // (xsect.c:1094,1113,1137,768).  No shape ever goes round the cycle, so it is unrolled here into
@@ -363,11 +367,12 @@ SWB_FI XsTabs xs_tabs(int type)
 }
 
 // ---- A(y)  (xsect.c:857-939) -------------------------------------------------------------------
+template <int S>
 SWB_FI double xs_a_of_y(const Xs &x, double y, const double *T)
 {
     double yNorm = y / x.yFull;
     if (y <= 0.0) return 0.0;
-    switch (x.type) {
+    switch (S >= 0 ? S : x.type) {
       case XS_FORCE_MAIN:
       case XS_CIRCULAR:    return x.aFull * xs_lookup(yNorm, T + XT_A_CIRC, XN_A_CIRC);
       case XS_FILLED_CIRCULAR: {
@@ -408,10 +413,11 @@ SWB_FI double xs_a_of_y(const Xs &x, double y, const double *T)
 }
 
 // ---- W(y)  (xsect.c:943-1027) ------------------------------------------------------------------
+template <int S>
 SWB_FI double xs_w_of_y(const Xs &x, double y, const double *T)
 {
     double yNorm = y / x.yFull;
-    switch (x.type) {
+    switch (S >= 0 ? S : x.type) {
       case XS_FORCE_MAIN:
       case XS_CIRCULAR:    return x.wMax * xs_lookup(yNorm, T + XT_W_CIRC, XN_W_CIRC);
       case XS_FILLED_CIRCULAR:
@@ -450,10 +456,11 @@ SWB_FI double xs_w_of_y(const Xs &x, double y, const double *T)
 }
 
 // ---- R(y)  (xsect.c:1031-1096) -----------------------------------------------------------------
+template <int S = -1>
 SWB_FI double xs_r_of_y_direct(const Xs &x, double y, const double *T)
 {
     double yNorm = y / x.yFull;
-    switch (x.type) {
+    switch (S >= 0 ? S : x.type) {
       case XS_FORCE_MAIN:
       case XS_CIRCULAR:    return x.rFull * xs_lookup(yNorm, T + XT_R_CIRC, XN_R_CIRC);
       case XS_FILLED_CIRCULAR:
@@ -523,10 +530,11 @@ SWB_HD double xs_y_of_a(const Xs &x, double a, const double *T)
 }
 
 // ---- R(a)  (xsect.c:1100-1142) -----------------------------------------------------------------
+template <int S = -1>
 SWB_FI double xs_r_of_a_direct(const Xs &x, double a, const double *T)
 {
     if (a <= 0.0) return 0.0;
-    switch (x.type) {
+    switch (S >= 0 ? S : x.type) {
       case XS_HORIZ_ELLIPSE: case XS_VERT_ELLIPSE: case XS_ARCH: case XS_IRREGULAR:
       case XS_FILLED_CIRCULAR: case XS_CUSTOM: case XS_STREET:
         return xs_r_of_y_direct(x, xs_y_of_a(x, a, T), T);
@@ -601,25 +609,28 @@ SWB_FI bool xs_r_of_a_via_s(int type)
       default: return false;
     }
 }
+template <int S = -1>
 SWB_FI double xs_r_of_a(const Xs &x, double a, const double *T)
 {
     if (a <= 0.0) return 0.0;
-    if (xs_r_of_a_via_s(x.type)) {
-        if (x.type == XS_DUMMY) return 0.0;
+    const int type = (S >= 0 ? S : x.type);
+    if (xs_r_of_a_via_s(type)) {
+        if (type == XS_DUMMY) return 0.0;
         double cathy = xs_s_of_a(x, a, T);
         if (cathy < SWB_TINY || a < SWB_TINY) return 0.0;
         return pow(cathy / a, 3. / 2.);
     }
-    return xs_r_of_a_direct(x, a, T);
+    return xs_r_of_a_direct<S>(x, a, T);
 }
 // shapes whose R(Y) is R(A(Y)) (default branch of xsect.c:1094)
+template <int S = -1>
 SWB_FI double xs_r_of_y(const Xs &x, double y, const double *T)
 {
-    switch (x.type) {
+    switch (S >= 0 ? S : x.type) {
       case XS_DUMMY: case XS_RECT_CLOSED: case XS_RECT_OPEN: case XS_MOD_BASKET: case XS_GOTHIC:
       case XS_CATENARY: case XS_SEMIELLIPTICAL: case XS_SEMICIRCULAR:
-        return xs_r_of_a(x, xs_a_of_y(x, y, T), T);
-      default: return xs_r_of_y_direct(x, y, T);
+        return xs_r_of_a<S>(x, xs_a_of_y<S>(x, y, T), T);
+      default: return xs_r_of_y_direct<S>(x, y, T);
     }
 }
 
@@ -891,11 +902,11 @@ SWB_NI double xs_ycrit_ni(const Xs &x, double q, const double *T) { return xs_yc
 
 // S >= 0: shape known at compile time (inlined, switch folded); S < 0: run-time shape (call)
 template <int S> SWB_FI double xa(const Xs &x, double y, const double *T)
-{ if constexpr (S >= 0) return xs_a_of_y(x, y, T); else return xs_a_of_y_ni(x, y, T); }
+{ if constexpr (S >= 0) return xs_a_of_y<S>(x, y, T); else return xs_a_of_y_ni(x, y, T); }
 template <int S> SWB_FI double xw(const Xs &x, double y, const double *T)
-{ if constexpr (S >= 0) return xs_w_of_y(x, y, T); else return xs_w_of_y_ni(x, y, T); }
+{ if constexpr (S >= 0) return xs_w_of_y<S>(x, y, T); else return xs_w_of_y_ni(x, y, T); }
 template <int S> SWB_FI double xr(const Xs &x, double y, const double *T)
-{ if constexpr (S >= 0) return xs_r_of_y(x, y, T); else return xs_r_of_y_ni(x, y, T); }
+{ if constexpr (S >= 0) return xs_r_of_y<S>(x, y, T); else return xs_r_of_y_ni(x, y, T); }
 
 // known-answer dispatcher used by swb_xsect_eval
 SWB_HD double xs_eval(int fn, const Xs &x, double arg, const double *T)

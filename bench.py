@@ -222,8 +222,11 @@ def run_ours(args):
             },
             "e2e": {"value": e2e_cu / max(e2e_s, 1e-9), "unit": "conduit-updates/s",
                     "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                    "steps": e2e["steps"], "what": "swb_step_host per routing step: pinned host lateral inflows + quality loads -> device, "
-                    "swap / dynwave / quality / Courant search in one launch, depths + flows + next dt + iterations -> host"},
+                    "steps": e2e["steps"], "member_blocks": e2e["blocks"],
+                    "what": "swb_step_host_batch per routing step over member blocks (copies of one block overlap the "
+                    "kernel of another): pinned host lateral inflows + quality loads + dt -> device, swap / dynwave / "
+                    "quality / Courant search in one launch per block, depths + flows + next dt + iterations -> host, "
+                    "next dt fed back by the host"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -248,15 +251,22 @@ def run_ours(args):
 
 
 def measure_e2e(s, case, args, n_true: int) -> dict:
-    """Whole routing steps through swb_step_host: lateral inflows and quality loads come from
-    pinned HOST buffers every step, node depths / link flows / next step / iteration counts go
-    back to pinned host buffers every step; wall clock around the calls."""
+    """Whole routing steps through the host-buffer C-ABI call: lateral inflows, quality loads and
+    the step to take come from pinned HOST buffers every step; node depths / link flows / next
+    step / iteration counts go back to pinned host buffers every step, and the host feeds the
+    returned next step into the following call (the seam's pattern).  The ensemble is held as
+    `--e2e-blocks` member blocks stepped by swb_step_host_batch, so one block's copies overlap
+    another block's routing kernel; wall clock around the calls."""
     net = case.net
     nP = net.n_pollut
     M = s.M
     steps = args.e2e_steps
     if steps <= 0:
-        return {"seconds": 1.0, "cu": 0, "steps": 0, "h2d": 0, "d2h": 0}
+        return {"seconds": 1.0, "cu": 0, "steps": 0, "h2d": 0, "d2h": 0, "blocks": 0}
+    blocks = max(1, min(args.e2e_blocks, M // 32))
+    while M % blocks or (M // blocks) % 32:
+        blocks -= 1
+    nb = M // blocks
     # the step's inputs, as the host engine would hand them over (values: the inflows the device
     # evaluated for its last step; they are re-sent from the host every step)
     lat = s.host_array((M, net.n_nodes))
@@ -269,17 +279,34 @@ def measure_e2e(s, case, args, n_true: int) -> dict:
         load[:] = np.maximum(lat, 0.0)[:, :, None] * conc[None]
     depth = s.host_array((M, net.n_nodes))
     flow = s.host_array((M, net.n_links))
+    dt = s.host_array((M,))
+    dt[:] = [x.next_dt for x in s.stats(0, M)]
     next_dt = s.host_array((M,))
     iters = s.host_array((M,), dtype=np.int32)
-    s.step_host(lat, qual_load=load, node_depth=depth, link_flow=flow, next_dt=next_dt, iters=iters)  # warm
-    cu0 = s.conduit_updates()
+    subs = [s] if blocks == 1 else [s.clone_members(b * nb, nb) for b in range(blocks)]
+    ios = []
+    for b in range(blocks):
+        sl = slice(b * nb, (b + 1) * nb)
+        ios.append(dict(latflow=lat[sl], dt=dt[sl], qual_load=load[sl] if nP else None,
+                        node_depth=depth[sl], link_flow=flow[sl], next_dt=next_dt[sl], iters=iters[sl]))
+
+    def one_step():
+        solver.step_host_batch(subs, ios)
+        dt[:] = next_dt                      # host feedback: the next call takes the returned step
+
+    one_step()                               # warm
+    cu0 = sum(x.conduit_updates() for x in subs)
     t0 = time.perf_counter()
     for _ in range(steps):
-        s.step_host(lat, qual_load=load, node_depth=depth, link_flow=flow, next_dt=next_dt, iters=iters)
+        one_step()
     sec = time.perf_counter() - t0
-    h2d = lat.nbytes + (load.nbytes if load is not None else 0)
+    cu = sum(x.conduit_updates() for x in subs) - cu0
+    h2d = lat.nbytes + dt.nbytes + (load.nbytes if load is not None else 0)
     d2h = depth.nbytes + flow.nbytes + next_dt.nbytes + iters.nbytes
-    return {"seconds": sec, "cu": s.conduit_updates() - cu0, "steps": steps, "h2d": h2d, "d2h": d2h}
+    if blocks > 1:
+        for x in subs:
+            x.close()
+    return {"seconds": sec, "cu": cu, "steps": steps, "h2d": h2d, "d2h": d2h, "blocks": blocks}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -403,6 +430,7 @@ def main():
     ap.add_argument("--spinup", type=float, default=6000.0, help="simulated seconds before timing")
     ap.add_argument("--routing-steps", type=int, default=10, help="routing steps per bench step / launch")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-blocks", type=int, default=4, help="member blocks pipelined by swb_step_host_batch")
     ap.add_argument("--cpu-steps", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

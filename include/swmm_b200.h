@@ -226,6 +226,11 @@ typedef struct swb_step_io {
 void *swb_host_alloc(unsigned long long bytes);
 void  swb_host_free(void *p);
 int   swb_step_host(swb_solver *s, const swb_step_io *io);
+/* One routing step of n solvers that hold disjoint member blocks of one ensemble, as a pipelined
+ * batch: each solver's host->device copies, routing launch and device->host copies are queued on
+ * its own stream, so the copies of one block overlap the routing kernel of another.  Results are
+ * identical to calling swb_step_host(solvers[i], &io[i]) for i = 0..n-1; returns when all are done. */
+int   swb_step_host_batch(swb_solver *const *solvers, const swb_step_io *io, int n);
 
 /*
  * Ensemble driver ("runoff once, route many"): lateral inflows are evaluated on the device from

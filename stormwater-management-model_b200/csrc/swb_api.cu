@@ -63,6 +63,30 @@ struct CudaCtx {
         return scan[0];
     }
     __device__ __forceinline__ void grid_sync() { cg::this_grid().sync(); }
+    // src is R rows x C columns (row-major); writes dst[row(c) * R + r] = src[r * C + c] with
+    // row(c) = c, or for planes > 0 (column c = item * planes + p) row(c) = p * (C / planes) + item.
+    // Grid-wide: CTAs stride over 32 x 32 tiles staged in shared memory, both sides coalesced.
+    double (*tile)[33];
+    __device__ __forceinline__ void transpose(double *dst, const double *src, int R, int C, int planes)
+    {
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const int tilesC = (C + 31) / 32, total = ((R + 31) / 32) * tilesC;
+        const int items = planes > 0 ? C / planes : 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const int r0 = (t / tilesC) * 32, c0 = (t % tilesC) * 32;
+            for (int r = ty; r < 32; r += nw)
+                if (r0 + r < R && c0 + tx < C) tile[r][tx] = src[(size_t)(r0 + r) * C + c0 + tx];
+            __syncthreads();
+            for (int c = ty; c < 32; c += nw) {
+                int cc = c0 + c;
+                if (cc < C && r0 + tx < R) {
+                    if (planes > 0) { int item = cc / planes; cc = (cc - item * planes) * items + item; }
+                    dst[(size_t)cc * R + r0 + tx] = tile[tx][c];
+                }
+            }
+            __syncthreads();
+        }
+    }
     __device__ __forceinline__ unsigned long long now_ns()
     { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
     __device__ __forceinline__ bool block_or(bool b) { return __syncthreads_or(b ? 1 : 0) != 0; }
@@ -91,6 +115,7 @@ swb_route_kernel(const __grid_constant__ Net net, const __grid_constant__ State 
     __shared__ double tab[XT_TOTAL];
     extern __shared__ int s_alive[];          // st.M entries (dynamic: keeps the L1 carve-out large)
     __shared__ int s_scan[1 + SWB_BLOCK / 32];
+    __shared__ double s_tile[32][33];
     for (int i = threadIdx.x; i < XT_TOTAL; i += blockDim.x) tab[i] = net.xs_tables[i];
     __syncthreads();
     CudaCtx ctx;
@@ -98,6 +123,7 @@ swb_route_kernel(const __grid_constant__ Net net, const __grid_constant__ State 
     ctx.warp_size = 32;
     ctx.warp_lane = threadIdx.x & 31;
     ctx.scan = s_scan;
+    ctx.tile = s_tile;
     ctx.tid = blockIdx.x * blockDim.x + threadIdx.x;
     ctx.G = gridDim.x * blockDim.x;
     ctx.lane = threadIdx.x;
@@ -115,41 +141,6 @@ __global__ void swb_xsect_kernel(int fn, Xs x, int n, const double *tables, cons
     if (i < n) out[i] = xs_eval(fn, x, args[i], tab);
 }
 
-// host layout [m][item][p]  ->  device layout [(p * items + item)][m]   (32 x 32 shared-memory tiles)
-__global__ void swb_transpose_in_kernel(double *dst, const double *src, int M, int items, int planes)
-{
-    __shared__ double tile[32][33];
-    const int cols = items * planes;                  // src is M rows x cols
-    int c0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int m = m0 + r, c = c0 + threadIdx.x;
-        if (m < M && c < cols) tile[r][threadIdx.x] = src[(size_t)m * cols + c];
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int c = c0 + r, m = m0 + threadIdx.x;
-        if (m < M && c < cols) {
-            int item = c / planes, p = c - item * planes;
-            dst[((size_t)p * items + item) * M + m] = tile[threadIdx.x][r];
-        }
-    }
-}
-// device layout [item][m] -> host layout [m][item]
-__global__ void swb_transpose_out_kernel(double *dst, const double *src, int M, int items)
-{
-    __shared__ double tile[32][33];
-    int i0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int i = i0 + r, m = m0 + threadIdx.x;
-        if (i < items && m < M) tile[r][threadIdx.x] = src[(size_t)i * M + m];
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int m = m0 + r, i = i0 + threadIdx.x;
-        if (i < items && m < M) dst[(size_t)m * items + i] = tile[threadIdx.x][r];
-    }
-}
-
 namespace swb { namespace backend {
 
 static std::string cuda_err(const char *what, cudaError_t e)
@@ -159,6 +150,16 @@ static std::string cuda_err(const char *what, cudaError_t e)
 
 static int g_device = -1, g_sms = 0, g_blocks_per_sm = 0;
 static cudaEvent_t g_ev0, g_ev1;
+static cudaStream_t g_stream = 0;      // stream every asynchronous operation below is queued on
+
+static void *stream_create()
+{
+    cudaStream_t st = 0;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    return (void *)st;
+}
+static void stream_destroy(void *st) { if (st) cudaStreamDestroy((cudaStream_t)st); }
+static void use_stream(void *st) { g_stream = (cudaStream_t)st; }
 
 static int device_count()
 {
@@ -180,6 +181,10 @@ static bool init(int device, std::string &err)
         if (e != cudaSuccess) { err = cuda_err("cudaGetDeviceProperties", e); return false; }
         if (!p.cooperativeLaunch) { err = "device does not support cooperative launch"; return false; }
         g_sms = p.multiProcessorCount;
+        // static (tables, transpose tile) + dynamic (member list, up to 32 KB) exceeds the 48 KB default
+        e = cudaFuncSetAttribute(swb_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(int) * SWB_MAX_MEMBERS));
+        if (e != cudaSuccess) { err = cuda_err("cudaFuncSetAttribute", e); return false; }
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_blocks_per_sm, swb_route_kernel, SWB_BLOCK,
                                                           sizeof(int) * SWB_MAX_MEMBERS);
         if (e != cudaSuccess || g_blocks_per_sm < 1) { err = cuda_err("occupancy query", e); return false; }
@@ -207,19 +212,8 @@ static void *host_alloc(size_t bytes)
     return p;
 }
 static void host_free(void *p) { if (p) cudaFreeHost(p); }
-static void h2d_async(void *d, const void *s, size_t b) { if (b) cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, 0); }
-static void d2h_async(void *d, const void *s, size_t b) { if (b) cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, 0); }
-static void transpose_in(double *dev, const double *stage, int M, int items, int planes)
-{
-    dim3 grid((items * planes + 31) / 32, (M + 31) / 32), block(32, 8);
-    swb_transpose_in_kernel<<<grid, block>>>(dev, stage, M, items, planes);
-}
-static void transpose_out(double *stage, const double *dev, int M, int items)
-{
-    dim3 grid((items + 31) / 32, (M + 31) / 32), block(32, 8);
-    swb_transpose_out_kernel<<<grid, block>>>(stage, dev, M, items);
-}
-
+static void h2d_async(void *d, const void *s, size_t b) { if (b) cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, g_stream); }
+static void d2h_async(void *d, const void *s, size_t b) { if (b) cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, g_stream); }
 static bool sync(std::string &err)
 {
     cudaError_t e = cudaDeviceSynchronize();
@@ -258,7 +252,8 @@ static int pick_blocks(int M, int maxItems)
     return (int)blocks;
 }
 
-static bool launch(const Net &net, const State &st, const RunArgs &args, int device, float *ms, std::string &err)
+static bool launch(const Net &net, const State &st, const RunArgs &args, int device, float *ms, std::string &err,
+                   bool wait = true)
 {
     if (!init(device, err)) return false;
     int blocks = pick_blocks(st.M, std::max(net.nN, net.nL));
@@ -267,11 +262,19 @@ static bool launch(const Net &net, const State &st, const RunArgs &args, int dev
         return false;
     }
     void *kargs[] = { (void *)&net, (void *)&st, (void *)&args };
-    cudaEventRecord(g_ev0, 0);
     size_t dyn = sizeof(int) * (size_t)((st.M + 31) / 32 * 32);
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)swb_route_kernel, dim3(blocks), dim3(SWB_BLOCK), kargs, dyn, 0);
+    if (!wait) {                          // left in flight on the current stream (swb_step_host_batch)
+        cudaError_t e = cudaLaunchCooperativeKernel((void *)swb_route_kernel, dim3(blocks), dim3(SWB_BLOCK), kargs,
+                                                    dyn, g_stream);
+        if (e != cudaSuccess) { err = cuda_err("cudaLaunchCooperativeKernel", e); return false; }
+        *ms = 0.f;
+        return true;
+    }
+    cudaEventRecord(g_ev0, g_stream);
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)swb_route_kernel, dim3(blocks), dim3(SWB_BLOCK), kargs, dyn,
+                                                g_stream);
     if (e != cudaSuccess) { err = cuda_err("cudaLaunchCooperativeKernel", e); return false; }
-    cudaEventRecord(g_ev1, 0);
+    cudaEventRecord(g_ev1, g_stream);
     e = cudaEventSynchronize(g_ev1);
     if (e != cudaSuccess) { err = cuda_err("swb_route_kernel", e); return false; }
     cudaEventElapsedTime(ms, g_ev0, g_ev1);

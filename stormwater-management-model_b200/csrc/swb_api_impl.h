@@ -13,8 +13,6 @@
 //     bool  sync(std::string &err);         int device_count();
 //     void *host_alloc(size_t);  void host_free(void *);
 //     void  h2d_async(void *dst, const void *src, size_t bytes);  void d2h_async(...);
-//     void  transpose_in(double *dev, const double *stage, int M, int items, int planes);   [m][item][p] -> [(p,item)][m]
-//     void  transpose_out(double *stage, const double *dev, int M, int items);
 //     bool  xsect_eval(int device, int fn, const Xs &x, int n, const double *args, double *out, std::string &err);
 //   } }
 #ifndef SWB_API_IMPL_H
@@ -51,6 +49,7 @@ struct swb_solver {
     std::vector<double> h_dt;
     // swb_step_host staging (device): host-layout landing zones and device-layout images
     double *stg_lat, *stg_loss, *stg_qual, *img_lat, *img_loss, *img_qual, *stg_depth, *stg_flow;
+    void *stream;               // own stream for swb_step_host_batch (created on first use)
 };
 
 template <class T>
@@ -124,7 +123,7 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     if (M > 1 && (M % 32) != 0) return fail(SWB_ERR_ARG, "n_members must be 1 or a multiple of 32");
     if (M > 8192) return fail(SWB_ERR_ARG, "n_members > 8192: split the ensemble over several solvers");
     swb_solver *s = new swb_solver();
-    s->net = nw; s->M = M; s->launches = 0; s->last_ms = 0.f; s->have_inflows = false;
+    s->net = nw; s->M = M; s->launches = 0; s->last_ms = 0.f; s->have_inflows = false; s->stream = nullptr;
     s->stg_lat = s->stg_loss = s->stg_qual = s->img_lat = s->img_loss = s->img_qual = nullptr;
     s->stg_depth = s->stg_flow = nullptr;
     memset(&s->inflows, 0, sizeof(s->inflows));
@@ -170,6 +169,7 @@ void swb_solver_destroy(swb_solver *s)
 {
     if (!s) return;
     for (void *p : s->allocs) backend::free_(p);
+    if (s->stream) backend::stream_destroy(s->stream);
     delete s;
 }
 int swb_solver_members(const swb_solver *s) { return s ? s->M : 0; }
@@ -255,16 +255,17 @@ int swb_qual_init(swb_solver *s, const double *init_concen)
 
 static int run(swb_solver *s, int phases, int n_steps, double t_end, double fixed_step,
                const double *host_lat = nullptr, const double *host_losses = nullptr,
-               const double *host_qual = nullptr)
+               const double *host_qual = nullptr, bool wait = true, const RunArgs *stg = nullptr)
 {
     RunArgs a;
     memset(&a, 0, sizeof(a));
+    if (stg) a = *stg;                       // host-layout staging pointers (swb_step_host)
     a.host_lat = host_lat; a.host_losses = host_losses; a.host_qual = host_qual;
     a.phases = phases; a.n_steps = n_steps; a.t_end = t_end; a.fixed_step = fixed_step;
     a.inflows = s->inflows;
     std::string err;
     float ms = 0.f;
-    if (!backend::launch(s->net->net, s->st, a, s->net->device, &ms, err)) return fail(SWB_ERR_CUDA, err);
+    if (!backend::launch(s->net->net, s->st, a, s->net->device, &ms, err, wait)) return fail(SWB_ERR_CUDA, err);
     s->launches++;
     s->last_ms = ms;
     return SWB_OK;
@@ -313,13 +314,10 @@ int swb_get_routing_step(swb_solver *s, double fixed_step, double *dt_out)
 void *swb_host_alloc(unsigned long long bytes) { return backend::host_alloc((size_t)bytes); }
 void swb_host_free(void *p) { backend::host_free(p); }
 
-int swb_step_host(swb_solver *s, const swb_step_io *io)
+static void ensure_staging(swb_solver *s)
 {
-    if (!s || !io || !io->latflow) return fail(SWB_ERR_ARG, "null argument");
     const Net &n = s->net->net;
     const int M = s->M, nN = n.nN, nL = n.nL, nP = n.nP;
-    const size_t nb = sizeof(double) * (size_t)nN * M, lb = sizeof(double) * (size_t)nL * M;
-    const bool withQual = nP > 0 && !n.opt.ignore_quality;
     if (!s->stg_lat) {
         s->stg_lat = (double *)dev_zero<double>(s->allocs, (size_t)nN * M);
         s->img_lat = (double *)dev_zero<double>(s->allocs, (size_t)nN * M);
@@ -330,17 +328,32 @@ int swb_step_host(swb_solver *s, const swb_step_io *io)
         s->stg_depth = (double *)dev_zero<double>(s->allocs, (size_t)nN * M);
         s->stg_flow = (double *)dev_zero<double>(s->allocs, (size_t)nL * M);
     }
+}
+
+// queues one solver's step on the backend's current stream; wait = false leaves it in flight
+static int step_host_enqueue(swb_solver *s, const swb_step_io *io, bool wait)
+{
+    if (!s || !io || !io->latflow) return fail(SWB_ERR_ARG, "null argument");
+    const Net &n = s->net->net;
+    const int M = s->M, nN = n.nN, nL = n.nL, nP = n.nP;
+    const size_t nb = sizeof(double) * (size_t)nN * M, lb = sizeof(double) * (size_t)nL * M;
+    const bool withQual = nP > 0 && !n.opt.ignore_quality;
+    ensure_staging(s);
+    RunArgs stg;
+    memset(&stg, 0, sizeof(stg));
     backend::h2d_async(s->stg_lat, io->latflow, nb);
-    backend::transpose_in(s->img_lat, s->stg_lat, M, nN, 1);
+    stg.stg_lat = s->stg_lat;
     if (io->node_losses) {
         backend::h2d_async(s->stg_loss, io->node_losses, nb);
-        backend::transpose_in(s->img_loss, s->stg_loss, M, nN, 1);
+        stg.stg_losses = s->stg_loss;
     }
     const bool haveQ = withQual && io->qual_load;
     if (haveQ) {
         backend::h2d_async(s->stg_qual, io->qual_load, nb * nP);
-        backend::transpose_in(s->img_qual, s->stg_qual, M, nN, nP);
+        stg.stg_qual = s->stg_qual;
     }
+    if (io->node_depth) stg.stg_depth = s->stg_depth;
+    if (io->link_flow) stg.stg_flow = s->stg_flow;
     int phases = PH_SWAP | PH_HOSTIN | PH_DYNWAVE | PH_NEXTDT;
     if (withQual) phases |= PH_QSWAP | PH_QUALITY;
     double t_end = 0.0;
@@ -352,17 +365,41 @@ int swb_step_host(swb_solver *s, const swb_step_io *io)
     }
     else { phases |= PH_ADVANCE; t_end = 1.0e300; }
     int rc = run(s, phases, 1, t_end, n.opt.route_step, s->img_lat, io->node_losses ? s->img_loss : nullptr,
-                 haveQ ? s->img_qual : nullptr);
+                 haveQ ? s->img_qual : nullptr, wait, &stg);
     if (rc) return rc;
-    if (io->node_depth) { backend::transpose_out(s->stg_depth, s->st.n_depth, M, nN);
-                          backend::d2h_async(io->node_depth, s->stg_depth, nb); }
-    if (io->link_flow)  { backend::transpose_out(s->stg_flow, s->st.l_flow, M, nL);
-                          backend::d2h_async(io->link_flow, s->stg_flow, lb); }
+    if (io->node_depth) backend::d2h_async(io->node_depth, s->stg_depth, nb);
+    if (io->link_flow)  backend::d2h_async(io->link_flow, s->stg_flow, lb);
     if (io->next_dt) backend::d2h_async(io->next_dt, s->st.var_step, sizeof(double) * M);
     if (io->iters)   backend::d2h_async(io->iters, s->st.iters, sizeof(int) * M);
+    if (!wait) return SWB_OK;
     std::string err;
     if (!backend::sync(err)) return fail(SWB_ERR_CUDA, err);
     return SWB_OK;
+}
+
+int swb_step_host(swb_solver *s, const swb_step_io *io) { return step_host_enqueue(s, io, true); }
+
+int swb_step_host_batch(swb_solver *const *solvers, const swb_step_io *io, int n)
+{
+    if (!solvers || !io || n < 1) return fail(SWB_ERR_ARG, "null argument");
+    std::string err;
+    for (int i = 0; i < n; i++) {
+        if (!solvers[i]) return fail(SWB_ERR_ARG, "null solver in batch");
+        for (int k = 0; k < i; k++)
+            if (solvers[k] == solvers[i]) return fail(SWB_ERR_ARG, "the same solver twice in one batch");
+        if (!solvers[i]->stream) solvers[i]->stream = backend::stream_create();
+        ensure_staging(solvers[i]);
+    }
+    // staging buffers are allocated (and zeroed on the default stream) at a solver's first step
+    if (!backend::sync(err)) return fail(SWB_ERR_CUDA, err);
+    int rc = SWB_OK;
+    for (int i = 0; i < n && rc == SWB_OK; i++) {
+        backend::use_stream(solvers[i]->stream);
+        rc = step_host_enqueue(solvers[i], &io[i], false);
+    }
+    backend::use_stream(nullptr);
+    if (!backend::sync(err)) return fail(SWB_ERR_CUDA, err);
+    return rc;
 }
 
 int swb_set_inflows(swb_solver *s, const swb_inflow_desc *d)

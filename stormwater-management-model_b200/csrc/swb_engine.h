@@ -61,7 +61,13 @@ struct RunArgs {
     double t_end;              // PH_ADVANCE: members stop at this simulated time (s)
     double fixed_step;         // RouteStep for PH_NEXTDT / PH_ADVANCE
     Inflows inflows;
-    const double *host_lat, *host_losses, *host_qual;   // PH_HOSTIN staging, device layout
+    const double *host_lat, *host_losses, *host_qual;   // PH_HOSTIN images, device layout
+    // host-layout landing zones of swb_step_host ([member][item(,p)]): when set, the kernel itself
+    // transposes them into the images above before the first step, and the step's depths / flows
+    // into stg_depth / stg_flow after the last one, so the copy engines are the only other
+    // consumers of the stream (no transpose launches queued behind another block's kernel)
+    const double *stg_lat, *stg_losses, *stg_qual;
+    double *stg_depth, *stg_flow;
 };
 
 // Object loop of one thread: round k covers objects [k*stride, (k+1)*stride) and the thread takes
@@ -197,6 +203,14 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
     const bool withQual = (nP > 0) && !net.opt.ignore_quality;
 
     unsigned long long tmark = (ctx.tid == 0) ? ctx.now_ns() : 0ull;
+
+    if (args.stg_lat || args.stg_losses || args.stg_qual) {
+        // host layout [m][item][p] -> device layout [(p, item)][m]
+        if (args.stg_lat) ctx.transpose(const_cast<double *>(args.host_lat), args.stg_lat, M, nN, 1);
+        if (args.stg_losses) ctx.transpose(const_cast<double *>(args.host_losses), args.stg_losses, M, nN, 1);
+        if (args.stg_qual) ctx.transpose(const_cast<double *>(args.host_qual), args.stg_qual, M, nN * nP, nP);
+        ctx.grid_sync();
+    }
 
     for (int step = 0; step < args.n_steps; step++) {
         // ================= step prologue =======================================================
@@ -510,6 +524,12 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
         }
         if (step + 1 < args.n_steps) ctx.grid_sync();
         SWB_TICK(TP_NEXTDT);
+    }
+    if (args.stg_depth || args.stg_flow) {
+        // device layout [item][m] -> host layout [m][item]
+        ctx.grid_sync();
+        if (args.stg_depth) ctx.transpose(args.stg_depth, st.n_depth, nN, M, 0);
+        if (args.stg_flow) ctx.transpose(args.stg_flow, st.l_flow, nL, M, 0);
     }
 }
 

@@ -61,6 +61,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_host_alloc.restype = C.c_void_p
     lib.swb_host_free.argtypes = [C.c_void_p]
     lib.swb_step_host.argtypes = [C.c_void_p, C.POINTER(abi.StepIO)]
+    lib.swb_step_host_batch.argtypes = [C.POINTER(C.c_void_p), C.POINTER(abi.StepIO), C.c_int]
     lib.swb_xsect_eval.argtypes = [C.c_int, C.c_int, C.c_int, _P_D, C.c_int, _P_D, _P_D]
     return lib
 
@@ -82,11 +83,29 @@ def xsect_eval(fn: str, xs_type: int, params, args, device: int = 0, lib_path: s
     return out
 
 
+def step_host_batch(solvers, ios):
+    """One routing step of several solvers (member blocks of one ensemble) as a pipelined batch
+    (swb_step_host_batch): copies of one block overlap the routing kernel of another.
+    ios: one dict of step_host keyword arguments (incl. "latflow") per solver."""
+    n = len(solvers)
+    arr = (abi.StepIO * n)()
+    keep = []
+    for i, kw in enumerate(ios):
+        io, k = Solver._step_io(**kw)
+        arr[i] = io
+        keep.append(k)
+    handles = (C.c_void_p * n)(*[s._h for s in solvers])
+    rc = solvers[0].lib.swb_step_host_batch(handles, arr, n)
+    if rc:
+        raise SwbError(f"swb error {rc}: {solvers[0].lib.swb_last_error().decode()}")
+
+
 class Solver:
     """M lockstep members of one flat network on one GPU."""
 
     def __init__(self, net: abi.Network, n_members: int = 1, device: int = 0, lib_path: str | None = None):
         self.lib = load_library(lib_path)
+        self._lib_path, self._device = lib_path, device
         self.net = net
         self.M = n_members
         self._desc, self._opt = net.to_c()        # keep alive
@@ -266,8 +285,9 @@ class Solver:
         buf = (C.c_char * nbytes).from_address(ptr)
         return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
-    def step_host(self, latflow, dt=None, node_losses=None, qual_load=None, node_depth=None,
-                  link_flow=None, next_dt=None, iters=None):
+    @staticmethod
+    def _step_io(latflow, dt=None, node_losses=None, qual_load=None, node_depth=None,
+                 link_flow=None, next_dt=None, iters=None):
         io = abi.StepIO()
         keep = []
 
@@ -285,7 +305,22 @@ class Solver:
         io.link_flow = ptr(link_flow, C.c_double)
         io.next_dt = ptr(next_dt, C.c_double)
         io.iters = ptr(iters, C.c_int)
+        return io, keep
+
+    def step_host(self, latflow, **kw):
+        """One routing step with host buffers (swb_step_host); keywords as in swb_step_io."""
+        io, keep = self._step_io(latflow, **kw)
         self._chk(self.lib.swb_step_host(self._h, C.byref(io)))
+
+    def clone_members(self, member0: int, n_members: int) -> "Solver":
+        """A new solver holding members [member0, member0 + n_members) of this one (state fields
+        only; per-member clocks stay with the parent: drive the clone with explicit dt)."""
+        c = Solver(self.net, n_members, device=self._device, lib_path=self._lib_path)
+        for f in self.STATE_FIELDS:
+            if f == "SWB_COND_Q2":
+                continue
+            c.set_field(f, self.get_field(f, member0, n_members))
+        return c
 
     # ---- convenience ---------------------------------------------------------------------------
     STATE_FIELDS = [

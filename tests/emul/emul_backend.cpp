@@ -21,23 +21,14 @@ static void upload(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 static void download(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 static void zero(void *d, size_t b) { std::memset(d, 0, b); }
 static bool sync(std::string &) { return true; }
+static void *stream_create() { return nullptr; }
+static void stream_destroy(void *) {}
+static void use_stream(void *) {}
 static int device_count() { return 1; }
 static void *host_alloc(size_t b) { return std::malloc(b ? b : 8); }
 static void host_free(void *p) { std::free(p); }
 static void h2d_async(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 static void d2h_async(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
-static void transpose_in(double *dev, const double *stage, int M, int items, int planes)
-{
-    for (int m = 0; m < M; m++)
-        for (int i = 0; i < items; i++)
-            for (int p = 0; p < planes; p++)
-                dev[((size_t)p * items + i) * M + m] = stage[((size_t)m * items + i) * planes + p];
-}
-static void transpose_out(double *stage, const double *dev, int M, int items)
-{
-    for (int m = 0; m < M; m++)
-        for (int i = 0; i < items; i++) stage[(size_t)m * items + i] = dev[(size_t)i * M + m];
-}
 static bool xsect_eval(int, int fn, const Xs &x, int n, const double *args, double *out, std::string &)
 {
     static const double tab[] = { SWB_XS_TABLE_DATA };
@@ -62,6 +53,16 @@ struct EmulCtx {
         return n;
     }
     void grid_sync() { bar->arrive_and_wait(); }
+    // same contract as CudaCtx::transpose, elements dealt round-robin to the G host threads
+    void transpose(double *dst, const double *src, int R, int C, int planes)
+    {
+        const int items = planes > 0 ? C / planes : 0;
+        for (size_t e = tid; e < (size_t)R * C; e += G) {
+            int r = (int)(e / C), c = (int)(e % C), cc = c;
+            if (planes > 0) { int item = c / planes; cc = (c - item * planes) * items + item; }
+            dst[(size_t)cc * R + r] = src[e];
+        }
+    }
     unsigned long long now_ns()
     { return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
           std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -86,7 +87,7 @@ struct EmulCtx {
     }
 };
 
-static bool launch(const Net &net, const State &st, const RunArgs &args, int, float *ms, std::string &)
+static bool launch(const Net &net, const State &st, const RunArgs &args, int, float *ms, std::string &, bool = true)
 {
     const int M = st.M;
     int k = 1;

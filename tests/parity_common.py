@@ -227,3 +227,56 @@ def run_golden_case(name: str, lib_path, max_steps: int | None = None, n_members
             "max_rel_flow": worst.get("SWB_LINK_NEW_FLOW", 0.0),
             "max_rel_qual": max(worst.get("SWB_NODE_NEW_QUAL", 0.0), worst.get("SWB_LINK_NEW_QUAL", 0.0)),
             "max_rel": max(worst.values()) if worst else 0.0, "snapshots": len([x for x in snap_steps if x <= n_run])}
+
+
+def batch_step_equals_sequential(lib_path, case="c2_grid12_slot", M=64, blocks=2, warm=25, steps=12):
+    """swb_step_host_batch on member blocks cloned from one ensemble gives, block for block, what
+    swb_step_host gives on the whole ensemble (host-chosen dt fed back every step)."""
+    from swmm_b200 import solver
+    net, g = load_golden(case)
+    nP = net.n_pollut
+    a = solver.Solver(net, M, lib_path=lib_path)
+    a.load_state({k[3:]: g[k] for k in g if k.startswith("s0_")})
+    a.set_inflows(node=g["inf_node"], ts_start=g["inf_ts_start"], ts_t=g["inf_ts_t"],
+                  ts_q=g["inf_ts_q"], sfactor=g["inf_sfactor"], baseline=g["inf_baseline"],
+                  concen=g["inf_concen"] if nP else None, member_scale=np.linspace(0.4, 1.6, M),
+                  start_day=float(g["inf_start"][0]), start_secs=float(g["inf_start"][1]))
+    a.run_steps(warm, 1e9)
+    nb = M // blocks
+    subs = [a.clone_members(b * nb, nb) for b in range(blocks)]
+    lat = a.host_array((M, net.n_nodes))
+    lat[:] = a.get_field("SWB_NODE_NEW_LATFLOW")
+    conc = np.zeros((net.n_nodes, nP))
+    conc[g["inf_node"]] = g["inf_concen"].reshape(-1, nP)
+    load = a.host_array((M, net.n_nodes, max(nP, 1)))
+    load[:] = 0.0
+    if nP:
+        load[:] = np.maximum(lat, 0.0)[:, :, None] * conc[None]
+    dt = a.host_array((M,))
+    dt[:] = [x.next_dt for x in a.stats()]
+    out = {}
+    for tag in ("a", "b"):
+        out[tag] = dict(depth=a.host_array((M, net.n_nodes)), flow=a.host_array((M, net.n_links)),
+                        next_dt=a.host_array((M,)), iters=a.host_array((M,), dtype=np.int32))
+    for step in range(steps):
+        oa, ob = out["a"], out["b"]
+        a.step_host(lat, dt=dt, qual_load=load if nP else None, node_depth=oa["depth"],
+                    link_flow=oa["flow"], next_dt=oa["next_dt"], iters=oa["iters"])
+        ios = []
+        for b in range(blocks):
+            sl = slice(b * nb, (b + 1) * nb)
+            ios.append(dict(latflow=lat[sl], dt=dt[sl], qual_load=load[sl] if nP else None,
+                            node_depth=ob["depth"][sl], link_flow=ob["flow"][sl],
+                            next_dt=ob["next_dt"][sl], iters=ob["iters"][sl]))
+        solver.step_host_batch(subs, ios)
+        for k in oa:
+            assert np.array_equal(oa[k], ob[k]), (step, k)
+        dt[:] = oa["next_dt"]
+    assert len(set(out["a"]["iters"].tolist())) >= 1
+    for b in range(blocks):
+        sl = slice(b * nb, (b + 1) * nb)
+        assert np.array_equal(subs[b].get_field("SWB_NODE_NEW_QUAL"),
+                              a.get_field("SWB_NODE_NEW_QUAL", b * nb, nb))
+    for s in subs:
+        s.close()
+    a.close()

@@ -162,3 +162,7 @@ def test_ragged_ensemble_members_equal_single_runs(emul_lib):
     scales = np.linspace(0.2, 3.0, 32)
     iters = _ensemble_vs_single(emul_lib, "c2_grid12_extran", 32, 700, scales, [0, 13, 31])
     assert max(iters) > min(iters)
+
+
+def test_step_host_batch_equals_sequential(emul_lib):
+    pc.batch_step_equals_sequential(emul_lib)

@@ -73,3 +73,8 @@ def test_cuda_ragged_ensemble_members_equal_single_runs(cuda_lib):
     scales = np.linspace(0.2, 3.0, 64)
     iters = _ensemble_vs_single(None, "c2_grid12_extran", 64, 900, scales, [0, 21, 40, 63])
     print("iterations per member: min", min(iters), "max", max(iters))
+
+
+def test_cuda_step_host_batch_equals_sequential(cuda_lib):
+    """Pipelined member blocks on their own streams give the same bits as one whole-ensemble step."""
+    pc.batch_step_equals_sequential(cuda_lib, M=128, blocks=4)

@@ -37,6 +37,17 @@ struct CudaCtx {
         if (warp_lane == 0) t = atomicAdd(p, 1ull);
         return __shfl_sync(0xffffffffu, t, 0);
     }
+    // the same ticket in two halves: the atomic is issued now, its value is broadcast later
+    __device__ __forceinline__ unsigned long long ticket_issue(unsigned long long *p)
+    {
+        unsigned long long t = 0;
+        if (warp_lane == 0) t = atomicAdd(p, 1ull);
+        return t;
+    }
+    __device__ __forceinline__ unsigned long long ticket_take(unsigned long long pending)
+    { return __shfl_sync(0xffffffffu, pending, 0); }
+    __device__ __forceinline__ void prefetch(const void *p)
+    { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
     int *alive_list;            // shared memory, SWB_MAX_MEMBERS entries
     int *scan;                  // shared memory, 1 + warps entries
     // Ordered stream compaction of the members for which alive(m) holds; every CTA computes the

@@ -472,9 +472,14 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
 
 // Real (non-inlined) entry points: one compact function per specialised shape plus the generic one.
 // A warp holds one link, so the dispatch in conduit_update is warp-uniform.
-SWB_NI void conduit_flow_circular(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
+#ifdef SWB_CONDUIT_INLINE
+#define SWB_CF SWB_FI
+#else
+#define SWB_CF SWB_NI
+#endif
+SWB_CF void conduit_flow_circular(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
 { conduit_flow<XS_CIRCULAR>(n, s, j, m, steps, dt, T); }
-SWB_NI void conduit_flow_rect_closed(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
+SWB_CF void conduit_flow_rect_closed(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
 { conduit_flow<XS_RECT_CLOSED>(n, s, j, m, steps, dt, T); }
 SWB_NI void conduit_flow_generic(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
 { conduit_flow<-1>(n, s, j, m, steps, dt, T); }

@@ -147,34 +147,104 @@ SWB_FI bool picard_node(const Net &net, const State &st, int i, int m, int k, do
 // Dynamic tile loop: tile t = (object t / nChunks, chunk t % nChunks of the member list); a warp
 // draws tickets until the phase is exhausted.  ctx.warp_size is 32 on the device, 1 in the host
 // emulation.
-template <class Ctx, class Body>
-SWB_ENGINE inline void for_tiles(Ctx &ctx, int nItems, int nAlive, unsigned long long *ticket, Body body)
+// first-touch lines of the next tile (see for_tiles): what conduit_flow / picard_node load up front
+template <class Ctx>
+SWB_ENGINE inline void prefetch_link(Ctx &ctx, const Net &net, const State &st, int j, int m)
+{
+    const int M = st.M;
+    const size_t ix = SWB_IX(j, m, M);
+    ctx.prefetch(&st.c_q1[ix]);
+    ctx.prefetch(&st.c_a2[ix]);
+    ctx.prefetch(&st.l_old_flow[ix]);
+    ctx.prefetch(&st.l_setting[ix]);
+    ctx.prefetch(&st.n_depth[SWB_IX(net.link_node1[j], m, M)]);
+    ctx.prefetch(&st.n_depth[SWB_IX(net.link_node2[j], m, M)]);
+}
+template <class Ctx>
+SWB_ENGINE inline void prefetch_node(Ctx &ctx, const Net &net, const State &st, int i, int m)
+{
+    const int M = st.M;
+    const size_t ix = SWB_IX(i, m, M);
+    ctx.prefetch(&st.n_depth[ix]);
+    ctx.prefetch(&st.n_old_depth[ix]);
+    ctx.prefetch(&st.n_latflow[ix]);
+    ctx.prefetch(&st.n_old_net_inflow[ix]);
+    ctx.prefetch(&st.n_old_volume[ix]);
+    if (net.nNonConduit > 0) return;                 // sums were stored by picard_node_presum
+    for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++) {
+        const int j = net.adj[e] >> 1;
+        const size_t jx = SWB_IX(j, m, M);
+        ctx.prefetch(&st.l_flow[jx]);
+        ctx.prefetch(&st.l_dqdh[jx]);
+        ctx.prefetch((net.adj[e] & 1) ? &st.l_surf_area2[jx] : &st.l_surf_area1[jx]);
+    }
+}
+
+struct NoPrefetch { SWB_ENGINE void operator()(int, int) const {} };
+
+// Tickets run two tiles ahead of the work: while a warp computes tile t it already knows tile t+1
+// (whose first cache lines it has asked for through `pre`) and has the atomic for tile t+2 in
+// flight, so neither the ~1 us round trip of the ticket counter nor the first DRAM round trip of a
+// tile sits on the warp's critical path.
+#ifndef SWB_TICKETS_AHEAD
+#define SWB_TICKETS_AHEAD 0
+#endif
+#ifndef SWB_PREFETCH
+#define SWB_PREFETCH 0
+#endif
+template <class Ctx, class Body, class Pre = NoPrefetch>
+SWB_ENGINE inline void for_tiles(Ctx &ctx, int nItems, int nAlive, unsigned long long *ticket, Body body,
+                                 Pre pre = Pre())
 {
     const int W = ctx.warp_size;
-    if (nAlive >= W) {
-        // wide ensembles: a tile is one object x W consecutive list entries
-        const int nChunks = (nAlive + W - 1) / W;
-        const long long total = (long long)nItems * nChunks;
-        for (;;) {
-            long long t = (long long)ctx.next_ticket(ticket);
-            if (t >= total) break;
+    const bool wide = (nAlive >= W);
+    // wide ensembles: a tile is one object x W consecutive list entries.  Few members (a single
+    // model has one): a tile is W / nAlive objects x all list entries, so a lone network still
+    // fills every lane with a different object.
+    const int nChunks = wide ? (nAlive + W - 1) / W : 1;
+    const int perTile = wide ? 1 : W / nAlive;
+    const long long total = wide ? (long long)nItems * nChunks : ((long long)nItems + perTile - 1) / perTile;
+    const int sub = wide ? 0 : ctx.warp_lane / nAlive;
+    const int lslot = wide ? ctx.warp_lane : ctx.warp_lane - sub * nAlive;
+    auto run = [&](long long t, auto &&fn) {
+        if (wide) {
             int item = (int)(t / nChunks);
-            int slot = (int)(t - (long long)item * nChunks) * W + ctx.warp_lane;
-            if (slot < nAlive) body(item, ctx.alive_list[slot]);
-        }
-    } else {
-        // few members (a single model has one): a tile is W / nAlive objects x all list entries,
-        // so a lone network still fills every lane with a different object
-        const int perTile = W / nAlive;
-        const long long total = ((long long)nItems + perTile - 1) / perTile;
-        const int sub = ctx.warp_lane / nAlive, slot = ctx.warp_lane - sub * nAlive;
-        for (;;) {
-            long long t = (long long)ctx.next_ticket(ticket);
-            if (t >= total) break;
+            int slot = (int)(t - (long long)item * nChunks) * W + lslot;
+            if (slot < nAlive) fn(item, ctx.alive_list[slot]);
+        } else {
             long long item = t * perTile + sub;
-            if (sub < perTile && item < nItems) body((int)item, ctx.alive_list[slot]);
+            if (sub < perTile && item < nItems) fn((int)item, ctx.alive_list[lslot]);
         }
+    };
+#if SWB_TICKETS_AHEAD == 0
+    for (;;) {
+        long long t = (long long)ctx.next_ticket(ticket);
+        if (t >= total) break;
+        run(t, body);
     }
+#elif SWB_TICKETS_AHEAD == 1
+    long long t = (long long)ctx.next_ticket(ticket);
+    while (t < total) {
+        long long tn = (long long)ctx.next_ticket(ticket);
+#if SWB_PREFETCH
+        if (tn < total) run(tn, pre);
+#endif
+        run(t, body);
+        t = tn;
+    }
+#else
+    long long t = (long long)ctx.next_ticket(ticket);
+    long long tn = (t < total) ? (long long)ctx.next_ticket(ticket) : total;
+    while (t < total) {
+        unsigned long long pending = (tn < total) ? ctx.ticket_issue(ticket) : 0ull;
+#if SWB_PREFETCH
+        if (tn < total) run(tn, pre);
+#endif
+        run(t, body);
+        t = tn;
+        tn = (tn < total) ? (long long)ctx.ticket_take(pending) : total;
+    }
+#endif
 }
 
 template <class Ctx>
@@ -373,7 +443,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 // ---- findLinkFlows, pass (i): true conduits (dynwave.c:387-395)
                 for_tiles(ctx, net.nTrue, nAlive, tickets + 0, [&](int jj, int mm) {
                     picard_link(net, st, net.link_order[jj], mm, k, st.dt[mm], T);
-                });
+                }, [&](int jj, int mm) { prefetch_link(ctx, net, st, net.link_order[jj], mm); });
                 ctx.grid_sync();
                 SWB_TICK(TP_LINKS);
                 // ---- networks with regulators / dummy links: ordered pass (A.4)
@@ -390,7 +460,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 // ---- findNodeDepths (dynwave.c:593-632)
                 for_tiles(ctx, nN, nAlive, tickets + 2, [&](int i, int mm) {
                     if (!picard_node(net, st, i, mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
-                });
+                }, [&](int i, int mm) { prefetch_node(ctx, net, st, i, mm); });
                 ctx.grid_sync();
                 SWB_TICK(TP_NODES);
                 // ---- loop control: Steps++ ; if (Steps > 1 && converged) break (:248-251).

@@ -54,7 +54,7 @@ SWB_FI bool xs_is_open(int type) { return xs_amax_ratio(type) >= 1.0; }
 
 // ---- table primitives -----------------------------------------------------------------------
 // xsect.c:1474-1507
-SWB_FI double xs_lookup(double x, const double *tb, int n)
+SWB_FI double xs_lookup_body(double x, const double *tb, int n)
 {
     double delta = 1.0 / ((double)n - 1);
     int i = (int)(x / delta);
@@ -69,6 +69,18 @@ SWB_FI double xs_lookup(double x, const double *tb, int n)
     }
     if (y < 0.0) y = 0.0;
     return y;
+}
+
+#ifdef SWB_LOOKUP_NI
+// one shared copy of the 51-entry lookup (all circular tables) instead of one per call site
+template <int N> SWB_NI double xs_lookup_fixed(double x, const double *tb) { return xs_lookup_body(x, tb, N); }
+#endif
+SWB_FI double xs_lookup(double x, const double *tb, int n)
+{
+#ifdef SWB_LOOKUP_NI
+    if (n == 51) return xs_lookup_fixed<51>(x, tb);
+#endif
+    return xs_lookup_body(x, tb, n);
 }
 
 // xsect.c:1571-1608

@@ -44,6 +44,9 @@ struct EmulCtx {
     std::vector<int> own_list;
     int warp_size = 1, warp_lane = 0;
     unsigned long long next_ticket(unsigned long long *p) { return __atomic_fetch_add(p, 1ull, __ATOMIC_RELAXED); }
+    unsigned long long ticket_issue(unsigned long long *p) { return next_ticket(p); }
+    unsigned long long ticket_take(unsigned long long pending) { return pending; }
+    void prefetch(const void *) {}
     template <class Pred> int compact_members(int M, Pred alive)
     {
         own_list.resize(M);

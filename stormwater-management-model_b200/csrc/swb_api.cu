@@ -78,6 +78,14 @@ struct CudaCtx {
     // row(c) = c, or for planes > 0 (column c = item * planes + p) row(c) = p * (C / planes) + item.
     // Grid-wide: CTAs stride over 32 x 32 tiles staged in shared memory, both sides coalesced.
     double (*tile)[33];
+    double *Tw;
+    // geometry tables -> shared memory (after the input transposes, which borrow the same bytes)
+    __device__ __forceinline__ void load_tables(const double *src)
+    {
+        __syncthreads();
+        for (int i = threadIdx.x; i < XT_TOTAL; i += blockDim.x) Tw[i] = src[i];
+        __syncthreads();
+    }
     __device__ __forceinline__ void transpose(double *dst, const double *src, int R, int C, int planes)
     {
         const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -126,15 +134,14 @@ swb_route_kernel(const __grid_constant__ Net net, const __grid_constant__ State 
     __shared__ double tab[XT_TOTAL];
     extern __shared__ int s_alive[];          // st.M entries (dynamic: keeps the L1 carve-out large)
     __shared__ int s_scan[1 + SWB_BLOCK / 32];
-    __shared__ double s_tile[32][33];
-    for (int i = threadIdx.x; i < XT_TOTAL; i += blockDim.x) tab[i] = net.xs_tables[i];
-    __syncthreads();
+    static_assert(XT_TOTAL >= 32 * 33, "the transpose tile aliases the geometry tables");
     CudaCtx ctx;
     ctx.alive_list = s_alive;
     ctx.warp_size = 32;
     ctx.warp_lane = threadIdx.x & 31;
     ctx.scan = s_scan;
-    ctx.tile = s_tile;
+    ctx.tile = (double (*)[33])tab;      // used only before load_tables() and after the last step
+    ctx.Tw = tab;
     ctx.tid = blockIdx.x * blockDim.x + threadIdx.x;
     ctx.G = gridDim.x * blockDim.x;
     ctx.lane = threadIdx.x;

@@ -281,6 +281,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
         if (args.stg_qual) ctx.transpose(const_cast<double *>(args.host_qual), args.stg_qual, M, nN * nP, nP);
         ctx.grid_sync();
     }
+    ctx.load_tables(net.xs_tables);
 
     for (int step = 0; step < args.n_steps; step++) {
         // ================= step prologue =======================================================

@@ -56,6 +56,7 @@ struct EmulCtx {
         return n;
     }
     void grid_sync() { bar->arrive_and_wait(); }
+    void load_tables(const double *) {}
     // same contract as CudaCtx::transpose, elements dealt round-robin to the G host threads
     void transpose(double *dst, const double *src, int R, int C, int planes)
     {

@@ -272,6 +272,42 @@ int  swb_get_massbal(swb_solver *s, int member0, int n_members, double *reacted,
 /* conduit-updates performed so far: sum over members of iterations x true conduits */
 long long swb_conduit_updates(swb_solver *s);
 
+/* ---- one network partitioned over several GPUs (BASELINE.json configs[4]) --------------
+ * The reference has no counterpart (one address space, dynwave.c:224-262 loops over all links and
+ * nodes).  Here every rank holds the nodes it owns, the far-end ("ghost") nodes of the conduits that
+ * cross its border, and every link with at least one owned end; a cut conduit is therefore computed
+ * on both sides (dwflow.c:57-293 is a pure function of the two end depths and the conduit's own
+ * state).  After every node update of a Picard trial the kernel itself stores the new depth and
+ * converged flag of its border nodes into the peers' receive windows (peer memory over NVLink, no
+ * host round trip, no NCCL on the data path), followed by a flag; the same exchange carries the OR of
+ * the convergence test (dynwave.c:248-251) and, once per step, the MIN of the Courant search
+ * (dynwave.c:799-921) and the border concentrations for qualrout.c:253-353.  Only true conduits may
+ * be cut (the ordered regulator pass, SURVEY A.4, stays on one rank).  n_members must be 1.
+ * Local numbering: nodes [0, n_owned_nodes) are owned, the rest are ghosts; links keep the relative
+ * order of the unpartitioned network so every node sum is formed in the reference's order (A.3). */
+typedef struct swb_partition_desc {
+    int rank, n_ranks;         /* n_ranks <= 8                                                  */
+    int n_owned_nodes;
+    int n_send;                /* border values this rank publishes after every node update     */
+    const int *send_node;      /* local (owned) node                                            */
+    const int *send_rank;      /* rank that holds it as a ghost                                 */
+    const int *send_slot;      /* slot in that rank's receive window                            */
+    int n_recv;
+    const int *recv_node;      /* local ghost node filled from receive slot r                   */
+    const int *link_owned;     /* per local link: 0 = copy of a cut conduit another rank reports */
+    double timeout_s;          /* a peer that does not answer within this time fails the launch
+                                  with SWB_ERR_CUDA instead of hanging the device (0 -> 30 s)     */
+} swb_partition_desc;
+#define SWB_MAX_RANKS 8
+#define SWB_WINDOW_HANDLE_BYTES 64
+/* allocates this rank's receive window; then exchange handles (any transport: torch.distributed,
+ * MPI, a file) and connect every peer before the first step */
+int  swb_partition_attach(swb_solver *s, const swb_partition_desc *p);
+int  swb_partition_export(swb_solver *s, void *handle /* SWB_WINDOW_HANDLE_BYTES */);
+int  swb_partition_connect(swb_solver *s, int peer_rank, const void *handle);
+/* halo exchanges completed so far (each is one barrier over all ranks) */
+long long swb_partition_exchanges(swb_solver *s);
+
 /* Known-answer hook for the geometry library (K1b): evaluates one xsect function on the device for
  * n arguments.  fn: 0 AofY 1 WofY 2 RofY 3 YofA 4 RofA 5 SofA 6 AofS 7 dSdA 8 Ycrit (xsect.c:714-1319);
  * params = {yFull,wMax,ywMax,aFull,rFull,sFull,sMax,yBot,aBot,sBot,rBot} (objects.h:581-599). */

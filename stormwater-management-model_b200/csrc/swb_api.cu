@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstring>
 #include <string>
 #include "swb_state.h"
 #include "swb_engine.h"
@@ -106,6 +107,14 @@ struct CudaCtx {
             __syncthreads();
         }
     }
+    // ---- partitioned network: system-scope accesses to windows that peers write over NVLink
+    __device__ __forceinline__ void fence_system() { __threadfence_system(); }
+    __device__ __forceinline__ void store_release_sys(unsigned long long *p, unsigned long long v)
+    { asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+    __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned long long *p)
+    { unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+    __device__ __forceinline__ double load_sys_f64(const double *p)
+    { double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
     __device__ __forceinline__ unsigned long long now_ns()
     { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
     __device__ __forceinline__ bool block_or(bool b) { return __syncthreads_or(b ? 1 : 0) != 0; }
@@ -222,6 +231,35 @@ static void free_(void *p) { cudaFree(p); }
 static void upload(void *d, const void *s, size_t b) { if (b) cudaMemcpy(d, s, b, cudaMemcpyHostToDevice); }
 static void download(void *d, const void *s, size_t b) { if (b) cudaMemcpy(d, s, b, cudaMemcpyDeviceToHost); }
 static void zero(void *d, size_t b) { if (b) cudaMemset(d, 0, b); }
+
+// receive window of a partitioned solver: plain device memory, exported to the peer processes as a
+// CUDA IPC handle and mapped by them with peer access over NVLink
+static_assert(sizeof(cudaIpcMemHandle_t) <= SWB_WINDOW_HANDLE_BYTES, "handle size");
+static void *window_alloc(size_t bytes, void *handle, std::string &err)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { err = cuda_err("cudaMalloc(window)", e); return nullptr; }
+    cudaMemset(p, 0, bytes);
+    cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { err = cuda_err("cudaIpcGetMemHandle", e); cudaFree(p); return nullptr; }
+    memset(handle, 0, SWB_WINDOW_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof(h));
+    return p;
+}
+static void *window_open(const void *handle, size_t, std::string &err)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { err = cuda_err("cudaIpcOpenMemHandle", e); return nullptr; }
+    return p;
+}
+static void window_close(void *p) { if (p) cudaIpcCloseMemHandle(p); }
+static void window_free(void *p, size_t, const void *) { if (p) cudaFree(p); }
 
 static void *host_alloc(size_t bytes)
 {

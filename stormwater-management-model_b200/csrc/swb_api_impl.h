@@ -50,7 +50,21 @@ struct swb_solver {
     // swb_step_host staging (device): host-layout landing zones and device-layout images
     double *stg_lat, *stg_loss, *stg_qual, *img_lat, *img_loss, *img_qual, *stg_depth, *stg_flow;
     void *stream;               // own stream for swb_step_host_batch (created on first use)
+    // partitioned network: own receive window, the peers' mapped windows
+    void *window; size_t window_bytes;
+    unsigned char window_handle[SWB_WINDOW_HANDLE_BYTES];
+    void *peer_window[SWB_MAX_RANKS];
 };
+
+static size_t window_size(int nRecv, int W)
+{ return sizeof(unsigned long long) * (HALO_CTRL_WORDS + 2 * SWB_MAX_RANKS * HALO_RED)
+         + sizeof(double) * 2 * (size_t)(nRecv > 0 ? nRecv : 1) * W; }
+static void window_views(void *base, unsigned long long *&ctrl, unsigned long long *&red, double *&stage)
+{
+    ctrl = (unsigned long long *)base;
+    red = ctrl + HALO_CTRL_WORDS;
+    stage = (double *)(red + 2 * SWB_MAX_RANKS * HALO_RED);
+}
 
 template <class T>
 static T *dev_copy(std::vector<void *> &allocs, const T *src, size_t n)
@@ -126,6 +140,8 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     s->net = nw; s->M = M; s->launches = 0; s->last_ms = 0.f; s->have_inflows = false; s->stream = nullptr;
     s->stg_lat = s->stg_loss = s->stg_qual = s->img_lat = s->img_loss = s->img_qual = nullptr;
     s->stg_depth = s->stg_flow = nullptr;
+    s->window = nullptr; s->window_bytes = 0;
+    memset(s->peer_window, 0, sizeof(s->peer_window));
     memset(&s->inflows, 0, sizeof(s->inflows));
     State &st = s->st;
     memset(&st, 0, sizeof(st));
@@ -170,6 +186,8 @@ void swb_solver_destroy(swb_solver *s)
     if (!s) return;
     for (void *p : s->allocs) backend::free_(p);
     if (s->stream) backend::stream_destroy(s->stream);
+    for (int p = 0; p < SWB_MAX_RANKS; p++) if (s->peer_window[p]) backend::window_close(s->peer_window[p]);
+    if (s->window) backend::window_free(s->window, s->window_bytes, s->window_handle);
     delete s;
 }
 int swb_solver_members(const swb_solver *s) { return s ? s->M : 0; }
@@ -265,9 +283,20 @@ static int run(swb_solver *s, int phases, int n_steps, double t_end, double fixe
     a.inflows = s->inflows;
     std::string err;
     float ms = 0.f;
+    if (s->st.halo.nRanks > 1) {
+        for (int p = 0; p < s->st.halo.nRanks; p++)
+            if (p != s->st.halo.rank && !s->peer_window[p])
+                return fail(SWB_ERR_ARG, "partitioned solver: swb_partition_connect has not been called for every peer");
+        if (!wait || (phases & PH_HOSTIN)) return fail(SWB_ERR_UNSUPP, "partitioned solver: use swb_run_steps");
+    }
     if (!backend::launch(s->net->net, s->st, a, s->net->device, &ms, err, wait)) return fail(SWB_ERR_CUDA, err);
     s->launches++;
     s->last_ms = ms;
+    if (s->st.halo.nRanks > 1) {
+        unsigned long long flag = 0;
+        backend::download(&flag, s->st.halo.ctrl + HALO_ERR, sizeof(flag));
+        if (flag) return fail(SWB_ERR_CUDA, "halo exchange timed out: a peer rank did not answer");
+    }
     return SWB_OK;
 }
 
@@ -437,6 +466,79 @@ int swb_run_steps(swb_solver *s, int n_steps, double t_end)
     int phases = PH_ADVANCE | PH_SWAP | PH_INFLOWS | PH_DYNWAVE | PH_NEXTDT;
     if (n.nP > 0 && !n.opt.ignore_quality) phases |= PH_QSWAP | PH_QUALITY;
     return run(s, phases, n_steps, t_end, n.opt.route_step);
+}
+
+int swb_partition_attach(swb_solver *s, const swb_partition_desc *p)
+{
+    if (!s || !p) return fail(SWB_ERR_ARG, "null argument");
+    if (s->M != 1) return fail(SWB_ERR_ARG, "a partitioned solver holds one member");
+    if (s->window) return fail(SWB_ERR_ARG, "partition already attached");
+    const Net &n = s->net->net;
+    if (p->n_ranks < 1 || p->n_ranks > SWB_MAX_RANKS || p->rank < 0 || p->rank >= p->n_ranks)
+        return fail(SWB_ERR_ARG, "bad rank / n_ranks");
+    if (p->n_owned_nodes < 0 || p->n_owned_nodes > n.nN || p->n_send < 0 || p->n_recv < 0 ||
+        p->n_owned_nodes + p->n_recv != n.nN || !p->link_owned)
+        return fail(SWB_ERR_ARG, "inconsistent partition descriptor");
+    for (int k = 0; k < p->n_send; k++)
+        if (p->send_node[k] < 0 || p->send_node[k] >= p->n_owned_nodes || p->send_rank[k] < 0 ||
+            p->send_rank[k] >= p->n_ranks || p->send_rank[k] == p->rank || p->send_slot[k] < 0)
+            return fail(SWB_ERR_ARG, "bad send entry");
+    for (int k = 0; k < p->n_recv; k++)
+        if (p->recv_node[k] < p->n_owned_nodes || p->recv_node[k] >= n.nN) return fail(SWB_ERR_ARG, "bad receive entry");
+    // only true conduits may touch a ghost node (ordered regulator pass)
+    const swb_network *nw = s->net;
+    std::vector<int> n1(n.nL), n2(n.nL);
+    backend::download(n1.data(), n.link_node1, sizeof(int) * n.nL);
+    backend::download(n2.data(), n.link_node2, sizeof(int) * n.nL);
+    for (int j = 0; j < n.nL; j++)
+        if ((n1[j] >= p->n_owned_nodes || n2[j] >= p->n_owned_nodes) && !(nw->der.link_flags[j] & LF_TRUE_CONDUIT))
+            return fail(SWB_ERR_UNSUPP, "a pump / regulator / dummy link crosses the partition border");
+    Halo &H = s->st.halo;
+    memset(&H, 0, sizeof(H));
+    H.rank = p->rank; H.nRanks = p->n_ranks; H.nOwnedN = p->n_owned_nodes;
+    H.nSend = p->n_send; H.nRecv = p->n_recv; H.W = n.nP > 2 ? n.nP : 2;
+    H.send_node = dev_copy<int>(s->allocs, p->send_node, p->n_send);
+    H.send_rank = dev_copy<int>(s->allocs, p->send_rank, p->n_send);
+    H.send_slot = dev_copy<int>(s->allocs, p->send_slot, p->n_send);
+    H.recv_node = dev_copy<int>(s->allocs, p->recv_node, p->n_recv);
+    H.link_owned = dev_copy<int>(s->allocs, p->link_owned, n.nL);
+    H.timeout_ns = (unsigned long long)((p->timeout_s > 0.0 ? p->timeout_s : 30.0) * 1.0e9);
+    std::string err;
+    s->window_bytes = window_size(H.nRecv, H.W);
+    s->window = backend::window_alloc(s->window_bytes, s->window_handle, err);
+    if (!s->window) { H.nRanks = 0; return fail(SWB_ERR_CUDA, err); }
+    window_views(s->window, H.ctrl, H.red, H.stage);
+    window_views(s->window, H.peer_ctrl[H.rank], H.peer_red[H.rank], H.peer_stage[H.rank]);
+    return SWB_OK;
+}
+
+int swb_partition_export(swb_solver *s, void *handle)
+{
+    if (!s || !handle || !s->window) return fail(SWB_ERR_ARG, "no partition attached");
+    memcpy(handle, s->window_handle, SWB_WINDOW_HANDLE_BYTES);
+    return SWB_OK;
+}
+
+int swb_partition_connect(swb_solver *s, int peer, const void *handle)
+{
+    if (!s || !handle || !s->window) return fail(SWB_ERR_ARG, "no partition attached");
+    Halo &H = s->st.halo;
+    if (peer < 0 || peer >= H.nRanks || peer == H.rank) return fail(SWB_ERR_ARG, "bad peer rank");
+    if (s->peer_window[peer]) return fail(SWB_ERR_ARG, "peer already connected");
+    std::string err;
+    void *w = backend::window_open(handle, 0, err);
+    if (!w) return fail(SWB_ERR_CUDA, err);
+    s->peer_window[peer] = w;
+    window_views(w, H.peer_ctrl[peer], H.peer_red[peer], H.peer_stage[peer]);
+    return SWB_OK;
+}
+
+long long swb_partition_exchanges(swb_solver *s)
+{
+    if (!s || !s->window) return 0;
+    unsigned long long e = 0;
+    backend::download(&e, s->st.halo.ctrl + HALO_EPOCH, sizeof(e));
+    return (long long)e;
 }
 
 int swb_get_stats(swb_solver *s, int m0, int nm, swb_member_stats *out)

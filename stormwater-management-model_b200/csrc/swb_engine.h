@@ -260,6 +260,53 @@ SWB_ENGINE inline void qual_acc_flush(Ctx &ctx, const State &st, int p, int m, i
     if (f != 0.0) ctx.atomic_add_f64(&st.mb_final_storage[p * M + m], f);
 }
 
+// ---- partitioned network: one exchange = push border values + reduction operands into every
+// peer's window, flag, wait for every peer's flag, pull.  Three grid barriers; rank-to-rank traffic
+// is a few KB of direct stores, so the cost is latency (NVLink round trip + barriers), not bandwidth.
+//   get(s, w)      value w of send entry s                      (any thread)
+//   put(r, w, v)   store value w of receive slot r              (any thread)
+//   red_in[]       this rank's reduction operands               (read by thread 0)
+//   fold(rows)     rows[p * HALO_RED + q] = operand q of rank p (thread 0, after the wait)
+template <class Ctx, class Get, class Put, class Fold>
+SWB_ENGINE inline void halo_exchange(Ctx &ctx, const Halo &H, unsigned long long &epoch, int nvals,
+                                     const unsigned long long *red_in, Get get, Put put, Fold fold)
+{
+    epoch++;
+    const int par = (int)(epoch & 1ull);
+    for (int e = ctx.tid; e < H.nSend * nvals; e += ctx.G) {
+        const int s = e / nvals, w = e - s * nvals;
+        H.peer_stage[H.send_rank[s]][((size_t)H.send_slot[s] * 2 + par) * H.W + w] = get(s, w);
+    }
+    if (ctx.tid == 0)
+        for (int p = 0; p < H.nRanks; p++)
+            for (int q = 0; q < HALO_RED; q++)
+                H.peer_red[p][((size_t)par * SWB_MAX_RANKS + H.rank) * HALO_RED + q] = red_in[q];
+    ctx.fence_system();
+    ctx.grid_sync();
+    if (ctx.tid == 0) {
+        for (int p = 0; p < H.nRanks; p++)
+            if (p != H.rank) ctx.store_release_sys(H.peer_ctrl[p] + H.rank, epoch);
+        const unsigned long long t0 = ctx.now_ns();
+        for (int p = 0; p < H.nRanks; p++) {
+            if (p == H.rank) continue;
+            while (ctx.load_acquire_sys(H.ctrl + p) < epoch) {
+                if (ctx.load_acquire_sys(H.ctrl + HALO_ERR) != 0ull) break;
+                if (ctx.now_ns() - t0 > H.timeout_ns) {       // never hang the device on a lost peer
+                    for (int r = 0; r < H.nRanks; r++) ctx.store_release_sys(H.peer_ctrl[r] + HALO_ERR, 1ull);
+                    break;
+                }
+            }
+        }
+        fold(H.red + (size_t)par * SWB_MAX_RANKS * HALO_RED);
+    }
+    ctx.grid_sync();
+    for (int e = ctx.tid; e < H.nRecv * nvals; e += ctx.G) {
+        const int r = e / nvals, w = e - r * nvals;
+        put(r, w, ctx.load_sys_f64(&H.stage[((size_t)r * 2 + par) * H.W + w]));
+    }
+    ctx.grid_sync();
+}
+
 template <class Ctx>
 SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs &args, Ctx &ctx)
 {
@@ -271,6 +318,12 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
     const int maxTrials = net.opt.max_trials < SWB_MAX_TRIALS_CAP ? net.opt.max_trials
                                                                   : SWB_MAX_TRIALS_CAP;
     const bool withQual = (nP > 0) && !net.opt.ignore_quality;
+    // partitioned network (M == 1): nodes [0, nNo) are this rank's, the rest are ghosts kept current
+    // by halo_exchange; every decision that shapes the control flow is reduced over all ranks
+    const Halo &H = st.halo;
+    const bool part = H.nRanks > 1;
+    const int nNo = part ? H.nOwnedN : nN;
+    unsigned long long epoch = part ? H.ctrl[HALO_EPOCH] : 0ull;
 
     unsigned long long tmark = (ctx.tid == 0) ? ctx.now_ns() : 0ull;
 
@@ -449,7 +502,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 SWB_TICK(TP_LINKS);
                 // ---- networks with regulators / dummy links: ordered pass (A.4)
                 if (net.nNonConduit > 0) {
-                    for_tiles(ctx, nN, nAlive, tickets + 1, [&](int i, int mm) { picard_node_presum(net, st, i, mm); });
+                    for_tiles(ctx, nNo, nAlive, tickets + 1, [&](int i, int mm) { picard_node_presum(net, st, i, mm); });
                     ctx.grid_sync();
                     if (ctx.tid < nAlive) {
                         int mm = ctx.alive_list[ctx.tid];
@@ -459,11 +512,27 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     SWB_TICK(TP_REGULATORS);
                 }
                 // ---- findNodeDepths (dynwave.c:593-632)
-                for_tiles(ctx, nN, nAlive, tickets + 2, [&](int i, int mm) {
+                for_tiles(ctx, nNo, nAlive, tickets + 2, [&](int i, int mm) {
                     if (!picard_node(net, st, i, mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
                 }, [&](int i, int mm) { prefetch_node(ctx, net, st, i, mm); });
                 ctx.grid_sync();
                 SWB_TICK(TP_NODES);
+                if (part) {
+                    // border depths + converged flags to the peers; "converged" becomes the AND over
+                    // all ranks (dynwave.c:248-251 tests the whole network)
+                    unsigned long long rin[HALO_RED] = { (unsigned long long)st.not_conv[k * M], 0ull, 0ull, 0ull };
+                    halo_exchange(ctx, H, epoch, 2, rin,
+                        [&](int sx, int w) { int i = H.send_node[sx];
+                                             return w == 0 ? st.n_depth[i] : (double)st.n_converged[i]; },
+                        [&](int r, int w, double v) { int i = H.recv_node[r];
+                                                      if (w == 0) st.n_depth[i] = v;
+                                                      else st.n_converged[i] = (v != 0.0) ? 1 : 0; },
+                        [&](const unsigned long long *rows) {
+                            int any = 0;
+                            for (int p = 0; p < H.nRanks; p++) any |= (rows[p * HALO_RED] != 0ull);
+                            st.not_conv[k * M] = any; });
+                    SWB_TICK(TP_HALO);
+                }
                 // ---- loop control: Steps++ ; if (Steps > 1 && converged) break (:248-251).
                 // Every CTA rebuilds the same ordered list of members that go on to trial k + 1.
                 if (k + 1 >= maxTrials) break;
@@ -511,15 +580,24 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             if (active)
                 for (int p = 0; p < nP; p++) {
                     QualAcc acc = {0.0, 0.0, 0.0};
-                    SWB_FOR_ITEMS(i, nN) qual_node(net, st, i, m, p, dt, acc);
+                    SWB_FOR_ITEMS(i, nNo) qual_node(net, st, i, m, p, dt, acc);
                     qual_acc_flush(ctx, st, p, m, M, dt, acc);
                 }
             ctx.grid_sync();
             SWB_TICK(TP_QUAL_NODES);
+            if (part) {                // a cut conduit mixes with its upstream node's new quality
+                unsigned long long rin[HALO_RED] = { 0ull, 0ull, 0ull, 0ull };
+                halo_exchange(ctx, H, epoch, nP, rin,
+                    [&](int sx, int w) { return st.n_qual[SWB_IXP(w, H.send_node[sx], nN, 0, M)]; },
+                    [&](int r, int w, double v) { st.n_qual[SWB_IXP(w, H.recv_node[r], nN, 0, M)] = v; },
+                    [&](const unsigned long long *) {});
+                SWB_TICK(TP_HALO);
+            }
             if (active)
                 for (int p = 0; p < nP; p++) {
-                    QualAcc acc = {0.0, 0.0, 0.0};
-                    SWB_FOR_ITEMS(j, nL) qual_link(net, st, j, m, p, dt, acc);
+                    QualAcc acc = {0.0, 0.0, 0.0}, copy = {0.0, 0.0, 0.0};
+                    // the copy of a cut conduit is routed too, but only its owner reports the losses
+                    SWB_FOR_ITEMS(j, nL) qual_link(net, st, j, m, p, dt, (part && !H.link_owned[j]) ? copy : acc);
                     qual_acc_flush(ctx, st, p, m, M, dt, acc);
                 }
         }
@@ -546,7 +624,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     double t = link_step(net, st, j, m);
                     if (t >= 0.0 && t < tl) { tl = t; il = j; }
                 }
-                SWB_FOR_ITEMS(i, nN) {
+                SWB_FOR_ITEMS(i, nNo) {
                     double t = node_step(net, st, i, m);
                     if (t >= 0.0 && t < tn) { tn = t; in = i; }
                 }
@@ -563,6 +641,19 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 }
             }
             ctx.grid_sync();
+            if (part) {                // MIN over the ranks (ordered bit images, like the atomics above)
+                unsigned long long rin[HALO_RED] = { st.tmin_bits[0], st.tmin_bits[M], 0ull, 0ull };
+                halo_exchange(ctx, H, epoch, 0, rin,
+                    [&](int, int) { return 0.0; }, [&](int, int, double) {},
+                    [&](const unsigned long long *rows) {
+                        unsigned long long a = rows[0], b = rows[1];
+                        for (int p = 1; p < H.nRanks; p++) {
+                            a = rows[p * HALO_RED] < a ? rows[p * HALO_RED] : a;
+                            b = rows[p * HALO_RED + 1] < b ? rows[p * HALO_RED + 1] : b;
+                        }
+                        st.tmin_bits[0] = a; st.tmin_bits[M] = b; });
+                SWB_TICK(TP_HALO);
+            }
             if (search) {
                 if (il >= 0 && dbits(tl) == st.tmin_bits[m]) ctx.atomic_min_i32(&st.crit_link[m], il);
                 if (in >= 0 && dbits(tn) == st.tmin_bits[M + m]) ctx.atomic_min_i32(&st.crit_node[m], in);
@@ -581,7 +672,10 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                         // the link step, and then the link is dropped
                         double tLink = dfrombits(st.tmin_bits[m]), tNode = dfrombits(st.tmin_bits[M + m]);
                         vs = tLink;
-                        if (cn >= 0 && tNode < tLink) { vs = tNode; cl = -1; } else cn = -1;
+                        // (partitioned: the critical node may live on another rank; a node
+                        // candidate exists iff the reduced node minimum is below the fixed step)
+                        const bool haveNode = cn >= 0 || (part && st.tmin_bits[M + m] < dbits(args.fixed_step));
+                        if (haveNode && tNode < tLink) { vs = tNode; cl = -1; } else cn = -1;
                         if (vs < net.opt.min_route_step) vs = net.opt.min_route_step;
                     }
                     st.crit_link[m] = cl; st.crit_node[m] = cn;
@@ -596,6 +690,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
         if (step + 1 < args.n_steps) ctx.grid_sync();
         SWB_TICK(TP_NEXTDT);
     }
+    if (part && ctx.tid == 0) H.ctrl[HALO_EPOCH] = epoch;
     if (args.stg_depth || args.stg_flow) {
         // device layout [item][m] -> host layout [m][item]
         ctx.grid_sync();

@@ -120,11 +120,33 @@ struct Net {
     X(double, l_total_load, SWB_LINK_TOTAL_LOAD, LP)
 
 enum { TP_PROLOGUE = 0, TP_LINKS, TP_REGULATORS, TP_NODES, TP_CONTROL, TP_EPILOGUE, TP_QUAL_NODES,
-       TP_QUAL_LINKS, TP_NEXTDT, SWB_N_PHASES = 12 };
+       TP_QUAL_LINKS, TP_NEXTDT, TP_HALO, SWB_N_PHASES = 12 };
 #define SWB_MAX_TRIALS_CAP 32     // alive / notConv bookkeeping rows (MaxTrials is 8 by default)
+
+// One network partitioned over several GPUs (include/swmm_b200.h: swb_partition_desc).  Every rank
+// owns a receive WINDOW in its own memory that the peers write into directly (peer memory over
+// NVLink on the device, shared memory in the host emulation):
+//   ctrl  [16] u64   [p] = last epoch rank p has published, [8] = error flag, [9] = epoch at launch end
+//   red   [2][SWB_MAX_RANKS][HALO_RED] u64   per-parity reduction operands, one row per source rank
+//   stage [n_recv][2][W] f64                  per-parity border values, W = max(2, pollutants)
+// Values are double-buffered by the parity of the exchange epoch: a peer can only write parity e & 1
+// again at epoch e + 2, i.e. after this rank has signalled e + 1, which it does after consuming e.
+enum { HALO_CTRL_WORDS = 16, HALO_ERR = 8, HALO_EPOCH = 9, HALO_RED = 4 };
+struct Halo {
+    int rank, nRanks;            // nRanks <= 1: not partitioned
+    int nOwnedN;                 // local nodes [0, nOwnedN) are updated here, the rest are ghosts
+    int nSend, nRecv, W;
+    const int *send_node, *send_rank, *send_slot, *recv_node, *link_owned;
+    unsigned long long *ctrl, *red;
+    double *stage;
+    unsigned long long *peer_ctrl[SWB_MAX_RANKS], *peer_red[SWB_MAX_RANKS];
+    double *peer_stage[SWB_MAX_RANKS];
+    unsigned long long timeout_ns;
+};
 
 struct State {
     int M;                       // members
+    Halo halo;
 #define X(T, name, id, kind) T *name;
     SWB_STATE_FIELDS(X)
 #undef X

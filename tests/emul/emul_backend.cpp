@@ -4,6 +4,10 @@
 // CPU-only suite exercises the kernels' arithmetic AND their control flow (barrier placement,
 // per-member convergence bookkeeping) against the reference.
 #include <barrier>
+#include <cstdio>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +33,47 @@ static void *host_alloc(size_t b) { return std::malloc(b ? b : 8); }
 static void host_free(void *p) { std::free(p); }
 static void h2d_async(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 static void d2h_async(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
+// receive window of a partitioned solver: POSIX shared memory, so that the peers of the CPU tests can
+// be threads of one process or separate processes (torch.distributed / gloo, world_size 2)
+struct ShmHandle { char name[48]; unsigned long long bytes; };
+static void *window_alloc(size_t bytes, void *handle, std::string &err)
+{
+    static int counter = 0;
+    ShmHandle h;
+    std::memset(&h, 0, sizeof(h));
+    std::snprintf(h.name, sizeof(h.name), "/swb_%d_%d", (int)getpid(), __atomic_fetch_add(&counter, 1, __ATOMIC_RELAXED));
+    h.bytes = bytes;
+    int fd = shm_open(h.name, O_CREAT | O_RDWR | O_EXCL, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) { err = "shm_open failed"; return nullptr; }
+    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { err = "mmap failed"; return nullptr; }
+    std::memset(p, 0, bytes);
+    static_assert(sizeof(ShmHandle) <= SWB_WINDOW_HANDLE_BYTES, "handle size");
+    std::memset(handle, 0, SWB_WINDOW_HANDLE_BYTES);
+    std::memcpy(handle, &h, sizeof(h));
+    return p;
+}
+static void *window_open(const void *handle, size_t, std::string &err)
+{
+    ShmHandle h;
+    std::memcpy(&h, handle, sizeof(h));
+    int fd = shm_open(h.name, O_RDWR, 0600);
+    if (fd < 0) { err = "shm_open(peer) failed"; return nullptr; }
+    void *p = mmap(nullptr, h.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { err = "mmap(peer) failed"; return nullptr; }
+    return p;
+}
+static void window_close(void *) {}          // mappings live until the test process exits
+static void window_free(void *p, size_t bytes, const void *handle)
+{
+    ShmHandle h;
+    std::memcpy(&h, handle, sizeof(h));
+    shm_unlink(h.name);
+    if (p) munmap(p, bytes);
+}
+
 static bool xsect_eval(int, int fn, const Xs &x, int n, const double *args, double *out, std::string &)
 {
     static const double tab[] = { SWB_XS_TABLE_DATA };
@@ -67,6 +112,11 @@ struct EmulCtx {
             dst[(size_t)cc * R + r] = src[e];
         }
     }
+    void fence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+    void store_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+    unsigned long long load_acquire_sys(const unsigned long long *p)
+    { std::this_thread::yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }      // only used in spin loops
+    double load_sys_f64(const double *p) { return *(const volatile double *)p; }
     unsigned long long now_ns()
     { return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
           std::chrono::steady_clock::now().time_since_epoch()).count(); }

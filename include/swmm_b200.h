@@ -316,7 +316,7 @@ int  swb_xsect_eval(int device, int fn, int xs_type, const double *params, int n
 
 /* device-side time per phase of the persistent kernel since the last reset, ms (thread 0, globaltimer):
  * 0 prologue, 1 link phase, 2 regulator pass, 3 node phase, 4 loop control / compaction,
- * 5 epilogue, 6 quality nodes, 7 quality links, 8 next-step search */
+ * 5 epilogue, 6 quality nodes, 7 quality links, 8 next-step search, 9 halo exchanges (partitioned) */
 int  swb_get_phase_times(swb_solver *s, double *ms, int n, int reset);
 
 /* launch bookkeeping for bench.py ("gpu_launches") and device timing of the last call */

@@ -254,7 +254,7 @@ class Solver:
         return {"reacted": r, "seepage": sp, "final_storage": f}
 
     PHASES = ["prologue", "links", "regulators", "nodes", "control", "epilogue", "qual_nodes",
-              "qual_links", "next_dt"]
+              "qual_links", "next_dt", "halo"]
 
     def phase_times(self, reset: bool = True) -> dict:
         ms = np.zeros(len(self.PHASES))

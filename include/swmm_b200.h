@@ -140,6 +140,7 @@ enum swb_field {
     SWB_NODE_OLD_NET_INFLOW, SWB_NODE_NEW_SURF_AREA, SWB_NODE_OLD_SURF_AREA, SWB_NODE_SUMDQDH,
     SWB_NODE_DYDT, SWB_NODE_CONVERGED, SWB_NODE_OUTFALL_STAGE, SWB_NODE_STORAGE_EVAP_LOSS,
     SWB_NODE_STORAGE_EXFIL_LOSS, SWB_NODE_HRT, SWB_NODE_NEW_QUAL, SWB_NODE_OLD_QUAL,
+    SWB_NODE_OLD_LATFLOW, SWB_NODE_OLD_INFLOW,   /* Node.oldLatFlow / oldFlowInflow (report interpolation) */
     SWB_LINK_NEW_FLOW = 32, SWB_LINK_OLD_FLOW, SWB_LINK_NEW_DEPTH, SWB_LINK_OLD_DEPTH,
     SWB_LINK_NEW_VOLUME, SWB_LINK_OLD_VOLUME, SWB_LINK_SETTING, SWB_LINK_TARGET_SETTING,
     SWB_LINK_DQDH, SWB_LINK_FROUDE, SWB_LINK_FLOW_CLASS, SWB_LINK_SURF_AREA1, SWB_LINK_SURF_AREA2,
@@ -308,6 +309,17 @@ int  swb_partition_connect(swb_solver *s, int peer_rank, const void *handle);
 /* halo exchanges completed so far (each is one barrier over all ranks) */
 long long swb_partition_exchanges(swb_solver *s);
 
+/* Report-time results: the float32 records the reference writes to the .out file,
+ * computed on the device -- node_getResults (node.c:497-528) and link_getResults (link.c:674-724)
+ * with the weighting factor of output.c:662-663, f[m] = (reportTime - OldRoutingTime) /
+ * (NewRoutingTime - OldRoutingTime), one per member (n_members_total entries).  Only these 4-byte
+ * records cross PCIe.  node_out: [n_members][n_nodes][6 + P] = {depth, head, volume, lateral inflow,
+ * total inflow, overflow, quality...}; link_out: [n_members][n_links][5 + P] = {flow, depth,
+ * velocity, volume, capacity, quality...} (enums.h:200-219), P = n_pollut unless ignore_quality.
+ * Either output may be NULL. */
+int  swb_get_results(swb_solver *s, const double *f, int member0, int n_members, float *node_out,
+                     float *link_out);
+
 /* Known-answer hook for the geometry library (K1b): evaluates one xsect function on the device for
  * n arguments.  fn: 0 AofY 1 WofY 2 RofY 3 YofA 4 RofA 5 SofA 6 AofS 7 dSdA 8 Ycrit (xsect.c:714-1319);
  * params = {yFull,wMax,ywMax,aFull,rFull,sFull,sMax,yBot,aBot,sBot,rBot} (objects.h:581-599). */
@@ -316,7 +328,8 @@ int  swb_xsect_eval(int device, int fn, int xs_type, const double *params, int n
 
 /* device-side time per phase of the persistent kernel since the last reset, ms (thread 0, globaltimer):
  * 0 prologue, 1 link phase, 2 regulator pass, 3 node phase, 4 loop control / compaction,
- * 5 epilogue, 6 quality nodes, 7 quality links, 8 next-step search, 9 halo exchanges (partitioned) */
+ * 5 epilogue, 6 quality nodes, 7 quality links, 8 next-step search, 9 halo exchanges (partitioned),
+ * 10 the part of 9 spent waiting for the slowest peer */
 int  swb_get_phase_times(swb_solver *s, double *ms, int n, int reset);
 
 /* launch bookkeeping for bench.py ("gpu_launches") and device timing of the last call */

@@ -152,6 +152,25 @@ class RefEngine:
                     concen=arr(d.concen, n * nP, np.float64) if nP else None,
                     start_day=d.start_day, start_secs=d.start_secs)
 
+    def results(self, f: float, n_nodes: int, n_links: int, n_pollut: int):
+        """The engine's own report records: node_getResults (node.c:497) / link_getResults
+        (link.c:674) for every object at weighting factor f -> float32 [n][6 + P], [n][5 + P]."""
+        L = self.lib
+        L.node_getResults.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_float)]
+        L.link_getResults.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_float)]
+        L.node_getResults.restype = None
+        L.link_getResults.restype = None
+        nd = np.zeros((n_nodes, 6 + n_pollut), dtype=np.float32)
+        ld = np.zeros((n_links, 5 + n_pollut), dtype=np.float32)
+        buf = (C.c_float * (16 + n_pollut))()
+        for j in range(n_nodes):
+            L.node_getResults(j, float(f), buf)
+            nd[j] = buf[:6 + n_pollut]
+        for j in range(n_links):
+            L.link_getResults(j, float(f), buf)
+            ld[j] = buf[:5 + n_pollut]
+        return nd, ld
+
     def total_duration_s(self) -> float:
         return self.hook.refhook_total_duration() / 1000.0
 

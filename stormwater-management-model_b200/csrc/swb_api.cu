@@ -15,6 +15,7 @@
 #include <string>
 #include "swb_state.h"
 #include "swb_engine.h"
+#include "swb_report.h"
 
 namespace cg = cooperative_groups;
 using namespace swb;
@@ -109,6 +110,7 @@ struct CudaCtx {
     }
     // ---- partitioned network: system-scope accesses to windows that peers write over NVLink
     __device__ __forceinline__ void fence_system() { __threadfence_system(); }
+    __device__ __forceinline__ void block_sync() { __syncthreads(); }
     __device__ __forceinline__ void store_release_sys(unsigned long long *p, unsigned long long v)
     { asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
     __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned long long *p)
@@ -166,6 +168,28 @@ __global__ void swb_xsect_kernel(int fn, Xs x, int n, const double *tables, cons
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = xs_eval(fn, x, args[i], tab);
+}
+
+// Report-time extraction: one thread per (object, member), members fastest, so every fp64 load is
+// coalesced; each thread writes its own float32 record (32 B for a node with two pollutants).
+__global__ void swb_report_kernel(const __grid_constant__ Net net, const __grid_constant__ State st,
+                                  const double *f, int m0, int nm, int links, float *out)
+{
+    __shared__ double tab[XT_TOTAL];
+    if (links) {
+        for (int i = threadIdx.x; i < XT_TOTAL; i += blockDim.x) tab[i] = net.xs_tables[i];
+        __syncthreads();
+    }
+    const int nItems = links ? net.nL : net.nN;
+    const int rec = links ? link_record_len(net) : node_record_len(net);
+    const long long total = (long long)nItems * nm;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int item = (int)(t / nm), mm = (int)(t - (long long)item * nm), m = m0 + mm;
+        float *x = out + ((size_t)mm * nItems + item) * rec;
+        if (links) link_results(net, st, item, m, f[m], x, tab);
+        else node_results(net, st, item, m, f[m], x);
+    }
 }
 
 namespace swb { namespace backend {
@@ -290,6 +314,21 @@ static bool xsect_eval(int device, int fn, const Xs &x, int n, const double *arg
     download(out, dO, sizeof(double) * n);
     free_(dT); free_(dA); free_(dO);
     if (e != cudaSuccess) { err = cuda_err("swb_xsect_kernel", e); return false; }
+    return true;
+}
+
+static bool report(const Net &net, const State &st, const double *f, int m0, int nm, float *node_out,
+                   float *link_out, std::string &err)
+{
+    for (int links = 0; links < 2; links++) {
+        float *out = links ? link_out : node_out;
+        if (!out) continue;
+        long long total = (long long)(links ? net.nL : net.nN) * nm;
+        int blocks = (int)std::min<long long>((total + 255) / 256, (long long)g_sms * 8);
+        swb_report_kernel<<<std::max(blocks, 1), 256, 0, g_stream>>>(net, st, f, m0, nm, links, out);
+    }
+    cudaError_t e = cudaStreamSynchronize(g_stream);
+    if (e != cudaSuccess) { err = cuda_err("swb_report_kernel", e); return false; }
     return true;
 }
 

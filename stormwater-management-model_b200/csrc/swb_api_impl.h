@@ -24,6 +24,7 @@
 #include <vector>
 #include "swb_host.h"
 #include "swb_engine.h"
+#include "swb_report.h"
 
 using namespace swb;
 
@@ -502,6 +503,7 @@ int swb_partition_attach(swb_solver *s, const swb_partition_desc *p)
     H.send_slot = dev_copy<int>(s->allocs, p->send_slot, p->n_send);
     H.recv_node = dev_copy<int>(s->allocs, p->recv_node, p->n_recv);
     H.link_owned = dev_copy<int>(s->allocs, p->link_owned, n.nL);
+    H.wait_ns = s->st.phase_ns + TP_HALO_WAIT;
     H.timeout_ns = (unsigned long long)((p->timeout_s > 0.0 ? p->timeout_s : 30.0) * 1.0e9);
     std::string err;
     s->window_bytes = window_size(H.nRecv, H.W);
@@ -600,6 +602,28 @@ int swb_xsect_eval(int device, int fn, int xs_type, const double *p, int n, cons
     x.sMax = p[6]; x.yBot = p[7]; x.aBot = p[8]; x.sBot = p[9]; x.rBot = p[10];
     std::string err;
     if (!backend::xsect_eval(device, fn, x, n, args, out, err)) return fail(SWB_ERR_CUDA, err);
+    return SWB_OK;
+}
+
+int swb_get_results(swb_solver *s, const double *f, int m0, int nm, float *node_out, float *link_out)
+{
+    if (!s || !f || m0 < 0 || nm < 1 || m0 + nm > s->M) return fail(SWB_ERR_ARG, "bad arguments");
+    const Net &n = s->net->net;
+    const size_t nrec = (size_t)node_record_len(n) * n.nN * nm, lrec = (size_t)link_record_len(n) * n.nL * nm;
+    std::string err;
+    if (!backend::init(s->net->device, err)) return fail(SWB_ERR_CUDA, err);
+    double *df = (double *)backend::alloc(sizeof(double) * s->M);
+    float *dn = node_out ? (float *)backend::alloc(sizeof(float) * nrec) : nullptr;
+    float *dl = link_out ? (float *)backend::alloc(sizeof(float) * lrec) : nullptr;
+    backend::upload(df, f, sizeof(double) * s->M);
+    bool ok = backend::report(n, s->st, df, m0, nm, dn, dl, err);
+    if (ok && dn) backend::download(node_out, dn, sizeof(float) * nrec);
+    if (ok && dl) backend::download(link_out, dl, sizeof(float) * lrec);
+    backend::free_(df);
+    if (dn) backend::free_(dn);
+    if (dl) backend::free_(dl);
+    if (!ok) return fail(SWB_ERR_CUDA, err);
+    s->launches += (node_out ? 1 : 0) + (link_out ? 1 : 0);
     return SWB_OK;
 }
 

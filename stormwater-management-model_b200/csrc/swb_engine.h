@@ -261,7 +261,7 @@ SWB_ENGINE inline void qual_acc_flush(Ctx &ctx, const State &st, int p, int m, i
 }
 
 // ---- partitioned network: one exchange = push border values + reduction operands into every
-// peer's window, flag, wait for every peer's flag, pull.  Three grid barriers; rank-to-rank traffic
+// peer's window, flag, wait for every peer's flag, pull.  Two grid barriers; rank-to-rank traffic
 // is a few KB of direct stores, so the cost is latency (NVLink round trip + barriers), not bandwidth.
 //   get(s, w)      value w of send entry s                      (any thread)
 //   put(r, w, v)   store value w of receive slot r              (any thread)
@@ -281,11 +281,14 @@ SWB_ENGINE inline void halo_exchange(Ctx &ctx, const Halo &H, unsigned long long
         for (int p = 0; p < H.nRanks; p++)
             for (int q = 0; q < HALO_RED; q++)
                 H.peer_red[p][((size_t)par * SWB_MAX_RANKS + H.rank) * HALO_RED + q] = red_in[q];
-    ctx.fence_system();
-    ctx.grid_sync();
-    if (ctx.tid == 0) {
+    if (ctx.tid == 0 || ctx.tid < H.nSend * nvals) ctx.fence_system();     // only threads that stored remotely
+    ctx.grid_sync();                                  // every push of this rank has been fenced
+    if (ctx.tid == 0)
         for (int p = 0; p < H.nRanks; p++)
             if (p != H.rank) ctx.store_release_sys(H.peer_ctrl[p] + H.rank, epoch);
+    // every CTA waits for the peers on its own (one thread polls, the block follows): no second
+    // grid barrier between the flag and the pull
+    if (ctx.lane == 0) {
         const unsigned long long t0 = ctx.now_ns();
         for (int p = 0; p < H.nRanks; p++) {
             if (p == H.rank) continue;
@@ -297,9 +300,12 @@ SWB_ENGINE inline void halo_exchange(Ctx &ctx, const Halo &H, unsigned long long
                 }
             }
         }
-        fold(H.red + (size_t)par * SWB_MAX_RANKS * HALO_RED);
+        if (ctx.tid == 0) {
+            H.wait_ns[0] += ctx.now_ns() - t0;      // time spent waiting for the slowest peer
+            fold(H.red + (size_t)par * SWB_MAX_RANKS * HALO_RED);
+        }
     }
-    ctx.grid_sync();
+    ctx.block_sync();
     for (int e = ctx.tid; e < H.nRecv * nvals; e += ctx.G) {
         const int r = e / nvals, w = e - r * nvals;
         put(r, w, ctx.load_sys_f64(&H.stage[((size_t)r * 2 + par) * H.W + w]));
@@ -396,6 +402,8 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 }
                 bool newLat = false;
                 int slot = -1;
+                // Node.oldLatFlow = newLatFlow (routing.c:330), only where this step sets a new one
+                const double prevLat = (ph & (PH_INFLOWS | PH_HOSTIN)) ? st.n_latflow[ix] : 0.0;
                 if (ph & PH_INFLOWS) {
                     // addExternalInflows (routing.c:435-490)
                     slot = args.inflows.node_slot[i];
@@ -424,12 +432,13 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                         if ((ph & PH_HOSTIN) && args.host_qual) c += hq[p];
                         st.n_qual[iq] = c;
                     }
-                if (newLat) { st.n_latflow[ix] = lat; st.n_losses[ix] = losses; }
+                if (newLat) { st.n_latflow[ix] = lat; st.n_losses[ix] = losses; st.n_old_latflow[ix] = prevLat; }
                 if (ph & PH_SWAP) {
                     // node_setOldHydState, node_initFlows, flowrout.c:153-162
                     st.n_old_depth[ix] = depth;
                     st.n_old_volume[ix] = volume;
                     st.n_old_net_inflow[ix] = inflow - outflow;
+                    st.n_old_inflow[ix] = inflow;              // oldFlowInflow (node.c:302)
                     st.n_inflow[ix] = lat;
                     st.n_outflow[ix] = losses;
                     double ov = 0.0, fullVolume = net.node_full_volume[i];

@@ -102,6 +102,7 @@ struct Net {
     X(double, n_evap_loss, SWB_NODE_STORAGE_EVAP_LOSS, N) X(double, n_exfil_loss, SWB_NODE_STORAGE_EXFIL_LOSS, N) \
     X(double, n_hrt, SWB_NODE_HRT, N) X(double, n_qual, SWB_NODE_NEW_QUAL, NP) \
     X(double, n_old_qual, SWB_NODE_OLD_QUAL, NP) \
+    X(double, n_old_latflow, SWB_NODE_OLD_LATFLOW, N) X(double, n_old_inflow, SWB_NODE_OLD_INFLOW, N) \
     X(double, l_flow, SWB_LINK_NEW_FLOW, L) X(double, l_old_flow, SWB_LINK_OLD_FLOW, L) \
     X(double, l_depth, SWB_LINK_NEW_DEPTH, L) X(double, l_old_depth, SWB_LINK_OLD_DEPTH, L) \
     X(double, l_volume, SWB_LINK_NEW_VOLUME, L) X(double, l_old_volume, SWB_LINK_OLD_VOLUME, L) \
@@ -120,7 +121,7 @@ struct Net {
     X(double, l_total_load, SWB_LINK_TOTAL_LOAD, LP)
 
 enum { TP_PROLOGUE = 0, TP_LINKS, TP_REGULATORS, TP_NODES, TP_CONTROL, TP_EPILOGUE, TP_QUAL_NODES,
-       TP_QUAL_LINKS, TP_NEXTDT, TP_HALO, SWB_N_PHASES = 12 };
+       TP_QUAL_LINKS, TP_NEXTDT, TP_HALO, TP_HALO_WAIT, SWB_N_PHASES = 12 };
 #define SWB_MAX_TRIALS_CAP 32     // alive / notConv bookkeeping rows (MaxTrials is 8 by default)
 
 // One network partitioned over several GPUs (include/swmm_b200.h: swb_partition_desc).  Every rank
@@ -142,6 +143,7 @@ struct Halo {
     unsigned long long *peer_ctrl[SWB_MAX_RANKS], *peer_red[SWB_MAX_RANKS];
     double *peer_stage[SWB_MAX_RANKS];
     unsigned long long timeout_ns;
+    unsigned long long *wait_ns;  // = phase_ns + TP_HALO_WAIT: the part of TP_HALO spent spinning on peers
 };
 
 struct State {

@@ -62,6 +62,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_host_free.argtypes = [C.c_void_p]
     lib.swb_step_host.argtypes = [C.c_void_p, C.POINTER(abi.StepIO)]
     lib.swb_step_host_batch.argtypes = [C.POINTER(C.c_void_p), C.POINTER(abi.StepIO), C.c_int]
+    lib.swb_get_results.argtypes = [C.c_void_p, _P_D, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.swb_xsect_eval.argtypes = [C.c_int, C.c_int, C.c_int, _P_D, C.c_int, _P_D, _P_D]
     return lib
 
@@ -254,12 +255,27 @@ class Solver:
         return {"reacted": r, "seepage": sp, "final_storage": f}
 
     PHASES = ["prologue", "links", "regulators", "nodes", "control", "epilogue", "qual_nodes",
-              "qual_links", "next_dt", "halo"]
+              "qual_links", "next_dt", "halo", "halo_wait"]
 
     def phase_times(self, reset: bool = True) -> dict:
         ms = np.zeros(len(self.PHASES))
         self._chk(self.lib.swb_get_phase_times(self._h, ms.ctypes.data_as(_P_D), ms.size, int(reset)))
         return dict(zip(self.PHASES, ms.tolist()))
+
+    def results(self, f, member0: int = 0, n_members: int | None = None, nodes: bool = True, links: bool = True):
+        """Report-time float32 records (swb_get_results): f = weighting factor per member (scalar or
+        [M]).  Returns (node[nm, n_nodes, 6 + P], link[nm, n_links, 5 + P]) in the reference's .out
+        variable order (enums.h:200-219)."""
+        nm = self.M - member0 if n_members is None else n_members
+        fa = np.ascontiguousarray(np.broadcast_to(np.asarray(f, dtype=np.float64), (self.M,)))
+        P = 0 if self.net.options["ignore_quality"] else self.net.n_pollut
+        nd = np.zeros((nm, self.net.n_nodes, 6 + P), dtype=np.float32) if nodes else None
+        ld = np.zeros((nm, self.net.n_links, 5 + P), dtype=np.float32) if links else None
+        pf = C.POINTER(C.c_float)
+        self._chk(self.lib.swb_get_results(self._h, fa.ctypes.data_as(_P_D), member0, nm,
+                                           nd.ctypes.data_as(pf) if nodes else None,
+                                           ld.ctypes.data_as(pf) if links else None))
+        return nd, ld
 
     def conduit_updates(self) -> int:
         return int(self.lib.swb_conduit_updates(self._h))

@@ -16,6 +16,7 @@
 #include <vector>
 #include "swb_state.h"
 #include "swb_engine.h"
+#include "swb_report.h"
 
 namespace swb { namespace backend {
 static bool init(int, std::string &) { return true; }
@@ -81,6 +82,21 @@ static bool xsect_eval(int, int fn, const Xs &x, int n, const double *args, doub
     return true;
 }
 
+static bool report(const Net &net, const State &st, const double *f, int m0, int nm, float *node_out,
+                   float *link_out, std::string &)
+{
+    const int nr = node_record_len(net), lr = link_record_len(net);
+    for (int mm = 0; mm < nm; mm++) {
+        if (node_out)
+            for (int i = 0; i < net.nN; i++)
+                node_results(net, st, i, m0 + mm, f[m0 + mm], node_out + ((size_t)mm * net.nN + i) * nr);
+        if (link_out)
+            for (int j = 0; j < net.nL; j++)
+                link_results(net, st, j, m0 + mm, f[m0 + mm], link_out + ((size_t)mm * net.nL + j) * lr, net.xs_tables);
+    }
+    return true;
+}
+
 struct EmulCtx {
     int tid, G, lane, block_size;
     const double *T;
@@ -112,6 +128,7 @@ struct EmulCtx {
             dst[(size_t)cc * R + r] = src[e];
         }
     }
+    void block_sync() {}                  // a host "block" is one thread
     void fence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
     void store_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
     unsigned long long load_acquire_sys(const unsigned long long *p)

@@ -21,6 +21,7 @@ def test_header_parses_and_field_ids_unique():
     ids = list(abi.FIELD.values())
     assert len(ids) == len(set(ids))
     assert abi.FIELD["SWB_LINK_NEW_FLOW"] == 32 and abi.FIELD["SWB_FIELD_COUNT"] == 96
+    assert abi.FIELD["SWB_NODE_OLD_INFLOW"] == 22
 
 
 def test_device_descriptor_macro_matches_header():

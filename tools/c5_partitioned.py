@@ -81,6 +81,8 @@ def main():
     flows = [None] * world
     if a.check:
         dist.all_gather_object(flows, ps.owned_field("SWB_LINK_NEW_FLOW"))
+    all_phases = [None] * world
+    dist.all_gather_object(all_phases, {k: round(v, 3) for k, v in phases.items()})
     ok = None
     if rank == 0:
         depth_all = np.zeros(net.n_nodes)
@@ -95,7 +97,7 @@ def main():
                "timed_iterations": int(st.iterations - it0), "kernel_s_max_over_ranks": t, "wall_s": wall,
                "conduit_updates_per_s": cu / t, "algorithmic_GBps": 200.0 * cu / t / 1e9,
                "halo_exchanges_timed": ps.exchanges() - ex0,
-               "halo_nodes_rank0": int(part.recv_node.size), "phase_ms_rank0": phases,
+               "halo_nodes_rank0": int(part.recv_node.size), "phase_ms_per_rank": all_phases,
                "build_s": build_s, "max_depth_ft": float(depth_all.max())}
         if a.check:
             single = solver.Solver(net, 1, device=local)

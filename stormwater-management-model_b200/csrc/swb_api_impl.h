@@ -115,6 +115,7 @@ int swb_network_create(const swb_network_desc *d, const swb_options *o, int devi
     nw->net.adjq_start = dev_copy<int>(nw->allocs, r.adjq_start.data(), r.adjq_start.size());
     nw->net.adjq = dev_copy<int>(nw->allocs, r.adjq.data(), r.adjq.size());
     nw->net.nc_links = dev_copy<int>(nw->allocs, r.nc_links.data(), r.nc_links.size());
+    nw->net.node_order = dev_copy<int>(nw->allocs, r.node_order.data(), r.node_order.size());
     nw->net.link_order = dev_copy<int>(nw->allocs, r.link_order.data(), r.link_order.size());
     nw->net.outfall_link = dev_copy<int>(nw->allocs, r.outfall_link.data(), r.outfall_link.size());
     nw->net.xs_tables = dev_copy<double>(nw->allocs, r.xs_tables.data(), r.xs_tables.size());
@@ -503,6 +504,12 @@ int swb_partition_attach(swb_solver *s, const swb_partition_desc *p)
     H.send_slot = dev_copy<int>(s->allocs, p->send_slot, p->n_send);
     H.recv_node = dev_copy<int>(s->allocs, p->recv_node, p->n_recv);
     H.link_owned = dev_copy<int>(s->allocs, p->link_owned, n.nL);
+    {
+        std::vector<int> type(n.nN), order;
+        backend::download(type.data(), n.node_type, sizeof(int) * n.nN);
+        node_order_expensive_first(type.data(), p->n_owned_nodes, n.nN, order);
+        H.node_order = dev_copy<int>(s->allocs, order.data(), order.size());
+    }
     H.wait_ns = s->st.phase_ns + TP_HALO_WAIT;
     H.timeout_ns = (unsigned long long)((p->timeout_s > 0.0 ? p->timeout_s : 30.0) * 1.0e9);
     std::string err;

@@ -330,6 +330,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
     const bool part = H.nRanks > 1;
     const int nNo = part ? H.nOwnedN : nN;
     unsigned long long epoch = part ? H.ctrl[HALO_EPOCH] : 0ull;
+    const int *nodeOrder = part ? H.node_order : net.node_order;
 
     unsigned long long tmark = (ctx.tid == 0) ? ctx.now_ns() : 0ull;
 
@@ -511,7 +512,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 SWB_TICK(TP_LINKS);
                 // ---- networks with regulators / dummy links: ordered pass (A.4)
                 if (net.nNonConduit > 0) {
-                    for_tiles(ctx, nNo, nAlive, tickets + 1, [&](int i, int mm) { picard_node_presum(net, st, i, mm); });
+                    for_tiles(ctx, nNo, nAlive, tickets + 1, [&](int ii, int mm) { picard_node_presum(net, st, nodeOrder[ii], mm); });
                     ctx.grid_sync();
                     if (ctx.tid < nAlive) {
                         int mm = ctx.alive_list[ctx.tid];
@@ -521,9 +522,9 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     SWB_TICK(TP_REGULATORS);
                 }
                 // ---- findNodeDepths (dynwave.c:593-632)
-                for_tiles(ctx, nNo, nAlive, tickets + 2, [&](int i, int mm) {
-                    if (!picard_node(net, st, i, mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
-                }, [&](int i, int mm) { prefetch_node(ctx, net, st, i, mm); });
+                for_tiles(ctx, nNo, nAlive, tickets + 2, [&](int ii, int mm) {
+                    if (!picard_node(net, st, nodeOrder[ii], mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
+                }, [&](int ii, int mm) { prefetch_node(ctx, net, st, nodeOrder[ii], mm); });
                 ctx.grid_sync();
                 SWB_TICK(TP_NODES);
                 if (part) {

@@ -17,7 +17,7 @@ namespace swb {
 
 struct Derived {
     std::vector<int> link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link, link_order,
-                     link_kernel;
+                     link_kernel, node_order;
     std::vector<double> link_z1, link_z2, xs_tables, culvert_params, road_tables;
     int nTrue = 0, nNonConduit = 0;
 };
@@ -57,6 +57,17 @@ inline std::string validate_desc(const swb_network_desc &d, const swb_options &o
         if (t >= d.n_shape_tbls) return "xs_table out of range";
     }
     return "";
+}
+
+// Ticket order of the node phase: outfalls (boundary depth = critical / normal depth solves) and
+// storage nodes (curve integration) first, so their long serial latency overlaps the bulk of the
+// phase instead of trailing it; the first nFirst entries are a permutation of [0, nFirst).
+inline void node_order_expensive_first(const int *node_type, int nFirst, int nN, std::vector<int> &order)
+{
+    order.clear();
+    for (int i = 0; i < nFirst; i++) if (node_type[i] == SWB_OUTFALL || node_type[i] == SWB_STORAGE) order.push_back(i);
+    for (int i = 0; i < nFirst; i++) if (!(node_type[i] == SWB_OUTFALL || node_type[i] == SWB_STORAGE)) order.push_back(i);
+    for (int i = nFirst; i < nN; i++) order.push_back(i);
 }
 
 inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
@@ -99,6 +110,7 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
                          if (r.link_kernel[a] != r.link_kernel[b]) return r.link_kernel[a] < r.link_kernel[b];
                          return d.xs_type[a] < d.xs_type[b];
                      });
+    node_order_expensive_first(d.node_type, nN, nN, r.node_order);
     // CSR incidence.  adjq: ascending link index.  adj: true conduits first, then the rest.
     std::vector<std::vector<int>> inc(nN);
     for (int j = 0; j < nL; j++) {

@@ -80,6 +80,7 @@ struct Net {
                                            // drawn in this order, so at any moment every warp of the
                                            // chip runs the same specialised conduit function (one
                                            // instruction-cache footprint instead of several)
+    const int    *node_order;              // node-phase ticket order: outfalls and storage nodes first
     const int    *nc_links;                // non-true-conduit links in ascending index order
     const int    *outfall_link;            // per node: its (single) link, or -1
     const int    *link_kernel;             // LK_*: which conduit function a true conduit runs
@@ -138,6 +139,7 @@ struct Halo {
     int nOwnedN;                 // local nodes [0, nOwnedN) are updated here, the rest are ghosts
     int nSend, nRecv, W;
     const int *send_node, *send_rank, *send_slot, *recv_node, *link_owned;
+    const int *node_order;       // Net::node_order restricted to the owned nodes
     unsigned long long *ctrl, *red;
     double *stage;
     unsigned long long *peer_ctrl[SWB_MAX_RANKS], *peer_red[SWB_MAX_RANKS];

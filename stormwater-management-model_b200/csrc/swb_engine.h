@@ -265,7 +265,7 @@ SWB_ENGINE inline void qual_acc_flush(Ctx &ctx, const State &st, int p, int m, i
 // is a few KB of direct stores, so the cost is latency (NVLink round trip + barriers), not bandwidth.
 //   get(s, w)      value w of send entry s                      (any thread)
 //   put(r, w, v)   store value w of receive slot r              (any thread)
-//   red_in[]       this rank's reduction operands               (read by thread 0)
+//   red_in[]       this rank's reduction operands               (same value in every thread)
 //   fold(rows)     rows[p * HALO_RED + q] = operand q of rank p (thread 0, after the wait)
 template <class Ctx, class Get, class Put, class Fold>
 SWB_ENGINE inline void halo_exchange(Ctx &ctx, const Halo &H, unsigned long long &epoch, int nvals,
@@ -277,35 +277,38 @@ SWB_ENGINE inline void halo_exchange(Ctx &ctx, const Halo &H, unsigned long long
         const int s = e / nvals, w = e - s * nvals;
         H.peer_stage[H.send_rank[s]][((size_t)H.send_slot[s] * 2 + par) * H.W + w] = get(s, w);
     }
-    if (ctx.tid == 0)
-        for (int p = 0; p < H.nRanks; p++)
-            for (int q = 0; q < HALO_RED; q++)
-                H.peer_red[p][((size_t)par * SWB_MAX_RANKS + H.rank) * HALO_RED + q] = red_in[q];
-    if (ctx.tid == 0 || ctx.tid < H.nSend * nvals) ctx.fence_system();     // only threads that stored remotely
-    ctx.grid_sync();                                  // every push of this rank has been fenced
-    if (ctx.tid == 0)
-        for (int p = 0; p < H.nRanks; p++)
-            if (p != H.rank) ctx.store_release_sys(H.peer_ctrl[p] + H.rank, epoch);
-    // every CTA waits for the peers on its own (one thread polls, the block follows): no second
-    // grid barrier between the flag and the pull
-    if (ctx.lane == 0) {
-        const unsigned long long t0 = ctx.now_ns();
-        for (int p = 0; p < H.nRanks; p++) {
-            if (p == H.rank) continue;
-            while (ctx.load_acquire_sys(H.ctrl + p) < epoch) {
-                if (ctx.load_acquire_sys(H.ctrl + HALO_ERR) != 0ull) break;
-                if (ctx.now_ns() - t0 > H.timeout_ns) {       // never hang the device on a lost peer
-                    for (int r = 0; r < H.nRanks; r++) ctx.store_release_sys(H.peer_ctrl[r] + HALO_ERR, 1ull);
-                    break;
-                }
+    if (ctx.tid < H.nSend * nvals) ctx.fence_system();   // only threads that stored remotely
+    ctx.grid_sync();                                     // every push of this rank has been fenced
+    // signal: thread p of the grid serves peer p (reduction operands, then the released epoch flag),
+    // so the peers are written in parallel, not one NVLink round trip after the other
+    for (int p = ctx.tid; p < H.nRanks; p += ctx.G) {
+        if (p == H.rank) continue;
+        for (int q = 0; q < HALO_RED; q++)
+            H.peer_red[p][((size_t)par * SWB_MAX_RANKS + H.rank) * HALO_RED + q] = red_in[q];
+        ctx.store_release_sys(H.peer_ctrl[p] + H.rank, epoch);
+    }
+    if (ctx.tid == 0)                                    // own row, folded by this same thread below
+        for (int q = 0; q < HALO_RED; q++)
+            H.red[((size_t)par * SWB_MAX_RANKS + H.rank) * HALO_RED + q] = red_in[q];
+    // wait: every CTA polls on its own (thread p watches peer p, the block follows): no second grid
+    // barrier between the flags and the pull
+    const unsigned long long t0 = (ctx.tid == 0) ? ctx.now_ns() : 0ull;
+    for (int p = ctx.lane; p < H.nRanks; p += ctx.block_size) {
+        if (p == H.rank) continue;
+        const unsigned long long tp = ctx.now_ns();
+        while (ctx.load_acquire_sys(H.ctrl + p) < epoch) {
+            if (ctx.load_acquire_sys(H.ctrl + HALO_ERR) != 0ull) break;
+            if (ctx.now_ns() - tp > H.timeout_ns) {           // never hang the device on a lost peer
+                for (int r = 0; r < H.nRanks; r++) ctx.store_release_sys(H.peer_ctrl[r] + HALO_ERR, 1ull);
+                break;
             }
-        }
-        if (ctx.tid == 0) {
-            H.wait_ns[0] += ctx.now_ns() - t0;      // time spent waiting for the slowest peer
-            fold(H.red + (size_t)par * SWB_MAX_RANKS * HALO_RED);
         }
     }
     ctx.block_sync();
+    if (ctx.tid == 0) {
+        H.wait_ns[0] += ctx.now_ns() - t0;              // time spent waiting for the slowest peer
+        fold(H.red + (size_t)par * SWB_MAX_RANKS * HALO_RED);
+    }
     for (int e = ctx.tid; e < H.nRecv * nvals; e += ctx.G) {
         const int r = e / nvals, w = e - r * nvals;
         put(r, w, ctx.load_sys_f64(&H.stage[((size_t)r * 2 + par) * H.W + w]));

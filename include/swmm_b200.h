@@ -270,6 +270,15 @@ int  swb_get_stats(swb_solver *s, int member0, int n_members, swb_member_stats *
  * reacted and seepage in mass (sum of rate x dt, massbal.c:517-540), final_storage in mass (:545) */
 int  swb_get_massbal(swb_solver *s, int member0, int n_members, double *reacted, double *seepage,
                      double *final_storage);
+/* Routing totals per member since the solver was created (removeSystemOutflows
+ * routing.c:776-925 + massbal_updateRoutingTotals massbal.c:587-617, kept on the device by
+ * swb_run_steps / swb_step_host).  flow: [member][5] volumes (ft3) = {external inflow, flooding,
+ * outflow, evaporation loss, seepage loss}; qual: [member][pollutant][6] masses = {external inflow,
+ * flooding, outflow, reacted, seepage, moved to final storage}, each weighted exactly as the
+ * reference's two half-step updates do.  With the initial / final stored volume and mass (sums of
+ * NEW_VOLUME and NEW_VOLUME x NEW_QUAL over nodes and links) these give the continuity errors of
+ * massbal_getFlowError / massbal_getQualError (massbal.c:858-960) for every member.  Either may be NULL. */
+int  swb_get_routing_totals(swb_solver *s, int member0, int n_members, double *flow, double *qual);
 /* conduit-updates performed so far: sum over members of iterations x true conduits */
 long long swb_conduit_updates(swb_solver *s);
 

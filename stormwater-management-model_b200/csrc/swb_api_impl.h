@@ -173,6 +173,9 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     st.mb_reacted = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
     st.mb_seepage = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
     st.mb_final_storage = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
+    st.mb_rate = dev_zero<double>(s->allocs, (size_t)(MB_FLOW_TERMS + MB_QUAL_TERMS * nP) * M);
+    st.mb_total = dev_zero<double>(s->allocs, (size_t)(MB_FLOW_TERMS + MB_QUAL_TERMS * nP) * M);
+    st.mb_dt_prev = dev_zero<double>(s->allocs, M);
     st.phase_ns = dev_zero<unsigned long long>(s->allocs, SWB_N_PHASES);
     st.tickets = dev_zero<unsigned long long>(s->allocs, 3 * SWB_MAX_TRIALS_CAP);
     // conduit / link settings default to fully open (Link.setting = 1.0, link.c:142)
@@ -385,7 +388,7 @@ static int step_host_enqueue(swb_solver *s, const swb_step_io *io, bool wait)
     }
     if (io->node_depth) stg.stg_depth = s->stg_depth;
     if (io->link_flow) stg.stg_flow = s->stg_flow;
-    int phases = PH_SWAP | PH_HOSTIN | PH_DYNWAVE | PH_NEXTDT;
+    int phases = PH_SWAP | PH_HOSTIN | PH_DYNWAVE | PH_NEXTDT | PH_MASSBAL;
     if (withQual) phases |= PH_QSWAP | PH_QUALITY;
     double t_end = 0.0;
     if (io->dt) {
@@ -465,7 +468,7 @@ int swb_run_steps(swb_solver *s, int n_steps, double t_end)
     if (!s || n_steps < 1) return fail(SWB_ERR_ARG, "bad arguments");
     if (!s->have_inflows) return fail(SWB_ERR_ARG, "swb_set_inflows has not been called");
     const Net &n = s->net->net;
-    int phases = PH_ADVANCE | PH_SWAP | PH_INFLOWS | PH_DYNWAVE | PH_NEXTDT;
+    int phases = PH_ADVANCE | PH_SWAP | PH_INFLOWS | PH_DYNWAVE | PH_NEXTDT | PH_MASSBAL;
     if (n.nP > 0 && !n.opt.ignore_quality) phases |= PH_QSWAP | PH_QUALITY;
     return run(s, phases, n_steps, t_end, n.opt.route_step);
 }
@@ -586,6 +589,28 @@ int swb_get_massbal(swb_solver *s, int m0, int nm, double *reacted, double *seep
         backend::download(h.data(), src[k], sizeof(double) * h.size());
         for (int mm = 0; mm < nm; mm++)
             for (int p = 0; p < nP; p++) dst[k][mm * nP + p] = h[(size_t)p * M + m0 + mm];
+    }
+    return SWB_OK;
+}
+
+int swb_get_routing_totals(swb_solver *s, int m0, int nm, double *flow, double *qual)
+{
+    if (!s || m0 < 0 || nm < 1 || m0 + nm > s->M) return fail(SWB_ERR_ARG, "bad arguments");
+    const int M = s->M, nP = s->net->net.nP, nMb = MB_FLOW_TERMS + MB_QUAL_TERMS * nP;
+    std::vector<double> tot((size_t)nMb * M), rate((size_t)nMb * M), dtp(M);
+    backend::download(tot.data(), s->st.mb_total, sizeof(double) * tot.size());
+    backend::download(rate.data(), s->st.mb_rate, sizeof(double) * rate.size());
+    backend::download(dtp.data(), s->st.mb_dt_prev, sizeof(double) * M);
+    for (int mm = 0; mm < nm; mm++) {
+        const int m = m0 + mm;
+        for (int q = 0; q < nMb; q++) {
+            // the last step's rates over its own second half (routing.c:264), still pending on the device
+            double v = tot[(size_t)q * M + m];
+            const bool mass = q >= MB_FLOW_TERMS && (q - MB_FLOW_TERMS) % MB_QUAL_TERMS == MBQ_FINAL;
+            v += mass ? rate[(size_t)q * M + m] : rate[(size_t)q * M + m] * (dtp[m] / 2.);
+            if (q < MB_FLOW_TERMS) { if (flow) flow[mm * MB_FLOW_TERMS + q] = v; }
+            else if (qual) qual[(size_t)mm * MB_QUAL_TERMS * nP + (q - MB_FLOW_TERMS)] = v;
+        }
     }
     return SWB_OK;
 }

@@ -43,7 +43,8 @@ enum {                         // RunArgs.phases
     PH_NEXTDT  = 16,           // dynwave_getRoutingStep -> var_step
     PH_ADVANCE = 32,           // ensemble clock: pick dt from var_step / t_end, advance sim_time
     PH_QSWAP   = 64,           // quality old <- new, new = 0 (routing.c:312-336)
-    PH_HOSTIN  = 128           // lateral inflows / losses / quality loads from host-fed staging
+    PH_HOSTIN  = 128,          // lateral inflows / losses / quality loads from host-fed staging
+    PH_MASSBAL = 256           // routing totals: removeSystemOutflows + massbal_updateRoutingTotals
 };
 
 struct Inflows {               // device image of swb_inflow_desc
@@ -192,6 +193,12 @@ struct NoPrefetch { SWB_ENGINE void operator()(int, int) const {} };
 #ifndef SWB_PREFETCH
 #define SWB_PREFETCH 0
 #endif
+#ifndef SWB_TICKET_BATCH
+#define SWB_TICKET_BATCH 1
+#endif
+#ifndef SWB_PREFETCH_CUR
+#define SWB_PREFETCH_CUR 0
+#endif
 template <class Ctx, class Body, class Pre = NoPrefetch>
 SWB_ENGINE inline void for_tiles(Ctx &ctx, int nItems, int nAlive, unsigned long long *ticket, Body body,
                                  Pre pre = Pre())
@@ -217,10 +224,22 @@ SWB_ENGINE inline void for_tiles(Ctx &ctx, int nItems, int nAlive, unsigned long
         }
     };
 #if SWB_TICKETS_AHEAD == 0
+    // One atomic hands out SWB_TICKET_BATCH consecutive tiles (same object, neighbouring member
+    // chunks): fewer round trips to the ticket counter, and inside a batch the next tile is known
+    // without an atomic, so its first cache lines can be requested while the current one computes.
     for (;;) {
-        long long t = (long long)ctx.next_ticket(ticket);
+        long long t = (long long)ctx.next_ticket(ticket) * SWB_TICKET_BATCH;
         if (t >= total) break;
-        run(t, body);
+#if SWB_PREFETCH_CUR
+        run(t, pre);
+#endif
+#pragma unroll 1
+        for (int b = 0; b < SWB_TICKET_BATCH && t + b < total; b++) {
+#if SWB_PREFETCH_CUR
+            if (b + 1 < SWB_TICKET_BATCH && t + b + 1 < total) run(t + b + 1, pre);
+#endif
+            run(t + b, body);
+        }
     }
 #elif SWB_TICKETS_AHEAD == 1
     long long t = (long long)ctx.next_ticket(ticket);
@@ -258,6 +277,11 @@ SWB_ENGINE inline void qual_acc_flush(Ctx &ctx, const State &st, int p, int m, i
     if (r != 0.0) ctx.atomic_add_f64(&st.mb_reacted[p * M + m], r);
     if (sp != 0.0) ctx.atomic_add_f64(&st.mb_seepage[p * M + m], sp);
     if (f != 0.0) ctx.atomic_add_f64(&st.mb_final_storage[p * M + m], f);
+    // the same three as step RATES for the routing totals (StepQualTotals, massbal.c:517-555)
+    double *rate = st.mb_rate + (size_t)(MB_FLOW_TERMS + p * MB_QUAL_TERMS) * M + m;
+    if (r != 0.0) ctx.atomic_add_f64(rate + (size_t)MBQ_REACTED * M, r / dt);
+    if (sp != 0.0) ctx.atomic_add_f64(rate + (size_t)MBQ_SEEP * M, sp / dt);
+    if (f != 0.0) ctx.atomic_add_f64(rate + (size_t)MBQ_FINAL * M, f);
 }
 
 // ---- partitioned network: one exchange = push border values + reduction operands into every
@@ -376,6 +400,24 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
         }
         const bool active = !((args.phases & PH_ADVANCE) && st.done[m]);
         const double dt = st.dt[m];
+        const int nMb = MB_FLOW_TERMS + MB_QUAL_TERMS * nP;
+        if ((args.phases & PH_MASSBAL) && owner && active) {
+            // massbal_updateRoutingTotals (massbal.c:587-617): the previous step's rates over the
+            // second half of that step (deferred from its end) and over the first half of this one
+            const double dtPrev = st.mb_dt_prev[m];
+            for (int q = 0; q < nMb; q++) {
+                const double r = st.mb_rate[q * M + m];
+                double tot = st.mb_total[q * M + m];
+                // (the mass moved to "final storage" is added unweighted by BOTH half-step
+                // updates, massbal.c:614 -- kept, it is what the reference reports)
+                const bool mass = q >= MB_FLOW_TERMS && (q - MB_FLOW_TERMS) % MB_QUAL_TERMS == MBQ_FINAL;
+                tot += mass ? r : r * (dtPrev / 2.);
+                tot += mass ? r : r * (dt / 2.);
+                st.mb_total[q * M + m] = tot;
+                st.mb_rate[q * M + m] = 0.0;
+            }
+            st.mb_dt_prev[m] = dt;
+        }
 
         if (active && (args.phases & (PH_SWAP | PH_INFLOWS | PH_QSWAP | PH_DYNWAVE | PH_HOSTIN))) {
             // getDateTime(NewRoutingTime): 1 ms after the routing time (swmm5.c:1551), in days
@@ -613,6 +655,78 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     SWB_FOR_ITEMS(j, nL) qual_link(net, st, j, m, p, dt, (part && !H.link_owned[j]) ? copy : acc);
                     qual_acc_flush(ctx, st, p, m, M, dt, acc);
                 }
+        }
+
+        // ================= removeSystemOutflows (routing.c:776-806, 812-925) =====================
+        // Step rates of everything that enters or leaves the system, summed per member: external
+        // inflows (routing.c:466-489), outfall discharge and flooding (node.c:438-493), negative
+        // lateral flows, storage and conduit losses.  Per-thread partial sums, one atomic per term.
+        if ((args.phases & PH_MASSBAL) && active) {
+            auto flush = [&](int q, double v) {
+                if (M == 1) v = ctx.warp_sum_f64(v);
+                if (v != 0.0 && (M != 1 || ctx.warp_lane == 0)) ctx.atomic_add_f64(&st.mb_rate[(size_t)q * M + m], v);
+            };
+            // pass 0: the flow terms and pollutants 0-1; further passes: two more pollutants each
+            // (keeps the partial sums in registers)
+            for (int p0 = 0; p0 == 0 || (withQual && p0 < nP); p0 += 2) {
+                double fl[MB_FLOW_TERMS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+                double ql[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+                SWB_FOR_ITEMS(i, nNo) {
+                    const size_t ix = SWB_IX(i, m, M);
+                    const double lat = st.n_latflow[ix];
+                    const int type = net.node_type[i];
+                    const double inflow = st.n_inflow[ix], outflow = st.n_outflow[ix];
+                    double q = 0.0;                       // node_getSystemOutflow (node.c:438-493)
+                    bool flooded = false;
+                    if (type == SWB_OUTFALL) {
+                        if (outflow == 0.0) q = inflow;
+                        else if (inflow == 0.0) q = -outflow;
+                    } else {
+                        if (st.n_volume[ix] <= net.node_full_volume[i]) q = st.n_overflow[ix];
+                        flooded = q > 0.0;
+                    }
+                    if (p0 == 0) {
+                        if (lat >= 0.0) fl[MB_EX_INFLOW] += lat; else fl[MB_OUTFLOW] -= lat;      // routing.c:466-469
+                        if (q > 0.0) { if (flooded) fl[MB_FLOODING] += q; else fl[MB_OUTFLOW] += q; }  // :904
+                        else fl[MB_EX_INFLOW] -= q;                                                // :911
+                        if (type == SWB_STORAGE) {                                                 // :812-836
+                            fl[MB_EVAP] += st.n_evap_loss[ix] / dt;
+                            fl[MB_SEEP] += st.n_exfil_loss[ix] / dt;
+                        }
+                    }
+                    if (withQual) {
+                        const int slot = (args.phases & PH_INFLOWS) ? args.inflows.node_slot[i] : -1;
+#pragma unroll
+                        for (int pp = 0; pp < 2; pp++) {
+                            const int p = p0 + pp;
+                            if (p >= nP) continue;
+                            const size_t iq = SWB_IXP(p, i, nN, m, M);
+                            const double c = st.n_qual[iq];
+                            if (slot >= 0 && lat >= 0.0) ql[pp][MBQ_EX_INFLOW] += args.inflows.concen[slot * nP + p] * lat;
+                            if ((args.phases & PH_HOSTIN) && args.host_qual) ql[pp][MBQ_EX_INFLOW] += args.host_qual[iq];
+                            if (q > 0.0) ql[pp][flooded ? MBQ_FLOODING : MBQ_OUTFLOW] += q * c;     // :906-908
+                            if (lat < 0.0) ql[pp][MBQ_OUTFLOW] += -lat * c;                         // :915-922
+                        }
+                    }
+                }
+                if (p0 == 0 && net.anyLossRate)                    // removeConduitLosses (:840-867)
+                    SWB_FOR_ITEMS(j, nL) {
+                        if (!(net.link_flags[j] & LF_HAS_LOSSRATE) || (part && !H.link_owned[j])) continue;
+                        const size_t ix = SWB_IX(j, m, M);
+                        const double barrels = (double)net.cond_barrels[j];
+                        fl[MB_EVAP] += st.c_evap_loss[ix] * barrels;
+                        fl[MB_SEEP] += st.c_seep_loss[ix] * barrels;
+                    }
+                if (p0 == 0)
+#pragma unroll
+                    for (int q = 0; q < MB_FLOW_TERMS; q++) flush(q, fl[q]);
+                if (withQual)
+#pragma unroll
+                    for (int pp = 0; pp < 2; pp++)
+                        if (p0 + pp < nP)
+#pragma unroll
+                            for (int t = 0; t < 3; t++) flush(MB_FLOW_TERMS + (p0 + pp) * MB_QUAL_TERMS + t, ql[pp][t]);
+            }
         }
 
         SWB_TICK(TP_QUAL_LINKS);

@@ -142,6 +142,8 @@ inline void fill_net_scalars(Net &n, const swb_network_desc &d, const swb_option
     n.nN = d.n_nodes; n.nL = d.n_links; n.nP = d.n_pollut; n.nCurves = d.n_curves;
     n.nShapeTbl = d.n_shape_tbls; n.shapeTblLen = d.shape_tbl_len;
     n.nTrue = r.nTrue; n.nNonConduit = r.nNonConduit; n.nOutfallLinks = 0;
+    n.anyLossRate = 0;
+    for (int f : r.link_flags) if (f & LF_HAS_LOSSRATE) n.anyLossRate = 1;
     n.opt = o;
     n.crownCutoff = (o.surcharge_method == SWB_SLOT) ? 0.985257 : 0.96;   // dynwave.c:64-65,159
 }

@@ -64,6 +64,7 @@ struct Net {
     int nTrue;               // true conduits
     int nNonConduit;         // links handled by the ordered regulator pass
     int nOutfallLinks;
+    int anyLossRate;         // some conduit can evaporate / seep (LF_HAS_LOSSRATE)
     swb_options opt;
     double crownCutoff;      // dynwave.c:159-160
 #define X(T, name, kind) const T *name;
@@ -121,6 +122,8 @@ struct Net {
     X(double, l_qual, SWB_LINK_NEW_QUAL, LP) X(double, l_old_qual, SWB_LINK_OLD_QUAL, LP) \
     X(double, l_total_load, SWB_LINK_TOTAL_LOAD, LP)
 
+enum { MB_EX_INFLOW = 0, MB_FLOODING, MB_OUTFLOW, MB_EVAP, MB_SEEP, MB_FLOW_TERMS,
+       MBQ_EX_INFLOW = 0, MBQ_FLOODING, MBQ_OUTFLOW, MBQ_REACTED, MBQ_SEEP, MBQ_FINAL, MB_QUAL_TERMS };
 enum { TP_PROLOGUE = 0, TP_LINKS, TP_REGULATORS, TP_NODES, TP_CONTROL, TP_EPILOGUE, TP_QUAL_NODES,
        TP_QUAL_LINKS, TP_NEXTDT, TP_HALO, TP_HALO_WAIT, SWB_N_PHASES = 12 };
 #define SWB_MAX_TRIALS_CAP 32     // alive / notConv bookkeeping rows (MaxTrials is 8 by default)
@@ -168,6 +171,13 @@ struct State {
     int    *done;                // member has reached t_end
     // mass-balance accumulators per member x pollutant (massbal.c:517-555)
     double *mb_reacted, *mb_seepage, *mb_final_storage;
+    // routing totals per member (massbal.c:587-633): MB_FLOW_TERMS flow terms and, per pollutant,
+    // MB_QUAL_TERMS mass terms.  mb_rate holds the rates of the step just taken (StepFlowTotals /
+    // StepQualTotals, summed with atomics), mb_total the time integral; a step's rates are weighted
+    // by half of its own step plus half of the NEXT one (routing.c:220,264), so the second half is
+    // added by the next step's prologue (or by the host when it reads the totals).
+    double *mb_rate, *mb_total;  // [(MB_FLOW_TERMS + MB_QUAL_TERMS * nP)][M]
+    double *mb_dt_prev;          // [M] step whose rates are pending in mb_rate (0 = none)
     // device-side phase timers (ns, accumulated by thread 0 between grid barriers)
     unsigned long long *phase_ns;    // [SWB_N_PHASES]
     unsigned long long *tickets;     // [3 * SWB_MAX_TRIALS_CAP] work-distribution counters of one step

@@ -49,6 +49,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_run_steps.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.swb_get_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.MemberStats)]
     lib.swb_get_massbal.argtypes = [C.c_void_p, C.c_int, C.c_int, _P_D, _P_D, _P_D]
+    lib.swb_get_routing_totals.argtypes = [C.c_void_p, C.c_int, C.c_int, _P_D, _P_D]
     lib.swb_conduit_updates.argtypes = [C.c_void_p]
     lib.swb_conduit_updates.restype = C.c_longlong
     lib.swb_launch_count.argtypes = [C.c_void_p]
@@ -253,6 +254,61 @@ class Solver:
         self._chk(self.lib.swb_get_massbal(self._h, 0, self.M, r.ctypes.data_as(_P_D),
                                            sp.ctypes.data_as(_P_D), f.ctypes.data_as(_P_D)))
         return {"reacted": r, "seepage": sp, "final_storage": f}
+
+    FLOW_TERMS = ["ex_inflow", "flooding", "outflow", "evap_loss", "seep_loss"]
+    QUAL_TERMS = ["ex_inflow", "flooding", "outflow", "reacted", "seepage", "final_storage"]
+
+    def routing_totals(self):
+        """Per-member routing totals kept on the device (swb_get_routing_totals): flow volumes
+        {term: [M]} and pollutant masses {term: [M, P]}."""
+        nP = self.net.n_pollut
+        fl = np.zeros((self.M, len(self.FLOW_TERMS)))
+        ql = np.zeros((self.M, max(nP, 1), len(self.QUAL_TERMS)))
+        self._chk(self.lib.swb_get_routing_totals(self._h, 0, self.M, fl.ctypes.data_as(_P_D),
+                                                  ql.ctypes.data_as(_P_D) if nP else None))
+        return ({k: fl[:, i].copy() for i, k in enumerate(self.FLOW_TERMS)},
+                {k: ql[:, :nP, i].copy() for i, k in enumerate(self.QUAL_TERMS)})
+
+    def storage(self):
+        """Stored volume [M] and pollutant mass [M, P] in nodes + links (massbal_getStorage
+        massbal.c:634-662, massbal_getStoredMass :1025-1047)."""
+        nP = self.net.n_pollut
+        nv, lv = self.get_field("SWB_NODE_NEW_VOLUME"), self.get_field("SWB_LINK_NEW_VOLUME")
+        vol = nv.sum(axis=1) + lv.sum(axis=1)
+        mass = np.zeros((self.M, nP))
+        if nP:
+            nq = self.get_field("SWB_NODE_NEW_QUAL").reshape(self.M, -1, nP)
+            lq = self.get_field("SWB_LINK_NEW_QUAL").reshape(self.M, -1, nP)
+            mass = (nv[:, :, None] * nq).sum(axis=1) + (lv[:, :, None] * lq).sum(axis=1)
+        return vol, mass
+
+    def continuity(self, init_storage):
+        """Flow-routing and quality continuity errors in percent for every member, computed like
+        massbal_getFlowError / massbal_getQualError (massbal.c:858-960).  init_storage = storage()
+        taken before the first step.  Returns (flow_pct[M], qual_pct[M, P])."""
+        fl, ql = self.routing_totals()
+        v0, w0 = init_storage
+        v1, w1 = self.storage()
+
+        def pct(tin, tout, small):
+            out = np.zeros_like(tin)
+            for idx in np.ndindex(tin.shape):
+                a, b = tin[idx], tout[idx]
+                if abs(a - b) < small:
+                    out[idx] = 1.0e-6
+                elif abs(a) > 0.0:
+                    out[idx] = 100.0 * (1.0 - b / a)
+                elif abs(b) > 0.0:
+                    out[idx] = 100.0 * (a / b - 1.0)
+            return out
+        ex, of = fl["ex_inflow"], fl["outflow"]
+        tin = v0 + np.where(ex >= 0.0, ex, 0.0) + np.where(of < 0.0, -of, 0.0)
+        tout = v1 + fl["flooding"] + fl["evap_loss"] + fl["seep_loss"] + np.where(ex < 0.0, -ex, 0.0) \
+            + np.where(of >= 0.0, of, 0.0)
+        flow_pct = pct(tin, tout, 1.0)
+        qin = ql["ex_inflow"] + w0
+        qout = ql["flooding"] + ql["outflow"] + ql["reacted"] + ql["seepage"] + ql["final_storage"] + w1
+        return flow_pct, pct(qin, qout, 0.001)
 
     PHASES = ["prologue", "links", "regulators", "nodes", "control", "epilogue", "qual_nodes",
               "qual_links", "next_dt", "halo", "halo_wait"]

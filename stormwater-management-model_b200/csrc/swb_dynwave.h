@@ -651,6 +651,45 @@ SWB_FI void node_add_link_end(const Net &n, const State &s, int j, int end, int 
     else a.sumdqdh += dqdh;
 }
 
+// The same contribution split into its loads and its arithmetic, so that a caller can issue the
+// loads of two link ends before consuming either (two DRAM round trips per node instead of four);
+// the accumulation order, hence every bit of the sums, is unchanged.
+struct LinkEndData { int flags, type, barrels, pumpType; double q, loss, sa, dqdh; };
+SWB_FI LinkEndData node_load_link_end(const Net &n, const State &s, int j, int end, int m)
+{
+    LinkEndData d;
+    const size_t ix = SWB_IX(j, m, s.M);
+    d.flags = n.link_flags[j];
+    d.type = n.link_type[j];
+    d.q = s.l_flow[ix];
+    d.sa = (end == 0 ? s.l_surf_area1[ix] : s.l_surf_area2[ix]);
+    d.dqdh = s.l_dqdh[ix];
+    d.barrels = 1; d.loss = 0.0; d.pumpType = 0;
+    if (d.type == SWB_CONDUIT) {
+        d.barrels = n.cond_barrels[j];
+        if (d.flags & LF_HAS_LOSSRATE) d.loss = s.c_evap_loss[ix] + s.c_seep_loss[ix];
+    } else if (d.type == SWB_PUMP) d.pumpType = n.pump_type[j];
+    return d;
+}
+SWB_FI void node_apply_link_end(const LinkEndData &d, int end, NodeAcc &a)
+{
+    const double q = d.q;
+    if (q >= 0.0) { if (end == 0) a.outflow += q; else a.inflow += q; }
+    else          { if (end == 0) a.inflow -= q;  else a.outflow -= q; }
+    if (d.type == SWB_CONDUIT && (d.flags & LF_HAS_LOSSRATE)) {
+        double lossRate = d.loss * d.barrels;
+        if (lossRate > 0.0) {
+            bool o1 = (d.flags & LF_N1_OUTFALL) != 0, o2 = (d.flags & LF_N2_OUTFALL) != 0;
+            if (!o1 && !o2) lossRate /= 2.0;
+            if (end == 0 ? !o1 : !o2) a.outflow += lossRate;
+        }
+    }
+    a.surfArea += d.sa * d.barrels;
+    if (end == 0) a.sumdqdh += d.dqdh;
+    else if (d.type == SWB_PUMP) { if (d.pumpType != 3 /*TYPE4_PUMP*/) a.sumdqdh += d.dqdh; }
+    else a.sumdqdh += d.dqdh;
+}
+
 // ---- K4: outfall boundary depth (link.c:728-766, node.c:1413-1492) ------------------------------
 SWB_NI void outfall_depth(const Net &n, const State &s, int i, int m, const double *T)
 {
@@ -770,10 +809,12 @@ SWB_FI double link_step(const Net &n, const State &s, int j, int m)
     if (n.link_type[j] != SWB_CONDUIT) return -1.0;
     size_t ix = SWB_IX(j, m, s.M);
     double barrels = (double)n.cond_barrels[j];
-    double q = fabs(s.l_flow[ix]) / barrels;
-    double froude = s.l_froude[ix];
-    if (q <= SWB_FUDGE || s.c_a1[ix] <= SWB_FUDGE || froude <= 0.01) return -1.0;
-    double t = s.l_volume[ix] / barrels / q;
+    // all four loads are issued before the first test: one DRAM round trip per link instead of a
+    // chain of dependent ones (the early exits only skip arithmetic)
+    const double flow = s.l_flow[ix], froude = s.l_froude[ix], a1 = s.c_a1[ix], volume = s.l_volume[ix];
+    double q = fabs(flow) / barrels;
+    if (q <= SWB_FUDGE || a1 <= SWB_FUDGE || froude <= 0.01) return -1.0;
+    double t = volume / barrels / q;
     t = t * n.cond_mod_length[j] / n.cond_length[j];
     t = t * froude / (1.0 + froude) * n.opt.courant_factor;
     return t;
@@ -782,13 +823,12 @@ SWB_FI double node_step(const Net &n, const State &s, int i, int m)
 {
     if (n.node_type[i] == SWB_OUTFALL) return -1.0;
     size_t ix = SWB_IX(i, m, s.M);
-    double depth = s.n_depth[ix];
+    const double depth = s.n_depth[ix], dYdT = s.n_dydt[ix];     // both loads up front
     double yCrown = n.node_crown_elev[i] - n.node_invert[i];
     if (depth <= SWB_FUDGE) return -1.0;
     if (depth + SWB_FUDGE >= yCrown) return -1.0;
     double maxDepth = yCrown * 0.25;
     if (maxDepth < SWB_FUDGE) return -1.0;
-    double dYdT = s.n_dydt[ix];
     if (dYdT < SWB_FUDGE) return -1.0;
     return maxDepth / dYdT;
 }

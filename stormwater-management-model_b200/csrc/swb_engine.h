@@ -134,8 +134,21 @@ SWB_FI bool picard_node(const Net &net, const State &st, int i, int m, int k, do
         acc.surfArea = st.n_new_surf_area[ix]; acc.sumdqdh = st.n_sumdqdh[ix];
     } else {
         acc = node_init_acc(net, st, i, m);
+#if SWB_GATHER2
+        int e = net.adj_start[i];
+        const int e1 = net.adj_start[i + 1];
+        for (; e + 1 < e1; e += 2) {
+            const int ea = net.adj[e], eb = net.adj[e + 1];
+            const LinkEndData da = node_load_link_end(net, st, ea >> 1, ea & 1, m);
+            const LinkEndData db = node_load_link_end(net, st, eb >> 1, eb & 1, m);
+            node_apply_link_end(da, ea & 1, acc);
+            node_apply_link_end(db, eb & 1, acc);
+        }
+        if (e < e1) node_add_link_end(net, st, net.adj[e] >> 1, net.adj[e] & 1, m, acc);
+#else
         for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++)
             node_add_link_end(net, st, net.adj[e] >> 1, net.adj[e] & 1, m, acc);
+#endif
     }
     if (net.node_type[i] == SWB_OUTFALL) {
         st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;
@@ -192,6 +205,9 @@ struct NoPrefetch { SWB_ENGINE void operator()(int, int) const {} };
 #endif
 #ifndef SWB_PREFETCH
 #define SWB_PREFETCH 0
+#endif
+#ifndef SWB_GATHER2
+#define SWB_GATHER2 0       // node gather: loads of two link ends in flight (A/B switch)
 #endif
 #ifndef SWB_TICKET_BATCH
 #define SWB_TICKET_BATCH 1

@@ -102,9 +102,13 @@ SWB_FI void qual_link(const Net &n, const State &s, int j, int m, int p, double 
     int up = n.link_node1[j];
     if (newFlow < 0.0) up = n.link_node2[j];
     double c1 = s.l_old_qual[iq];
-    s.l_total_load[iq] += qAbs * c1 * tStep;
+    // every load of this link is issued before its first store (the arrays may alias as far as
+    // the compiler knows, so a load placed after a store waits for a second DRAM round trip)
+    const double load0 = s.l_total_load[iq];
+    const double cUp = s.n_qual[SWB_IXP(p, up, n.nN, m, M)];
     if (!(n.link_flags[j] & LF_TRUE_CONDUIT)) {
-        s.l_qual[iq] = s.n_qual[SWB_IXP(p, up, n.nN, m, M)];
+        s.l_total_load[iq] = load0 + qAbs * c1 * tStep;
+        s.l_qual[iq] = cUp;
         return;
     }
     double barrels = (double)n.cond_barrels[j];
@@ -115,6 +119,8 @@ SWB_FI void qual_link(const Net &n, const State &s, int j, int m, int p, double 
         vEvap = s.c_evap_loss[ix] * barrels * tStep;
     }
     double v1 = s.l_old_volume[ix], v2 = s.l_volume[ix];
+    const double depth = s.l_depth[ix];
+    s.l_total_load[iq] = load0 + qAbs * c1 * tStep;
     double vLosses = qSeep * tStep + vEvap;
     double fEvap = 1.0;
     if (vEvap > 0.0 && v1 > SWB_ZERO_VOLUME) fEvap += vEvap / v1;
@@ -123,9 +129,9 @@ SWB_FI void qual_link(const Net &n, const State &s, int j, int m, int p, double 
     acc.seepage += qSeep * c1;
     c1 *= fEvap;
     double c2 = qual_reacted(n.pollut_kdecay[p], c1, v1, tStep, acc.reacted);
-    double wIn = s.n_qual[SWB_IXP(p, up, n.nN, m, M)] * qIn;
+    double wIn = cUp * qIn;
     c2 = qual_mixed(c2, v1, wIn, qIn, tStep);
-    if (v2 < SWB_ZERO_VOLUME || s.l_depth[ix] <= SWB_ZERO_DEPTH) { acc.finalStorage += c2 * v2; c2 = 0.0; }
+    if (v2 < SWB_ZERO_VOLUME || depth <= SWB_ZERO_DEPTH) { acc.finalStorage += c2 * v2; c2 = 0.0; }
     s.l_qual[iq] = c2;
 }
 

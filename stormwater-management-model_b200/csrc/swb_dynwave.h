@@ -728,8 +728,15 @@ SWB_NI void outfall_depth(const Net &n, const State &s, int i, int m, const doub
 }
 
 // ---- K5: setNodeDepth + getFloodedDepth (dynwave.c:636-795); returns the converged flag ---------
+struct NodeOld { double yOld, oldNetInflow; };      // loaded by the caller before the link gather
+SWB_FI NodeOld node_load_old(const State &s, int i, int m)
+{
+    const size_t ix = SWB_IX(i, m, s.M);
+    NodeOld o = { s.n_old_depth[ix], s.n_old_net_inflow[ix] };
+    return o;
+}
 SWB_FI bool node_set_depth(const Net &n, const State &s, int i, int m, int steps, double dt,
-                                  const NodeAcc &acc)
+                                  const NodeAcc &acc, const NodeOld &old)
 {
     const size_t ix = SWB_IX(i, m, s.M);
     const double fullDepth = n.node_full_depth[i];
@@ -737,12 +744,12 @@ SWB_FI bool node_set_depth(const Net &n, const State &s, int i, int m, int steps
     const double yLast = s.n_depth[ix];
     const bool isPonded = (canPond && yLast > fullDepth);
     const double yCrown = n.node_crown_elev[i] - n.node_invert[i];
-    const double yOld = s.n_old_depth[ix];
+    const double yOld = old.yOld;
     double overflow = 0.0, newVolume;
     double surfArea = acc.surfArea;
     surfArea = SWB_MAX(surfArea, n.opt.min_surf_area);
     double dQ = acc.inflow - acc.outflow;
-    double dV = 0.5 * (s.n_old_net_inflow[ix] + dQ) * dt;
+    double dV = 0.5 * (old.oldNetInflow + dQ) * dt;
     bool isSurcharged = false;
     double yNew, dy;
 

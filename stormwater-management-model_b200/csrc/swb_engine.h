@@ -33,6 +33,14 @@
 #define SWB_ENGINE
 #endif
 
+// build switches of the node phase (measured variants, profiles/README.md)
+#ifndef SWB_GATHER2
+#define SWB_GATHER2 1       // node gather: loads of two link ends in flight (nodes 150 -> 137 ms, profiles/README.md)
+#endif
+#ifndef SWB_NODE_EARLY
+#define SWB_NODE_EARLY 0    // A/B switch: old depth / net inflow loaded before the gather
+#endif
+
 namespace swb {
 
 enum {                         // RunArgs.phases
@@ -129,6 +137,11 @@ SWB_FI bool picard_node(const Net &net, const State &st, int i, int m, int k, do
 {
     NodeAcc acc;
     size_t ix = SWB_IX(i, m, st.M);
+#if SWB_NODE_EARLY
+    // old depth / old net inflow requested together with the node's first loads, not after the
+    // link gather (nothing in between stores, but the compiler does not hoist loads over the loop)
+    const NodeOld old = node_load_old(st, i, m);
+#endif
     if (net.nNonConduit > 0) {
         acc.inflow = st.n_inflow[ix]; acc.outflow = st.n_outflow[ix];
         acc.surfArea = st.n_new_surf_area[ix]; acc.sumdqdh = st.n_sumdqdh[ix];
@@ -155,7 +168,10 @@ SWB_FI bool picard_node(const Net &net, const State &st, int i, int m, int k, do
         outfall_depth(net, st, i, m, T);
         return true;
     }
-    return node_set_depth(net, st, i, m, k, dt, acc);
+#if !SWB_NODE_EARLY
+    const NodeOld old = node_load_old(st, i, m);
+#endif
+    return node_set_depth(net, st, i, m, k, dt, acc, old);
 }
 
 // Dynamic tile loop: tile t = (object t / nChunks, chunk t % nChunks of the member list); a warp
@@ -205,9 +221,6 @@ struct NoPrefetch { SWB_ENGINE void operator()(int, int) const {} };
 #endif
 #ifndef SWB_PREFETCH
 #define SWB_PREFETCH 0
-#endif
-#ifndef SWB_GATHER2
-#define SWB_GATHER2 0       // node gather: loads of two link ends in flight (A/B switch)
 #endif
 #ifndef SWB_TICKET_BATCH
 #define SWB_TICKET_BATCH 1
@@ -691,14 +704,17 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     const size_t ix = SWB_IX(i, m, M);
                     const double lat = st.n_latflow[ix];
                     const int type = net.node_type[i];
-                    const double inflow = st.n_inflow[ix], outflow = st.n_outflow[ix];
                     double q = 0.0;                       // node_getSystemOutflow (node.c:438-493)
                     bool flooded = false;
-                    if (type == SWB_OUTFALL) {
+                    if (type == SWB_OUTFALL) {            // (warp-uniform: a warp holds one node)
+                        const double inflow = st.n_inflow[ix], outflow = st.n_outflow[ix];
                         if (outflow == 0.0) q = inflow;
                         else if (inflow == 0.0) q = -outflow;
                     } else {
-                        if (st.n_volume[ix] <= net.node_full_volume[i]) q = st.n_overflow[ix];
+                        // q = overflow if newVolume <= fullVolume: the volume only matters when
+                        // there is an overflow at all, so junctions cost two loads here
+                        const double ov = st.n_overflow[ix];
+                        if (ov != 0.0 && st.n_volume[ix] <= net.node_full_volume[i]) q = ov;
                         flooded = q > 0.0;
                     }
                     if (p0 == 0) {
@@ -717,11 +733,13 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                             const int p = p0 + pp;
                             if (p >= nP) continue;
                             const size_t iq = SWB_IXP(p, i, nN, m, M);
-                            const double c = st.n_qual[iq];
                             if (slot >= 0 && lat >= 0.0) ql[pp][MBQ_EX_INFLOW] += args.inflows.concen[slot * nP + p] * lat;
                             if ((args.phases & PH_HOSTIN) && args.host_qual) ql[pp][MBQ_EX_INFLOW] += args.host_qual[iq];
-                            if (q > 0.0) ql[pp][flooded ? MBQ_FLOODING : MBQ_OUTFLOW] += q * c;     // :906-908
-                            if (lat < 0.0) ql[pp][MBQ_OUTFLOW] += -lat * c;                         // :915-922
+                            if (q > 0.0 || lat < 0.0) {   // the concentration only where mass leaves
+                                const double c = st.n_qual[iq];
+                                if (q > 0.0) ql[pp][flooded ? MBQ_FLOODING : MBQ_OUTFLOW] += q * c;  // :906-908
+                                if (lat < 0.0) ql[pp][MBQ_OUTFLOW] += -lat * c;                      // :915-922
+                            }
                         }
                     }
                 }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 5 on ONE GPU: the 1000 x 500 looped grid (~1M conduits, SLOT, no pollutants) as a
-single model (M = 1), stepped entirely on the device.  The multi-GPU halo partition is future work;
-this gives the single-GPU number next to the reference's 4.5e6 conduit-updates/s (8 threads)."""
+single model (M = 1), stepped entirely on the device: the single-GPU number next to the reference's
+4.5e6 conduit-updates/s (8 threads).  tools/c5_partitioned.py runs the same model striped over N GPUs."""
 import sys
 import time
 

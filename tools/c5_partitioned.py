@@ -79,8 +79,11 @@ def main():
     gids = [None] * world
     dist.all_gather_object(gids, gid)
     flows = [None] * world
+    quals = [None] * world
     if a.check:
         dist.all_gather_object(flows, ps.owned_field("SWB_LINK_NEW_FLOW"))
+        if nP:
+            dist.all_gather_object(quals, ps.owned_field("SWB_LINK_NEW_QUAL"))
     all_phases = [None] * world
     dist.all_gather_object(all_phases, {k: round(v, 3) for k, v in phases.items()})
     ok = None
@@ -111,6 +114,10 @@ def main():
             flow_all = partition.assemble(flows, net.n_links)
             ok = bool(np.array_equal(depth_all, ref_d) and np.array_equal(flow_all, ref_q)
                       and s0.iterations == st.iterations and s0.sim_time == st.sim_time and s0.steps == st.steps)
+            if nP:      # the border concentrations travel through the same windows (qualrout.c:253-353)
+                qual_all = partition.assemble(quals, net.n_links, nP)
+                ok = ok and bool(np.array_equal(qual_all, single.get_field("SWB_LINK_NEW_QUAL")[0]))
+                out["max_link_concentration"] = float(qual_all.max())
             out["single_gpu_kernel_s"] = single.last_kernel_ms() / 1000.0
             out["single_gpu_conduit_updates_per_s"] = cu / (single.last_kernel_ms() / 1000.0)
             out["identical_to_single_gpu"] = ok

@@ -502,9 +502,20 @@ int swb_partition_attach(swb_solver *s, const swb_partition_desc *p)
     memset(&H, 0, sizeof(H));
     H.rank = p->rank; H.nRanks = p->n_ranks; H.nOwnedN = p->n_owned_nodes;
     H.nSend = p->n_send; H.nRecv = p->n_recv; H.W = n.nP > 2 ? n.nP : 2;
-    H.send_node = dev_copy<int>(s->allocs, p->send_node, p->n_send);
-    H.send_rank = dev_copy<int>(s->allocs, p->send_rank, p->n_send);
-    H.send_slot = dev_copy<int>(s->allocs, p->send_slot, p->n_send);
+    {   // send entries sorted by node + CSR over the owned nodes
+        std::vector<int> idx(p->n_send), sn(p->n_send), sr(p->n_send), ss(p->n_send), start(p->n_owned_nodes + 1, 0);
+        for (int k = 0; k < p->n_send; k++) idx[k] = k;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return p->send_node[a] < p->send_node[b]; });
+        for (int k = 0; k < p->n_send; k++) {
+            sn[k] = p->send_node[idx[k]]; sr[k] = p->send_rank[idx[k]]; ss[k] = p->send_slot[idx[k]];
+            start[sn[k] + 1]++;
+        }
+        for (int i = 0; i < p->n_owned_nodes; i++) start[i + 1] += start[i];
+        H.send_node = dev_copy<int>(s->allocs, sn.data(), sn.size());
+        H.send_rank = dev_copy<int>(s->allocs, sr.data(), sr.size());
+        H.send_slot = dev_copy<int>(s->allocs, ss.data(), ss.size());
+        H.send_start = dev_copy<int>(s->allocs, start.data(), start.size());
+    }
     H.recv_node = dev_copy<int>(s->allocs, p->recv_node, p->n_recv);
     H.link_owned = dev_copy<int>(s->allocs, p->link_owned, n.nL);
     {

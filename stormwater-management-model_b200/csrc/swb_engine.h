@@ -314,7 +314,8 @@ SWB_ENGINE inline void qual_acc_flush(Ctx &ctx, const State &st, int p, int m, i
 }
 
 // ---- partitioned network: one exchange = push border values + reduction operands into every
-// peer's window, flag, wait for every peer's flag, pull.  Two grid barriers; rank-to-rank traffic
+// peer's window, flag, wait for every peer's flag, pull.  Two grid barriers (one when the producing
+// phase pushes its values itself, as the node phase does); rank-to-rank traffic
 // is a few KB of direct stores, so the cost is latency (NVLink round trip + barriers), not bandwidth.
 //   get(s, w)      value w of send entry s                      (any thread)
 //   put(r, w, v)   store value w of receive slot r              (any thread)
@@ -322,16 +323,21 @@ SWB_ENGINE inline void qual_acc_flush(Ctx &ctx, const State &st, int p, int m, i
 //   fold(rows)     rows[p * HALO_RED + q] = operand q of rank p (thread 0, after the wait)
 template <class Ctx, class Get, class Put, class Fold>
 SWB_ENGINE inline void halo_exchange(Ctx &ctx, const Halo &H, unsigned long long &epoch, int nvals,
-                                     const unsigned long long *red_in, Get get, Put put, Fold fold)
+                                     const unsigned long long *red_in, Get get, Put put, Fold fold,
+                                     bool prepushed = false)
 {
     epoch++;
     const int par = (int)(epoch & 1ull);
-    for (int e = ctx.tid; e < H.nSend * nvals; e += ctx.G) {
-        const int s = e / nvals, w = e - s * nvals;
-        H.peer_stage[H.send_rank[s]][((size_t)H.send_slot[s] * 2 + par) * H.W + w] = get(s, w);
+    // prepushed: the producing phase has already stored (and fenced) this epoch's border values and
+    // its closing grid barrier has passed -- no push loop and no extra barrier here
+    if (!prepushed) {
+        for (int e = ctx.tid; e < H.nSend * nvals; e += ctx.G) {
+            const int s = e / nvals, w = e - s * nvals;
+            H.peer_stage[H.send_rank[s]][((size_t)H.send_slot[s] * 2 + par) * H.W + w] = get(s, w);
+        }
+        if (ctx.tid < H.nSend * nvals) ctx.fence_system();   // only threads that stored remotely
+        ctx.grid_sync();                                     // every push of this rank has been fenced
     }
-    if (ctx.tid < H.nSend * nvals) ctx.fence_system();   // only threads that stored remotely
-    ctx.grid_sync();                                     // every push of this rank has been fenced
     // signal: thread p of the grid serves peer p (reduction operands, then the released epoch flag),
     // so the peers are written in parallel, not one NVLink round trip after the other
     for (int p = ctx.tid; p < H.nRanks; p += ctx.G) {
@@ -597,7 +603,19 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 }
                 // ---- findNodeDepths (dynwave.c:593-632)
                 for_tiles(ctx, nNo, nAlive, tickets + 2, [&](int ii, int mm) {
-                    if (!picard_node(net, st, nodeOrder[ii], mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
+                    const int i = nodeOrder[ii];
+                    if (!picard_node(net, st, i, mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
+                    if (part && H.send_start[i + 1] > H.send_start[i]) {
+                        // a border node: its new depth and converged flag go straight into the
+                        // peers' windows (parity of the exchange that follows this phase)
+                        const int par = (int)((epoch + 1ull) & 1ull);
+                        const double d = st.n_depth[i], c = (double)st.n_converged[i];
+                        for (int e = H.send_start[i]; e < H.send_start[i + 1]; e++) {
+                            double *dst = H.peer_stage[H.send_rank[e]] + ((size_t)H.send_slot[e] * 2 + par) * H.W;
+                            dst[0] = d; dst[1] = c;
+                        }
+                        ctx.fence_system();
+                    }
                 }, [&](int ii, int mm) { prefetch_node(ctx, net, st, nodeOrder[ii], mm); });
                 ctx.grid_sync();
                 SWB_TICK(TP_NODES);
@@ -614,7 +632,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                         [&](const unsigned long long *rows) {
                             int any = 0;
                             for (int p = 0; p < H.nRanks; p++) any |= (rows[p * HALO_RED] != 0ull);
-                            st.not_conv[k * M] = any; });
+                            st.not_conv[k * M] = any; }, true);
                     SWB_TICK(TP_HALO);
                 }
                 // ---- loop control: Steps++ ; if (Steps > 1 && converged) break (:248-251).

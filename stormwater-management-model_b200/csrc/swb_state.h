@@ -143,6 +143,8 @@ struct Halo {
     int nSend, nRecv, W;
     const int *send_node, *send_rank, *send_slot, *recv_node, *link_owned;
     const int *node_order;       // Net::node_order restricted to the owned nodes
+    const int *send_start;       // [nOwnedN + 1] CSR over the send entries (sorted by node): the node
+                                 // phase publishes a border node the moment it has computed it
     unsigned long long *ctrl, *red;
     double *stage;
     unsigned long long *peer_ctrl[SWB_MAX_RANKS], *peer_red[SWB_MAX_RANKS];

@@ -19,6 +19,13 @@ FIELDS = ["SWB_NODE_NEW_DEPTH", "SWB_NODE_NEW_VOLUME", "SWB_NODE_OVERFLOW", "SWB
           "SWB_LINK_NEW_QUAL", "SWB_LINK_FLOW_CLASS", "SWB_COND_CAPACITY_LIMITED"]
 
 
+def free_port() -> str:
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return str(sk.getsockname()[1])
+
+
 def golden_setup(case):
     net, g = pc.load_golden(case)
     state = {k[3:]: g[k] for k in g if k.startswith("s0_")}
@@ -131,7 +138,7 @@ def test_two_gloo_processes(emul_lib, tmp_path):
     script = os.path.join(pc.ROOT, "tests", "partition_worker.py")
     env = dict(os.environ, SWB_LIB=emul_lib, PYTHONPATH=os.pathsep.join([pc.ROOT, os.path.join(pc.ROOT, "tests")]))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29731", script, "--backend", "gloo",
+                        "--master-addr", "127.0.0.1", "--master-port", free_port(), script, "--backend", "gloo",
                         "--case", "c2_grid12_slot", "--steps", "120"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
@@ -147,7 +154,7 @@ def test_partitioned_gpu_two_processes_share_one_or_two_devices():
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([pc.ROOT, os.path.join(pc.ROOT, "tests")]))
     env.pop("SWB_LIB", None)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29732", script, "--backend", "gloo",
+                        "--master-addr", "127.0.0.1", "--master-port", free_port(), script, "--backend", "gloo",
                         "--case", "c2_grid12_slot", "--steps", "300", "--cuda"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]

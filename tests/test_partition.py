@@ -3,6 +3,7 @@ it owns, exactly what the unpartitioned solver computes -- same variable steps, 
 counts, bit-identical depths / flows / concentrations -- with the border exchange running inside the
 kernel.  CPU suite: the host emulation of the engine, ranks as threads of one process and as two
 `torch.distributed` (gloo) processes; the GPU test runs the same comparison on the device."""
+import ctypes as C
 import os
 import subprocess
 import sys
@@ -159,3 +160,32 @@ def test_partitioned_gpu_two_processes_share_one_or_two_devices():
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "partition parity ok" in r.stdout, r.stdout[-2000:]
+
+
+def test_partition_argument_checks(emul_lib):
+    """Error behaviour of the partition entry points (all SWB_ERR_ARG / SWB_ERR_UNSUPP, no crash)."""
+    net, state, inflows, t_end = golden_setup("c2_grid12_slot")
+    parts = partition.split_network(net, partition.stripes(12, 12, 2, extra_nodes=1), 2)
+    # a partitioned solver holds one member
+    s = solver.Solver(parts[0].net, 32, lib_path=emul_lib)
+    d = partition.PartitionDesc()
+    d.rank, d.n_ranks, d.n_owned_nodes = 0, 2, parts[0].n_owned
+    s.lib.swb_partition_attach.argtypes = [C.c_void_p, C.POINTER(partition.PartitionDesc)]
+    with pytest.raises(solver.SwbError, match="one member"):
+        s._chk(s.lib.swb_partition_attach(s._h, C.byref(d)))
+    s.close()
+    # stepping before every peer is connected is refused
+    ps = partition.PartitionedSolver(parts[0], lib_path=emul_lib)
+    ps.load_state(partition.split_state(ps.part, state, net.n_pollut))
+    ps.set_inflows(**partition.split_inflows(ps.part, inflows, net.n_pollut))
+    with pytest.raises(solver.SwbError, match="swb_partition_connect"):
+        ps.run_steps(1, t_end)
+    # a second attach, a bad peer rank and connecting twice are refused
+    other = partition.PartitionedSolver(parts[1], lib_path=emul_lib)
+    with pytest.raises(solver.SwbError, match="bad peer rank"):
+        ps._chk(ps.lib.swb_partition_connect(ps._h, 0, C.create_string_buffer(other.export_handle(), 64)))
+    ps.connect([None, other.export_handle()])
+    with pytest.raises(solver.SwbError, match="already connected"):
+        ps.connect([None, other.export_handle()])
+    ps.close()
+    other.close()

@@ -130,3 +130,14 @@ def test_cuda_results_equal_host_emulation():
     assert np.array_equal(an, bn) and np.array_equal(al, bl)
     a.close()
     b.close()
+
+
+def test_results_argument_checks(emul_lib):
+    net, g = pc.load_golden("c1_tree")
+    s = solver.Solver(net, 1, lib_path=emul_lib)
+    with pytest.raises(solver.SwbError):
+        s.results(0.5, member0=1, n_members=1)          # member range out of bounds
+    nd, ld = s.results(0.5)
+    assert nd.shape == (1, net.n_nodes, 6) and ld.shape == (1, net.n_links, 5)   # no pollutants
+    assert not np.any(nd[:, :, 0]) and not np.any(ld[:, :, 0])                      # fresh solver: all zero
+    s.close()

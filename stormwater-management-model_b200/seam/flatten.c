@@ -288,6 +288,8 @@ static int field_rw(int field, double *buf, int set)
       case SWB_NODE_OUTFLOW:        NODE_LOOP(Node[i].outflow);
       case SWB_NODE_OVERFLOW:       NODE_LOOP(Node[i].overflow);
       case SWB_NODE_OLD_NET_INFLOW: NODE_LOOP(Node[i].oldNetInflow);
+      case SWB_NODE_OLD_LATFLOW:    NODE_LOOP(Node[i].oldLatFlow);
+      case SWB_NODE_OLD_INFLOW:     NODE_LOOP(Node[i].oldFlowInflow);
       case SWB_NODE_OUTFALL_STAGE:
         for (i = 0; i < nN; i++)
             if (!set) buf[i] = (Node[i].type == OUTFALL) ? outfall_stage(i) : 0.0;

@@ -400,7 +400,7 @@ class Solver:
         "SWB_NODE_NEW_LATFLOW", "SWB_NODE_LOSSES", "SWB_NODE_INFLOW", "SWB_NODE_OUTFLOW",
         "SWB_NODE_OVERFLOW", "SWB_NODE_OLD_NET_INFLOW", "SWB_NODE_OUTFALL_STAGE",
         "SWB_NODE_STORAGE_EVAP_LOSS", "SWB_NODE_STORAGE_EXFIL_LOSS", "SWB_NODE_HRT",
-        "SWB_NODE_NEW_QUAL", "SWB_NODE_OLD_QUAL",
+        "SWB_NODE_NEW_QUAL", "SWB_NODE_OLD_QUAL", "SWB_NODE_OLD_LATFLOW", "SWB_NODE_OLD_INFLOW",
         "SWB_LINK_NEW_FLOW", "SWB_LINK_OLD_FLOW", "SWB_LINK_NEW_DEPTH", "SWB_LINK_OLD_DEPTH",
         "SWB_LINK_NEW_VOLUME", "SWB_LINK_OLD_VOLUME", "SWB_LINK_SETTING", "SWB_LINK_TARGET_SETTING",
         "SWB_LINK_DQDH", "SWB_LINK_FROUDE", "SWB_LINK_FLOW_CLASS", "SWB_LINK_SURF_AREA1",

@@ -2,8 +2,8 @@
 
 bench.py and the ensemble driver use this on the GPU box, where only this repo exists.  It restates
 the reference's SETUP arithmetic for the element types those configs use, so that a built network
-equals the one the engine produces from the equivalent ``.inp`` bit for bit (tests check this
-against oracle/_ref):
+equals the one the engine produces from the equivalent ``.inp`` bit for bit
+(tests/test_baseline_size.py::test_network_builder_equals_engine_flattening, against oracle/_ref):
   xsect_setParams       xsect.c:216-330   (CIRCULAR, RECT_CLOSED)
   conduit_validate      link.c:992-1154   (slope, reversal, roughFactor, beta, qFull, qMax)
   conduit_getSlope      link.c:1258-1300
@@ -253,7 +253,7 @@ def build_grid(spec: scenarios.GridSpec | None = None, lib_path=None) -> BuiltCa
     nodes, sf = [], []
     for (i, j, sc) in s.inflow_nodes():
         nodes.append(ids[(i, j)])
-        sf.append(float(f"{sc * s.inflow_scale:.6f}"))
+        sf.append(s.sfactor(sc))
     order = np.argsort(nodes, kind="stable")
     nodes = np.array(nodes, dtype=np.int32)[order]
     sf = np.array(sf)[order]

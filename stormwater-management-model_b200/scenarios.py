@@ -155,6 +155,16 @@ class GridSpec:
                 k += 1
         return out
 
+    def sfactor(self, sc: float) -> float:
+        """Scale factor written for an inflow node: the base model's 6-decimal value, times the
+        member scale in ONE double multiplication -- exactly what the device forms from
+        (sfactor, member_scale), so a perturbed .inp and an ensemble member see the same bits."""
+        base = float(f"{sc:.6f}")
+        return base if self.inflow_scale == 1.0 else base * float(self.inflow_scale)
+
+    def sfactor_text(self, sc: float) -> str:
+        return f"{sc:.6f}" if self.inflow_scale == 1.0 else repr(self.sfactor(sc))
+
     def hydrograph(self) -> list[tuple[float, float]]:
         """Breakpoints after the member time shift (hours >= 0, value)."""
         pts = [(t + self.inflow_shift_h, v) for t, v in self.hydro]
@@ -195,7 +205,7 @@ def c2_grid_inp(spec: GridSpec | None = None) -> str:
     L += ["[INFLOWS]"]
     for (i, j, sc) in s.inflow_nodes():
         nid = s.node_id(i, j)
-        L.append(f"{nid} FLOW HYDRO FLOW 1.0 {sc * s.inflow_scale:.6f}")
+        L.append(f"{nid} FLOW HYDRO FLOW 1.0 {s.sfactor_text(sc)}")
         if s.pollutants:
             L.append(f"{nid} TSS CTSS CONCEN 1.0 1.0")
             L.append(f"{nid} DYE CDYE CONCEN 1.0 1.0")

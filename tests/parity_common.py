@@ -124,11 +124,16 @@ def make_solver_from_engine(e, lib_path, n_members=1, member_scale=None, member_
 
 
 def lockstep_vs_reference(inp_text: str, lib_path, max_steps: int | None = None, every: int = 1,
-                          n_members: int = 1) -> dict:
-    """Step the reference and the solver (ensemble driver, one step per launch) side by side."""
+                          n_members: int = 1, continuity: bool = False) -> dict:
+    """Step the reference and the solver (ensemble driver, one step per launch) side by side.
+    continuity=True (whole runs only) adds the flow / quality continuity errors of the solver's
+    device-side routing totals next to the reference's own swmm_getMassBalErr."""
     e, _ = open_reference(inp_text)
+    out = None
     try:
         s = make_solver_from_engine(e, lib_path, n_members)
+        init_storage = s.storage() if continuity else None
+        ref_iters = 0
         t_end = e.total_duration_s()
         worst = {f: 0.0 for f in SNAP_FIELDS}
         worst_dt = 0.0
@@ -137,6 +142,7 @@ def lockstep_vs_reference(inp_text: str, lib_path, max_steps: int | None = None,
         prev_crit = None
         while True:
             t = e.step()
+            ref_iters += e.last_iterations()
             # the reference searched the step it just took on the state BEFORE it: compare with
             # the arg-min our previous step left behind
             if prev_crit is not None and steps >= 1:
@@ -166,11 +172,18 @@ def lockstep_vs_reference(inp_text: str, lib_path, max_steps: int | None = None,
                "non_converged": int(st[0].non_converged), "ref_non_converged": e.non_converge_count()}
         out.update({"rel_" + f: v for f, v in worst.items()})
         out["max_rel"] = max(worst.values())
+        out["ref_iterations"] = ref_iters
+        if continuity:
+            flow, qual = s.continuity(init_storage)
+            out["flow_error_pct"] = float(flow[0])
+            out["qual_error_pct"] = float(qual[0][np.argmax(np.abs(qual[0]))]) if qual.size else 0.0
         s.close()
-        return out
     finally:
         e.end()
+        if continuity and out is not None:
+            _, out["ref_flow_error_pct"], out["ref_qual_error_pct"] = e.mass_bal_err()
         e.close()
+    return out
 
 
 # ---- golden fixtures ---------------------------------------------------------------------------------

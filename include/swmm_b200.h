@@ -340,6 +340,10 @@ int  swb_xsect_eval(int device, int fn, int xs_type, const double *params, int n
  * 5 epilogue, 6 quality nodes, 7 quality links, 8 next-step search, 9 halo exchanges (partitioned),
  * 10 the part of 9 spent waiting for the slowest peer */
 int  swb_get_phase_times(swb_solver *s, double *ms, int n, int reset);
+/* Profiling aid: n_steps of the phase mask `phases` (csrc/swb_engine.h PH_*) with the debug switches
+   `debug` (DBG_*: skip the link or the node phase of the Picard loop); profile != 0 brackets the launch
+   with cudaProfilerStart/Stop so that `ncu --profile-from-start off` captures exactly this launch. */
+int  swb_debug_run(swb_solver *s, int phases, int n_steps, int debug, int profile);
 
 /* launch bookkeeping for bench.py ("gpu_launches") and device timing of the last call */
 long long swb_launch_count(const swb_solver *s);

@@ -10,6 +10,7 @@
 // device is usable.
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
+#include <cuda_profiler_api.h>
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -38,6 +39,17 @@ struct CudaCtx {
         unsigned long long t = 0;
         if (warp_lane == 0) t = atomicAdd(p, 1ull);
         return __shfl_sync(0xffffffffu, t, 0);
+    }
+    // one atomic for the whole CTA: returns the first of blockDim / 32 consecutive tiles
+    unsigned long long *blk_ticket;        // shared memory, two slots (alternating rounds)
+    int blk_round;
+    __device__ __forceinline__ unsigned long long next_ticket_block(unsigned long long *p)
+    {
+        unsigned long long *slot = blk_ticket + (blk_round & 1);
+        blk_round++;
+        if (threadIdx.x == 0) *slot = atomicAdd(p, (unsigned long long)(blockDim.x >> 5));
+        __syncthreads();
+        return *slot;
     }
     // the same ticket in two halves: the atomic is issued now, its value is broadcast later
     __device__ __forceinline__ unsigned long long ticket_issue(unsigned long long *p)
@@ -145,12 +157,15 @@ swb_route_kernel(const __grid_constant__ Net net, const __grid_constant__ State 
     __shared__ double tab[XT_TOTAL];
     extern __shared__ int s_alive[];          // st.M entries (dynamic: keeps the L1 carve-out large)
     __shared__ int s_scan[1 + SWB_BLOCK / 32];
+    __shared__ unsigned long long s_blk_ticket[2];
     static_assert(XT_TOTAL >= 32 * 33, "the transpose tile aliases the geometry tables");
     CudaCtx ctx;
     ctx.alive_list = s_alive;
     ctx.warp_size = 32;
     ctx.warp_lane = threadIdx.x & 31;
     ctx.scan = s_scan;
+    ctx.blk_ticket = s_blk_ticket;
+    ctx.blk_round = 0;
     ctx.tile = (double (*)[33])tab;      // used only before load_tables() and after the last step
     ctx.Tw = tab;
     ctx.tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,9 +214,21 @@ static std::string cuda_err(const char *what, cudaError_t e)
     return std::string(what) + ": " + cudaGetErrorString(e);
 }
 
-static int g_device = -1, g_sms = 0, g_blocks_per_sm = 0;
-static cudaEvent_t g_ev0, g_ev1;
-static cudaStream_t g_stream = 0;      // stream every asynchronous operation below is queued on
+// per-device state (a process may hold solvers on several devices: every entry point that allocates
+// or launches calls init(device) first, which makes that device current and fills its record)
+struct DevInfo { bool ready; int sms, blocks_per_sm; size_t persist_max; cudaEvent_t ev0, ev1; };
+#define SWB_MAX_DEVICES 64
+static DevInfo g_dev[SWB_MAX_DEVICES];
+static thread_local cudaStream_t g_stream = 0;   // stream the asynchronous operations below are queued on
+static thread_local std::string g_cuda_msg;
+static const char *last_error() { return g_cuda_msg.c_str(); }
+static bool ok(const char *what, cudaError_t e)
+{
+    if (e == cudaSuccess) return true;
+    g_cuda_msg = cuda_err(what, e);
+    cudaGetLastError();                          // clear the non-sticky error state
+    return false;
+}
 
 static void *stream_create()
 {
@@ -223,24 +250,31 @@ static bool init(int device, std::string &err)
 {
     int n = device_count();
     if (n <= 0) { err = "no CUDA device available (libswmm_b200 has no CPU path)"; return false; }
-    if (device < 0 || device >= n) { err = "CUDA device ordinal out of range"; return false; }
+    if (device < 0 || device >= n || device >= SWB_MAX_DEVICES) { err = "CUDA device ordinal out of range"; return false; }
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { err = cuda_err("cudaSetDevice", e); return false; }
-    if (g_device != device) {
+    DevInfo &D = g_dev[device];
+    if (!D.ready) {
         cudaDeviceProp p;
         e = cudaGetDeviceProperties(&p, device);
         if (e != cudaSuccess) { err = cuda_err("cudaGetDeviceProperties", e); return false; }
         if (!p.cooperativeLaunch) { err = "device does not support cooperative launch"; return false; }
-        g_sms = p.multiProcessorCount;
+        D.sms = p.multiProcessorCount;
+        D.persist_max = (size_t)p.persistingL2CacheMaxSize;
         // static (tables, transpose tile) + dynamic (member list, up to 32 KB) exceeds the 48 KB default
         e = cudaFuncSetAttribute(swb_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(sizeof(int) * SWB_MAX_MEMBERS));
         if (e != cudaSuccess) { err = cuda_err("cudaFuncSetAttribute", e); return false; }
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_blocks_per_sm, swb_route_kernel, SWB_BLOCK,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.blocks_per_sm, swb_route_kernel, SWB_BLOCK,
                                                           sizeof(int) * SWB_MAX_MEMBERS);
-        if (e != cudaSuccess || g_blocks_per_sm < 1) { err = cuda_err("occupancy query", e); return false; }
-        if (g_device < 0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
-        g_device = device;
+        if (e != cudaSuccess || D.blocks_per_sm < 1) { err = cuda_err("occupancy query", e); return false; }
+        if ((e = cudaEventCreate(&D.ev0)) != cudaSuccess || (e = cudaEventCreate(&D.ev1)) != cudaSuccess) {
+            err = cuda_err("cudaEventCreate", e); return false;
+        }
+        // room for the static network arrays to stay resident in L2 (see persist_window)
+        if (D.persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, D.persist_max);
+        cudaGetLastError();
+        D.ready = true;
     }
     return true;
 }
@@ -248,13 +282,36 @@ static bool init(int device, std::string &err)
 static void *alloc(size_t bytes)
 {
     void *p = nullptr;
-    if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr;
+    if (!ok("cudaMalloc", cudaMalloc(&p, bytes ? bytes : 8))) return nullptr;
     return p;
 }
 static void free_(void *p) { cudaFree(p); }
-static void upload(void *d, const void *s, size_t b) { if (b) cudaMemcpy(d, s, b, cudaMemcpyHostToDevice); }
-static void download(void *d, const void *s, size_t b) { if (b) cudaMemcpy(d, s, b, cudaMemcpyDeviceToHost); }
-static void zero(void *d, size_t b) { if (b) cudaMemset(d, 0, b); }
+static bool upload(void *d, const void *s, size_t b) { return !b || ok("cudaMemcpy(H2D)", cudaMemcpy(d, s, b, cudaMemcpyHostToDevice)); }
+static bool download(void *d, const void *s, size_t b) { return !b || ok("cudaMemcpy(D2H)", cudaMemcpy(d, s, b, cudaMemcpyDeviceToHost)); }
+static bool zero(void *d, size_t b) { return !b || ok("cudaMemset", cudaMemset(d, 0, b)); }
+
+// Pin [base, base + bytes) in L2 for the kernels launched on `stream`: accesses inside the window are
+// "persisting" (not displaced by normal or streaming lines).  The window is the static network
+// (Net::arena); the ensemble state streams past it.  Larger-than-L2 networks get the fraction that fits.
+#ifndef SWB_PERSIST_NET
+#define SWB_PERSIST_NET 1
+#endif
+static void persist_window(int device, cudaStream_t stream, const void *base, size_t bytes)
+{
+#if SWB_PERSIST_NET
+    const DevInfo &D = g_dev[device];
+    if (!base || !bytes || D.persist_max == 0) return;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+    v.accessPolicyWindow.num_bytes = bytes;
+    v.accessPolicyWindow.hitRatio = bytes <= D.persist_max ? 1.0f : (float)((double)D.persist_max / (double)bytes);
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaGetLastError();
+#endif
+}
 
 // receive window of a partitioned solver: plain device memory, exported to the peer processes as a
 // CUDA IPC handle and mapped by them with peer access over NVLink
@@ -301,6 +358,8 @@ static bool sync(std::string &err)
     return true;
 }
 
+static void profiler(bool on) { if (on) cudaProfilerStart(); else { cudaDeviceSynchronize(); cudaProfilerStop(); } }
+
 static bool xsect_eval(int device, int fn, const Xs &x, int n, const double *args, double *out, std::string &err)
 {
     if (!init(device, err)) return false;
@@ -317,14 +376,14 @@ static bool xsect_eval(int device, int fn, const Xs &x, int n, const double *arg
     return true;
 }
 
-static bool report(const Net &net, const State &st, const double *f, int m0, int nm, float *node_out,
+static bool report(int device, const Net &net, const State &st, const double *f, int m0, int nm, float *node_out,
                    float *link_out, std::string &err)
 {
     for (int links = 0; links < 2; links++) {
         float *out = links ? link_out : node_out;
         if (!out) continue;
         long long total = (long long)(links ? net.nL : net.nN) * nm;
-        int blocks = (int)std::min<long long>((total + 255) / 256, (long long)g_sms * 8);
+        int blocks = (int)std::min<long long>((total + 255) / 256, (long long)g_dev[device].sms * 8);
         swb_report_kernel<<<std::max(blocks, 1), 256, 0, g_stream>>>(net, st, f, m0, nm, links, out);
     }
     cudaError_t e = cudaStreamSynchronize(g_stream);
@@ -334,9 +393,9 @@ static bool report(const Net &net, const State &st, const double *f, int m0, int
 
 // CTAs to launch: all that can be co-resident, but (i) threads % M == 0 so a thread keeps one
 // member, (ii) no more threads than (objects x members), (iii) at least one CTA per 256 members.
-static int pick_blocks(int M, int maxItems)
+static int pick_blocks(const DevInfo &D, int M, int maxItems)
 {
-    long long maxBlocks = (long long)g_sms * g_blocks_per_sm;
+    long long maxBlocks = (long long)D.sms * D.blocks_per_sm;
     long long work = ((long long)maxItems * M + SWB_BLOCK - 1) / SWB_BLOCK;
     long long blocks = std::max(1LL, std::min(maxBlocks, work));
     int g = M, b = SWB_BLOCK;                 // gcd(M, SWB_BLOCK)
@@ -351,13 +410,15 @@ static bool launch(const Net &net, const State &st, const RunArgs &args, int dev
                    bool wait = true)
 {
     if (!init(device, err)) return false;
-    int blocks = pick_blocks(st.M, std::max(net.nN, net.nL));
-    if ((long long)blocks > (long long)g_sms * g_blocks_per_sm) {
+    const DevInfo &D = g_dev[device];
+    int blocks = pick_blocks(D, st.M, std::max(net.nN, net.nL));
+    if ((long long)blocks > (long long)D.sms * D.blocks_per_sm) {
         err = "ensemble too wide for one cooperative launch on this device";
         return false;
     }
     void *kargs[] = { (void *)&net, (void *)&st, (void *)&args };
     size_t dyn = sizeof(int) * (size_t)((st.M + 31) / 32 * 32);
+    persist_window(device, g_stream, net.arena, net.arena_bytes);
     if (!wait) {                          // left in flight on the current stream (swb_step_host_batch)
         cudaError_t e = cudaLaunchCooperativeKernel((void *)swb_route_kernel, dim3(blocks), dim3(SWB_BLOCK), kargs,
                                                     dyn, g_stream);
@@ -365,14 +426,16 @@ static bool launch(const Net &net, const State &st, const RunArgs &args, int dev
         *ms = 0.f;
         return true;
     }
-    cudaEventRecord(g_ev0, g_stream);
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)swb_route_kernel, dim3(blocks), dim3(SWB_BLOCK), kargs, dyn,
+    cudaError_t e = cudaEventRecord(D.ev0, g_stream);
+    if (e != cudaSuccess) { err = cuda_err("cudaEventRecord", e); return false; }
+    e = cudaLaunchCooperativeKernel((void *)swb_route_kernel, dim3(blocks), dim3(SWB_BLOCK), kargs, dyn,
                                                 g_stream);
     if (e != cudaSuccess) { err = cuda_err("cudaLaunchCooperativeKernel", e); return false; }
-    cudaEventRecord(g_ev1, g_stream);
-    e = cudaEventSynchronize(g_ev1);
+    e = cudaEventRecord(D.ev1, g_stream);
+    if (e != cudaSuccess) { err = cuda_err("cudaEventRecord", e); return false; }
+    e = cudaEventSynchronize(D.ev1);
     if (e != cudaSuccess) { err = cuda_err("swb_route_kernel", e); return false; }
-    cudaEventElapsedTime(ms, g_ev0, g_ev1);
+    cudaEventElapsedTime(ms, D.ev0, D.ev1);
     return true;
 }
 

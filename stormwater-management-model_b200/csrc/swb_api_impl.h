@@ -43,6 +43,7 @@ struct swb_solver {
     State st;
     int M;
     std::vector<void *> allocs;
+    std::vector<void *> inflow_allocs;      // device arrays of the current swb_set_inflows call
     Inflows inflows;
     bool have_inflows;
     long long launches;
@@ -67,22 +68,63 @@ static void window_views(void *base, unsigned long long *&ctrl, unsigned long lo
     stage = (double *)(red + 2 * SWB_MAX_RANKS * HALO_RED);
 }
 
+// allocation failures surface as SWB_ERR_CUDA from the creating entry point (never as a null device
+// pointer inside Net / State): the helpers throw, the entry points catch, free and report
+struct DeviceError { std::string what; };
+static void *checked_alloc(size_t bytes)
+{
+    void *p = backend::alloc(bytes ? bytes : 8);
+    if (!p) throw DeviceError{"device allocation of " + std::to_string(bytes) + " bytes failed: " + backend::last_error()};
+    return p;
+}
+static void checked(bool ok, const char *what) { if (!ok) throw DeviceError{std::string(what) + ": " + backend::last_error()}; }
 template <class T>
 static T *dev_copy(std::vector<void *> &allocs, const T *src, size_t n)
 {
-    T *p = (T *)backend::alloc(sizeof(T) * (n ? n : 1));
-    if (n) backend::upload(p, src, sizeof(T) * n);
+    T *p = (T *)checked_alloc(sizeof(T) * (n ? n : 1));
     allocs.push_back(p);
+    if (n) checked(backend::upload(p, src, sizeof(T) * n), "host -> device copy");
     return p;
 }
 template <class T>
 static T *dev_zero(std::vector<void *> &allocs, size_t n)
 {
-    T *p = (T *)backend::alloc(sizeof(T) * (n ? n : 1));
-    backend::zero(p, sizeof(T) * (n ? n : 1));
+    T *p = (T *)checked_alloc(sizeof(T) * (n ? n : 1));
     allocs.push_back(p);
+    checked(backend::zero(p, sizeof(T) * (n ? n : 1)), "device memset");
     return p;
 }
+// static network arrays: packed (256-byte aligned) into one host image, uploaded into one allocation
+struct Arena {
+    std::vector<char> image;
+    std::vector<std::pair<const void **, size_t>> slots;
+    template <class T> void add(const T *&slot, const T *src, size_t n)
+    {
+        size_t off = (image.size() + 255) & ~(size_t)255;
+        image.resize(off + sizeof(T) * (n ? n : 1), 0);
+        if (n) memcpy(image.data() + off, src, sizeof(T) * n);
+        slots.push_back({(const void **)&slot, off});
+    }
+    void *commit(std::vector<void *> &allocs)
+    {
+        char *base = (char *)checked_alloc(image.size());
+        allocs.push_back(base);
+        checked(backend::upload(base, image.data(), image.size()), "host -> device copy");
+        for (auto &sl : slots) *sl.first = base + sl.second;
+        return base;
+    }
+};
+
+// every solver entry point that allocates, copies or launches makes the solver's device current first
+// (a process may hold networks on several devices)
+static int enter(const swb_network *nw)
+{
+    std::string err;
+    if (!backend::init(nw->device, err)) return fail(SWB_ERR_CUDA, err);
+    return SWB_OK;
+}
+static int enter(const swb_solver *s) { return enter(s->net); }
+#define SWB_ENTER(obj) do { int _rc = enter(obj); if (_rc) return _rc; } while (0)
 
 extern "C" {
 
@@ -90,6 +132,7 @@ const char *swb_last_error(void) { return g_err.c_str(); }
 int swb_version(void) { return SWB_VERSION; }
 int swb_device_count(void) { return backend::device_count(); }
 
+void swb_network_destroy(swb_network *nw);
 int swb_network_create(const swb_network_desc *d, const swb_options *o, int device, swb_network **out)
 {
     if (!d || !o || !out) return fail(SWB_ERR_ARG, "null argument");
@@ -103,25 +146,23 @@ int swb_network_create(const swb_network_desc *d, const swb_options *o, int devi
     nw->device = device;
     derive(*d, *o, nw->der);
     fill_net_scalars(nw->net, *d, *o, nw->der);
-#define X(T, name, kind) nw->net.name = dev_copy<T>(nw->allocs, d->name, desc_count(*d, #kind[0], #kind[1]));
-    SWB_DESC_ARRAYS(X)
+    try {
+        Arena ar;
+#define X(T, name, kind) ar.add<T>(nw->net.name, d->name, desc_count(*d, #kind[0], #kind[1]));
+        SWB_DESC_ARRAYS(X)
 #undef X
-    const Derived &r = nw->der;
-    nw->net.link_flags = dev_copy<int>(nw->allocs, r.link_flags.data(), r.link_flags.size());
-    nw->net.link_z1 = dev_copy<double>(nw->allocs, r.link_z1.data(), r.link_z1.size());
-    nw->net.link_z2 = dev_copy<double>(nw->allocs, r.link_z2.data(), r.link_z2.size());
-    nw->net.adj_start = dev_copy<int>(nw->allocs, r.adj_start.data(), r.adj_start.size());
-    nw->net.adj = dev_copy<int>(nw->allocs, r.adj.data(), r.adj.size());
-    nw->net.adjq_start = dev_copy<int>(nw->allocs, r.adjq_start.data(), r.adjq_start.size());
-    nw->net.adjq = dev_copy<int>(nw->allocs, r.adjq.data(), r.adjq.size());
-    nw->net.nc_links = dev_copy<int>(nw->allocs, r.nc_links.data(), r.nc_links.size());
-    nw->net.node_order = dev_copy<int>(nw->allocs, r.node_order.data(), r.node_order.size());
-    nw->net.link_order = dev_copy<int>(nw->allocs, r.link_order.data(), r.link_order.size());
-    nw->net.outfall_link = dev_copy<int>(nw->allocs, r.outfall_link.data(), r.outfall_link.size());
-    nw->net.xs_tables = dev_copy<double>(nw->allocs, r.xs_tables.data(), r.xs_tables.size());
-    nw->net.link_kernel = dev_copy<int>(nw->allocs, r.link_kernel.data(), r.link_kernel.size());
-    nw->net.culvert_params = dev_copy<double>(nw->allocs, r.culvert_params.data(), r.culvert_params.size());
-    nw->net.road_tables = dev_copy<double>(nw->allocs, r.road_tables.data(), r.road_tables.size());
+        const Derived &r = nw->der;
+#define D(name) ar.add(nw->net.name, r.name.data(), r.name.size());
+        D(link_flags) D(link_z1) D(link_z2) D(xs_rcp_yfull) D(cond_rcp_mod_length) D(adj_start) D(adj)
+        D(adjq_start) D(adjq) D(nc_links) D(node_order) D(link_order) D(outfall_link) D(xs_tables)
+        D(link_kernel) D(culvert_params) D(road_tables)
+#undef D
+        nw->net.arena_bytes = ar.image.size();
+        nw->net.arena = ar.commit(nw->allocs);
+    } catch (const DeviceError &e) {
+        swb_network_destroy(nw);
+        return fail(SWB_ERR_CUDA, e.what);
+    }
     *out = nw;
     return SWB_OK;
 }
@@ -133,11 +174,13 @@ void swb_network_destroy(swb_network *nw)
     delete nw;
 }
 
+void swb_solver_destroy(swb_solver *s);
 int swb_solver_create(swb_network *nw, int M, swb_solver **out)
 {
     if (!nw || !out || M < 1) return fail(SWB_ERR_ARG, "bad solver arguments");
     if (M > 1 && (M % 32) != 0) return fail(SWB_ERR_ARG, "n_members must be 1 or a multiple of 32");
     if (M > 8192) return fail(SWB_ERR_ARG, "n_members > 8192: split the ensemble over several solvers");
+    SWB_ENTER(nw);
     swb_solver *s = new swb_solver();
     s->net = nw; s->M = M; s->launches = 0; s->last_ms = 0.f; s->have_inflows = false; s->stream = nullptr;
     s->stg_lat = s->stg_loss = s->stg_qual = s->img_lat = s->img_loss = s->img_qual = nullptr;
@@ -149,6 +192,7 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     memset(&st, 0, sizeof(st));
     st.M = M;
     const int nN = nw->net.nN, nL = nw->net.nL, nP = nw->net.nP;
+    try {
     for (const FieldInfo &f : field_table()) {
         size_t n = field_items(f, nN, nL, nP) * (size_t)M;
         void *p = f.is_u8 ? (void *)dev_zero<unsigned char>(s->allocs, n) : (void *)dev_zero<double>(s->allocs, n);
@@ -180,8 +224,12 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     st.tickets = dev_zero<unsigned long long>(s->allocs, 3 * SWB_MAX_TRIALS_CAP);
     // conduit / link settings default to fully open (Link.setting = 1.0, link.c:142)
     std::vector<double> ones((size_t)nL * M, 1.0);
-    backend::upload(st.l_setting, ones.data(), sizeof(double) * ones.size());
-    backend::upload(st.l_target_setting, ones.data(), sizeof(double) * ones.size());
+    checked(backend::upload(st.l_setting, ones.data(), sizeof(double) * ones.size()), "host -> device copy");
+    checked(backend::upload(st.l_target_setting, ones.data(), sizeof(double) * ones.size()), "host -> device copy");
+    } catch (const DeviceError &e) {
+        swb_solver_destroy(s);
+        return fail(SWB_ERR_CUDA, e.what);
+    }
     *out = s;
     return SWB_OK;
 }
@@ -190,6 +238,7 @@ void swb_solver_destroy(swb_solver *s)
 {
     if (!s) return;
     for (void *p : s->allocs) backend::free_(p);
+    for (void *p : s->inflow_allocs) backend::free_(p);
     if (s->stream) backend::stream_destroy(s->stream);
     for (int p = 0; p < SWB_MAX_RANKS; p++) if (s->peer_window[p]) backend::window_close(s->peer_window[p]);
     if (s->window) backend::window_free(s->window, s->window_bytes, s->window_handle);
@@ -202,6 +251,7 @@ static int field_xfer(swb_solver *s, int field, int m0, int nm, double *buf, con
                       bool broadcast)
 {
     if (!s || (!buf && !cbuf)) return fail(SWB_ERR_ARG, "null argument");
+    SWB_ENTER(s);
     const FieldInfo *f = find_field(field);
     if (!f) return fail(SWB_ERR_ARG, "unknown field id");
     const int M = s->M, nN = s->net->net.nN, nL = s->net->net.nL, nP = s->net->net.nP;
@@ -249,6 +299,7 @@ int swb_broadcast_field(swb_solver *s, int field, const double *buf)
 int swb_set_climate(swb_solver *s, double evap_rate, double hydcon_factor)
 {
     if (!s) return fail(SWB_ERR_ARG, "null solver");
+    SWB_ENTER(s);
     std::vector<double> ev(s->M, evap_rate), hc(s->M, hydcon_factor);
     backend::upload(s->st.evap_rate, ev.data(), sizeof(double) * s->M);
     backend::upload(s->st.hydcon, hc.data(), sizeof(double) * s->M);
@@ -258,6 +309,7 @@ int swb_set_climate(swb_solver *s, double evap_rate, double hydcon_factor)
 int swb_qual_init(swb_solver *s, const double *init_concen)
 {
     if (!s) return fail(SWB_ERR_ARG, "null solver");
+    SWB_ENTER(s);
     const int M = s->M, nN = s->net->net.nN, nL = s->net->net.nL, nP = s->net->net.nP;
     if (nP == 0) return SWB_OK;
     std::vector<double> nd((size_t)nN * M), ld((size_t)nL * M);
@@ -308,6 +360,7 @@ static int run(swb_solver *s, int phases, int n_steps, double t_end, double fixe
 static int put_dt(swb_solver *s, const double *dt)
 {
     if (!s || !dt) return fail(SWB_ERR_ARG, "null argument");
+    SWB_ENTER(s);
     backend::upload(s->st.dt, dt, sizeof(double) * s->M);
     return SWB_OK;
 }
@@ -339,6 +392,7 @@ int swb_qualrout_execute(swb_solver *s, const double *dt)
 int swb_get_routing_step(swb_solver *s, double fixed_step, double *dt_out)
 {
     if (!s || !dt_out) return fail(SWB_ERR_ARG, "null argument");
+    SWB_ENTER(s);
     int rc = run(s, PH_NEXTDT, 1, 0.0, fixed_step);
     if (rc) return rc;
     backend::download(dt_out, s->st.var_step, sizeof(double) * s->M);
@@ -372,7 +426,8 @@ static int step_host_enqueue(swb_solver *s, const swb_step_io *io, bool wait)
     const int M = s->M, nN = n.nN, nL = n.nL, nP = n.nP;
     const size_t nb = sizeof(double) * (size_t)nN * M, lb = sizeof(double) * (size_t)nL * M;
     const bool withQual = nP > 0 && !n.opt.ignore_quality;
-    ensure_staging(s);
+    SWB_ENTER(s);
+    try { ensure_staging(s); } catch (const DeviceError &e) { return fail(SWB_ERR_CUDA, e.what); }
     RunArgs stg;
     memset(&stg, 0, sizeof(stg));
     backend::h2d_async(s->stg_lat, io->latflow, nb);
@@ -421,8 +476,9 @@ int swb_step_host_batch(swb_solver *const *solvers, const swb_step_io *io, int n
         if (!solvers[i]) return fail(SWB_ERR_ARG, "null solver in batch");
         for (int k = 0; k < i; k++)
             if (solvers[k] == solvers[i]) return fail(SWB_ERR_ARG, "the same solver twice in one batch");
+        SWB_ENTER(solvers[i]);
         if (!solvers[i]->stream) solvers[i]->stream = backend::stream_create();
-        ensure_staging(solvers[i]);
+        try { ensure_staging(solvers[i]); } catch (const DeviceError &e) { return fail(SWB_ERR_CUDA, e.what); }
     }
     // staging buffers are allocated (and zeroed on the default stream) at a solver's first step
     if (!backend::sync(err)) return fail(SWB_ERR_CUDA, err);
@@ -445,20 +501,33 @@ int swb_set_inflows(swb_solver *s, const swb_inflow_desc *d)
         if (d->node[k] < 0 || d->node[k] >= nN) return fail(SWB_ERR_ARG, "inflow node out of range");
         slot[d->node[k]] = k;
     }
+    SWB_ENTER(s);
+    // a second call replaces the first: its device arrays are released, not leaked
+    for (void *q : s->inflow_allocs) backend::free_(q);
+    s->inflow_allocs.clear();
+    s->have_inflows = false;
     Inflows &f = s->inflows;
     f.n = n; f.start_day = d->start_day; f.start_secs = d->start_secs;
-    f.node = dev_copy<int>(s->allocs, d->node, n);
-    f.ts_start = dev_copy<int>(s->allocs, d->ts_start, n + 1);
-    f.ts_t = dev_copy<double>(s->allocs, d->ts_t, d->n_ts_pts);
-    f.ts_q = dev_copy<double>(s->allocs, d->ts_q, d->n_ts_pts);
-    f.sfactor = dev_copy<double>(s->allocs, d->sfactor, n);
-    f.baseline = dev_copy<double>(s->allocs, d->baseline, n);
-    std::vector<double> zc((size_t)n * (nP ? nP : 1), 0.0);
-    f.concen = dev_copy<double>(s->allocs, d->concen ? d->concen : zc.data(), (size_t)n * nP);
-    std::vector<double> one(s->M, 1.0), zero(s->M, 0.0);
-    f.member_scale = dev_copy<double>(s->allocs, d->member_scale ? d->member_scale : one.data(), s->M);
-    f.member_shift = dev_copy<double>(s->allocs, d->member_shift ? d->member_shift : zero.data(), s->M);
-    f.node_slot = dev_copy<int>(s->allocs, slot.data(), nN);
+    try {
+        std::vector<void *> &al = s->inflow_allocs;
+        f.node = dev_copy<int>(al, d->node, n);
+        f.ts_start = dev_copy<int>(al, d->ts_start, n + 1);
+        f.ts_t = dev_copy<double>(al, d->ts_t, d->n_ts_pts);
+        f.ts_q = dev_copy<double>(al, d->ts_q, d->n_ts_pts);
+        f.sfactor = dev_copy<double>(al, d->sfactor, n);
+        f.baseline = dev_copy<double>(al, d->baseline, n);
+        std::vector<double> zc((size_t)n * (nP ? nP : 1), 0.0);
+        f.concen = dev_copy<double>(al, d->concen ? d->concen : zc.data(), (size_t)n * nP);
+        std::vector<double> one(s->M, 1.0), zero(s->M, 0.0);
+        f.member_scale = dev_copy<double>(al, d->member_scale ? d->member_scale : one.data(), s->M);
+        f.member_shift = dev_copy<double>(al, d->member_shift ? d->member_shift : zero.data(), s->M);
+        f.node_slot = dev_copy<int>(al, slot.data(), nN);
+    } catch (const DeviceError &e) {
+        for (void *q : s->inflow_allocs) backend::free_(q);
+        s->inflow_allocs.clear();
+        memset(&s->inflows, 0, sizeof(s->inflows));
+        return fail(SWB_ERR_CUDA, e.what);
+    }
     s->have_inflows = true;
     return SWB_OK;
 }
@@ -467,6 +536,7 @@ int swb_run_steps(swb_solver *s, int n_steps, double t_end)
 {
     if (!s || n_steps < 1) return fail(SWB_ERR_ARG, "bad arguments");
     if (!s->have_inflows) return fail(SWB_ERR_ARG, "swb_set_inflows has not been called");
+    SWB_ENTER(s);
     const Net &n = s->net->net;
     int phases = PH_ADVANCE | PH_SWAP | PH_INFLOWS | PH_DYNWAVE | PH_NEXTDT | PH_MASSBAL;
     if (n.nP > 0 && !n.opt.ignore_quality) phases |= PH_QSWAP | PH_QUALITY;
@@ -478,6 +548,7 @@ int swb_partition_attach(swb_solver *s, const swb_partition_desc *p)
     if (!s || !p) return fail(SWB_ERR_ARG, "null argument");
     if (s->M != 1) return fail(SWB_ERR_ARG, "a partitioned solver holds one member");
     if (s->window) return fail(SWB_ERR_ARG, "partition already attached");
+    SWB_ENTER(s);
     const Net &n = s->net->net;
     if (p->n_ranks < 1 || p->n_ranks > SWB_MAX_RANKS || p->rank < 0 || p->rank >= p->n_ranks)
         return fail(SWB_ERR_ARG, "bad rank / n_ranks");
@@ -500,6 +571,7 @@ int swb_partition_attach(swb_solver *s, const swb_partition_desc *p)
             return fail(SWB_ERR_UNSUPP, "a pump / regulator / dummy link crosses the partition border");
     Halo &H = s->st.halo;
     memset(&H, 0, sizeof(H));
+    try {
     H.rank = p->rank; H.nRanks = p->n_ranks; H.nOwnedN = p->n_owned_nodes;
     H.nSend = p->n_send; H.nRecv = p->n_recv; H.W = n.nP > 2 ? n.nP : 2;
     {   // send entries sorted by node + CSR over the owned nodes
@@ -524,6 +596,7 @@ int swb_partition_attach(swb_solver *s, const swb_partition_desc *p)
         node_order_expensive_first(type.data(), p->n_owned_nodes, n.nN, order);
         H.node_order = dev_copy<int>(s->allocs, order.data(), order.size());
     }
+    } catch (const DeviceError &e) { memset(&H, 0, sizeof(H)); return fail(SWB_ERR_CUDA, e.what); }
     H.wait_ns = s->st.phase_ns + TP_HALO_WAIT;
     H.timeout_ns = (unsigned long long)((p->timeout_s > 0.0 ? p->timeout_s : 30.0) * 1.0e9);
     std::string err;
@@ -567,6 +640,7 @@ long long swb_partition_exchanges(swb_solver *s)
 int swb_get_stats(swb_solver *s, int m0, int nm, swb_member_stats *out)
 {
     if (!s || !out || m0 < 0 || nm < 1 || m0 + nm > s->M) return fail(SWB_ERR_ARG, "bad arguments");
+    SWB_ENTER(s);
     const int M = s->M;
     std::vector<double> t(M), dt(M), vs(M);
     std::vector<long long> st(M), it(M), nc(M);
@@ -591,6 +665,7 @@ int swb_get_stats(swb_solver *s, int m0, int nm, swb_member_stats *out)
 int swb_get_massbal(swb_solver *s, int m0, int nm, double *reacted, double *seepage, double *final_storage)
 {
     if (!s || m0 < 0 || nm < 1 || m0 + nm > s->M) return fail(SWB_ERR_ARG, "bad arguments");
+    SWB_ENTER(s);
     const int M = s->M, nP = s->net->net.nP;
     std::vector<double> h((size_t)(nP ? nP : 1) * M);
     double *dst[3] = { reacted, seepage, final_storage };
@@ -607,6 +682,7 @@ int swb_get_massbal(swb_solver *s, int m0, int nm, double *reacted, double *seep
 int swb_get_routing_totals(swb_solver *s, int m0, int nm, double *flow, double *qual)
 {
     if (!s || m0 < 0 || nm < 1 || m0 + nm > s->M) return fail(SWB_ERR_ARG, "bad arguments");
+    SWB_ENTER(s);
     const int M = s->M, nP = s->net->net.nP, nMb = MB_FLOW_TERMS + MB_QUAL_TERMS * nP;
     std::vector<double> tot((size_t)nMb * M), rate((size_t)nMb * M), dtp(M);
     backend::download(tot.data(), s->st.mb_total, sizeof(double) * tot.size());
@@ -628,7 +704,7 @@ int swb_get_routing_totals(swb_solver *s, int m0, int nm, double *flow, double *
 
 long long swb_conduit_updates(swb_solver *s)
 {
-    if (!s) return 0;
+    if (!s || enter(s)) return 0;
     std::vector<long long> it(s->M);
     backend::download(it.data(), s->st.tot_iters, sizeof(long long) * s->M);
     long long sum = 0;
@@ -643,6 +719,7 @@ int swb_xsect_eval(int device, int fn, int xs_type, const double *p, int n, cons
     x.type = xs_type; x.ntbl = 0; x.atbl = x.rtbl = x.wtbl = nullptr;
     x.yFull = p[0]; x.wMax = p[1]; x.ywMax = p[2]; x.aFull = p[3]; x.rFull = p[4]; x.sFull = p[5];
     x.sMax = p[6]; x.yBot = p[7]; x.aBot = p[8]; x.sBot = p[9]; x.rBot = p[10];
+    x.rYFull = exact_rcp(x.yFull);
     std::string err;
     if (!backend::xsect_eval(device, fn, x, n, args, out, err)) return fail(SWB_ERR_CUDA, err);
     return SWB_OK;
@@ -659,7 +736,7 @@ int swb_get_results(swb_solver *s, const double *f, int m0, int nm, float *node_
     float *dn = node_out ? (float *)backend::alloc(sizeof(float) * nrec) : nullptr;
     float *dl = link_out ? (float *)backend::alloc(sizeof(float) * lrec) : nullptr;
     backend::upload(df, f, sizeof(double) * s->M);
-    bool ok = backend::report(n, s->st, df, m0, nm, dn, dl, err);
+    bool ok = backend::report(s->net->device, n, s->st, df, m0, nm, dn, dl, err);
     if (ok && dn) backend::download(node_out, dn, sizeof(float) * nrec);
     if (ok && dl) backend::download(link_out, dl, sizeof(float) * lrec);
     backend::free_(df);
@@ -673,6 +750,7 @@ int swb_get_results(swb_solver *s, const double *f, int m0, int nm, float *node_
 int swb_get_phase_times(swb_solver *s, double *ms, int n, int reset)
 {
     if (!s || !ms || n < 1) return fail(SWB_ERR_ARG, "bad arguments");
+    SWB_ENTER(s);
     unsigned long long h[SWB_N_PHASES];
     backend::download(h, s->st.phase_ns, sizeof(h));
     for (int i = 0; i < n; i++) ms[i] = i < SWB_N_PHASES ? (double)h[i] * 1.0e-6 : 0.0;
@@ -680,11 +758,26 @@ int swb_get_phase_times(swb_solver *s, double *ms, int n, int reset)
     return SWB_OK;
 }
 
+// profiling aid (tools/profile_phase.py): n_steps of the given phase mask with debug switches
+// (swb_engine.h: DBG_*), optionally bracketed by the profiler start / stop markers
+int swb_debug_run(swb_solver *s, int phases, int n_steps, int debug, int profile)
+{
+    if (!s || n_steps < 1) return fail(SWB_ERR_ARG, "bad arguments");
+    SWB_ENTER(s);
+    RunArgs a;
+    memset(&a, 0, sizeof(a));
+    a.debug = debug;
+    if (profile) backend::profiler(true);
+    int rc = run(s, phases, n_steps, 1.0e300, s->net->net.opt.route_step, nullptr, nullptr, nullptr, true, &a);
+    if (profile) backend::profiler(false);
+    return rc;
+}
+
 long long swb_launch_count(const swb_solver *s) { return s ? s->launches : 0; }
 double swb_last_kernel_ms(const swb_solver *s) { return s ? (double)s->last_ms : 0.0; }
 int swb_sync(swb_solver *s)
 {
-    (void)s;
+    if (s) SWB_ENTER(s);
     std::string err;
     if (!backend::sync(err)) return fail(SWB_ERR_CUDA, err);
     return SWB_OK;

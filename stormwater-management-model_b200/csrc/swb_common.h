@@ -46,7 +46,39 @@
 #define SWB_MAX_POLLUT 8       // pollutants carried per member (register accumulators)
 
 #include <string.h>
+#include <math.h>
 namespace swb {
+// ---- exact division by a divisor known in advance ------------------------------------------------
+// x / d == fma(fma(-q, d, x), r, q) with q = x * r and r = RN(1 / d), correctly rounded for EVERY
+// finite x away from over/underflow, whenever exact_rcp_ok(d) holds (Markstein's correction step).
+// With d * r = 1 + e, t = |e| / 2^-53 and m the significand of d in [1, 2):
+//   * q is within 0.5 + t * m_Q / 2 < 1 ulp of Q = x / d when t <= 0.5, so the residual
+//     x - q * d is exactly representable and the inner fma is exact;
+//   * the outer fma then rounds Q + (Q - q) * e, which is within (0.5 + t) * t * 2^-53 ulp of Q,
+//     while a quotient of two doubles is at least 2^-53 / m ulp away from any rounding midpoint:
+//     same rounding whenever (0.5 + t) * t < 1 / m.
+// Three dependent operations instead of the ~18 of the generic division sequence (reciprocal
+// seed, four Newton steps, range check).  The reference's own `/` is what this reproduces bit for
+// bit; divisors that fail the test keep the plain division.
+SWB_FI double div_rcp(double x, double d, double r)
+{
+    double q = x * r;
+    double e = fma(-q, d, x);
+    return fma(e, r, q);
+}
+// host-side test for a divisor (network set-up); returns RN(1 / d) or 0 when d does not qualify
+inline double exact_rcp(double d)
+{
+    if (!(d > 1.0e-100 && d < 1.0e100)) return 0.0;
+    const double r = 1.0 / d;
+    const double t = fabs(fma(d, r, -1.0)) / 1.1102230246251565e-16;      // exact residual / 2^-53
+    int ex;
+    const double m = 2.0 * frexp(d, &ex);
+    return (t <= 0.5 && (0.5 + t) * t < 1.0 / m) ? r : 0.0;
+}
+// r == 0 marks "no exact reciprocal": warp-uniform choice (r is a per-link constant)
+SWB_FI double div_by(double x, double d, double r) { return r != 0.0 ? div_rcp(x, d, r) : x / d; }
+
 // order-preserving integer image of a non-negative double (for integer atomicMin)
 SWB_HD unsigned long long dbits(double v)
 {

@@ -31,6 +31,7 @@ SWB_FI Xs load_xs(const Net &n, int j)
     x.aFull = n.xs_afull[j]; x.rFull = n.xs_rfull[j]; x.sFull = n.xs_sfull[j];
     x.sMax = n.xs_smax[j];   x.yBot = n.xs_ybot[j];   x.aBot = n.xs_abot[j];
     x.sBot = n.xs_sbot[j];   x.rBot = n.xs_rbot[j];
+    x.rYFull = n.xs_rcp_yfull[j];
     x.ntbl = 0; x.atbl = x.rtbl = x.wtbl = nullptr;
     int t = n.xs_table[j];
     if (t >= 0) {
@@ -46,7 +47,7 @@ SWB_FI Xs load_xs(const Net &n, int j)
 SWB_FI double dw_sjoberg(double yNorm) { return exp(-pow(yNorm, 2.4)); }
 SWB_FI double dw_slot_width(const Net &n, const Xs &x, bool isOpen, double y)
 {
-    double yNorm = y / x.yFull;
+    double yNorm = xs_ynorm(x, y);
     if (n.opt.surcharge_method != SWB_SLOT || isOpen || yNorm < n.crownCutoff) return 0.0;
     if (yNorm > 1.78) return 0.01 * x.wMax;
     return x.wMax * 0.5423 * dw_sjoberg(yNorm);
@@ -56,7 +57,7 @@ SWB_FI double dw_width(const Net &n, const Xs &x, bool isOpen, double y, const d
 {
     double wSlot = dw_slot_width(n, x, isOpen, y);
     if (wSlot > 0.0) return wSlot;
-    if (y / x.yFull >= n.crownCutoff && !isOpen) y = n.crownCutoff * x.yFull;
+    if (xs_ynorm(x, y) >= n.crownCutoff && !isOpen) y = n.crownCutoff * x.yFull;
     return xw<S>(x, y, T);
 }
 // top width given the slot width already evaluated at the same depth (dwflow.c:592-605)
@@ -64,7 +65,7 @@ template <int S>
 SWB_FI double dw_width_ws(const Net &n, const Xs &x, bool isOpen, double y, double wSlot, const double *T)
 {
     if (wSlot > 0.0) return wSlot;
-    if (y / x.yFull >= n.crownCutoff && !isOpen) y = n.crownCutoff * x.yFull;
+    if (xs_ynorm(x, y) >= n.crownCutoff && !isOpen) y = n.crownCutoff * x.yFull;
     return xw<S>(x, y, T);
 }
 template <int S>
@@ -243,7 +244,7 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     y2 = SWB_MAX(y2, SWB_FUDGE);
     if (!slot) { y1 = SWB_MIN(y1, x.yFull); y2 = SWB_MIN(y2, x.yFull); }
 
-    const double length = n.cond_mod_length[j];
+    const double length = n.cond_mod_length[j], rLength = n.cond_rcp_mod_length[j];
 
     // --- findSurfArea (dwflow.c:417-550) on the previous iteration's flow
     int flowClass;
@@ -288,7 +289,7 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
             if (fdMid < SWB_FUDGE) fdMid = SWB_FUDGE;
             wsM = dw_slot_width(n, x, isOpen, fdMid);
             widthMid = dw_width_ws<S>(n, x, isOpen, fdMid, wsM, T);
-            widthMidPlain = !(wsM > 0.0) && !(fdMid / x.yFull >= n.crownCutoff && !isOpen);
+            widthMidPlain = !(wsM > 0.0) && !(xs_ynorm(x, fdMid) >= n.crownCutoff && !isOpen);
             if (flowClass != SWB_UP_CRITICAL) {
                 ws1 = dw_slot_width(n, x, isOpen, fd1);
                 width1 = dw_width_ws<S>(n, x, isOpen, fd1, ws1, T);
@@ -345,7 +346,7 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
         double a1s = 0.5 * (a1 + a2);
         s.c_a1[ix] = a1s;
         s.c_q1[ix] = 0.0;
-        s.l_dqdh[ix] = SWB_GRAVITY * dt * aMid / length * barrels;
+        s.l_dqdh[ix] = div_by(SWB_GRAVITY * dt * aMid, length, rLength) * barrels;
         s.l_froude[ix] = 0.0;
         s.l_depth[ix] = SWB_MIN(yMid, x.yFull);
         s.l_volume[ix] = a1s * trueLength * barrels;
@@ -390,11 +391,11 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     if (S < 0 && x.type == XS_FORCE_MAIN && isFull)
          dq1 = dt * forcemain_fric_slope(n, x, fabs(v), rMid);
     else dq1 = dt * n.cond_rough_factor[j] / pow(rWtd, 1.33333) * fabs(v);
-    double dq2 = dt * SWB_GRAVITY * aWtd * (h2 - h1) / length;
+    double dq2 = div_by(dt * SWB_GRAVITY * aWtd * (h2 - h1), length, rLength);
     double dq3 = 0.0, dq4 = 0.0;
     if (sigma > 0.0) {
         dq3 = 2.0 * v * (aMid - aOld) * sigma;
-        dq4 = dt * v * v * (a2 - a1) / length * sigma;
+        dq4 = div_by(dt * v * v * (a2 - a1), length, rLength) * sigma;
     }
     double dq5 = 0.0;
     if (n.cond_has_losses[j]) {
@@ -402,7 +403,7 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
         if (a1 > SWB_FUDGE)   losses += n.link_closs_in[j]  * (qa / a1);
         if (a2 > SWB_FUDGE)   losses += n.link_closs_out[j] * (qa / a2);
         if (aMid > SWB_FUDGE) losses += n.link_closs_avg[j] * (qa / aMid);
-        dq5 = losses / 2.0 / length * dt;
+        dq5 = div_by(losses / 2.0, length, rLength) * dt;
     }
     double dq6 = 0.0;
     if (flags & LF_HAS_LOSSRATE) {
@@ -413,7 +414,7 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
 
     double denom = 1.0 + dq1 + dq5;
     double q = (qOld - dq2 + dq3 + dq4 + dq6) / denom;
-    double dqdh = 1.0 / denom * SWB_GRAVITY * dt * aWtd / length * barrels;
+    double dqdh = div_by(1.0 / denom * SWB_GRAVITY * dt * aWtd, length, rLength) * barrels;
 
     // --- flow limitations (dwflow.c:245-259); culvert-coded links always run the generic instance
     unsigned char normalFlow = 0, inletControl = 0;

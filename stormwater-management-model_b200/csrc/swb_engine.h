@@ -64,9 +64,12 @@ struct Inflows {               // device image of swb_inflow_desc
     double start_day, start_secs;
 };
 
+enum { DBG_SKIP_LINKS = 1, DBG_SKIP_NODES = 2 };   // RunArgs.debug (profiling aid: isolate one Picard phase)
+
 struct RunArgs {
     int    phases;
     int    n_steps;
+    int    debug;
     double t_end;              // PH_ADVANCE: members stop at this simulated time (s)
     double fixed_step;         // RouteStep for PH_NEXTDT / PH_ADVANCE
     Inflows inflows;
@@ -177,39 +180,6 @@ SWB_FI bool picard_node(const Net &net, const State &st, int i, int m, int k, do
 // Dynamic tile loop: tile t = (object t / nChunks, chunk t % nChunks of the member list); a warp
 // draws tickets until the phase is exhausted.  ctx.warp_size is 32 on the device, 1 in the host
 // emulation.
-// first-touch lines of the next tile (see for_tiles): what conduit_flow / picard_node load up front
-template <class Ctx>
-SWB_ENGINE inline void prefetch_link(Ctx &ctx, const Net &net, const State &st, int j, int m)
-{
-    const int M = st.M;
-    const size_t ix = SWB_IX(j, m, M);
-    ctx.prefetch(&st.c_q1[ix]);
-    ctx.prefetch(&st.c_a2[ix]);
-    ctx.prefetch(&st.l_old_flow[ix]);
-    ctx.prefetch(&st.l_setting[ix]);
-    ctx.prefetch(&st.n_depth[SWB_IX(net.link_node1[j], m, M)]);
-    ctx.prefetch(&st.n_depth[SWB_IX(net.link_node2[j], m, M)]);
-}
-template <class Ctx>
-SWB_ENGINE inline void prefetch_node(Ctx &ctx, const Net &net, const State &st, int i, int m)
-{
-    const int M = st.M;
-    const size_t ix = SWB_IX(i, m, M);
-    ctx.prefetch(&st.n_depth[ix]);
-    ctx.prefetch(&st.n_old_depth[ix]);
-    ctx.prefetch(&st.n_latflow[ix]);
-    ctx.prefetch(&st.n_old_net_inflow[ix]);
-    ctx.prefetch(&st.n_old_volume[ix]);
-    if (net.nNonConduit > 0) return;                 // sums were stored by picard_node_presum
-    for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++) {
-        const int j = net.adj[e] >> 1;
-        const size_t jx = SWB_IX(j, m, M);
-        ctx.prefetch(&st.l_flow[jx]);
-        ctx.prefetch(&st.l_dqdh[jx]);
-        ctx.prefetch((net.adj[e] & 1) ? &st.l_surf_area2[jx] : &st.l_surf_area1[jx]);
-    }
-}
-
 struct NoPrefetch { SWB_ENGINE void operator()(int, int) const {} };
 
 // Tickets run two tiles ahead of the work: while a warp computes tile t it already knows tile t+1
@@ -218,6 +188,9 @@ struct NoPrefetch { SWB_ENGINE void operator()(int, int) const {} };
 // tile sits on the warp's critical path.
 #ifndef SWB_TICKETS_AHEAD
 #define SWB_TICKETS_AHEAD 0
+#endif
+#ifndef SWB_TILE_MODE
+#define SWB_TILE_MODE 0      // 0: one ticket per warp and tile; 1: static striding; 2: one ticket per CTA
 #endif
 #ifndef SWB_PREFETCH
 #define SWB_PREFETCH 0
@@ -252,7 +225,22 @@ SWB_ENGINE inline void for_tiles(Ctx &ctx, int nItems, int nAlive, unsigned long
             if (sub < perTile && item < nItems) fn((int)item, ctx.alive_list[lslot]);
         }
     };
-#if SWB_TICKETS_AHEAD == 0
+#if defined(__CUDACC__) && SWB_TILE_MODE == 1
+    // A/B: static striding, no counter at all (tile = global warp id + round * warps in the grid)
+    {
+        const long long nW = (long long)ctx.G / W, w0 = (long long)ctx.tid / W;
+        for (long long t = w0; t < total; t += nW) run(t, body);
+    }
+#elif defined(__CUDACC__) && SWB_TILE_MODE == 2
+    // A/B: one atomic per CTA hands every warp of the block its own tile (neighbouring member chunks of
+    // one object): 16x fewer round trips to the counter, and the block's warps run the same object
+    for (;;) {
+        const long long t0 = (long long)ctx.next_ticket_block(ticket);
+        if (t0 >= total) break;
+        const long long t = t0 + ctx.lane / W;
+        if (t < total) run(t, body);
+    }
+#elif SWB_TICKETS_AHEAD == 0
     // One atomic hands out SWB_TICKET_BATCH consecutive tiles (same object, neighbouring member
     // chunks): fewer round trips to the ticket counter, and inside a batch the next tile is known
     // without an atomic, so its first cache lines can be requested while the current one computes.
@@ -585,9 +573,10 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             for (int k = 0; k < maxTrials && nAlive > 0; k++) {
                 unsigned long long *tickets = st.tickets + 3 * k;
                 // ---- findLinkFlows, pass (i): true conduits (dynwave.c:387-395)
+                if (!(args.debug & DBG_SKIP_LINKS))
                 for_tiles(ctx, net.nTrue, nAlive, tickets + 0, [&](int jj, int mm) {
                     picard_link(net, st, net.link_order[jj], mm, k, st.dt[mm], T);
-                }, [&](int jj, int mm) { prefetch_link(ctx, net, st, net.link_order[jj], mm); });
+                });
                 ctx.grid_sync();
                 SWB_TICK(TP_LINKS);
                 // ---- networks with regulators / dummy links: ordered pass (A.4)
@@ -602,6 +591,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     SWB_TICK(TP_REGULATORS);
                 }
                 // ---- findNodeDepths (dynwave.c:593-632)
+                if (!(args.debug & DBG_SKIP_NODES))
                 for_tiles(ctx, nNo, nAlive, tickets + 2, [&](int ii, int mm) {
                     const int i = nodeOrder[ii];
                     if (!picard_node(net, st, i, mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
@@ -616,7 +606,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                         }
                         ctx.fence_system();
                     }
-                }, [&](int ii, int mm) { prefetch_node(ctx, net, st, nodeOrder[ii], mm); });
+                });
                 ctx.grid_sync();
                 SWB_TICK(TP_NODES);
                 if (part) {

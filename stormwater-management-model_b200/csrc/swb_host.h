@@ -18,7 +18,7 @@ namespace swb {
 struct Derived {
     std::vector<int> link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link, link_order,
                      link_kernel, node_order;
-    std::vector<double> link_z1, link_z2, xs_tables, culvert_params, road_tables;
+    std::vector<double> link_z1, link_z2, xs_tables, culvert_params, road_tables, xs_rcp_yfull, cond_rcp_mod_length;
     int nTrue = 0, nNonConduit = 0;
 };
 
@@ -40,6 +40,7 @@ inline std::string validate_desc(const swb_network_desc &d, const swb_options &o
     if (d.n_nodes <= 0 || d.n_links < 0) return "empty network";
     if (d.n_pollut > SWB_MAX_POLLUT) return "more than SWB_MAX_POLLUT pollutants";
     if (o.max_trials < 1) return "max_trials < 1";
+    if (o.max_trials > SWB_MAX_TRIALS_CAP) return "max_trials > 32 is not supported (per-trial bookkeeping rows)";
 #define X(T, name, kind) if (desc_count(d, #kind[0], #kind[1]) > 0 && d.name == nullptr) return "null array: " #name;
     SWB_DESC_ARRAYS(X)
 #undef X
@@ -75,6 +76,7 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
     const int nN = d.n_nodes, nL = d.n_links;
     r.link_flags.assign(nL, 0); r.link_z1.assign(nL, 0.0); r.link_z2.assign(nL, 0.0);
     r.outfall_link.assign(nN, -1); r.link_kernel.assign(nL, LK_GENERIC);
+    r.xs_rcp_yfull.assign(nL, 0.0); r.cond_rcp_mod_length.assign(nL, 0.0);
     r.nc_links.clear(); r.nTrue = 0;
     for (int j = 0; j < nL; j++) {
         int a = d.link_node1[j], b = d.link_node2[j], f = 0;
@@ -95,6 +97,8 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
             if (d.xs_type[j] == XS_CIRCULAR) r.link_kernel[j] = LK_CIRCULAR;
             else if (d.xs_type[j] == XS_RECT_CLOSED) r.link_kernel[j] = LK_RECT_CLOSED;
         }
+        r.xs_rcp_yfull[j] = exact_rcp(d.xs_yfull[j]);
+        r.cond_rcp_mod_length[j] = exact_rcp(d.cond_mod_length[j]);
         r.link_z1[j] = d.node_invert[a] + d.link_offset1[j];
         r.link_z2[j] = d.node_invert[b] + d.link_offset2[j];
         // link_setOutfallDepth (link.c:743-753) tests node2 first; a later link overrides an

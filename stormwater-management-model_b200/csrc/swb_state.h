@@ -73,6 +73,8 @@ struct Net {
     // derived
     const int    *link_flags;
     const double *link_z1, *link_z2;       // Node[n].invertElev + Link.offset (dwflow.c:110-111)
+    const double *xs_rcp_yfull;            // exact_rcp(xs_yfull): reciprocal for div_rcp, or 0 (swb_common.h)
+    const double *cond_rcp_mod_length;     // exact_rcp(cond_mod_length)
     const int    *adj_start;               // nN+1: CSR node -> incident link ends
     const int    *adj;                     // (link << 1) | end, ordered true conduits first, then
                                            // other links, each ascending by link index (A.3)
@@ -88,6 +90,11 @@ struct Net {
     const double *culvert_params;          // [58][5] FHWA inlet-control coefficients (culvert.c:33)
     const double *road_tables;             // RT_TOTAL (x, y) pairs (roadway.c:42-69)
     const double *xs_tables;               // XT_TOTAL doubles (global copy of the shape tables)
+    // every array above lives in ONE device allocation [arena, arena + arena_bytes): the launcher pins
+    // that range in L2 (persisting access-policy window), so the ~100 dependent static loads of a
+    // conduit / node update hit L2 instead of being evicted by the streaming ensemble state
+    const void *arena;
+    size_t arena_bytes;
 };
 
 // ---- dynamic fields: X(ctype, member name, field id, kind) ; kind N = per node, L = per link,
@@ -153,10 +160,39 @@ struct Halo {
     unsigned long long *wait_ns;  // = phase_ns + TP_HALO_WAIT: the part of TP_HALO spent spinning on peers
 };
 
+// Dynamic state is touched once per phase and a wide ensemble's state (2.5 GB for 512 members) never
+// fits the 126 MB L2, so on the device every field access carries the streaming hint (ld/st.global.cs:
+// first candidate for eviction).  What the hint protects is the kernel's own local-memory lines
+// (register spills of the conduit update), which ARE re-read within microseconds: without it the
+// state streams push them out to HBM (profiles/README.md round 2).  SPtr<T> is layout-identical to T*.
+#ifndef SWB_STREAM_STATE
+#define SWB_STREAM_STATE 0
+#endif
+#if defined(__CUDACC__) && SWB_STREAM_STATE
+template <class T> struct SRef {
+    T *p;
+#ifdef __CUDA_ARCH__
+    __host__ __device__ __forceinline__ operator T() const { return __ldcs(p); }
+    __host__ __device__ __forceinline__ const SRef &operator=(T v) const { __stcs(p, v); return *this; }
+#else
+    __host__ __device__ __forceinline__ operator T() const { return *p; }
+    __host__ __device__ __forceinline__ const SRef &operator=(T v) const { *p = v; return *this; }
+#endif
+    __host__ __device__ __forceinline__ const SRef &operator=(const SRef &o) const { return *this = (T)o; }
+};
+template <class T> struct SPtr {
+    T *p;
+    __host__ __device__ __forceinline__ SRef<T> operator[](size_t i) const { return SRef<T>{p + i}; }
+    __host__ __device__ __forceinline__ operator T *() const { return p; }
+};
+#else
+template <class T> using SPtr = T *;
+#endif
+
 struct State {
     int M;                       // members
     Halo halo;
-#define X(T, name, id, kind) T *name;
+#define X(T, name, id, kind) SPtr<T> name;
     SWB_STATE_FIELDS(X)
 #undef X
     // per member

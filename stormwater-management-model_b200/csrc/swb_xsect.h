@@ -34,7 +34,9 @@ struct Xs {                 // objects.h:581-599, plus resolved per-object table
     int    ntbl;            // entries in the per-object tables (IRREGULAR / CUSTOM / STREET)
     const double *atbl, *rtbl, *wtbl;
     double yFull, wMax, ywMax, aFull, rFull, sFull, sMax, yBot, aBot, sBot, rBot;
+    double rYFull;          // exact_rcp(yFull): RN(1 / yFull) when y / yFull may go through div_rcp, else 0
 };
+SWB_FI double xs_ynorm(const Xs &x, double y) { return div_by(y, x.yFull, x.rYFull); }
 
 // ratio of area at max. flow to full area (xsect.c:55-81); >= 1 means an open shape
 SWB_FI double xs_amax_ratio(int type)
@@ -57,12 +59,17 @@ SWB_FI bool xs_is_open(int type) { return xs_amax_ratio(type) >= 1.0; }
 SWB_FI double xs_lookup_body(double x, const double *tb, int n)
 {
     double delta = 1.0 / ((double)n - 1);
-    int i = (int)(x / delta);
+    // 51- and 26-entry tables (every circular table): delta = RN(1/50), RN(1/25) pass exact_rcp()
+    // with reciprocals 50 and 25, so both divisions by delta are three operations each
+    // (tests/test_exact_division.py); other table sizes divide
+    const bool viaRcp = (n == 51 || n == 26);
+    const double rDelta = (double)n - 1;
+    int i = (int)(viaRcp ? div_rcp(x, delta, rDelta) : x / delta);
     if (i >= n - 1) return tb[n - 1];
     double x0 = i * delta;
     double x1 = ((double)i + 1) * delta;
     double t0 = tb[i], t1 = tb[i + 1];
-    double y = t0 + (x - x0) * (t1 - t0) / delta;
+    double y = t0 + (viaRcp ? div_rcp((x - x0) * (t1 - t0), delta, rDelta) : (x - x0) * (t1 - t0) / delta);
     if (i < 2) {
         double y2 = y + (x - x0) * (x - x1) / (delta * delta) * (t0 / 2.0 - t1 + tb[i + 2] / 2.0);
         if (y2 > 0.0) y = y2;
@@ -382,7 +389,7 @@ SWB_FI XsTabs xs_tabs(int type)
 template <int S>
 SWB_FI double xs_a_of_y(const Xs &x, double y, const double *T)
 {
-    double yNorm = y / x.yFull;
+    double yNorm = xs_ynorm(x, y);
     if (y <= 0.0) return 0.0;
     switch (S >= 0 ? S : x.type) {
       case XS_FORCE_MAIN:
@@ -428,7 +435,7 @@ SWB_FI double xs_a_of_y(const Xs &x, double y, const double *T)
 template <int S>
 SWB_FI double xs_w_of_y(const Xs &x, double y, const double *T)
 {
-    double yNorm = y / x.yFull;
+    double yNorm = xs_ynorm(x, y);
     switch (S >= 0 ? S : x.type) {
       case XS_FORCE_MAIN:
       case XS_CIRCULAR:    return x.wMax * xs_lookup(yNorm, T + XT_W_CIRC, XN_W_CIRC);
@@ -471,7 +478,7 @@ SWB_FI double xs_w_of_y(const Xs &x, double y, const double *T)
 template <int S = -1>
 SWB_FI double xs_r_of_y_direct(const Xs &x, double y, const double *T)
 {
-    double yNorm = y / x.yFull;
+    double yNorm = xs_ynorm(x, y);
     switch (S >= 0 ? S : x.type) {
       case XS_FORCE_MAIN:
       case XS_CIRCULAR:    return x.rFull * xs_lookup(yNorm, T + XT_R_CIRC, XN_R_CIRC);

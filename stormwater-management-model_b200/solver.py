@@ -58,6 +58,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_last_kernel_ms.restype = C.c_double
     lib.swb_sync.argtypes = [C.c_void_p]
     lib.swb_get_phase_times.argtypes = [C.c_void_p, _P_D, C.c_int, C.c_int]
+    lib.swb_debug_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.swb_host_alloc.argtypes = [C.c_ulonglong]
     lib.swb_host_alloc.restype = C.c_void_p
     lib.swb_host_free.argtypes = [C.c_void_p]
@@ -332,6 +333,10 @@ class Solver:
                                            nd.ctypes.data_as(pf) if nodes else None,
                                            ld.ctypes.data_as(pf) if links else None))
         return nd, ld
+
+    def debug_run(self, phases: int, n_steps: int, debug: int = 0, profile: bool = False):
+        """Profiling aid (swb_debug_run): phase mask + debug switches, see include/swmm_b200.h."""
+        self._chk(self.lib.swb_debug_run(self._h, phases, n_steps, debug, int(profile)))
 
     def conduit_updates(self) -> int:
         return int(self.lib.swb_conduit_updates(self._h))

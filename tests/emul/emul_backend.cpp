@@ -22,10 +22,12 @@ namespace swb { namespace backend {
 static bool init(int, std::string &) { return true; }
 static void *alloc(size_t b) { return std::malloc(b ? b : 8); }
 static void free_(void *p) { std::free(p); }
-static void upload(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
-static void download(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
-static void zero(void *d, size_t b) { std::memset(d, 0, b); }
+static bool upload(void *d, const void *s, size_t b) { std::memcpy(d, s, b); return true; }
+static bool download(void *d, const void *s, size_t b) { std::memcpy(d, s, b); return true; }
+static bool zero(void *d, size_t b) { std::memset(d, 0, b); return true; }
+static const char *last_error() { return "host allocation failed"; }
 static bool sync(std::string &) { return true; }
+static void profiler(bool) {}
 static void *stream_create() { return nullptr; }
 static void stream_destroy(void *) {}
 static void use_stream(void *) {}
@@ -82,7 +84,7 @@ static bool xsect_eval(int, int fn, const Xs &x, int n, const double *args, doub
     return true;
 }
 
-static bool report(const Net &net, const State &st, const double *f, int m0, int nm, float *node_out,
+static bool report(int, const Net &net, const State &st, const double *f, int m0, int nm, float *node_out,
                    float *link_out, std::string &)
 {
     const int nr = node_record_len(net), lr = link_record_len(net);

@@ -9,6 +9,7 @@ extern "C" void emul_xsect_eval(int fn, int type, const double *p, int n, const 
     x.type = type; x.ntbl = 0; x.atbl = x.rtbl = x.wtbl = nullptr;
     x.yFull = p[0]; x.wMax = p[1]; x.ywMax = p[2]; x.aFull = p[3]; x.rFull = p[4];
     x.sFull = p[5]; x.sMax = p[6]; x.yBot = p[7]; x.aBot = p[8]; x.sBot = p[9]; x.rBot = p[10];
+    x.rYFull = swb::exact_rcp(x.yFull);
     const double *T = g_tab;
     for (int i = 0; i < n; i++) switch (fn) {
         case 0: out[i] = xs_a_of_y(x, arg[i], T); break;

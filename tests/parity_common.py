@@ -41,7 +41,7 @@ def build_emul() -> str:
     srcs += [os.path.join(EMUL_DIR, "emul_backend.cpp"), os.path.join(ROOT, "include", "swmm_b200.h")]
     if os.path.exists(EMUL_LIB) and all(os.path.getmtime(s) <= os.path.getmtime(EMUL_LIB) for s in srcs):
         return EMUL_LIB
-    subprocess.run([HOST_CXX, "-O2", "-std=c++20", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+    subprocess.run([HOST_CXX, "-O2", "-std=c++20", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
                     "-Wno-unused-function", f"-I{CSRC}", f"-I{ROOT}/include",
                     os.path.join(EMUL_DIR, "emul_backend.cpp"), "-o", EMUL_LIB], check=True)
     return EMUL_LIB

@@ -1,14 +1,15 @@
 #!/usr/bin/env python
 """Benchmark of the dynamic-wave + quality routing hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--members M] [--grid n] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--members-total M] [--impl reference]
 
-Workload (config.workload): BASELINE config 4, a rainfall ensemble of the config-2 network
-(n x n looped grid, 19 801 conduits at n = 100, circular + rect_closed, 2 pollutants), M members
-per GPU in lockstep (weak scaling: 512 members per GPU -> 4 096 on 8 GPUs).  One bench "step" is
-ONE persistent launch that advances every member `--routing-steps` routing steps (Picard loops,
-quality routing, Courant search, all on the device).  The ensemble is first spun up, untimed, to
-`--spinup` simulated seconds so that the timed steps run on a wet, surcharging network.
+Workload (config.workload): BASELINE config 4, the 4 096-member rainfall ensemble of the config-2
+network (100 x 100 looped grid, 19 801 conduits, circular + rect_closed, SLOT, 2 pollutants), split in
+contiguous member blocks over the N GPUs ("scaling": "strong" -- every N runs the same 4 096 members;
+one B200 holds all of them: 19.7 GB of state).  One bench "step" is ONE persistent launch per GPU that
+advances every member `--routing-steps` routing steps (Picard loops, quality routing, Courant search,
+all on the device).  The ensemble is first spun up, untimed, to `--spinup` simulated seconds so that
+the timed steps run on a wet, surcharging network.
 
 Numbers on the JSON line:
   value            conduit-updates/s, whole job, inputs resident in HBM, CUDA-event timed in the
@@ -17,8 +18,13 @@ Numbers on the JSON line:
                    buffers (lateral inflows + quality loads in, depths/flows/steps out), wall
                    clock around the calls, host<->device copies included;
   roofline         200 B per conduit-update (SURVEY.md 8d) / kernel time vs measured HBM copy peak;
-  cpu_baseline     the unmodified reference (oracle/_ref, all host cores) on a bounded sample of
-                   the same spun-up workload (one member).
+  cpu_baseline     the unmodified reference (oracle/_ref) on a bounded sample of the same spun-up
+                   workload: one member with THREADS = all cores, and `packed_value` = one
+                   single-threaded reference process per core, each on its own member;
+  weak_512_per_gpu the round-1 configuration (512 members per GPU) for continuity;
+  c2_single        config 2 as ONE model on one GPU, the whole 2 h in a single launch;
+  c5               config 5 (1000 x 500 grid, 998 501 conduits) as ONE model striped over the N GPUs
+                   with the in-kernel halo exchange, checked bit for bit against the single-GPU run.
 """
 from __future__ import annotations
 
@@ -39,16 +45,19 @@ import swmm_b200  # noqa: E402,F401
 from swmm_b200 import network, scenarios, solver  # noqa: E402
 
 BYTES_PER_CU = 200.0          # SURVEY.md 8(d), fixed for grading (r = 0.505, k = 3)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
 
 
-def measured_traffic():
+def measured_traffic(members: int, grid: int, rs: int):
     """dram__bytes_read + dram__bytes_write of one swb_route_kernel launch from the committed
-    `ncu --set full` capture of the default bench step (profiles/ncu_traffic_r01.json)."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
-    if not os.path.exists(p):
+    `ncu --set full` capture of this tree (profiles/ncu_traffic_r02.json), together with the
+    conduit-updates of THAT launch, so traffic / algorithmic bytes is like for like."""
+    if not os.path.exists(TRAFFIC_FILE):
         return None
-    d = json.load(open(p))
-    return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    d = json.load(open(TRAFFIC_FILE))
+    if d.get("members") != members or d.get("grid") != grid or d.get("routing_steps") != rs:
+        return None
+    return d
 
 
 def measured_peak():
@@ -119,12 +128,13 @@ def dist_env():
 
 
 # ---------------------------------------------------------------------------------------------------
-def make_ensemble(args, device: int, member0: int):
+def make_ensemble(args, device: int, member0: int, members: int | None = None):
+    members = members or args.members
     spec = scenarios.GridSpec(nx=args.grid, ny=args.grid, hours=args.hours, surcharge=args.surcharge)
     case = network.build_grid(spec)
-    scale, shift_h = scenarios.c4_members(args.members_total, 2024)
-    sl = slice(member0, member0 + args.members)
-    s = solver.Solver(case.net, args.members, device=device)
+    scale, shift_h = scenarios.c4_members(max(args.members_total, member0 + members), 2024)
+    sl = slice(member0, member0 + members)
+    s = solver.Solver(case.net, members, device=device)
     s.load_state(case.state0)
     inf = dict(case.inflows)
     s.set_inflows(member_scale=scale[sl], member_shift=shift_h[sl] / 24.0, **inf)
@@ -139,18 +149,54 @@ def spin_up(s, t_spin: float, chunk: int = 50):
         s.run_steps(chunk, t_spin)
 
 
+def timed_launches(s, t_end, rs, warmup, steps, barrier):
+    """W untimed + K timed launches of `rs` routing steps; returns per-launch kernel ms and counters."""
+    for _ in range(warmup):
+        s.run_steps(rs, t_end)
+    barrier()
+    st0 = s.stats(0, s.M)
+    cu0, l0 = s.conduit_updates(), s.launch_count()
+    it0 = sum(x.iterations for x in st0)
+    n0 = sum(x.steps for x in st0)
+    sim0 = float(np.sum([x.sim_time for x in st0]))
+    s.phase_times(reset=True)
+    kern_ms = []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.run_steps(rs, t_end)
+        kern_ms.append(s.last_kernel_ms())
+    barrier()
+    wall = time.perf_counter() - t0
+    st1 = s.stats(0, s.M)
+    return dict(kern_ms=kern_ms, wall=wall, cu=s.conduit_updates() - cu0, launches=s.launch_count() - l0,
+                iters=sum(x.iterations for x in st1) - it0, member_steps=sum(x.steps for x in st1) - n0,
+                sim_hours=(float(np.sum([x.sim_time for x in st1])) - sim0) / 3600.0, phases=s.phase_times())
+
+
+def note(rank, t0, what):
+    if rank == 0:
+        print(f"[bench {time.perf_counter() - t0:7.1f} s] {what}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
+    T0 = time.perf_counter()
     rank, world, local = dist_env()
+    dist = torch = None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
     device = local
+    if args.members_total % (32 * world):
+        raise SystemExit("--members-total must be a multiple of 32 x GPUs")
+    args.members = args.members_total // world
     s, case, spec = make_ensemble(args, device, rank * args.members)
     n_true = int(case.net.true_conduit_mask().sum())
     t_end = case.t_end
+    note(rank, T0, "ensemble built")
     spin_up(s, args.spinup)
+    note(rank, T0, "spun up")
     rs = args.routing_steps
 
     def barrier():
@@ -158,71 +204,82 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
-    for _ in range(args.warmup):
-        s.run_steps(rs, t_end)
-    barrier()
     sampler = ClockSampler(device)
     if rank == 0:
         sampler.start()
-    cu0, l0 = s.conduit_updates(), s.launch_count()
-    s.phase_times(reset=True)
-    sim_before = float(np.sum([x.sim_time for x in s.stats(0, s.M)]))
-    kern_ms = []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        s.run_steps(rs, t_end)
-        kern_ms.append(s.last_kernel_ms())
-    barrier()
-    wall = time.perf_counter() - t0
+    r = timed_launches(s, t_end, rs, args.warmup, args.steps, barrier)
     clocks = sampler.stop() if rank == 0 else None
-    cu = s.conduit_updates() - cu0
-    phases = s.phase_times()
-    launches = s.launch_count() - l0
-    dev_s = sum(kern_ms) / 1000.0
-    sim_hours = (float(np.sum([x.sim_time for x in s.stats(0, s.M)])) - sim_before) / 3600.0
+    dev_s = sum(r["kern_ms"]) / 1000.0
 
     # ---- e2e: per-step C-ABI sequence with host buffers (the seam's call pattern) ------------
+    note(rank, T0, "timed launches done")
     e2e = measure_e2e(s, case, args, n_true)
+    s.close()
+    del s
+    note(rank, T0, "e2e done")
+
+    # ---- sub-records (each on every rank that takes part) ------------------------------------
+    weak = None
+    if not args.no_weak and args.members != 512:
+        w, _, _ = make_ensemble(args, device, rank * 512, members=512)
+        spin_up(w, args.spinup)
+
+        def wbarrier():
+            w.sync()
+            if world > 1:
+                dist.barrier()
+        wr = timed_launches(w, t_end, rs, args.warmup, max(args.steps // 2, 5), wbarrier)
+        weak = {"cu": wr["cu"], "s": sum(wr["kern_ms"]) / 1000.0, "launches": wr["launches"]}
+        w.close()
+        del w
+    note(rank, T0, "weak-scaling record done")
+    c5 = None if args.no_c5 else run_c5(args, rank, world, local, dist, torch)
+    note(rank, T0, "c5 done")
+    c2 = run_c2_single(args, local) if (rank == 0 and not args.no_c2_single) else None
+    note(rank, T0, "c2_single done")
 
     if world > 1:
-        t = torch.tensor([dev_s, e2e["seconds"]], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_s, e2e["seconds"], weak["s"] if weak else 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        c = torch.tensor([float(cu), float(e2e["cu"]), float(launches), sim_hours], dtype=torch.float64,
-                         device="cuda")
+        c = torch.tensor([float(r["cu"]), float(e2e["cu"]), float(r["launches"] + e2e["launches"]), r["sim_hours"],
+                          float(r["iters"]), float(r["member_steps"]), float(weak["cu"]) if weak else 0.0,
+                          float(weak["launches"]) if weak else 0.0],
+                         dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        dev_s, e2e_s = t.tolist()
-        cu_all, e2e_cu, launches_all, sim_hours = c.tolist()
-        # result gather over NCCL (the only collective the ensemble path needs): every rank's
-        # per-member outfall flow lands on every rank
-        out_flow = s.get_field("SWB_LINK_NEW_FLOW")[:, -1].copy()
-        mine = torch.tensor(out_flow, dtype=torch.float64, device="cuda")
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
+        dev_s_max, e2e_s, weak_s = t.tolist()
+        cu_all, e2e_cu, launches_all, sim_hours, iters_all, msteps_all, weak_cu, weak_l = c.tolist()
     else:
-        cu_all, e2e_cu, launches_all, e2e_s = cu, e2e["cu"], launches, e2e["seconds"]
+        dev_s_max, e2e_s, weak_s = dev_s, e2e["seconds"], (weak["s"] if weak else 0.0)
+        cu_all, e2e_cu, launches_all, sim_hours = r["cu"], e2e["cu"], r["launches"] + e2e["launches"], r["sim_hours"]
+        iters_all, msteps_all = r["iters"], r["member_steps"]
+        weak_cu, weak_l = (weak["cu"], weak["launches"]) if weak else (0.0, 0.0)
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        value = cu_all / dev_s
-        per_gpu_cu = cu / (sum(kern_ms) / 1000.0)
+        value = cu_all / dev_s_max
+        per_gpu_cu = r["cu"] / dev_s
         achieved = per_gpu_cu * BYTES_PER_CU / 1e9
+        tr = measured_traffic(args.members, args.grid, rs)
+        launches_all += (c5 or {}).get("launches", 0) + (c2 or {}).get("launches", 0) + weak_l
         line = {
             "metric": "conduit-updates/sec", "value": value, "unit": "conduit-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1000.0 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"C4 ensemble of C2 {args.grid}x{args.grid} looped grid ({n_true} conduits, "
-                            f"2 pollutants, {args.surcharge}), {args.members} members/GPU in lockstep",
-                "members_per_gpu": args.members, "members_total": args.members * world,
+                "workload": f"C4: {args.members_total}-member rainfall ensemble of the C2 {args.grid}x{args.grid} looped "
+                            f"grid ({n_true} conduits, 2 pollutants, {args.surcharge}), contiguous member blocks over "
+                            f"{world} GPU(s), {args.members} members per GPU in lockstep",
+                "members_total": args.members_total, "members_per_gpu": args.members,
                 "true_conduits": n_true, "routing_steps_per_step": rs, "spinup_sim_s": args.spinup,
                 "l2_policy": "state per GPU (%.2f GB) >> 126 MB L2, no flush needed" %
                              (4.8e-3 * args.members * (n_true / 19801.0)),
                 "timing": "CUDA events around each cooperative launch (library stream), max over ranks",
             },
+            "picard_iterations_per_step": iters_all / max(msteps_all, 1),
             "e2e": {"value": e2e_cu / max(e2e_s, 1e-9), "unit": "conduit-updates/s",
-                    "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                    "steps": e2e["steps"], "member_blocks": e2e["blocks"],
+                    "h2d_bytes_per_step": e2e["h2d"] * world, "d2h_bytes_per_step": e2e["d2h"] * world,
+                    "steps": e2e["steps"], "member_blocks_per_gpu": e2e["blocks"],
                     "what": "swb_step_host_batch per routing step over member blocks (copies of one block overlap the "
                     "kernel of another): pinned host lateral inflows + quality loads + dt -> device, swap / dynwave / "
                     "quality / Courant search in one launch per block, depths + flows + next dt + iterations -> host, "
@@ -231,23 +288,33 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": measured_traffic() if (args.members == 512 and args.grid == 100 and rs == 10) else None,
-                         "traffic_unit": "bytes per launch (ncu capture of the default step, profiles/ncu_traffic_r01.json)",
-                         "algorithmic_bytes_per_launch": BYTES_PER_CU * cu / max(args.steps, 1),
+                         "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr else None,
+                         "traffic_launch": ({"conduit_updates_in_launch": tr["conduit_updates_in_launch"],
+                                             "algorithmic_bytes": BYTES_PER_CU * tr["conduit_updates_in_launch"],
+                                             "kernel_ms": tr["gpu_time_ms"], "source": "profiles/ncu_traffic_r02.json"}
+                                            if tr else None),
+                         "algorithmic_bytes_per_launch": BYTES_PER_CU * r["cu"] / max(args.steps, 1),
                          "peak_source": peak_src,
                          "bytes_per_conduit_update": BYTES_PER_CU,
-                         "kernel": "swb_route_kernel", "kernel_ms_avg": float(np.mean(kern_ms)),
-                         "phase_ms": {k: round(v, 3) for k, v in phases.items()}},
-            "sim_hours_per_wall_s": sim_hours / max(dev_s, 1e-9),
-            "wall_s_timed_region": wall,
+                         "kernel": "swb_route_kernel", "kernel_ms_avg": float(np.mean(r["kern_ms"])),
+                         "phase_ms": {k: round(v, 3) for k, v in r["phases"].items()}},
+            "sim_hours_per_wall_s": sim_hours / max(dev_s_max, 1e-9),
+            "wall_s_timed_region": r["wall"],
         }
+        if weak:
+            line["weak_512_per_gpu"] = {"value": weak_cu / max(weak_s, 1e-9), "unit": "conduit-updates/s",
+                                        "members_total": 512 * world, "kernel_s": weak_s}
+        if c2:
+            line["c2_single"] = c2
+        if c5:
+            line["c5"] = c5
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
+            note(rank, T0, "cpu baseline done")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    s.close()
 
 
 def measure_e2e(s, case, args, n_true: int) -> dict:
@@ -262,7 +329,7 @@ def measure_e2e(s, case, args, n_true: int) -> dict:
     M = s.M
     steps = args.e2e_steps
     if steps <= 0:
-        return {"seconds": 1.0, "cu": 0, "steps": 0, "h2d": 0, "d2h": 0, "blocks": 0}
+        return {"seconds": 1.0, "cu": 0, "steps": 0, "h2d": 0, "d2h": 0, "blocks": 0, "launches": 0}
     blocks = max(1, min(args.e2e_blocks, M // 32))
     while M % blocks or (M // blocks) % 32:
         blocks -= 1
@@ -276,7 +343,7 @@ def measure_e2e(s, case, args, n_true: int) -> dict:
         conc = np.zeros((net.n_nodes, nP))
         conc[case.inflows["node"]] = case.inflows["concen"].reshape(-1, nP)
         load = s.host_array((M, net.n_nodes, nP))
-        load[:] = np.maximum(lat, 0.0)[:, :, None] * conc[None]
+        np.multiply(np.maximum(lat, 0.0)[:, :, None], conc[None], out=load)
     depth = s.host_array((M, net.n_nodes))
     flow = s.host_array((M, net.n_links))
     dt = s.host_array((M,))
@@ -296,31 +363,148 @@ def measure_e2e(s, case, args, n_true: int) -> dict:
 
     one_step()                               # warm
     cu0 = sum(x.conduit_updates() for x in subs)
+    l0 = sum(x.launch_count() for x in subs)
     t0 = time.perf_counter()
     for _ in range(steps):
         one_step()
     sec = time.perf_counter() - t0
     cu = sum(x.conduit_updates() for x in subs) - cu0
+    launches = sum(x.launch_count() for x in subs) - l0
     h2d = lat.nbytes + dt.nbytes + (load.nbytes if load is not None else 0)
     d2h = depth.nbytes + flow.nbytes + next_dt.nbytes + iters.nbytes
     if blocks > 1:
         for x in subs:
             x.close()
-    return {"seconds": sec, "cu": cu, "steps": steps, "h2d": h2d, "d2h": d2h, "blocks": blocks}
+    return {"seconds": sec, "cu": cu, "steps": steps, "h2d": h2d, "d2h": d2h, "blocks": blocks, "launches": launches}
+
+
+# ---- single-model sub-records -------------------------------------------------------------------
+C2_SINGLE_REFERENCE = {"steps": 1502, "iterations": 4757}     # the reference's own counts for this model
+                                                              # (tests/test_baseline_size.py, live oracle/_ref)
+
+
+def run_c2_single(args, device: int) -> dict:
+    """BASELINE config 2 as ONE model: the whole 2 h (1 502 routing steps) in a single launch."""
+    spec = scenarios.GridSpec(nx=100, ny=100, hours=2.0, surcharge="SLOT")
+    case = network.build_grid(spec)
+    n_true = int(case.net.true_conduit_mask().sum())
+    out = None
+    for rep in range(2):                     # first pass warms the instruction cache / clocks
+        s = solver.Solver(case.net, 1, device=device)
+        s.load_state(case.state0)
+        s.set_inflows(**case.inflows)
+        s.run_steps(10_000_000, case.t_end)
+        st = s.stats()[0]
+        out = {"workload": f"C2 100x100 looped grid as one model ({n_true} conduits, 2 pollutants, SLOT), 2 h simulated",
+               "kernel_s": s.last_kernel_ms() / 1000.0, "steps": int(st.steps), "iterations": int(st.iterations),
+               "conduit_updates_per_s": st.iterations * n_true / (s.last_kernel_ms() / 1000.0),
+               "sim_hours_per_wall_s": st.sim_time / 3600.0 / (s.last_kernel_ms() / 1000.0),
+               "counts_equal_reference": (int(st.steps) == C2_SINGLE_REFERENCE["steps"]
+                                          and int(st.iterations) == C2_SINGLE_REFERENCE["iterations"]),
+               "launches": 2}
+        s.close()
+    return out
+
+
+def run_c5(args, rank, world, local, dist, torch) -> dict | None:
+    """BASELINE config 5: the 1000 x 500 grid as ONE model striped over the `world` GPUs (one process
+    per GPU, border depths exchanged inside the persistent kernel over peer windows); rank 0 then
+    runs the same model unpartitioned and compares every depth and flow bit for bit."""
+    from swmm_b200 import partition
+    t0 = time.perf_counter()
+    spec = scenarios.GridSpec(nx=args.c5_nx, ny=args.c5_ny, hours=1.0, pollutants=False, surcharge="SLOT")
+    case = network.build_grid(spec)
+    net = case.net
+    n_true = int(net.true_conduit_mask().sum())
+    sim_s = args.c5_sim_s
+    single_ms = None
+    depth_all = flow_all = None
+    if world == 1:
+        s = solver.Solver(net, 1, device=local)
+        s.load_state(case.state0)
+        s.set_inflows(**case.inflows)
+        s.run_steps(5, sim_s)
+        it0 = s.stats()[0].iterations
+        s.run_steps(10_000_000, sim_s)
+        st = s.stats()[0]
+        ms = s.last_kernel_ms()
+        phases = [{k: round(v, 3) for k, v in s.phase_times().items() if v}]
+        s.close()
+        ident, exchanges = None, 0
+    else:
+        parts = partition.split_network(net, partition.stripes(args.c5_ny, args.c5_nx, world, extra_nodes=1), world)
+        part = parts[rank]
+        del parts
+        ps = partition.PartitionedSolver(part, device=local, timeout_s=20.0)
+        handles = [None] * world
+        dist.all_gather_object(handles, ps.export_handle())
+        ps.connect(handles)
+        ps.load_state(partition.split_state(part, case.state0, 0))
+        ps.set_inflows(**partition.split_inflows(part, case.inflows, 0))
+        dist.barrier()
+        ps.run_steps(5, sim_s)               # warm-up launch (also pages the peer mappings in)
+        it0 = ps.stats()[0].iterations
+        ex0 = ps.exchanges()
+        ps.phase_times()
+        dist.barrier()
+        ps.run_steps(10_000_000, sim_s)      # ONE launch to the end of the simulation
+        t = torch.tensor([ps.last_kernel_ms()], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        st = ps.stats()[0]
+        exchanges = ps.exchanges() - ex0
+        pieces_d, pieces_q, all_ph = [None] * world, [None] * world, [None] * world
+        dist.all_gather_object(pieces_d, ps.owned_field("SWB_NODE_NEW_DEPTH"))
+        dist.all_gather_object(pieces_q, ps.owned_field("SWB_LINK_NEW_FLOW"))
+        dist.all_gather_object(all_ph, {k: round(v, 3) for k, v in ps.phase_times().items() if v})
+        phases = all_ph
+        ps.close()
+        ident = None
+        if rank == 0:
+            depth_all = partition.assemble(pieces_d, net.n_nodes)
+            flow_all = partition.assemble(pieces_q, net.n_links)
+            single = solver.Solver(net, 1, device=local)
+            single.load_state(case.state0)
+            single.set_inflows(**case.inflows)
+            single.run_steps(5, sim_s)
+            single.run_steps(10_000_000, sim_s)
+            s0 = single.stats()[0]
+            ident = bool(np.array_equal(depth_all, single.get_field("SWB_NODE_NEW_DEPTH")[0])
+                         and np.array_equal(flow_all, single.get_field("SWB_LINK_NEW_FLOW")[0])
+                         and s0.iterations == st.iterations and s0.steps == st.steps)
+            single_ms = single.last_kernel_ms()
+            single.close()
+        dist.barrier()
+    if rank != 0:
+        return None
+    cu = (st.iterations - it0) * n_true
+    out = {"workload": f"C5 {args.c5_nx}x{args.c5_ny} looped grid as one model, {n_true} conduits, SLOT, "
+                       f"{sim_s:.0f} s simulated, striped over {world} GPU(s)",
+           "n_gpus": world, "steps": int(st.steps), "iterations": int(st.iterations),
+           "kernel_s_max_over_ranks": ms / 1000.0, "conduit_updates_per_s": cu / (ms / 1000.0),
+           "halo_exchanges": int(exchanges), "identical_to_single_gpu": ident,
+           "single_gpu_kernel_s": None if single_ms is None else single_ms / 1000.0,
+           "phase_ms_per_rank": phases, "build_s": time.perf_counter() - t0,
+           "launches": 2 * world + (2 if world > 1 else 0)}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
-def reference_sample(args, n_routing_steps: int, threads: int):
-    """Times the UNMODIFIED reference (oracle/_ref) on one member of the same workload: spin up
-    untimed, then time n routing steps end to end (swmm_step) and inside the seam functions."""
+def reference_run(grid, hours, surcharge, spinup, warm_steps, timed_steps, threads, member=None):
+    """The UNMODIFIED reference (oracle/_ref) on one member of the workload: spin up untimed, then
+    time `timed_steps` routing steps end to end (swmm_step) and inside the seam functions."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refengine
     if not refengine.available():
         return None
-    os.environ.setdefault("OMP_PROC_BIND", "true")
-    os.environ.setdefault("OMP_WAIT_POLICY", "active")
-    spec = scenarios.GridSpec(nx=args.grid, ny=args.grid, hours=args.hours, surcharge=args.surcharge,
-                              threads=threads)
+    if threads > 1:
+        os.environ.setdefault("OMP_PROC_BIND", "true")
+        os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    kw = {}
+    if member is not None:
+        scale, shift_h = scenarios.c4_members(4096, 2024)
+        kw = dict(inflow_scale=float(scale[member]), inflow_shift_h=float(shift_h[member]))
+    spec = scenarios.GridSpec(nx=grid, ny=grid, hours=hours, surcharge=surcharge, threads=threads, **kw)
     d = tempfile.mkdtemp(prefix="swb_ref_")
     path = os.path.join(d, "c2.inp")
     open(path, "w").write(scenarios.c2_grid_inp(spec))
@@ -328,13 +512,15 @@ def reference_sample(args, n_routing_steps: int, threads: int):
     e.open(path)
     e.start(save=False)
     n_true = int(e.network().true_conduit_mask().sum())
-    while e.routing_time_ms() / 1000.0 < args.spinup:
+    while e.routing_time_ms() / 1000.0 < spinup:
         if e.step() == 0:
             break
+    for _ in range(warm_steps):
+        e.step()
     e.reset_seam_totals()
     t0 = time.perf_counter()
     n = 0
-    for _ in range(n_routing_steps):
+    for _ in range(timed_steps):
         n += 1
         if e.step() == 0:
             break
@@ -342,24 +528,67 @@ def reference_sample(args, n_routing_steps: int, threads: int):
     tot = e.seam_totals()
     e.end()
     e.close()
-    cu = tot["iterations"] * n_true
     hot = tot["t_dynwave_execute"] + tot["t_get_routing_step"] + tot["t_qualrout_execute"]
-    return {"cu": cu, "wall": wall, "hot": hot, "steps": n, "n_true": n_true,
+    return {"cu": tot["iterations"] * n_true, "wall": wall, "hot": hot, "steps": n, "n_true": n_true,
             "iters_per_step": tot["iterations"] / max(n, 1)}
+
+
+def packed_reference(args, n_procs: int, timed_steps: int, warm_steps: int = 0) -> dict | None:
+    """One single-threaded reference process per core, each on its own config-4 member, all running
+    at the same time: the honest ensemble figure of the CPU (the engine holds one project per
+    process, swmm5.h:129-151).  Aggregate = sum of conduit-updates / longest timed region."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-worker", "--grid", str(args.grid),
+           "--hours", str(args.hours), "--surcharge", args.surcharge, "--spinup", str(args.spinup),
+           "--cpu-steps", str(timed_steps), "--worker-warm", str(warm_steps)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env.pop("OMP_PROC_BIND", None)           # (would pin every worker's only thread to the same first core)
+    cpus = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(n_procs))
+    procs = [subprocess.Popen(cmd + ["--member", str(17 * k), "--cpu", str(cpus[k % len(cpus)])], stdout=subprocess.PIPE,
+                              stderr=subprocess.DEVNULL, text=True, env=env) for k in range(n_procs)]
+    outs = []
+    for p in procs:
+        o, _ = p.communicate()
+        try:
+            outs.append(json.loads(o.strip().splitlines()[-1]))
+        except Exception:
+            pass
+    if not outs:
+        return None
+    return {"value": sum(o["cu"] for o in outs) / max(o["wall"] for o in outs), "procs": len(outs),
+            "wall": max(o["wall"] for o in outs), "cu": sum(o["cu"] for o in outs),
+            "iters_per_step": float(np.mean([o["iters_per_step"] for o in outs])),
+            "per_process_value": float(np.mean([o["cu"] / o["wall"] for o in outs]))}
 
 
 def cpu_baseline(args) -> dict:
     cores = os.cpu_count() or 1
-    r = reference_sample(args, args.cpu_steps, cores)
+    r = reference_run(args.grid, args.hours, args.surcharge, args.spinup, 0, args.cpu_steps, cores)
     if r is None:
         return {"value": None, "unit": "conduit-updates/s", "cores": cores, "kind": "reference",
                 "sample": "oracle/_ref not present on this box"}
-    return {"value": r["cu"] / r["wall"], "unit": "conduit-updates/s", "cores": cores, "kind": "reference",
-            "hot_path_only_value": r["cu"] / max(r["hot"], 1e-9),
-            "sample": f"unmodified reference (oracle/_ref, THREADS {cores}, OMP_PROC_BIND=true), one member "
-                      f"of the same {args.grid}x{args.grid} grid spun up to {args.spinup:.0f} s, then "
-                      f"{r['steps']} routing steps timed end to end ({r['wall']:.1f} s, "
-                      f"{r['iters_per_step']:.2f} iterations/step)"}
+    out = {"value": r["cu"] / r["wall"], "unit": "conduit-updates/s", "cores": cores, "kind": "reference",
+           "hot_path_only_value": r["cu"] / max(r["hot"], 1e-9), "picard_iterations_per_step": r["iters_per_step"],
+           "sample": f"unmodified reference (oracle/_ref, THREADS {cores}, OMP_PROC_BIND=true), the unperturbed member "
+                     f"of the same {args.grid}x{args.grid} grid spun up to {args.spinup:.0f} s, then "
+                     f"{r['steps']} routing steps timed end to end ({r['wall']:.1f} s)"}
+    if not args.no_packed:
+        p = packed_reference(args, cores, args.cpu_steps)
+        if p:
+            out["packed_value"] = p["value"]
+            out["packed_procs"] = p["procs"]
+            out["packed_picard_iterations_per_step"] = p["iters_per_step"]
+            out["packed_sample"] = (f"{p['procs']} single-threaded reference processes at once (THREADS 1), each on its own "
+                                    f"config-4 member (perturbed .inp), spun up to {args.spinup:.0f} s, then {args.cpu_steps} "
+                                    f"routing steps; sum of conduit-updates / longest timed region")
+    return out
+
+
+def run_reference_worker(args):
+    if args.cpu >= 0 and hasattr(os, "sched_setaffinity"):
+        os.sched_setaffinity(0, {args.cpu})   # one worker per core
+    r = reference_run(args.grid, args.hours, args.surcharge, args.spinup, args.worker_warm, args.cpu_steps, 1,
+                      member=args.member)
+    print(json.dumps(r if r else {"cu": 0, "wall": 1.0, "iters_per_step": 0.0}), flush=True)
 
 
 def run_reference(args):
@@ -368,49 +597,43 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     rs = args.routing_steps
-    per_step = []
-    cu_total = 0
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refengine
     if not refengine.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
         return
-    # one engine run: spin up, W warm-up chunks, then K timed chunks of `rs` routing steps
-    os.environ.setdefault("OMP_PROC_BIND", "true")
-    os.environ.setdefault("OMP_WAIT_POLICY", "active")
-    spec = scenarios.GridSpec(nx=args.grid, ny=args.grid, hours=args.hours, surcharge=args.surcharge,
-                              threads=cores)
-    d = tempfile.mkdtemp(prefix="swb_ref_")
-    path = os.path.join(d, "c2.inp")
-    open(path, "w").write(scenarios.c2_grid_inp(spec))
-    e = refengine.RefEngine()
-    e.open(path)
-    e.start(save=False)
-    n_true = int(e.network().true_conduit_mask().sum())
-    while e.routing_time_ms() / 1000.0 < args.spinup:
-        e.step()
-    for _ in range(args.warmup * rs):
-        e.step()
-    e.reset_seam_totals()
-    t0 = time.perf_counter()
-    for _ in range(args.steps * rs):
-        if e.step() == 0:
-            break
-    wall = time.perf_counter() - t0
-    tot = e.seam_totals()
-    e.end()
-    e.close()
-    cu = tot["iterations"] * n_true
-    value = cu / wall
+    r = reference_run(args.grid, args.hours, args.surcharge, args.spinup, args.warmup * rs, args.steps * rs, cores)
+    openmp = r["cu"] / r["wall"]
+    cb = {"value": openmp, "unit": "conduit-updates/s", "cores": cores, "kind": "reference",
+          "picard_iterations_per_step": r["iters_per_step"],
+          "sample": f"ONE member, {r['steps']} routing steps after spin-up, swmm_step wall clock, THREADS {cores} "
+                    f"(the reference's OpenMP routing, OMP_PROC_BIND=true)"}
+    # the ensemble figure of the CPU: one single-threaded engine per core, `steps` x `routing-steps`
+    # routing steps each after `warmup` x `routing-steps` untimed ones
+    packed = None if args.no_packed else packed_reference(args, cores, args.steps * rs, args.warmup * rs)
+    value, wall, ips, what = openmp, r["wall"], r["iters_per_step"], "OpenMP routing of one member (THREADS = all cores)"
+    if packed:
+        cb.update(packed_value=packed["value"], packed_procs=packed["procs"],
+                  packed_picard_iterations_per_step=packed["iters_per_step"],
+                  packed_sample=f"{packed['procs']} single-threaded reference processes at once, pinned one per core, "
+                                f"each on its own config-4 member (perturbed .inp)")
+        if packed["value"] > value:
+            value, wall, ips = packed["value"], packed["wall"], packed["iters_per_step"]
+            what = f"{packed['procs']} single-threaded engines at once, one config-4 member per core"
+    cb["value"] = value
+    cb["openmp_one_member_value"] = openmp
     line = {
         "impl": "reference", "metric": "conduit-updates/sec", "value": value, "unit": "conduit-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"ONE member of the C2 {args.grid}x{args.grid} looped grid ({n_true} conduits, "
-                               f"2 pollutants, {args.surcharge}); the reference cannot batch members",
-                   "routing_steps_per_step": rs, "spinup_sim_s": args.spinup, "threads": cores},
-        "cpu_baseline": {"value": value, "unit": "conduit-updates/s", "cores": cores, "kind": "reference",
-                         "sample": f"{args.steps * rs} routing steps after spin-up, swmm_step wall clock"},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C4: members of the {args.members_total}-member rainfall ensemble of the C2 {args.grid}x{args.grid} "
+                               f"looped grid ({r['n_true']} conduits, 2 pollutants, {args.surcharge}) on the host CPU; the "
+                               f"reference holds one project per process (swmm5.h:129-151), so the ensemble runs as "
+                               f"independent engines: value = the faster of {what}",
+                   "members_total": args.members_total, "routing_steps_per_step": rs, "spinup_sim_s": args.spinup,
+                   "threads": cores, "value_is": what},
+        "picard_iterations_per_step": ips,
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "conduit-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -422,8 +645,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--members", type=int, default=512, help="members per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-worker"])
+    ap.add_argument("--members-total", type=int, default=4096, help="ensemble members over all GPUs (BASELINE config 4)")
+    ap.add_argument("--members", type=int, default=0, help="members per GPU (overrides --members-total: weak scaling)")
     ap.add_argument("--grid", type=int, default=100)
     ap.add_argument("--hours", type=float, default=6.0)
     ap.add_argument("--surcharge", default="SLOT")
@@ -432,12 +656,25 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-blocks", type=int, default=4, help="member blocks pipelined by swb_step_host_batch")
     ap.add_argument("--cpu-steps", type=int, default=60)
+    ap.add_argument("--member", type=int, default=0, help="(reference-worker) config-4 member to run")
+    ap.add_argument("--cpu", type=int, default=-1, help="(reference-worker) core to pin to")
+    ap.add_argument("--worker-warm", type=int, default=0, help="(reference-worker) untimed routing steps after spin-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-packed", action="store_true")
+    ap.add_argument("--no-weak", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--no-c2-single", action="store_true")
+    ap.add_argument("--c5-nx", type=int, default=1000)
+    ap.add_argument("--c5-ny", type=int, default=500)
+    ap.add_argument("--c5-sim-s", type=float, default=3600.0)
     args = ap.parse_args()
     _, world, _ = dist_env()
-    args.members_total = args.members * max(world, 1)
+    if args.members:
+        args.members_total = args.members * max(world, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-worker":
+        run_reference_worker(args)
     else:
         run_ours(args)
 

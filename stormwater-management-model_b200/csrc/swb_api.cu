@@ -216,7 +216,7 @@ static std::string cuda_err(const char *what, cudaError_t e)
 
 // per-device state (a process may hold solvers on several devices: every entry point that allocates
 // or launches calls init(device) first, which makes that device current and fills its record)
-struct DevInfo { bool ready; int sms, blocks_per_sm; size_t persist_max; cudaEvent_t ev0, ev1; };
+struct DevInfo { bool ready; int sms, blocks_per_sm; size_t persist_max, persist_set; cudaEvent_t ev0, ev1; };
 #define SWB_MAX_DEVICES 64
 static DevInfo g_dev[SWB_MAX_DEVICES];
 static thread_local cudaStream_t g_stream = 0;   // stream the asynchronous operations below are queued on
@@ -271,9 +271,6 @@ static bool init(int device, std::string &err)
         if ((e = cudaEventCreate(&D.ev0)) != cudaSuccess || (e = cudaEventCreate(&D.ev1)) != cudaSuccess) {
             err = cuda_err("cudaEventCreate", e); return false;
         }
-        // room for the static network arrays to stay resident in L2 (see persist_window)
-        if (D.persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, D.persist_max);
-        cudaGetLastError();
         D.ready = true;
     }
     return true;
@@ -289,23 +286,40 @@ static void free_(void *p) { cudaFree(p); }
 static bool upload(void *d, const void *s, size_t b) { return !b || ok("cudaMemcpy(H2D)", cudaMemcpy(d, s, b, cudaMemcpyHostToDevice)); }
 static bool download(void *d, const void *s, size_t b) { return !b || ok("cudaMemcpy(D2H)", cudaMemcpy(d, s, b, cudaMemcpyDeviceToHost)); }
 static bool zero(void *d, size_t b) { return !b || ok("cudaMemset", cudaMemset(d, 0, b)); }
+static bool copy2d(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, bool to_device)
+{
+    if (!width || !height) return true;
+    return ok("cudaMemcpy2D", cudaMemcpy2D(d, dpitch, s, spitch, width, height,
+                                           to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
+}
 
 // Pin [base, base + bytes) in L2 for the kernels launched on `stream`: accesses inside the window are
 // "persisting" (not displaced by normal or streaming lines).  The window is the static network
 // (Net::arena); the ensemble state streams past it.  Larger-than-L2 networks get the fraction that fits.
+// Measured (profiles/README.md, round 2): +1 % on the 512-member ensemble, but the carve-out is taken from
+// the L2 everything else uses -- with the 250 MB arena of the 1M-link model it doubled the kernel time.
+// Off by default; networks up to SWB_PERSIST_MAX_BYTES may opt in at build time.
 #ifndef SWB_PERSIST_NET
-#define SWB_PERSIST_NET 1
+#define SWB_PERSIST_NET 0
 #endif
+#define SWB_PERSIST_MAX_BYTES ((size_t)16 << 20)
 static void persist_window(int device, cudaStream_t stream, const void *base, size_t bytes)
 {
 #if SWB_PERSIST_NET
-    const DevInfo &D = g_dev[device];
-    if (!base || !bytes || D.persist_max == 0) return;
+    DevInfo &D = g_dev[device];
+    if (!base || !bytes || D.persist_max == 0 || bytes > SWB_PERSIST_MAX_BYTES) return;
+    // the persisting carve-out is taken away from everything else in L2 (register spills, the state
+    // streams): reserve what the network needs, never the device maximum
+    const size_t want = std::min(D.persist_max, (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1));
+    if (want > D.persist_set) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        D.persist_set = want;
+    }
     cudaStreamAttrValue v;
     memset(&v, 0, sizeof(v));
     v.accessPolicyWindow.base_ptr = const_cast<void *>(base);
     v.accessPolicyWindow.num_bytes = bytes;
-    v.accessPolicyWindow.hitRatio = bytes <= D.persist_max ? 1.0f : (float)((double)D.persist_max / (double)bytes);
+    v.accessPolicyWindow.hitRatio = bytes <= D.persist_set ? 1.0f : (float)((double)D.persist_set / (double)bytes);
     v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);

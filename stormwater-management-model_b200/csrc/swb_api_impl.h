@@ -153,7 +153,7 @@ int swb_network_create(const swb_network_desc *d, const swb_options *o, int devi
 #undef X
         const Derived &r = nw->der;
 #define D(name) ar.add(nw->net.name, r.name.data(), r.name.size());
-        D(link_flags) D(link_z1) D(link_z2) D(xs_rcp_yfull) D(cond_rcp_mod_length) D(adj_start) D(adj)
+        D(adj_packed) D(link_flags) D(link_z1) D(link_z2) D(xs_rcp_yfull) D(cond_rcp_mod_length) D(adj_start) D(adj)
         D(adjq_start) D(adjq) D(nc_links) D(node_order) D(link_order) D(outfall_link) D(xs_tables)
         D(link_kernel) D(culvert_params) D(road_tables)
 #undef D
@@ -261,31 +261,37 @@ static int field_xfer(swb_solver *s, int field, int m0, int nm, double *buf, con
     const size_t base = (f->kind == 'n') ? nN : (f->kind == 'l') ? nL : items;   // objects per plane
     const int planes = (int)(items / (base ? base : 1));
     void *dev = *(void **)((char *)&s->st + f->offset);
-    const size_t total = items * (size_t)M;
-    std::vector<double> h(total);
+    // only the member columns [m0, m0 + nm) of every row travel (strided 2-D copy): reading one
+    // member of a wide ensemble does not download the whole field
+    const size_t esz = f->is_u8 ? 1 : sizeof(double);
+    const size_t cols = (size_t)nm;
+    std::vector<double> h(items * cols);
     std::vector<unsigned char> h8;
-    auto pull = [&]() {
-        if (f->is_u8) { h8.resize(total); backend::download(h8.data(), dev, total);
-                        for (size_t i = 0; i < total; i++) h[i] = h8[i]; }
-        else backend::download(h.data(), dev, sizeof(double) * total);
-    };
+    void *hostp = h.data();
+    if (f->is_u8) { h8.resize(items * cols); hostp = h8.data(); }
+    char *devp = (char *)dev + (size_t)m0 * esz;
     if (!set) {
-        pull();
-        for (int mm = 0; mm < nm; mm++)
-            for (size_t it = 0; it < base; it++)
-                for (int p = 0; p < planes; p++)
-                    buf[(size_t)mm * items + it * planes + p] = h[((size_t)p * base + it) * M + (m0 + mm)];
+        if (!backend::copy2d(hostp, cols * esz, devp, (size_t)M * esz, cols * esz, items, false))
+            return fail(SWB_ERR_CUDA, backend::last_error());
+        if (f->is_u8) for (size_t i = 0; i < h8.size(); i++) h[i] = h8[i];
+        for (size_t it = 0; it < base; it++)
+            for (int p = 0; p < planes; p++) {
+                const double *row = h.data() + ((size_t)p * base + it) * cols;
+                double *dst = buf + it * planes + p;
+                for (int mm = 0; mm < nm; mm++) dst[(size_t)mm * items] = row[mm];
+            }
         return SWB_OK;
     }
-    if (nm != M) pull();
-    for (int mm = 0; mm < nm; mm++)
-        for (size_t it = 0; it < base; it++)
-            for (int p = 0; p < planes; p++)
-                h[((size_t)p * base + it) * M + (m0 + mm)] =
-                    cbuf[(broadcast ? 0 : (size_t)mm * items) + it * planes + p];
-    if (f->is_u8) { h8.resize(total); for (size_t i = 0; i < total; i++) h8[i] = (unsigned char)h[i];
-                    backend::upload(dev, h8.data(), total); }
-    else backend::upload(dev, h.data(), sizeof(double) * total);
+    for (size_t it = 0; it < base; it++)
+        for (int p = 0; p < planes; p++) {
+            double *row = h.data() + ((size_t)p * base + it) * cols;
+            const double *src = cbuf + it * planes + p;
+            if (broadcast) { const double v = *src; for (int mm = 0; mm < nm; mm++) row[mm] = v; }
+            else for (int mm = 0; mm < nm; mm++) row[mm] = src[(size_t)mm * items];
+        }
+    if (f->is_u8) for (size_t i = 0; i < h8.size(); i++) h8[i] = (unsigned char)h[i];
+    if (!backend::copy2d(devp, (size_t)M * esz, hostp, cols * esz, cols * esz, items, true))
+        return fail(SWB_ERR_CUDA, backend::last_error());
     return SWB_OK;
 }
 

@@ -44,7 +44,44 @@ SWB_FI Xs load_xs(const Net &n, int j)
 }
 
 // ---- dwflow.c:575-633 ---------------------------------------------------------------------------
-SWB_FI double dw_sjoberg(double yNorm) { return exp(-pow(yNorm, 2.4)); }
+// Sjoberg slot factor exp(-yNorm^2.4) (dwflow.c:620-633).  The caller only gets here for
+// crownCutoff <= yNorm <= 1.78.  Host build: the reference's own expression.  Device: the exponent by
+// a degree-16 polynomial in u = (yNorm - mid) / half on [0.98, 1.785] (tools/gen_sjoberg_poly.py)
+// instead of libdevice's pow() -- 17 fused operations against ~110 plus a call, three times per
+// surcharged conduit; exp(-p) is then within 7 ulp of the exact value (glibc's exp(-pow()) itself:
+// 3.8 ulp, CUDA's: similar), i.e. the same class of deviation the device's libm already has.
+#define SWB_SJOBERG_MID   0x1.61eb851eb851fp+0
+#define SWB_SJOBERG_RHALF 0x1.3e032e1c9f019p+1
+SWB_FI double dw_sjoberg_exponent_poly(double yNorm)
+{
+    const double u = (yNorm - SWB_SJOBERG_MID) * SWB_SJOBERG_RHALF;
+    double p = -0x1.8bf5330e8f840p-41;
+    p = fma(p, u, 0x1.acc159b30c145p-39);
+    p = fma(p, u, -0x1.6f3b90eba18e4p-37);
+    p = fma(p, u, 0x1.a1447fdb2f40bp-35);
+    p = fma(p, u, -0x1.f1adf6c3c8bf8p-33);
+    p = fma(p, u, 0x1.2a1cf2279644ep-30);
+    p = fma(p, u, -0x1.721f57be79f3cp-28);
+    p = fma(p, u, 0x1.e18d3a7a91c8ep-26);
+    p = fma(p, u, -0x1.4c49fa880ecbep-23);
+    p = fma(p, u, 0x1.f03c23a7c93e8p-21);
+    p = fma(p, u, -0x1.9e4735d9d1908p-18);
+    p = fma(p, u, 0x1.9a77c9469b612p-15);
+    p = fma(p, u, -0x1.135d671fe64f8p-11);
+    p = fma(p, u, 0x1.8a174c2adda9fp-7);
+    p = fma(p, u, 0x1.3d41041976bc2p-2);
+    p = fma(p, u, 0x1.852d91bfd53b0p+0);
+    p = fma(p, u, 0x1.167ce5f9f7a7fp+1);
+    return p;
+}
+SWB_FI double dw_sjoberg(double yNorm)
+{
+#if defined(__CUDA_ARCH__) && !defined(SWB_SJOBERG_LIBM)
+    return exp(-dw_sjoberg_exponent_poly(yNorm));
+#else
+    return exp(-pow(yNorm, 2.4));
+#endif
+}
 SWB_FI double dw_slot_width(const Net &n, const Xs &x, bool isOpen, double y)
 {
     double yNorm = xs_ynorm(x, y);
@@ -653,42 +690,61 @@ SWB_FI void node_add_link_end(const Net &n, const State &s, int j, int end, int 
 }
 
 // The same contribution split into its loads and its arithmetic, so that a caller can issue the
-// loads of two link ends before consuming either (two DRAM round trips per node instead of four);
-// the accumulation order, hence every bit of the sums, is unchanged.
-struct LinkEndData { int flags, type, barrels, pumpType; double q, loss, sa, dqdh; };
-SWB_FI LinkEndData node_load_link_end(const Net &n, const State &s, int j, int end, int m)
+// loads of several link ends before consuming any of them (one DRAM round trip per node instead of one
+// per link end); the accumulation order, hence every bit of the sums, is unchanged.  All static
+// attributes come from the packed incidence entry.
+struct LinkEndData { double q, loss, sa, dqdh; };
+SWB_FI LinkEndData node_load_link_end(const State &s, const AdjEntry &a, int m)
 {
     LinkEndData d;
+    const int j = a.je >> 1;
     const size_t ix = SWB_IX(j, m, s.M);
-    d.flags = n.link_flags[j];
-    d.type = n.link_type[j];
     d.q = s.l_flow[ix];
-    d.sa = (end == 0 ? s.l_surf_area1[ix] : s.l_surf_area2[ix]);
+    d.sa = ((a.je & 1) == 0 ? s.l_surf_area1[ix] : s.l_surf_area2[ix]);
     d.dqdh = s.l_dqdh[ix];
-    d.barrels = 1; d.loss = 0.0; d.pumpType = 0;
-    if (d.type == SWB_CONDUIT) {
-        d.barrels = n.cond_barrels[j];
-        if (d.flags & LF_HAS_LOSSRATE) d.loss = s.c_evap_loss[ix] + s.c_seep_loss[ix];
-    } else if (d.type == SWB_PUMP) d.pumpType = n.pump_type[j];
+    d.loss = 0.0;
+    if ((a.kind & 0xff) == SWB_CONDUIT && (a.flags & LF_HAS_LOSSRATE)) d.loss = s.c_evap_loss[ix] + s.c_seep_loss[ix];
     return d;
 }
-SWB_FI void node_apply_link_end(const LinkEndData &d, int end, NodeAcc &a)
+SWB_FI void node_apply_link_end(const LinkEndData &d, const AdjEntry &a, NodeAcc &acc)
 {
+    const int end = a.je & 1, type = a.kind & 0xff;
     const double q = d.q;
-    if (q >= 0.0) { if (end == 0) a.outflow += q; else a.inflow += q; }
-    else          { if (end == 0) a.inflow -= q;  else a.outflow -= q; }
-    if (d.type == SWB_CONDUIT && (d.flags & LF_HAS_LOSSRATE)) {
-        double lossRate = d.loss * d.barrels;
+    if (q >= 0.0) { if (end == 0) acc.outflow += q; else acc.inflow += q; }
+    else          { if (end == 0) acc.inflow -= q;  else acc.outflow -= q; }
+    if (type == SWB_CONDUIT && (a.flags & LF_HAS_LOSSRATE)) {
+        double lossRate = d.loss * a.barrels;
         if (lossRate > 0.0) {
-            bool o1 = (d.flags & LF_N1_OUTFALL) != 0, o2 = (d.flags & LF_N2_OUTFALL) != 0;
+            bool o1 = (a.flags & LF_N1_OUTFALL) != 0, o2 = (a.flags & LF_N2_OUTFALL) != 0;
             if (!o1 && !o2) lossRate /= 2.0;
-            if (end == 0 ? !o1 : !o2) a.outflow += lossRate;
+            if (end == 0 ? !o1 : !o2) acc.outflow += lossRate;
         }
     }
-    a.surfArea += d.sa * d.barrels;
-    if (end == 0) a.sumdqdh += d.dqdh;
-    else if (d.type == SWB_PUMP) { if (d.pumpType != 3 /*TYPE4_PUMP*/) a.sumdqdh += d.dqdh; }
-    else a.sumdqdh += d.dqdh;
+    acc.surfArea += d.sa * a.barrels;
+    if (end == 0) acc.sumdqdh += d.dqdh;
+    else if (type == SWB_PUMP) { if ((a.kind >> 8) != 3 /*TYPE4_PUMP*/) acc.sumdqdh += d.dqdh; }
+    else acc.sumdqdh += d.dqdh;
+}
+// entries [e0, e1) of the packed incidence list, four link ends in flight at a time (named scalars,
+// not arrays: conditionally initialised arrays end up in local memory)
+SWB_FI void node_gather(const Net &n, const State &s, int e0, int e1, int m, NodeAcc &acc)
+{
+    const AdjEntry none = {0, 0, 0, -1};
+    for (int e = e0; e < e1; e += 4) {
+        const int cnt = e1 - e;
+        const AdjEntry a0 = n.adj_packed[e];
+        const AdjEntry a1 = cnt > 1 ? n.adj_packed[e + 1] : none;
+        const AdjEntry a2 = cnt > 2 ? n.adj_packed[e + 2] : none;
+        const AdjEntry a3 = cnt > 3 ? n.adj_packed[e + 3] : none;
+        LinkEndData d0 = node_load_link_end(s, a0, m), d1 = {0.0, 0.0, 0.0, 0.0}, d2 = d1, d3 = d1;
+        if (cnt > 1) d1 = node_load_link_end(s, a1, m);
+        if (cnt > 2) d2 = node_load_link_end(s, a2, m);
+        if (cnt > 3) d3 = node_load_link_end(s, a3, m);
+        node_apply_link_end(d0, a0, acc);
+        if (cnt > 1) node_apply_link_end(d1, a1, acc);
+        if (cnt > 2) node_apply_link_end(d2, a2, acc);
+        if (cnt > 3) node_apply_link_end(d3, a3, acc);
+    }
 }
 
 // ---- K4: outfall boundary depth (link.c:728-766, node.c:1413-1492) ------------------------------

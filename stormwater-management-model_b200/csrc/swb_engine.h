@@ -34,9 +34,6 @@
 #endif
 
 // build switches of the node phase (measured variants, profiles/README.md)
-#ifndef SWB_GATHER2
-#define SWB_GATHER2 1       // node gather: loads of two link ends in flight (nodes 150 -> 137 ms, profiles/README.md)
-#endif
 #ifndef SWB_NODE_EARLY
 #define SWB_NODE_EARLY 0    // A/B switch: old depth / net inflow loaded before the gather
 #endif
@@ -126,11 +123,9 @@ SWB_FI void picard_link(const Net &net, const State &st, int j, int m, int k, do
 SWB_FI void picard_node_presum(const Net &net, const State &st, int i, int m)
 {
     NodeAcc acc = node_init_acc(net, st, i, m);
-    for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++) {
-        int j = net.adj[e] >> 1;
-        if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) break;
-        node_add_link_end(net, st, j, net.adj[e] & 1, m, acc);
-    }
+    int e1 = net.adj_start[i];
+    while (e1 < net.adj_start[i + 1] && (net.adj_packed[e1].flags & LF_TRUE_CONDUIT)) e1++;
+    node_gather(net, st, net.adj_start[i], e1, m, acc);
     size_t ix = SWB_IX(i, m, st.M);
     st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;
     st.n_new_surf_area[ix] = acc.surfArea; st.n_sumdqdh[ix] = acc.sumdqdh;
@@ -150,21 +145,7 @@ SWB_FI bool picard_node(const Net &net, const State &st, int i, int m, int k, do
         acc.surfArea = st.n_new_surf_area[ix]; acc.sumdqdh = st.n_sumdqdh[ix];
     } else {
         acc = node_init_acc(net, st, i, m);
-#if SWB_GATHER2
-        int e = net.adj_start[i];
-        const int e1 = net.adj_start[i + 1];
-        for (; e + 1 < e1; e += 2) {
-            const int ea = net.adj[e], eb = net.adj[e + 1];
-            const LinkEndData da = node_load_link_end(net, st, ea >> 1, ea & 1, m);
-            const LinkEndData db = node_load_link_end(net, st, eb >> 1, eb & 1, m);
-            node_apply_link_end(da, ea & 1, acc);
-            node_apply_link_end(db, eb & 1, acc);
-        }
-        if (e < e1) node_add_link_end(net, st, net.adj[e] >> 1, net.adj[e] & 1, m, acc);
-#else
-        for (int e = net.adj_start[i]; e < net.adj_start[i + 1]; e++)
-            node_add_link_end(net, st, net.adj[e] >> 1, net.adj[e] & 1, m, acc);
-#endif
+        node_gather(net, st, net.adj_start[i], net.adj_start[i + 1], m, acc);
     }
     if (net.node_type[i] == SWB_OUTFALL) {
         st.n_inflow[ix] = acc.inflow; st.n_outflow[ix] = acc.outflow;

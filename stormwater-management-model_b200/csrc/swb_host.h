@@ -19,6 +19,7 @@ struct Derived {
     std::vector<int> link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link, link_order,
                      link_kernel, node_order;
     std::vector<double> link_z1, link_z2, xs_tables, culvert_params, road_tables, xs_rcp_yfull, cond_rcp_mod_length;
+    std::vector<AdjEntry> adj_packed;
     int nTrue = 0, nNonConduit = 0;
 };
 
@@ -132,6 +133,16 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
     }
     r.adjq_start[nN] = (int)r.adjq.size();
     r.adj_start[nN] = (int)r.adj.size();
+    r.adj_packed.resize(r.adj.size());
+    for (size_t e = 0; e < r.adj.size(); e++) {
+        const int j = r.adj[e] >> 1;
+        AdjEntry a;
+        a.je = r.adj[e];
+        a.barrels = (d.link_type[j] == SWB_CONDUIT) ? d.cond_barrels[j] : 1;
+        a.flags = r.link_flags[j];
+        a.kind = d.link_type[j] | ((d.link_type[j] == SWB_PUMP ? d.pump_type[j] : 0) << 8);
+        r.adj_packed[e] = a;
+    }
     static const double tab[] = { SWB_XS_TABLE_DATA };
     r.xs_tables.assign(tab, tab + XT_TOTAL);
     static const double cul[] = { SWB_CULVERT_PARAM_DATA };

@@ -59,6 +59,15 @@ enum {
 
 enum { LK_CIRCULAR = 0, LK_RECT_CLOSED = 1, LK_GENERIC = 2 };
 
+// one incident link end of a node, everything static the gather needs in ONE 16-byte load
+// (instead of the chain adj -> link_flags -> link_type -> cond_barrels -> pump_type)
+struct alignas(16) AdjEntry {
+    int je;          // (link << 1) | end
+    int barrels;     // Conduit.barrels, 1 for other link types
+    int flags;       // link_flags of the link
+    int kind;        // link_type | pump_type << 8
+};
+
 struct Net {
     int nN, nL, nP, nCurves, nShapeTbl, shapeTblLen;
     int nTrue;               // true conduits
@@ -78,6 +87,7 @@ struct Net {
     const int    *adj_start;               // nN+1: CSR node -> incident link ends
     const int    *adj;                     // (link << 1) | end, ordered true conduits first, then
                                            // other links, each ascending by link index (A.3)
+    const AdjEntry *adj_packed;            // adj[] with the static link attributes of each entry
     const int    *adjq_start, *adjq;       // same incidence ordered by plain link index (quality)
     const int    *link_order;              // true conduits grouped by cross-section shape: tickets are
                                            // drawn in this order, so at any moment every warp of the
@@ -188,11 +198,22 @@ template <class T> struct SPtr {
 #else
 template <class T> using SPtr = T *;
 #endif
+// SWB_STREAM_STATE: 0 off, 1 every field, 2 link / conduit fields only (node fields are re-read within
+// a step: quality mixing reads what the node phase has just written)
+#if SWB_STREAM_STATE == 2
+#define SWB_FIELD_PTR_N(T)  T *
+#define SWB_FIELD_PTR_NP(T) T *
+#else
+#define SWB_FIELD_PTR_N(T)  SPtr<T>
+#define SWB_FIELD_PTR_NP(T) SPtr<T>
+#endif
+#define SWB_FIELD_PTR_L(T)  SPtr<T>
+#define SWB_FIELD_PTR_LP(T) SPtr<T>
 
 struct State {
     int M;                       // members
     Halo halo;
-#define X(T, name, id, kind) SPtr<T> name;
+#define X(T, name, id, kind) SWB_FIELD_PTR_##kind(T) name;
     SWB_STATE_FIELDS(X)
 #undef X
     // per member

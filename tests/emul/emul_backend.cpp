@@ -25,6 +25,11 @@ static void free_(void *p) { std::free(p); }
 static bool upload(void *d, const void *s, size_t b) { std::memcpy(d, s, b); return true; }
 static bool download(void *d, const void *s, size_t b) { std::memcpy(d, s, b); return true; }
 static bool zero(void *d, size_t b) { std::memset(d, 0, b); return true; }
+static bool copy2d(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, bool)
+{
+    for (size_t r = 0; r < height; r++) std::memcpy((char *)d + r * dpitch, (const char *)s + r * spitch, width);
+    return true;
+}
 static const char *last_error() { return "host allocation failed"; }
 static bool sync(std::string &) { return true; }
 static void profiler(bool) {}

@@ -533,6 +533,22 @@ def reference_run(grid, hours, surcharge, spinup, warm_steps, timed_steps, threa
             "iters_per_step": tot["iterations"] / max(n, 1)}
 
 
+def reference_subprocess(args, threads: int, timed_steps: int, warm_steps: int = 0) -> dict | None:
+    """reference_run in a process of its own (the unperturbed member, THREADS = threads): an OpenMP team
+    with OMP_WAIT_POLICY=active keeps spinning on every core after its last parallel region, so it must
+    not live in the process that later hosts or spawns anything else."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-worker", "--grid", str(args.grid),
+           "--hours", str(args.hours), "--surcharge", args.surcharge, "--spinup", str(args.spinup),
+           "--cpu-steps", str(timed_steps), "--worker-warm", str(warm_steps), "--threads", str(threads),
+           "--member", "-1"]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    try:
+        r = json.loads(p.stdout.strip().splitlines()[-1])
+        return r if r.get("cu") else None
+    except Exception:
+        return None
+
+
 def packed_reference(args, n_procs: int, timed_steps: int, warm_steps: int = 0) -> dict | None:
     """One single-threaded reference process per core, each on its own config-4 member, all running
     at the same time: the honest ensemble figure of the CPU (the engine holds one project per
@@ -562,7 +578,7 @@ def packed_reference(args, n_procs: int, timed_steps: int, warm_steps: int = 0) 
 
 def cpu_baseline(args) -> dict:
     cores = os.cpu_count() or 1
-    r = reference_run(args.grid, args.hours, args.surcharge, args.spinup, 0, args.cpu_steps, cores)
+    r = reference_subprocess(args, cores, args.cpu_steps)
     if r is None:
         return {"value": None, "unit": "conduit-updates/s", "cores": cores, "kind": "reference",
                 "sample": "oracle/_ref not present on this box"}
@@ -586,8 +602,8 @@ def cpu_baseline(args) -> dict:
 def run_reference_worker(args):
     if args.cpu >= 0 and hasattr(os, "sched_setaffinity"):
         os.sched_setaffinity(0, {args.cpu})   # one worker per core
-    r = reference_run(args.grid, args.hours, args.surcharge, args.spinup, args.worker_warm, args.cpu_steps, 1,
-                      member=args.member)
+    r = reference_run(args.grid, args.hours, args.surcharge, args.spinup, args.worker_warm, args.cpu_steps,
+                      args.threads, member=args.member if args.member >= 0 else None)
     print(json.dumps(r if r else {"cu": 0, "wall": 1.0, "iters_per_step": 0.0}), flush=True)
 
 
@@ -602,7 +618,10 @@ def run_reference(args):
     if not refengine.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
         return
-    r = reference_run(args.grid, args.hours, args.surcharge, args.spinup, args.warmup * rs, args.steps * rs, cores)
+    r = reference_subprocess(args, cores, args.steps * rs, args.warmup * rs)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "the reference worker process failed"}))
+        return
     openmp = r["cu"] / r["wall"]
     cb = {"value": openmp, "unit": "conduit-updates/s", "cores": cores, "kind": "reference",
           "picard_iterations_per_step": r["iters_per_step"],
@@ -658,6 +677,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=60)
     ap.add_argument("--member", type=int, default=0, help="(reference-worker) config-4 member to run")
     ap.add_argument("--cpu", type=int, default=-1, help="(reference-worker) core to pin to")
+    ap.add_argument("--threads", type=int, default=1, help="(reference-worker) THREADS option of the model")
     ap.add_argument("--worker-warm", type=int, default=0, help="(reference-worker) untimed routing steps after spin-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-packed", action="store_true")

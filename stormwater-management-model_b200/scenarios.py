@@ -608,3 +608,172 @@ def c3c_culverts_inp(eqn: str = "H-W") -> str:
 
 def c5_mega_spec(hours: float = 1.0) -> GridSpec:
     return GridSpec(nx=1000, ny=500, hours=hours, pollutants=False, surcharge="SLOT")
+
+
+# --------------------------------------------------------------------------------------------
+# config 3 at its stated size: ~1 000 links, mixed elements, 24 h, DWF patterns,
+# control rules
+# --------------------------------------------------------------------------------------------
+@dataclass
+class C3Spec:
+    n: int = 22                  # n x n collector grid: 2 n (n - 1) conduits
+    facilities: int = 8          # storage + orifice + weir + outlet + wet well + pump groups
+    hours: float = 24.0
+    surcharge: str = "SLOT"
+    controls: bool = True
+    pollutants: bool = True
+    inflow_scale: float = 1.0    # member scale on the storm hydrographs (ensembles)
+    seed: int = 3
+    threads: int = 1
+
+
+def c3_large_inp(spec: C3Spec | None = None) -> str:
+    """Mixed-element network: an n x n sloping collector grid (circular / rect_closed / egg pipes and
+    trapezoidal open channels along the low edge) and `facilities` treatment groups hung off it.  Each
+    group: a storage unit (FUNCTIONAL or TABULAR) fed from the grid, emptied by a side or bottom
+    orifice, a transverse or V-notch weir and a rating outlet into a lower grid node, plus a wet well
+    with a pump (types 1-4 in turn) lifting to a higher grid node.  FREE, FIXED (flap gate) and TIDAL
+    outfalls, DWF with hourly patterns, storm hydrographs, two pollutants, five control rules on pump
+    status and orifice settings."""
+    s = spec or C3Spec()
+    n, F = s.n, s.facilities
+    rng = random.Random(s.seed)
+    L = ["[OPTIONS]", "FLOW_UNITS CFS", "FLOW_ROUTING DYNWAVE", "START_DATE 01/01/2020", "START_TIME 00:00:00",
+         "END_DATE " + ("01/02/2020" if s.hours >= 24 else "01/01/2020"),
+         "END_TIME " + ("00:00:00" if s.hours >= 24 else _hms(s.hours)), "REPORT_STEP 00:15:00", "ROUTING_STEP 5",
+         "VARIABLE_STEP 0.75", "ALLOW_PONDING YES", f"SURCHARGE_METHOD {s.surcharge}", f"THREADS {s.threads}"]
+    elev = lambda i, j: 100.0 + 0.5 * ((n - 1 - i) + (n - 1 - j))
+    nid = lambda i, j: f"N{i}_{j}"
+    L += ["[JUNCTIONS]"]
+    for i in range(n):
+        for j in range(n):
+            pond = 300 if (i + j) % 7 == 0 else 0
+            L.append(f"{nid(i, j)} {elev(i, j):.3f} 8 0 0 {pond}")
+    for k in range(F):
+        L.append(f"WW{k} {elev(*_fac_low(k, n, F)) - 6.0:.3f} 14 0 0 0")
+    base = elev(n - 1, n - 1)
+    L += ["[OUTFALLS]", f"OF {base - 1.0:.3f} FREE NO", f"OX {base - 1.5:.3f} FIXED {base + 0.5:.3f} YES",
+          f"OT {base - 1.5:.3f} TIDAL TIDE NO"]
+    L += ["[STORAGE]"]
+    for k in range(F):
+        z = elev(*_fac_out(k, n, F)) + 0.5           # above the node it drains to, below its feeder
+        if k % 2 == 0:
+            L.append(f"S{k} {z:.3f} 12 1 FUNCTIONAL {800 + 100 * k} 0 300 0 0")
+        else:
+            L.append(f"S{k} {z:.3f} 12 0.5 TABULAR SCURVE 0 0")
+    cond, xs, losses = [], [], []
+    shapes = ["CIRCULAR 2 0 0 0 1", "RECT_CLOSED 2 2.5 0 0 1", "EGG 2.5 0 0 0 1", "CIRCULAR 2.5 0 0 0 1"]
+    c = 0
+    for i in range(n):
+        for j in range(n):
+            for (di, dj) in ((1, 0), (0, 1)):
+                ii, jj = i + di, j + dj
+                if ii >= n or jj >= n:
+                    continue
+                cid = f"C{c}"
+                off2 = 0.2 if c % 37 == 5 else 0
+                cond.append(f"{cid} {nid(i, j)} {nid(ii, jj)} 300 0.013 0 {off2} 0 0")
+                if i == n - 1 or j == n - 1:
+                    xs.append(f"{cid} TRAPEZOIDAL 6 4 1 1 1")       # open collector along the low edges
+                else:
+                    xs.append(f"{cid} {shapes[c % len(shapes)]}")
+                if c % 53 == 7:
+                    losses.append(f"{cid} 0.3 0.3 0 NO 0")
+                c += 1
+    cond.append(f"COF {nid(n - 1, n - 1)} OF 300 0.013 0 0 0 0")
+    xs.append("COF TRAPEZOIDAL 6 6 1 1 1")
+    cond.append(f"COX {nid(n - 1, n - 3)} OX 300 0.013 0 0 0 0")
+    xs.append("COX CIRCULAR 4 0 0 0 2")
+    cond.append(f"COT {nid(n - 3, n - 1)} OT 300 0.013 0 0 0 0")
+    xs.append("COT CIRCULAR 4 0 0 0 1")
+    pumps, orifs, weirs, outlets = [], [], [], []
+    for k in range(F):
+        a, b, lo, hi = _fac_in(k, n, F), _fac_out(k, n, F), _fac_low(k, n, F), _fac_high(k, n, F)
+        cond.append(f"CS{k} {nid(*a)} S{k} 200 0.013 0 1 0 0")
+        xs.append(f"CS{k} CIRCULAR 3 0 0 0 1")
+        if k % 2 == 0:
+            orifs.append(f"OR{k} S{k} {nid(*b)} SIDE 0.5 0.65 NO 0")
+            xs.append(f"OR{k} CIRCULAR 1.5 0 0 0")
+            weirs.append(f"W{k} S{k} {nid(*b)} TRANSVERSE 8 3.33 NO 0 0 YES")
+            xs.append(f"W{k} RECT_OPEN 3 8 0 0")
+        else:
+            orifs.append(f"OR{k} S{k} {nid(*b)} BOTTOM 0 0.6 NO 0.1")
+            xs.append(f"OR{k} RECT_CLOSED 1 1.5 0 0")
+            weirs.append(f"W{k} S{k} {nid(*b)} V-NOTCH 6 2.5 NO 0 0 YES")
+            xs.append(f"W{k} TRIANGULAR 4 6 0 0")
+        if k % 4 == 1:
+            outlets.append(f"OL{k} S{k} {nid(*b)} 2 FUNCTIONAL/DEPTH 2.0 0.5 NO")
+        elif k % 4 == 3:
+            outlets.append(f"OL{k} S{k} {nid(*b)} 2 TABULAR/HEAD RATE NO")
+        cond.append(f"CW{k} {nid(*lo)} WW{k} 150 0.013 0 0 0 0")
+        xs.append(f"CW{k} CIRCULAR 2 0 0 0 1")
+        ptype = k % 4
+        if ptype == 0:            # TYPE1 needs a storage inlet: pump straight from the storage unit
+            pumps.append(f"P{k} S{k} {nid(*hi)} PC1 ON 0 0")
+            pumps.append(f"PW{k} WW{k} {nid(*hi)} PC3 ON 4 1")
+        elif ptype == 1:
+            pumps.append(f"P{k} WW{k} {nid(*hi)} PC2 ON 0 0")
+        elif ptype == 2:
+            pumps.append(f"P{k} WW{k} {nid(*hi)} PC3 ON 4 1")
+        else:
+            pumps.append(f"P{k} WW{k} {nid(*hi)} PC4 ON 2 0.5")
+    L += ["[CONDUITS]"] + cond + ["[PUMPS]"] + pumps + ["[ORIFICES]"] + orifs + ["[WEIRS]"] + weirs
+    L += ["[OUTLETS]"] + outlets + ["[XSECTIONS]"] + xs + ["[LOSSES]"] + losses
+    if s.controls:
+        L += ["[CONTROLS]",
+              "RULE R1", "IF NODE S0 DEPTH > 6", "THEN ORIFICE OR0 SETTING = 1.0", "ELSE ORIFICE OR0 SETTING = 0.3",
+              "PRIORITY 1",
+              "RULE R2", "IF SIMULATION TIME > 12", "THEN PUMP P2 STATUS = OFF",
+              "RULE R3", "IF NODE S1 DEPTH > 5", "AND LINK OR1 FLOW < 20", "THEN ORIFICE OR1 SETTING = 1.0",
+              "ELSE ORIFICE OR1 SETTING = 0.5", "PRIORITY 2",
+              "RULE R4", f"IF NODE {nid(n - 1, n - 1)} DEPTH > 3", "OR SIMULATION TIME > 20",
+              "THEN PUMP P1 STATUS = OFF", "ELSE PUMP P1 STATUS = ON",
+              "RULE R5", "IF LINK COF FLOW > 60", "THEN WEIR W2 SETTING = 0.5", "ELSE WEIR W2 SETTING = 1.0"]
+    if s.pollutants:
+        L += ["[POLLUTANTS]", "TSS MG/L 0 0 0 0.5", "DYE MG/L 0 0 0 0"]
+    L += ["[INFLOWS]"]
+    dwf = []
+    q = 0
+    for i in range(n):
+        for j in range(n):
+            if (i * n + j) % 3 == 0 and i + j < 2 * n - 6:
+                sc = rng.uniform(0.1, 0.3) * s.inflow_scale
+                txt = f"{sc:.6f}" if s.inflow_scale == 1.0 else repr(float(f"{sc / s.inflow_scale:.6f}") * s.inflow_scale)
+                L.append(f"{nid(i, j)} FLOW STORM FLOW 1.0 {txt}")
+                if s.pollutants and q % 2 == 0:
+                    L.append(f"{nid(i, j)} TSS CTSS CONCEN 1.0 1.0")
+                if s.pollutants and q % 5 == 0:
+                    L.append(f"{nid(i, j)} DYE CDYE CONCEN 1.0 1.0")
+                q += 1
+            if (i * n + j) % 11 == 4:
+                dwf.append(f"{nid(i, j)} FLOW 0.05 DAILYP")
+    L += ["[DWF]"] + dwf
+    L += ["[PATTERNS]", "DAILYP HOURLY 0.5 0.5 0.5 0.5 0.6 0.8 1.2 1.5 1.4 1.2 1.1 1.0 1.0 1.0 1.0 1.1 1.2 1.4 1.5 1.3 1.0 "
+          "0.8 0.6 0.5"]
+    L += ["[CURVES]", "SCURVE STORAGE 0 800 5 1500 10 3000 12 3500", "PC1 PUMP1 100 2 300 4 600 6 2000 8",
+          "PC2 PUMP2 1 1 2 2 4 3 8 4", "PC3 PUMP3 0 8 5 6 10 3 15 0", "PC4 PUMP4 0 0 1 1 3 3 6 4",
+          "RATE RATING 0 0 1 2 3 5 6 7", f"TIDE TIDAL 0 {base - 1.0:.2f} 6 {base + 0.5:.2f} 12 {base - 1.0:.2f} "
+          f"18 {base + 0.5:.2f} 24 {base - 1.0:.2f}"]
+    L += ["[TIMESERIES]", "STORM 0:00 0", "STORM 2:00 0.5", "STORM 5:00 3.0", "STORM 9:00 0.8", "STORM 16:00 0.2",
+          "STORM 24:00 0.1", "CTSS 0:00 100", "CTSS 48:00 100", "CDYE 0:00 50", "CDYE 48:00 50"]
+    L += ["[REPORT]", "NODES ALL", "LINKS ALL", "CONTROLS YES"]
+    return "\n".join(L) + "\n"
+
+
+def _fac_in(k, n, F):       # grid node feeding storage k (upper part of the grid)
+    return (2 + (k * (n - 6)) // max(F - 1, 1), 3 + (k * 5) % (n - 8))
+
+
+def _fac_out(k, n, F):      # lower grid node the storage drains to
+    i, j = _fac_in(k, n, F)
+    return (min(i + 3, n - 2), min(j + 3, n - 2))
+
+
+def _fac_low(k, n, F):      # grid node draining into wet well k
+    i, j = _fac_out(k, n, F)
+    return (min(i + 1, n - 2), j)
+
+
+def _fac_high(k, n, F):     # grid node the pump lifts to
+    i, j = _fac_in(k, n, F)
+    return (max(i - 1, 0), max(j - 1, 0))

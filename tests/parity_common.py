@@ -77,6 +77,12 @@ def case_inp(name: str) -> str:
                                                         pollutants="noq" not in parts))
     if name == "c3_mixed":
         return scenarios.c3_mixed_inp()
+    if name == "c3_large":
+        return scenarios.c3_large_inp()
+    if name == "c3_large_6h":
+        return scenarios.c3_large_inp(scenarios.C3Spec(hours=6.0))
+    if name == "c3_large_nocontrols":
+        return scenarios.c3_large_inp(scenarios.C3Spec(controls=False))
     if name == "c3b_shapes":
         return scenarios.c3b_shapes_inp()
     if name == "c3c_culverts_hw":

@@ -68,7 +68,7 @@ def out_results(path):
 
 
 @pytest.mark.parametrize("case", ["c1_tree", "c2_grid12_slot", "c2_grid12_extran", "c3_mixed", "c3b_shapes",
-                                  "c3c_culverts_hw", "c3c_culverts_dw"])
+                                  "c3c_culverts_hw", "c3c_culverts_dw", "c3_large_6h"])
 def test_cli_with_emulated_seam_is_byte_identical(case, emul_lib, have_reference):
     if not have_reference or not build_seam_emul(emul_lib):
         pytest.skip("oracle/_ref or the seam shim is not built")
@@ -81,7 +81,7 @@ def test_cli_with_emulated_seam_is_byte_identical(case, emul_lib, have_reference
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["c1_tree", "c2_grid12_slot", "c3_mixed", "c3b_shapes", "c2_grid30_slot",
-                                  "c3c_culverts_hw", "c3c_culverts_dw"])
+                                  "c3c_culverts_hw", "c3c_culverts_dw", "c3_large"])
 def test_cli_with_cuda_seam_matches_reference(case, cuda_lib, have_reference):
     assert have_reference and os.path.exists(SEAM_CUDA), "oracle/_ref and the CUDA seam must travel"
     text = pc.case_inp(case)

@@ -151,6 +151,45 @@ enum swb_field {
     SWB_FIELD_COUNT = 96
 };
 
+/*
+ * Per-object routing statistics of every member (stats.c:449-754), kept on the device once
+ * swb_enable_statistics has been called.  Plane ids of swb_get_node_stats / swb_get_link_stats /
+ * swb_get_system_stats; times are seconds, *_TIME planes hold the elapsed simulated time (new routing
+ * time of the step) at which the maximum occurred, flows cfs, volumes ft3, depths ft.
+ */
+enum swb_node_stat {
+    SWB_NS_SUM_DEPTH = 0,      /* NodeStats.avgDepth before the division by the step count   */
+    SWB_NS_MAX_DEPTH, SWB_NS_MAX_DEPTH_TIME, SWB_NS_TIME_FLOODED, SWB_NS_VOL_FLOODED,
+    SWB_NS_MAX_PONDED_VOL, SWB_NS_TIME_SURCHARGED, SWB_NS_TOT_LATFLOW, SWB_NS_MAX_LATFLOW,
+    SWB_NS_MAX_INFLOW, SWB_NS_MAX_INFLOW_TIME, SWB_NS_MAX_OVERFLOW, SWB_NS_MAX_OVERFLOW_TIME,
+    SWB_NS_NONCONV_COUNT,      /* stats_updateConvergenceStats                               */
+    SWB_NS_TIME_COURANT,       /* times the node was time-step critical                      */
+    /* storage units: sum of volume, max volume, its time, max outflow, evaporation, exfiltration;
+       outfalls: sum of flow (periods with flow), max flow, number of such periods               */
+    SWB_NS_X_SUM, SWB_NS_X_MAX, SWB_NS_X_MAX_TIME, SWB_NS_X_MAX_FLOW, SWB_NS_X_EVAP, SWB_NS_X_EXFIL,
+    SWB_NS_LOAD0,              /* outfalls: total load of pollutant p in plane SWB_NS_LOAD0 + p */
+    SWB_NS_PLANES = SWB_NS_LOAD0
+};
+enum swb_link_stat {
+    SWB_LS_MAX_FLOW = 0, SWB_LS_MAX_FLOW_TIME, SWB_LS_MAX_VELOC, SWB_LS_MAX_DEPTH,
+    SWB_LS_TIME_FULL_FLOW, SWB_LS_TIME_CAP_LIMITED, SWB_LS_TIME_SURCHARGED, SWB_LS_TIME_FULL_UP,
+    SWB_LS_TIME_FULL_DN, SWB_LS_TURN_SIGN, SWB_LS_TURNS, SWB_LS_TIME_COURANT,
+    /* conduits */
+    SWB_LS_TIME_NORMAL, SWB_LS_TIME_INLET, SWB_LS_TIME_CLASS0,   /* + flow class 0..6 */
+    /* pumps (same planes as the conduit-only block above) */
+    SWB_LS_PUMP_MIN_FLOW = SWB_LS_TIME_NORMAL, SWB_LS_PUMP_SUM_FLOW, SWB_LS_PUMP_VOLUME,
+    SWB_LS_PUMP_UTILIZED, SWB_LS_PUMP_ENERGY, SWB_LS_PUMP_OFF_LOW, SWB_LS_PUMP_OFF_HIGH,
+    SWB_LS_PUMP_STARTUPS, SWB_LS_PUMP_PERIODS,
+    SWB_LS_PLANES = SWB_LS_TIME_CLASS0 + 7
+};
+enum swb_system_stat {
+    SWB_SS_REPORT_STEPS = 0,   /* ReportStepCount                                            */
+    SWB_SS_ROUTING_SPAN,       /* RoutingTimeSpan, s                                         */
+    SWB_SS_MAX_OUTFALL_FLOW,   /* MaxOutfallFlow                                             */
+    SWB_SS_MIN_DT, SWB_SS_MAX_DT, SWB_SS_ROUTING_TIME, SWB_SS_STEP_COUNT, SWB_SS_TRIALS,  /* TimeStepStats */
+    SWB_SS_PLANES
+};
+
 /* per-member accumulators kept on the device (massbal.c:517-555, stats.c:522-540) */
 typedef struct swb_member_stats {
     double sim_time;          /* elapsed simulated time, s                                  */
@@ -339,6 +378,20 @@ int  swb_xsect_eval(int device, int fn, int xs_type, const double *params, int n
  * 0 prologue, 1 link phase, 2 regulator pass, 3 node phase, 4 loop control / compaction,
  * 5 epilogue, 6 quality nodes, 7 quality links, 8 next-step search, 9 halo exchanges (partitioned),
  * 10 the part of 9 spent waiting for the slowest peer */
+/*
+ * Per-object statistics.  swb_enable_statistics allocates and zeroes the planes;
+ * from then on every routing step of swb_run_steps / swb_step_host updates them on the device
+ * (stats_updateFlowStats, stats_updateTimeStepStats, stats_updateConvergenceStats,
+ * stats_updateCriticalTimeCount) for steps whose new routing time is >= report_start_s.
+ *   node_out  [n_members][SWB_NS_PLANES + n_pollut][n_nodes]
+ *   link_out  [n_members][SWB_LS_PLANES][n_links]
+ *   sys_out   [n_members][SWB_SS_PLANES]
+ */
+int  swb_enable_statistics(swb_solver *s, double report_start_s);
+int  swb_get_node_stats(swb_solver *s, int member0, int n_members, double *node_out);
+int  swb_get_link_stats(swb_solver *s, int member0, int n_members, double *link_out);
+int  swb_get_system_stats(swb_solver *s, int member0, int n_members, double *sys_out);
+
 int  swb_get_phase_times(swb_solver *s, double *ms, int n, int reset);
 /* Profiling aid: n_steps of the phase mask `phases` (csrc/swb_engine.h PH_*) with the debug switches
    `debug` (DBG_*: skip the link or the node phase of the Picard loop); profile != 0 brackets the launch

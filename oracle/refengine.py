@@ -171,6 +171,19 @@ class RefEngine:
             ld[j] = buf[:5 + n_pollut]
         return nd, ld
 
+    def statistics(self, n_nodes: int, n_links: int, n_pollut: int):
+        """(node[planes, n_nodes], link[planes, n_links], MaxOutfallFlow) of the live engine in the plane
+        order of include/swmm_b200.h (refhook_node_stats / refhook_link_stats)."""
+        nd = np.zeros((self.abi.NODE_STAT["SWB_NS_PLANES"] + n_pollut, n_nodes))
+        ld = np.zeros((self.abi.LINK_STAT["SWB_LS_PLANES"], n_links))
+        P = C.POINTER(C.c_double)
+        self.hook.refhook_node_stats.argtypes = [P]
+        self.hook.refhook_link_stats.argtypes = [P]
+        self.hook.refhook_max_outfall_flow.restype = C.c_double
+        self.hook.refhook_node_stats(nd.ctypes.data_as(P))
+        self.hook.refhook_link_stats(ld.ctypes.data_as(P))
+        return nd, ld, self.hook.refhook_max_outfall_flow()
+
     def total_duration_s(self) -> float:
         return self.hook.refhook_total_duration() / 1000.0
 

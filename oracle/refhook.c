@@ -125,3 +125,74 @@ const swb_inflow_desc *refhook_inflows(void)
     return &g_inf;
 }
 double refhook_total_duration(void) { return TotalDuration; }
+
+/* ---- statistics of the live engine in the plane order of include/swmm_b200.h (swb_node_stat /
+ * swb_link_stat): NodeStats / StorageStats / OutfallStats / LinkStats / PumpStats (stats.c:63-68).
+ * Dates become elapsed seconds since StartDateTime. */
+extern TNodeStats *NodeStats;
+extern TLinkStats *LinkStats;
+extern TStorageStats *StorageStats;
+extern TOutfallStats *OutfallStats;
+extern TPumpStats *PumpStats;
+extern double MaxOutfallFlow;
+static double secs(DateTime d) { return (d - StartDateTime) * 86400.0; }
+
+void refhook_node_stats(double *out)
+{
+    int nN = Nobjects[NODE], nP = Nobjects[POLLUT], i, p, k;
+#define NS(plane) out[(size_t)(plane) * nN + i]
+    for (i = 0; i < nN; i++) {
+        TNodeStats *s = &NodeStats[i];
+        NS(SWB_NS_SUM_DEPTH) = s->avgDepth; NS(SWB_NS_MAX_DEPTH) = s->maxDepth;
+        NS(SWB_NS_MAX_DEPTH_TIME) = secs(s->maxDepthDate); NS(SWB_NS_TIME_FLOODED) = s->timeFlooded;
+        NS(SWB_NS_VOL_FLOODED) = s->volFlooded; NS(SWB_NS_MAX_PONDED_VOL) = s->maxPondedVol;
+        NS(SWB_NS_TIME_SURCHARGED) = s->timeSurcharged; NS(SWB_NS_TOT_LATFLOW) = s->totLatFlow;
+        NS(SWB_NS_MAX_LATFLOW) = s->maxLatFlow; NS(SWB_NS_MAX_INFLOW) = s->maxInflow;
+        NS(SWB_NS_MAX_INFLOW_TIME) = secs(s->maxInflowDate); NS(SWB_NS_MAX_OVERFLOW) = s->maxOverflow;
+        NS(SWB_NS_MAX_OVERFLOW_TIME) = secs(s->maxOverflowDate);
+        NS(SWB_NS_NONCONV_COUNT) = s->nonConvergedCount; NS(SWB_NS_TIME_COURANT) = s->timeCourantCritical;
+        NS(SWB_NS_X_SUM) = NS(SWB_NS_X_MAX) = NS(SWB_NS_X_MAX_TIME) = NS(SWB_NS_X_MAX_FLOW) = 0.0;
+        NS(SWB_NS_X_EVAP) = NS(SWB_NS_X_EXFIL) = 0.0;
+        for (p = 0; p < nP; p++) NS(SWB_NS_LOAD0 + p) = 0.0;
+        k = Node[i].subIndex;
+        if (Node[i].type == STORAGE) {
+            NS(SWB_NS_X_SUM) = StorageStats[k].avgVol; NS(SWB_NS_X_MAX) = StorageStats[k].maxVol;
+            NS(SWB_NS_X_MAX_TIME) = secs(StorageStats[k].maxVolDate); NS(SWB_NS_X_MAX_FLOW) = StorageStats[k].maxFlow;
+            NS(SWB_NS_X_EVAP) = StorageStats[k].evapLosses; NS(SWB_NS_X_EXFIL) = StorageStats[k].exfilLosses;
+        } else if (Node[i].type == OUTFALL) {
+            NS(SWB_NS_X_SUM) = OutfallStats[k].avgFlow; NS(SWB_NS_X_MAX) = OutfallStats[k].maxFlow;
+            NS(SWB_NS_X_MAX_TIME) = OutfallStats[k].totalPeriods;
+            for (p = 0; p < nP; p++) NS(SWB_NS_LOAD0 + p) = OutfallStats[k].totalLoad[p];
+        }
+    }
+#undef NS
+}
+
+void refhook_link_stats(double *out)
+{
+    int nL = Nobjects[LINK], j, c, k;
+#define LS(plane) out[(size_t)(plane) * nL + j]
+    for (j = 0; j < nL; j++) {
+        TLinkStats *s = &LinkStats[j];
+        for (c = 0; c < SWB_LS_PLANES; c++) LS(c) = 0.0;
+        LS(SWB_LS_MAX_FLOW) = s->maxFlow; LS(SWB_LS_MAX_FLOW_TIME) = secs(s->maxFlowDate);
+        LS(SWB_LS_MAX_VELOC) = s->maxVeloc; LS(SWB_LS_MAX_DEPTH) = s->maxDepth;
+        LS(SWB_LS_TIME_FULL_FLOW) = s->timeFullFlow; LS(SWB_LS_TIME_CAP_LIMITED) = s->timeCapacityLimited;
+        LS(SWB_LS_TIME_SURCHARGED) = s->timeSurcharged; LS(SWB_LS_TIME_FULL_UP) = s->timeFullUpstream;
+        LS(SWB_LS_TIME_FULL_DN) = s->timeFullDnstream; LS(SWB_LS_TURN_SIGN) = s->flowTurnSign;
+        LS(SWB_LS_TURNS) = s->flowTurns; LS(SWB_LS_TIME_COURANT) = s->timeCourantCritical;
+        if (Link[j].type == PUMP) {
+            k = Link[j].subIndex;
+            LS(SWB_LS_PUMP_MIN_FLOW) = PumpStats[k].minFlow; LS(SWB_LS_PUMP_SUM_FLOW) = PumpStats[k].avgFlow;
+            LS(SWB_LS_PUMP_VOLUME) = PumpStats[k].volume; LS(SWB_LS_PUMP_UTILIZED) = PumpStats[k].utilized;
+            LS(SWB_LS_PUMP_ENERGY) = PumpStats[k].energy; LS(SWB_LS_PUMP_OFF_LOW) = PumpStats[k].offCurveLow;
+            LS(SWB_LS_PUMP_OFF_HIGH) = PumpStats[k].offCurveHigh; LS(SWB_LS_PUMP_STARTUPS) = PumpStats[k].startUps;
+            LS(SWB_LS_PUMP_PERIODS) = PumpStats[k].totalPeriods;
+        } else {
+            LS(SWB_LS_TIME_NORMAL) = s->timeNormalFlow; LS(SWB_LS_TIME_INLET) = s->timeInletControl;
+            for (c = 0; c < MAX_FLOW_CLASSES; c++) LS(SWB_LS_TIME_CLASS0 + c) = s->timeInFlowClass[c];
+        }
+    }
+#undef LS
+}
+double refhook_max_outfall_flow(void) { return MaxOutfallFlow; }

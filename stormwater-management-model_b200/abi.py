@@ -57,7 +57,9 @@ def _parse_enum(text: str, name: str) -> dict:
             continue
         if "=" in item:
             k, v = item.split("=")
-            val = int(v)
+            v = v.strip()
+            # an enumerator may be defined by another one (+ a constant)
+            val = sum(out[t.strip()] if t.strip() in out else int(t) for t in v.split("+"))
             out[k.strip()] = val
         else:
             val += 1
@@ -73,6 +75,9 @@ _STATS_FIELDS = _parse_struct(_TEXT, "swb_member_stats")
 _STEPIO_FIELDS = _parse_struct(_TEXT, "swb_step_io")
 FIELD = _parse_enum(_TEXT, "swb_field")
 FIELD_NAME = {v: k for k, v in FIELD.items()}
+NODE_STAT = _parse_enum(_TEXT, "swb_node_stat")
+LINK_STAT = _parse_enum(_TEXT, "swb_link_stat")
+SYSTEM_STAT = _parse_enum(_TEXT, "swb_system_stat")
 
 
 class NetworkDesc(C.Structure):

@@ -153,7 +153,7 @@ int swb_network_create(const swb_network_desc *d, const swb_options *o, int devi
 #undef X
         const Derived &r = nw->der;
 #define D(name) ar.add(nw->net.name, r.name.data(), r.name.size());
-        D(adj_packed) D(link_flags) D(link_z1) D(link_z2) D(xs_rcp_yfull) D(cond_rcp_mod_length) D(adj_start) D(adj)
+        D(outfall_nodes) D(adj_packed) D(link_flags) D(link_z1) D(link_z2) D(xs_rcp_yfull) D(cond_rcp_mod_length) D(adj_start) D(adj)
         D(adjq_start) D(adjq) D(nc_links) D(node_order) D(link_order) D(outfall_link) D(xs_tables)
         D(link_kernel) D(culvert_params) D(road_tables)
 #undef D
@@ -449,7 +449,7 @@ static int step_host_enqueue(swb_solver *s, const swb_step_io *io, bool wait)
     }
     if (io->node_depth) stg.stg_depth = s->stg_depth;
     if (io->link_flow) stg.stg_flow = s->stg_flow;
-    int phases = PH_SWAP | PH_HOSTIN | PH_DYNWAVE | PH_NEXTDT | PH_MASSBAL;
+    int phases = PH_SWAP | PH_HOSTIN | PH_DYNWAVE | PH_NEXTDT | PH_MASSBAL | PH_STATS;
     if (withQual) phases |= PH_QSWAP | PH_QUALITY;
     double t_end = 0.0;
     if (io->dt) {
@@ -544,7 +544,7 @@ int swb_run_steps(swb_solver *s, int n_steps, double t_end)
     if (!s->have_inflows) return fail(SWB_ERR_ARG, "swb_set_inflows has not been called");
     SWB_ENTER(s);
     const Net &n = s->net->net;
-    int phases = PH_ADVANCE | PH_SWAP | PH_INFLOWS | PH_DYNWAVE | PH_NEXTDT | PH_MASSBAL;
+    int phases = PH_ADVANCE | PH_SWAP | PH_INFLOWS | PH_DYNWAVE | PH_NEXTDT | PH_MASSBAL | PH_STATS;
     if (n.nP > 0 && !n.opt.ignore_quality) phases |= PH_QSWAP | PH_QUALITY;
     return run(s, phases, n_steps, t_end, n.opt.route_step);
 }
@@ -762,6 +762,55 @@ int swb_get_phase_times(swb_solver *s, double *ms, int n, int reset)
     for (int i = 0; i < n; i++) ms[i] = i < SWB_N_PHASES ? (double)h[i] * 1.0e-6 : 0.0;
     if (reset) backend::zero(s->st.phase_ns, sizeof(h));
     return SWB_OK;
+}
+
+int swb_enable_statistics(swb_solver *s, double report_start_s)
+{
+    if (!s) return fail(SWB_ERR_ARG, "null solver");
+    SWB_ENTER(s);
+    const Net &n = s->net->net;
+    const size_t M = s->M;
+    try {
+        if (!s->st.stat_node) {
+            s->st.stat_node = dev_zero<double>(s->allocs, (size_t)(SWB_NS_PLANES + n.nP) * n.nN * M);
+            s->st.stat_link = dev_zero<double>(s->allocs, (size_t)SWB_LS_PLANES * n.nL * M);
+            s->st.stat_sys = dev_zero<double>(s->allocs, (size_t)SWB_SS_PLANES * M);
+        } else {
+            checked(backend::zero(s->st.stat_node, sizeof(double) * (size_t)(SWB_NS_PLANES + n.nP) * n.nN * M), "memset");
+            checked(backend::zero(s->st.stat_link, sizeof(double) * (size_t)SWB_LS_PLANES * n.nL * M), "memset");
+            checked(backend::zero(s->st.stat_sys, sizeof(double) * (size_t)SWB_SS_PLANES * M), "memset");
+        }
+        // TimeStepStats.minTimeStep starts at RouteStep (stats.c:293)
+        std::vector<double> mn(M, n.opt.route_step);
+        checked(backend::upload(s->st.stat_sys + (size_t)SWB_SS_MIN_DT * M, mn.data(), sizeof(double) * M), "copy");
+    } catch (const DeviceError &e) { s->st.stat_node = s->st.stat_link = s->st.stat_sys = nullptr; return fail(SWB_ERR_CUDA, e.what); }
+    s->st.stat_report_start = report_start_s;
+    return SWB_OK;
+}
+
+// planes [K][items][M] on the device -> [member][plane][item] on the host
+static int stats_xfer(swb_solver *s, const double *dev, int planes, size_t items, int m0, int nm, double *out)
+{
+    if (!s || !out || m0 < 0 || nm < 1 || m0 + nm > s->M) return fail(SWB_ERR_ARG, "bad arguments");
+    if (!dev) return fail(SWB_ERR_ARG, "swb_enable_statistics has not been called");
+    SWB_ENTER(s);
+    const size_t rows = (size_t)planes * items, cols = (size_t)nm;
+    std::vector<double> h(rows * cols);
+    if (!backend::copy2d(h.data(), cols * sizeof(double), dev + m0, (size_t)s->M * sizeof(double),
+                         cols * sizeof(double), rows, false))
+        return fail(SWB_ERR_CUDA, backend::last_error());
+    for (size_t r = 0; r < rows; r++)
+        for (int mm = 0; mm < nm; mm++) out[(size_t)mm * rows + r] = h[r * cols + mm];
+    return SWB_OK;
+}
+int swb_get_node_stats(swb_solver *s, int m0, int nm, double *out)
+{ return s ? stats_xfer(s, s->st.stat_node, SWB_NS_PLANES + s->net->net.nP, s->net->net.nN, m0, nm, out) : fail(SWB_ERR_ARG, "null solver"); }
+int swb_get_link_stats(swb_solver *s, int m0, int nm, double *out)
+{ return s ? stats_xfer(s, s->st.stat_link, SWB_LS_PLANES, s->net->net.nL, m0, nm, out) : fail(SWB_ERR_ARG, "null solver"); }
+int swb_get_system_stats(swb_solver *s, int m0, int nm, double *out)
+{
+    if (!s) return fail(SWB_ERR_ARG, "null solver");
+    return stats_xfer(s, s->st.stat_sys, SWB_SS_PLANES, 1, m0, nm, out);
 }
 
 // profiling aid (tools/profile_phase.py): n_steps of the given phase mask with debug switches

@@ -26,6 +26,7 @@
 #include "swb_dynwave.h"
 #include "swb_qual.h"
 #include "swb_regulator.h"
+#include "swb_stats.h"
 
 #ifdef __CUDACC__
 #define SWB_ENGINE __device__
@@ -49,7 +50,8 @@ enum {                         // RunArgs.phases
     PH_ADVANCE = 32,           // ensemble clock: pick dt from var_step / t_end, advance sim_time
     PH_QSWAP   = 64,           // quality old <- new, new = 0 (routing.c:312-336)
     PH_HOSTIN  = 128,          // lateral inflows / losses / quality loads from host-fed staging
-    PH_MASSBAL = 256           // routing totals: removeSystemOutflows + massbal_updateRoutingTotals
+    PH_MASSBAL = 256,          // routing totals: removeSystemOutflows + massbal_updateRoutingTotals
+    PH_STATS   = 512           // per-object statistics (swb_stats.h), only when the planes are allocated
 };
 
 struct Inflows {               // device image of swb_inflow_desc
@@ -630,6 +632,10 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     st.tot_steps[m] += 1;
                     if (st.not_conv[(itersDone - 1) * M + m]) st.non_conv[m] += 1;
                 }
+                // stats_updateConvergenceStats (dynwave.c:266-272): every node that missed the
+                // tolerance in a step that ended without convergence (outfalls count: their flag is
+                // never raised, dynwave.c:611)
+                // (node-level convergence counts: see the statistics phase below)
                 SWB_FOR_ITEMS(j, nL) {
                     if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) continue;
                     size_t ix = SWB_IX(j, m, M);
@@ -752,6 +758,55 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             }
         }
 
+        // ================= statistics (routing.c:256-260, stats.c:449-754) ======================
+        if ((args.phases & PH_STATS) && st.stat_node && active) {
+            // new routing time of this step in elapsed seconds, formed like NewRoutingTime (ms)
+            const double tNew = (1000.0 * st.sim_time[m] + 1000.0 * dt) / 1000.0;
+            if (tNew >= st.stat_report_start) {
+                // this thread's copy of "iterations used" (the owner's write to st.iters is not
+                // ordered against other CTAs): the step ended unconverged iff its last trial did
+                int itersDone = maxTrials;
+                for (int kk = 1; kk < maxTrials; kk++)
+                    if (st.not_conv[kk * M + m] == 0) { itersDone = kk + 1; break; }
+                if (maxTrials == 1) itersDone = 1;
+                const bool stepFailed = (args.phases & PH_DYNWAVE) && st.not_conv[(itersDone - 1) * M + m] != 0;
+                SWB_FOR_ITEMS(i, nNo) {
+                    stats_node(net, st, i, m, dt, tNew, withQual);
+                    if (stepFailed && !st.n_converged[SWB_IX(i, m, M)]) nstat(st, net, SWB_NS_NONCONV_COUNT, i, m) += 1.0;
+                }
+                SWB_FOR_ITEMS(j, nL) {
+                    if (part && !H.link_owned[j]) continue;
+                    stats_link(net, st, j, m, dt, tNew, T);
+                }
+                if (owner) {
+                    double *sys = st.stat_sys;
+                    sys[SWB_SS_REPORT_STEPS * M + m] += 1.0;
+                    sys[SWB_SS_ROUTING_SPAN * M + m] += dt;
+                    // SysOutfallFlow: the outfalls' inflows summed in node order like stats.c:626 (the
+                    // node phase wrote them several grid barriers ago); MaxOutfallFlow = running maximum
+                    double sysOut = 0.0;
+                    for (int k = 0; k < net.nOutfallNodes; k++) {
+                        const int i = net.outfall_nodes[k];
+                        if (i < nNo) sysOut += st.n_inflow[SWB_IX(i, m, M)];
+                    }
+                    double &mx = sys[SWB_SS_MAX_OUTFALL_FLOW * M + m];
+                    mx = SWB_MAX(mx, sysOut);
+                }
+            }
+            if (owner) {                      // stats_updateTimeStepStats (stats.c:486-518), no steady state
+                double *sys = st.stat_sys;
+                if (st.sim_time[m] > 0.0) {   // OldRoutingTime > 0: the first step does not set the minimum
+                    double &mn = sys[SWB_SS_MIN_DT * M + m];
+                    mn = SWB_MIN(mn, dt);
+                }
+                double &mx = sys[SWB_SS_MAX_DT * M + m];
+                mx = SWB_MAX(mx, dt);
+                sys[SWB_SS_ROUTING_TIME * M + m] += dt;
+                sys[SWB_SS_STEP_COUNT * M + m] += 1.0;
+                sys[SWB_SS_TRIALS * M + m] += (double)st.iters[m];
+            }
+        }
+
         SWB_TICK(TP_QUAL_LINKS);
         // ================= dynwave_getRoutingStep (dynwave.c:195-220, 799-921) =================
         // Two-level arg-min with integer atomics only (deterministic): the minimum itself as the
@@ -830,6 +885,11 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     }
                     st.crit_link[m] = cl; st.crit_node[m] = cn;
                     st.var_step[m] = floor(1000.0 * vs) / 1000.0;
+                    // stats_updateCriticalTimeCount (stats.c:522-533; called from getVariableStep)
+                    if (st.stat_node && (args.phases & PH_STATS)) {
+                        if (cn >= 0) nstat(st, net, SWB_NS_TIME_COURANT, cn, m) += 1.0;
+                        else if (cl >= 0) lstat(st, net, SWB_LS_TIME_COURANT, cl, m) += 1.0;
+                    }
                 }
             }
         }

@@ -16,7 +16,7 @@
 namespace swb {
 
 struct Derived {
-    std::vector<int> link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link, link_order,
+    std::vector<int> outfall_nodes, link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link, link_order,
                      link_kernel, node_order;
     std::vector<double> link_z1, link_z2, xs_tables, culvert_params, road_tables, xs_rcp_yfull, cond_rcp_mod_length;
     std::vector<AdjEntry> adj_packed;
@@ -108,6 +108,8 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
         else if (d.node_type[a] == SWB_OUTFALL) r.outfall_link[a] = j;
     }
     r.nNonConduit = (int)r.nc_links.size();
+    r.outfall_nodes.clear();
+    for (int i = 0; i < nN; i++) if (d.node_type[i] == SWB_OUTFALL) r.outfall_nodes.push_back(i);
     r.link_order.clear();
     for (int j = 0; j < nL; j++) if (r.link_flags[j] & LF_TRUE_CONDUIT) r.link_order.push_back(j);
     std::stable_sort(r.link_order.begin(), r.link_order.end(),
@@ -157,6 +159,7 @@ inline void fill_net_scalars(Net &n, const swb_network_desc &d, const swb_option
     n.nN = d.n_nodes; n.nL = d.n_links; n.nP = d.n_pollut; n.nCurves = d.n_curves;
     n.nShapeTbl = d.n_shape_tbls; n.shapeTblLen = d.shape_tbl_len;
     n.nTrue = r.nTrue; n.nNonConduit = r.nNonConduit; n.nOutfallLinks = 0;
+    n.nOutfallNodes = (int)r.outfall_nodes.size();
     n.anyLossRate = 0;
     for (int f : r.link_flags) if (f & LF_HAS_LOSSRATE) n.anyLossRate = 1;
     n.opt = o;

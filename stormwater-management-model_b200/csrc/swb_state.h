@@ -96,6 +96,8 @@ struct Net {
     const int    *node_order;              // node-phase ticket order: outfalls and storage nodes first
     const int    *nc_links;                // non-true-conduit links in ascending index order
     const int    *outfall_link;            // per node: its (single) link, or -1
+    const int    *outfall_nodes;           // outfall nodes in ascending index order
+    int           nOutfallNodes;
     const int    *link_kernel;             // LK_*: which conduit function a true conduit runs
     const double *culvert_params;          // [58][5] FHWA inlet-control coefficients (culvert.c:33)
     const double *road_tables;             // RT_TOTAL (x, y) pairs (roadway.c:42-69)
@@ -237,6 +239,11 @@ struct State {
     // added by the next step's prologue (or by the host when it reads the totals).
     double *mb_rate, *mb_total;  // [(MB_FLOW_TERMS + MB_QUAL_TERMS * nP)][M]
     double *mb_dt_prev;          // [M] step whose rates are pending in mb_rate (0 = none)
+    // per-object statistics (swb_stats.h); null until swb_enable_statistics
+    double *stat_node;               // [(SWB_NS_PLANES + nP)][nN][M]
+    double *stat_link;               // [SWB_LS_PLANES][nL][M]
+    double *stat_sys;                // [SWB_SS_PLANES][M]
+    double stat_report_start;        // statistics start at this elapsed simulated time (s)
     // device-side phase timers (ns, accumulated by thread 0 between grid barriers)
     unsigned long long *phase_ns;    // [SWB_N_PHASES]
     unsigned long long *tickets;     // [3 * SWB_MAX_TRIALS_CAP] work-distribution counters of one step

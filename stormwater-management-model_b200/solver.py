@@ -58,6 +58,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_last_kernel_ms.restype = C.c_double
     lib.swb_sync.argtypes = [C.c_void_p]
     lib.swb_get_phase_times.argtypes = [C.c_void_p, _P_D, C.c_int, C.c_int]
+    lib.swb_enable_statistics.argtypes = [C.c_void_p, C.c_double]
+    lib.swb_get_node_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, _P_D]
+    lib.swb_get_link_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, _P_D]
+    lib.swb_get_system_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, _P_D]
     lib.swb_debug_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.swb_host_alloc.argtypes = [C.c_ulonglong]
     lib.swb_host_alloc.restype = C.c_void_p
@@ -333,6 +337,22 @@ class Solver:
                                            nd.ctypes.data_as(pf) if nodes else None,
                                            ld.ctypes.data_as(pf) if links else None))
         return nd, ld
+
+    # ---- per-object statistics (stats.c), kept per member on the device -----------------------
+    def enable_statistics(self, report_start_s: float = 0.0):
+        self._chk(self.lib.swb_enable_statistics(self._h, float(report_start_s)))
+
+    def statistics(self, member0: int = 0, n_members: int | None = None):
+        """(node[nm, planes, n_nodes], link[nm, planes, n_links], system[nm, planes]); plane ids are
+        abi.NODE_STAT / abi.LINK_STAT / abi.SYSTEM_STAT (include/swmm_b200.h)."""
+        nm = self.M - member0 if n_members is None else n_members
+        nd = np.zeros((nm, abi.NODE_STAT["SWB_NS_PLANES"] + self.net.n_pollut, self.net.n_nodes))
+        ld = np.zeros((nm, abi.LINK_STAT["SWB_LS_PLANES"], self.net.n_links))
+        sd = np.zeros((nm, abi.SYSTEM_STAT["SWB_SS_PLANES"]))
+        self._chk(self.lib.swb_get_node_stats(self._h, member0, nm, nd.ctypes.data_as(_P_D)))
+        self._chk(self.lib.swb_get_link_stats(self._h, member0, nm, ld.ctypes.data_as(_P_D)))
+        self._chk(self.lib.swb_get_system_stats(self._h, member0, nm, sd.ctypes.data_as(_P_D)))
+        return nd, ld, sd
 
     def debug_run(self, phases: int, n_steps: int, debug: int = 0, profile: bool = False):
         """Profiling aid (swb_debug_run): phase mask + debug switches, see include/swmm_b200.h."""

@@ -400,6 +400,13 @@ int  swb_debug_run(swb_solver *s, int phases, int n_steps, int debug, int profil
 
 /* launch bookkeeping for bench.py ("gpu_launches") and device timing of the last call */
 long long swb_launch_count(const swb_solver *s);
+/* Execution form.  Ensembles of at least `min_members` members (0 = never; default 256, or the environment
+   variable SWB_STAGED_MIN_M) on an unpartitioned network run every routing step as a chain of kernels,
+   one per phase with its own register budget (csrc/swb_staged.cuh); everything else runs the persistent
+   cooperative kernel.  Both forms execute the same phase functions and give bit-identical states (the
+   mass-balance sums agree to rounding: their atomic adds are unordered in either form).  Process-wide;
+   returns the previous value. */
+int  swb_set_staged_min_members(int min_members);
 double    swb_last_kernel_ms(const swb_solver *s);
 int       swb_sync(swb_solver *s);
 

@@ -12,6 +12,7 @@
 #include <cooperative_groups.h>
 #include <cuda_profiler_api.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include "swb_state.h"
@@ -420,8 +421,8 @@ static int pick_blocks(const DevInfo &D, int M, int maxItems)
     return (int)blocks;
 }
 
-static bool launch(const Net &net, const State &st, const RunArgs &args, int device, float *ms, std::string &err,
-                   bool wait = true)
+static bool launch_persistent(const Net &net, const State &st, const RunArgs &args, int device, float *ms, std::string &err,
+                              bool wait = true)
 {
     if (!init(device, err)) return false;
     const DevInfo &D = g_dev[device];
@@ -455,4 +456,5 @@ static bool launch(const Net &net, const State &st, const RunArgs &args, int dev
 
 } }
 
+#include "swb_staged.cuh"
 #include "swb_api_impl.h"

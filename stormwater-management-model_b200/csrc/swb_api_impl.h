@@ -211,7 +211,13 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     st.crit_node = dev_zero<int>(s->allocs, M);
     st.crit_link = dev_zero<int>(s->allocs, M);
     st.tmin_bits = dev_zero<unsigned long long>(s->allocs, 2 * (size_t)M);
-    st.alive = dev_zero<int>(s->allocs, (size_t)(SWB_MAX_TRIALS_CAP + 1) * M);
+    st.alive = dev_zero<int>(s->allocs, (size_t)M);
+    st.ctl = dev_zero<int>(s->allocs, SWB_CTL_WORDS);
+    st.dt_cand = nullptr; st.dt_cand_stride = 0;
+    if (M >= 32 && backend::staged_max_threads(nw->device) > 0) {   // staged kernels: per-thread Courant candidates
+        st.dt_cand_stride = backend::staged_max_threads(nw->device);
+        st.dt_cand = dev_zero<double>(s->allocs, 4 * (size_t)st.dt_cand_stride);
+    }
     st.not_conv = dev_zero<int>(s->allocs, (size_t)SWB_MAX_TRIALS_CAP * M);
     st.done = dev_zero<int>(s->allocs, M);
     st.mb_reacted = dev_zero<double>(s->allocs, (size_t)(nP ? nP : 1) * M);
@@ -221,7 +227,7 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     st.mb_total = dev_zero<double>(s->allocs, (size_t)(MB_FLOW_TERMS + MB_QUAL_TERMS * nP) * M);
     st.mb_dt_prev = dev_zero<double>(s->allocs, M);
     st.phase_ns = dev_zero<unsigned long long>(s->allocs, SWB_N_PHASES);
-    st.tickets = dev_zero<unsigned long long>(s->allocs, 3 * SWB_MAX_TRIALS_CAP);
+    st.tickets = dev_zero<unsigned long long>(s->allocs, SWB_TICKETS_PER_TRIAL * SWB_MAX_TRIALS_CAP);
     // conduit / link settings default to fully open (Link.setting = 1.0, link.c:142)
     std::vector<double> ones((size_t)nL * M, 1.0);
     checked(backend::upload(st.l_setting, ones.data(), sizeof(double) * ones.size()), "host -> device copy");
@@ -352,8 +358,9 @@ static int run(swb_solver *s, int phases, int n_steps, double t_end, double fixe
                 return fail(SWB_ERR_ARG, "partitioned solver: swb_partition_connect has not been called for every peer");
         if (!wait || (phases & PH_HOSTIN)) return fail(SWB_ERR_UNSUPP, "partitioned solver: use swb_run_steps");
     }
-    if (!backend::launch(s->net->net, s->st, a, s->net->device, &ms, err, wait)) return fail(SWB_ERR_CUDA, err);
-    s->launches++;
+    int kernels = 1;
+    if (!backend::launch(s->net->net, s->st, a, s->net->device, &ms, err, wait, &kernels)) return fail(SWB_ERR_CUDA, err);
+    s->launches += kernels;
     s->last_ms = ms;
     if (s->st.halo.nRanks > 1) {
         unsigned long long flag = 0;
@@ -829,6 +836,7 @@ int swb_debug_run(swb_solver *s, int phases, int n_steps, int debug, int profile
 }
 
 long long swb_launch_count(const swb_solver *s) { return s ? s->launches : 0; }
+int swb_set_staged_min_members(int min_members) { return backend::set_staged_min_members(min_members); }
 double swb_last_kernel_ms(const swb_solver *s) { return s ? (double)s->last_ms : 0.0; }
 int swb_sync(swb_solver *s)
 {

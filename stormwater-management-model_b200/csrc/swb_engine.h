@@ -346,16 +346,504 @@ SWB_ENGINE inline void halo_exchange(Ctx &ctx, const Halo &H, unsigned long long
     ctx.grid_sync();
 }
 
+// ticket counters of one Picard trial (State::tickets[SWB_TICKETS_PER_TRIAL * k + ...]): the persistent
+// kernel draws every conduit tile from TK_LINKS; the staged link kernels draw per conduit-function class
+// (TK_LINKS + LK_*)
+enum { TK_LINKS = 0, TK_PRESUM = 3, TK_NODES = 4 };
+
+// member mm goes on to trial k + 1: still running and not converged in any trial 1..k (dynwave.c:249-251)
+SWB_ENGINE inline bool member_iterates(const State &st, const RunArgs &args, int mm, int k)
+{
+    bool a = !((args.phases & PH_ADVANCE) && st.done[mm]);
+    for (int kk = 1; kk <= k && a; kk++) a = (st.not_conv[kk * st.M + mm] != 0);
+    return a;
+}
+
+// ---- the phases of one routing step ---------------------------------------------------------------
+// Every function below is the work BETWEEN two grid-wide synchronisation points.  engine_run() chains
+// them with grid barriers inside one persistent cooperative kernel (narrow ensembles, single models,
+// partitioned networks, the host emulation); swb_staged.cuh launches each of them as a kernel of its
+// own with its own register budget (wide ensembles), where the kernel boundary is the barrier.
+//
+// Streaming phases use a fixed mapping: thread t works on member t % M and walks objects
+// t / M + k * (G / M) (see SWB_FOR_ITEMS).
+struct ThreadMap { int m, first, stride; bool owner; };
+template <class Ctx>
+SWB_ENGINE inline ThreadMap thread_map(const Ctx &ctx, int M)
+{
+    ThreadMap t;
+    t.m = ctx.tid % M; t.first = ctx.tid / M; t.stride = ctx.G / M;
+    t.owner = (t.first == 0);            // the one thread that owns member m's scalars
+    return t;
+}
+SWB_ENGINE inline int engine_max_trials(const Net &net)
+{
+    return net.opt.max_trials < SWB_MAX_TRIALS_CAP ? net.opt.max_trials : SWB_MAX_TRIALS_CAP;
+}
+SWB_ENGINE inline bool member_active(const State &st, const RunArgs &args, int m)
+{
+    return !((args.phases & PH_ADVANCE) && st.done[m]);
+}
+
+// execRouting (swmm5.c:528-546): step = variable step, shortened to end at t_end (owner threads)
+SWB_ENGINE inline void ph_advance(const Net &net, const State &st, const RunArgs &args, int m)
+{
+    double t = st.sim_time[m];
+    int done = (t >= args.t_end) ? 1 : 0;
+    double dt = st.var_step[m];
+    if (net.opt.courant_factor == 0.0) dt = args.fixed_step;
+    else if (dt == 0.0) {      // first call of dynwave_getRoutingStep (dynwave.c:209-218)
+        dt = floor(1000.0 * net.opt.min_route_step) / 1000.0;
+        st.var_step[m] = dt;
+    }
+    // time is kept in milliseconds like NewRoutingTime (routing.c:301)
+    double tms = 1000.0 * t, nextms = tms + 1000.0 * dt, endms = 1000.0 * args.t_end;
+    if (!done && nextms > endms) {
+        dt = (endms - tms) / 1000.0;
+        dt = SWB_MAX(dt, 1. / 1000.0);
+    }
+    st.dt[m] = dt;
+    st.done[m] = done;
+}
+
+// massbal_updateRoutingTotals (massbal.c:587-617): the previous step's rates over the second half of
+// that step (deferred from its end) and over the first half of this one (owner threads)
+SWB_ENGINE inline void ph_massbal_fold(const Net &net, const State &st, int m, double dt)
+{
+    const int M = st.M, nMb = MB_FLOW_TERMS + MB_QUAL_TERMS * net.nP;
+    const double dtPrev = st.mb_dt_prev[m];
+    for (int q = 0; q < nMb; q++) {
+        const double r = st.mb_rate[q * M + m];
+        double tot = st.mb_total[q * M + m];
+        // (the mass moved to "final storage" is added unweighted by BOTH half-step
+        // updates, massbal.c:614 -- kept, it is what the reference reports)
+        const bool mass = q >= MB_FLOW_TERMS && (q - MB_FLOW_TERMS) % MB_QUAL_TERMS == MBQ_FINAL;
+        tot += mass ? r : r * (dtPrev / 2.);
+        tot += mass ? r : r * (dt / 2.);
+        st.mb_total[q * M + m] = tot;
+        st.mb_rate[q * M + m] = 0.0;
+    }
+    st.mb_dt_prev[m] = dt;
+}
+
+// old <- new, node_initFlows, overflow reset, lateral inflows + quality preload, initRoutingStep
+SWB_ENGINE inline void ph_prologue(const Net &net, const State &st, const RunArgs &args, const ThreadMap &tm, double dt)
+{
+    const int M = st.M, nN = net.nN, nL = net.nL, nP = net.nP;
+    const int m = tm.m, first = tm.first, stride = tm.stride;
+    // getDateTime(NewRoutingTime): 1 ms after the routing time (swmm5.c:1551), in days
+    const double tNow = args.inflows.start_day +
+        (args.inflows.start_secs + (1000.0 * st.sim_time[m] + 1.0) / 1000.0) / 86400.0;
+    // Every body below issues ALL of its loads before its first store: the state arrays may
+    // alias as far as the compiler knows, so a load written after a store cannot be hoisted
+    // above it and each load/store pair would cost a full DRAM round trip.
+    const int ph = args.phases;
+    SWB_FOR_ITEMS(i, nN) {
+        const size_t ix = SWB_IX(i, m, M);
+        // ---- loads
+        double qv[SWB_MAX_POLLUT], hq[SWB_MAX_POLLUT];
+        const bool touchQual = (ph & (PH_QSWAP | PH_INFLOWS)) || ((ph & PH_HOSTIN) && args.host_qual);
+#pragma unroll
+        for (int p = 0; p < SWB_MAX_POLLUT; p++) {
+            qv[p] = 0.0; hq[p] = 0.0;
+            if (p < nP && touchQual) {
+                size_t iq = SWB_IXP(p, i, nN, m, M);
+                qv[p] = st.n_qual[iq];
+                if ((ph & PH_HOSTIN) && args.host_qual) hq[p] = args.host_qual[iq];
+            }
+        }
+        double depth = 0.0, volume = 0.0, inflow = 0.0, outflow = 0.0, lat = 0.0, losses = 0.0;
+        if (ph & PH_SWAP) {
+            depth = st.n_depth[ix]; volume = st.n_volume[ix];
+            inflow = st.n_inflow[ix]; outflow = st.n_outflow[ix];
+        }
+        bool newLat = false;
+        int slot = -1;
+        // Node.oldLatFlow = newLatFlow (routing.c:330), only where this step sets a new one
+        const double prevLat = (ph & (PH_INFLOWS | PH_HOSTIN)) ? st.n_latflow[ix] : 0.0;
+        if (ph & PH_INFLOWS) {
+            // addExternalInflows (routing.c:435-490)
+            slot = args.inflows.node_slot[i];
+            if (slot >= 0) {
+                double tsv = inflow_series(args.inflows, slot, tNow - args.inflows.member_shift[m])
+                             * (args.inflows.sfactor[slot] * args.inflows.member_scale[m]);
+                lat = tsv + args.inflows.baseline[slot];
+                if (fabs(lat) < SWB_FLOW_TOL) lat = 0.0;
+            }
+            newLat = true;
+        }
+        if (ph & PH_HOSTIN) {
+            lat = args.host_lat[ix];
+            losses = args.host_losses ? args.host_losses[ix] : 0.0;
+            newLat = true;
+        }
+        if (!newLat && (ph & PH_SWAP)) { lat = st.n_latflow[ix]; losses = st.n_losses[ix]; }
+        // ---- stores
+#pragma unroll
+        for (int p = 0; p < SWB_MAX_POLLUT; p++)
+            if (p < nP && touchQual) {
+                size_t iq = SWB_IXP(p, i, nN, m, M);
+                double c = qv[p];
+                if (ph & PH_QSWAP) { st.n_old_qual[iq] = c; c = 0.0; }      // routing.c:312-336
+                if ((ph & PH_INFLOWS) && slot >= 0 && lat >= 0.0) c += args.inflows.concen[slot * nP + p] * lat;
+                if ((ph & PH_HOSTIN) && args.host_qual) c += hq[p];
+                st.n_qual[iq] = c;
+            }
+        if (newLat) { st.n_latflow[ix] = lat; st.n_losses[ix] = losses; st.n_old_latflow[ix] = prevLat; }
+        if (ph & PH_SWAP) {
+            // node_setOldHydState, node_initFlows, flowrout.c:153-162
+            st.n_old_depth[ix] = depth;
+            st.n_old_volume[ix] = volume;
+            st.n_old_net_inflow[ix] = inflow - outflow;
+            st.n_old_inflow[ix] = inflow;              // oldFlowInflow (node.c:302)
+            st.n_inflow[ix] = lat;
+            st.n_outflow[ix] = losses;
+            double ov = 0.0, fullVolume = net.node_full_volume[i];
+            if (net.node_type[i] != SWB_STORAGE && volume > fullVolume) ov = (volume - fullVolume) / dt;
+            st.n_overflow[ix] = ov;
+        }
+        if (ph & PH_DYNWAVE) {                 // initRoutingStep (dynwave.c:276-293)
+            st.n_converged[ix] = 0;
+            st.n_dydt[ix] = 0.0;
+        }
+    }
+    SWB_FOR_ITEMS(j, nL) {
+        const size_t ix = SWB_IX(j, m, M);
+        // ---- loads
+        double qv[SWB_MAX_POLLUT];
+#pragma unroll
+        for (int p = 0; p < SWB_MAX_POLLUT; p++) {
+            qv[p] = 0.0;
+            if (p < nP && (ph & PH_QSWAP)) qv[p] = st.l_qual[SWB_IXP(p, j, nL, m, M)];
+        }
+        double depth = 0.0, flow = 0.0, volume = 0.0, a1 = 0.0;
+        const bool isConduit = (net.link_type[j] == SWB_CONDUIT);
+        if (ph & PH_SWAP) { depth = st.l_depth[ix]; flow = st.l_flow[ix]; volume = st.l_volume[ix]; }
+        if ((ph & PH_DYNWAVE) && isConduit) a1 = st.c_a1[ix];
+        // ---- stores
+#pragma unroll
+        for (int p = 0; p < SWB_MAX_POLLUT; p++)
+            if (p < nP && (ph & PH_QSWAP)) {
+                size_t iq = SWB_IXP(p, j, nL, m, M);
+                st.l_old_qual[iq] = qv[p];
+                st.l_qual[iq] = 0.0;
+            }
+        if (ph & PH_SWAP) {                     // link_setOldHydState (link.c:564-583)
+            st.l_old_depth[ix] = depth;
+            st.l_old_flow[ix] = flow;
+            st.l_old_volume[ix] = volume;
+        }
+        if (ph & PH_DYNWAVE) {
+            st.l_bypassed[ix] = 0;
+            if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) {
+                st.l_surf_area1[ix] = 0.0;
+                st.l_surf_area2[ix] = 0.0;
+            }
+            if (isConduit) st.c_a2[ix] = a1;    // dynwave.c:292
+        }
+    }
+}
+
+// updateConvergenceStats, findLimitedLinks (dynwave.c:257-260, 349-378); active members only
+SWB_ENGINE inline void ph_epilogue(const Net &net, const State &st, const ThreadMap &tm)
+{
+    const int M = st.M, nL = net.nL, m = tm.m, first = tm.first, stride = tm.stride;
+    const int maxTrials = engine_max_trials(net);
+    if (tm.owner) {
+        // iterations used: first trial k >= 1 that ended converged, else MaxTrials
+        int itersDone = maxTrials;
+        for (int kk = 1; kk < maxTrials; kk++)
+            if (st.not_conv[kk * M + m] == 0) { itersDone = kk + 1; break; }
+        if (maxTrials == 1) itersDone = 1;
+        st.iters[m] = itersDone;
+        st.tot_iters[m] += itersDone;
+        st.tot_steps[m] += 1;
+        if (st.not_conv[(itersDone - 1) * M + m]) st.non_conv[m] += 1;
+    }
+    // stats_updateConvergenceStats (dynwave.c:266-272): every node that missed the
+    // tolerance in a step that ended without convergence (outfalls count: their flag is
+    // never raised, dynwave.c:611)
+    // (node-level convergence counts: see the statistics phase below)
+    SWB_FOR_ITEMS(j, nL) {
+        if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) continue;
+        size_t ix = SWB_IX(j, m, M);
+        unsigned char lim = 0;
+        if (st.c_a1[ix] >= net.xs_afull[j]) {
+            int n1 = net.link_node1[j], n2 = net.link_node2[j];
+            double h1 = st.n_depth[SWB_IX(n1, m, M)] + net.node_invert[n1];
+            double h2 = st.n_depth[SWB_IX(n2, m, M)] + net.node_invert[n2];
+            // Conduit.length is the user's length (dynwave.c:374), not the true length
+            if ((h1 - h2) > fabs(net.cond_slope[j]) * net.cond_user_length[j]) lim = 1;
+        }
+        st.c_cap_limited[ix] = lim;
+    }
+}
+
+// qualrout_execute (qualrout.c:100-142), node pass then link pass; pollutant-major loops keep the
+// three mass-balance partial sums in registers
+template <class Ctx>
+SWB_ENGINE inline void ph_qual_nodes(const Net &net, const State &st, Ctx &ctx, const ThreadMap &tm, double dt, int nNo)
+{
+    const int M = st.M, m = tm.m, first = tm.first, stride = tm.stride;
+    for (int p = 0; p < net.nP; p++) {
+        QualAcc acc = {0.0, 0.0, 0.0};
+        SWB_FOR_ITEMS(i, nNo) qual_node(net, st, i, m, p, dt, acc);
+        qual_acc_flush(ctx, st, p, m, M, dt, acc);
+    }
+}
+template <class Ctx>
+SWB_ENGINE inline void ph_qual_links(const Net &net, const State &st, Ctx &ctx, const ThreadMap &tm, double dt)
+{
+    const int M = st.M, nL = net.nL, m = tm.m, first = tm.first, stride = tm.stride;
+    const Halo &H = st.halo;
+    const bool part = H.nRanks > 1;
+    for (int p = 0; p < net.nP; p++) {
+        QualAcc acc = {0.0, 0.0, 0.0}, copy = {0.0, 0.0, 0.0};
+        // the copy of a cut conduit is routed too, but only its owner reports the losses
+        SWB_FOR_ITEMS(j, nL) qual_link(net, st, j, m, p, dt, (part && !H.link_owned[j]) ? copy : acc);
+        qual_acc_flush(ctx, st, p, m, M, dt, acc);
+    }
+}
+
+// removeSystemOutflows (routing.c:776-806, 812-925).  Step rates of everything that enters or leaves
+// the system, summed per member: external inflows (routing.c:466-489), outfall discharge and flooding
+// (node.c:438-493), negative lateral flows, storage and conduit losses.  Per-thread partial sums, one
+// atomic per term.
+template <class Ctx>
+SWB_ENGINE inline void ph_outflows(const Net &net, const State &st, const RunArgs &args, Ctx &ctx, const ThreadMap &tm,
+                                   double dt, bool withQual, int nNo)
+{
+    const int M = st.M, nN = net.nN, nL = net.nL, nP = net.nP, m = tm.m, first = tm.first, stride = tm.stride;
+    const Halo &H = st.halo;
+    const bool part = H.nRanks > 1;
+    auto flush = [&](int q, double v) {
+        if (M == 1) v = ctx.warp_sum_f64(v);
+        if (v != 0.0 && (M != 1 || ctx.warp_lane == 0)) ctx.atomic_add_f64(&st.mb_rate[(size_t)q * M + m], v);
+    };
+    // pass 0: the flow terms and pollutants 0-1; further passes: two more pollutants each
+    // (keeps the partial sums in registers)
+    for (int p0 = 0; p0 == 0 || (withQual && p0 < nP); p0 += 2) {
+        double fl[MB_FLOW_TERMS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        double ql[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+        SWB_FOR_ITEMS(i, nNo) {
+            const size_t ix = SWB_IX(i, m, M);
+            const double lat = st.n_latflow[ix];
+            const int type = net.node_type[i];
+            double q = 0.0;                       // node_getSystemOutflow (node.c:438-493)
+            bool flooded = false;
+            if (type == SWB_OUTFALL) {            // (warp-uniform: a warp holds one node)
+                const double inflow = st.n_inflow[ix], outflow = st.n_outflow[ix];
+                if (outflow == 0.0) q = inflow;
+                else if (inflow == 0.0) q = -outflow;
+            } else {
+                // q = overflow if newVolume <= fullVolume: the volume only matters when
+                // there is an overflow at all, so junctions cost two loads here
+                const double ov = st.n_overflow[ix];
+                if (ov != 0.0 && st.n_volume[ix] <= net.node_full_volume[i]) q = ov;
+                flooded = q > 0.0;
+            }
+            if (p0 == 0) {
+                if (lat >= 0.0) fl[MB_EX_INFLOW] += lat; else fl[MB_OUTFLOW] -= lat;      // routing.c:466-469
+                if (q > 0.0) { if (flooded) fl[MB_FLOODING] += q; else fl[MB_OUTFLOW] += q; }  // :904
+                else fl[MB_EX_INFLOW] -= q;                                                // :911
+                if (type == SWB_STORAGE) {                                                 // :812-836
+                    fl[MB_EVAP] += st.n_evap_loss[ix] / dt;
+                    fl[MB_SEEP] += st.n_exfil_loss[ix] / dt;
+                }
+            }
+            if (withQual) {
+                const int slot = (args.phases & PH_INFLOWS) ? args.inflows.node_slot[i] : -1;
+#pragma unroll
+                for (int pp = 0; pp < 2; pp++) {
+                    const int p = p0 + pp;
+                    if (p >= nP) continue;
+                    const size_t iq = SWB_IXP(p, i, nN, m, M);
+                    if (slot >= 0 && lat >= 0.0) ql[pp][MBQ_EX_INFLOW] += args.inflows.concen[slot * nP + p] * lat;
+                    if ((args.phases & PH_HOSTIN) && args.host_qual) ql[pp][MBQ_EX_INFLOW] += args.host_qual[iq];
+                    if (q > 0.0 || lat < 0.0) {   // the concentration only where mass leaves
+                        const double c = st.n_qual[iq];
+                        if (q > 0.0) ql[pp][flooded ? MBQ_FLOODING : MBQ_OUTFLOW] += q * c;  // :906-908
+                        if (lat < 0.0) ql[pp][MBQ_OUTFLOW] += -lat * c;                      // :915-922
+                    }
+                }
+            }
+        }
+        if (p0 == 0 && net.anyLossRate)                    // removeConduitLosses (:840-867)
+            SWB_FOR_ITEMS(j, nL) {
+                if (!(net.link_flags[j] & LF_HAS_LOSSRATE) || (part && !H.link_owned[j])) continue;
+                const size_t ix = SWB_IX(j, m, M);
+                const double barrels = (double)net.cond_barrels[j];
+                fl[MB_EVAP] += st.c_evap_loss[ix] * barrels;
+                fl[MB_SEEP] += st.c_seep_loss[ix] * barrels;
+            }
+        if (p0 == 0)
+#pragma unroll
+            for (int q = 0; q < MB_FLOW_TERMS; q++) flush(q, fl[q]);
+        if (withQual)
+#pragma unroll
+            for (int pp = 0; pp < 2; pp++)
+                if (p0 + pp < nP)
+#pragma unroll
+                    for (int t = 0; t < 3; t++) flush(MB_FLOW_TERMS + (p0 + pp) * MB_QUAL_TERMS + t, ql[pp][t]);
+    }
+}
+
+// statistics (routing.c:256-260, stats.c:449-754); the caller has checked st.stat_node
+SWB_ENGINE inline void ph_stats(const Net &net, const State &st, const RunArgs &args, const ThreadMap &tm, bool active,
+                                double dt, bool withQual, int nNo, const double *T)
+{
+    const int M = st.M, nL = net.nL, m = tm.m, first = tm.first, stride = tm.stride;
+    const Halo &H = st.halo;
+    const bool part = H.nRanks > 1;
+    const int maxTrials = engine_max_trials(net);
+    if (!active) return;
+    // new routing time of this step in elapsed seconds, formed like NewRoutingTime (ms)
+    const double tNew = (1000.0 * st.sim_time[m] + 1000.0 * dt) / 1000.0;
+    if (tNew >= st.stat_report_start) {
+        // this thread's copy of "iterations used" (the owner's write to st.iters is not
+        // ordered against other CTAs): the step ended unconverged iff its last trial did
+        int itersDone = maxTrials;
+        for (int kk = 1; kk < maxTrials; kk++)
+            if (st.not_conv[kk * M + m] == 0) { itersDone = kk + 1; break; }
+        if (maxTrials == 1) itersDone = 1;
+        const bool stepFailed = (args.phases & PH_DYNWAVE) && st.not_conv[(itersDone - 1) * M + m] != 0;
+        SWB_FOR_ITEMS(i, nNo) {
+            stats_node(net, st, i, m, dt, tNew, withQual);
+            if (stepFailed && !st.n_converged[SWB_IX(i, m, M)]) nstat(st, net, SWB_NS_NONCONV_COUNT, i, m) += 1.0;
+        }
+        SWB_FOR_ITEMS(j, nL) {
+            if (part && !H.link_owned[j]) continue;
+            stats_link(net, st, j, m, dt, tNew, T);
+        }
+        if (tm.owner) {
+            double *sys = st.stat_sys;
+            sys[SWB_SS_REPORT_STEPS * M + m] += 1.0;
+            sys[SWB_SS_ROUTING_SPAN * M + m] += dt;
+            // SysOutfallFlow: the outfalls' inflows summed in node order like stats.c:626 (the
+            // node phase wrote them several grid barriers ago); MaxOutfallFlow = running maximum
+            double sysOut = 0.0;
+            for (int k = 0; k < net.nOutfallNodes; k++) {
+                const int i = net.outfall_nodes[k];
+                if (i < nNo) sysOut += st.n_inflow[SWB_IX(i, m, M)];
+            }
+            double &mx = sys[SWB_SS_MAX_OUTFALL_FLOW * M + m];
+            mx = SWB_MAX(mx, sysOut);
+        }
+    }
+    if (tm.owner) {                      // stats_updateTimeStepStats (stats.c:486-518), no steady state
+        double *sys = st.stat_sys;
+        if (st.sim_time[m] > 0.0) {   // OldRoutingTime > 0: the first step does not set the minimum
+            double &mn = sys[SWB_SS_MIN_DT * M + m];
+            mn = SWB_MIN(mn, dt);
+        }
+        double &mx = sys[SWB_SS_MAX_DT * M + m];
+        mx = SWB_MAX(mx, dt);
+        sys[SWB_SS_ROUTING_TIME * M + m] += dt;
+        sys[SWB_SS_STEP_COUNT * M + m] += 1.0;
+        sys[SWB_SS_TRIALS * M + m] += (double)st.iters[m];
+    }
+}
+
+// dynwave_getRoutingStep (dynwave.c:195-220, 799-921).  Two-level arg-min with integer atomics only
+// (deterministic): the minimum itself as the ordered bit image of the positive double, then the
+// smallest object index among the objects that attain it ("first index wins", like the reference's
+// strict `<` loops).  reset (owner) | barrier | search | barrier | arg | barrier | final (owner).
+struct DtCand { double tl, tn; int il, in; };    // a thread's own best link / node candidate
+SWB_ENGINE inline void ph_nextdt_reset(const State &st, const RunArgs &args, int m)
+{
+    const int M = st.M;
+    unsigned long long t0 = dbits(args.fixed_step);
+    st.tmin_bits[m] = t0;                 // links: min(maxStep, link candidates)
+    st.tmin_bits[M + m] = t0;             // nodes
+    st.crit_link[m] = 0x7fffffff; st.crit_node[m] = 0x7fffffff;
+}
+SWB_ENGINE inline bool nextdt_variable(const Net &net, const RunArgs &args)
+{
+    return !(net.opt.courant_factor == 0.0 || args.fixed_step < SWB_MINTIMESTEP);
+}
+template <class Ctx>
+SWB_ENGINE inline DtCand ph_nextdt_search(const Net &net, const State &st, const RunArgs &args, Ctx &ctx,
+                                          const ThreadMap &tm, bool search, int nNo)
+{
+    const int M = st.M, nL = net.nL, m = tm.m, first = tm.first, stride = tm.stride;
+    DtCand c;
+    c.tl = args.fixed_step; c.tn = args.fixed_step; c.il = -1; c.in = -1;
+    if (search) {
+        SWB_FOR_ITEMS(j, nL) {
+            double t = link_step(net, st, j, m);
+            if (t >= 0.0 && t < c.tl) { c.tl = t; c.il = j; }
+        }
+        SWB_FOR_ITEMS(i, nNo) {
+            double t = node_step(net, st, i, m);
+            if (t >= 0.0 && t < c.tn) { c.tn = t; c.in = i; }
+        }
+        unsigned long long bl = dbits(c.tl), bn = dbits(c.tn);
+        if (M == 1) {          // all lanes share the member: shuffle-reduce, one atomic per warp
+            bl = ctx.warp_min_u64(bl); bn = ctx.warp_min_u64(bn);
+            if (ctx.warp_lane == 0) {
+                if (bl < dbits(args.fixed_step)) ctx.atomic_min_u64(&st.tmin_bits[m], bl);
+                if (bn < dbits(args.fixed_step)) ctx.atomic_min_u64(&st.tmin_bits[M + m], bn);
+            }
+        } else {
+            if (c.il >= 0) ctx.atomic_min_u64(&st.tmin_bits[m], bl);
+            if (c.in >= 0) ctx.atomic_min_u64(&st.tmin_bits[M + m], bn);
+        }
+    }
+    return c;
+}
+template <class Ctx>
+SWB_ENGINE inline void ph_nextdt_arg(const State &st, Ctx &ctx, int m, const DtCand &c)
+{
+    const int M = st.M;
+    if (c.il >= 0 && dbits(c.tl) == st.tmin_bits[m]) ctx.atomic_min_i32(&st.crit_link[m], c.il);
+    if (c.in >= 0 && dbits(c.tn) == st.tmin_bits[M + m]) ctx.atomic_min_i32(&st.crit_node[m], c.in);
+}
+SWB_ENGINE inline void ph_nextdt_final(const Net &net, const State &st, const RunArgs &args, int m)
+{
+    const int M = st.M;
+    const bool part = st.halo.nRanks > 1;
+    if (!nextdt_variable(net, args)) st.var_step[m] = args.fixed_step;
+    else {
+        double vs;
+        int cl = st.crit_link[m], cn = st.crit_node[m];
+        if (cl == 0x7fffffff) cl = -1;
+        if (cn == 0x7fffffff) cn = -1;
+        if (st.var_step[m] == 0.0) { vs = net.opt.min_route_step; cl = cn = -1; }
+        else {
+            // getVariableStep (dynwave.c:813-831): a node wins only when strictly below
+            // the link step, and then the link is dropped
+            double tLink = dfrombits(st.tmin_bits[m]), tNode = dfrombits(st.tmin_bits[M + m]);
+            vs = tLink;
+            // (partitioned: the critical node may live on another rank; a node
+            // candidate exists iff the reduced node minimum is below the fixed step)
+            const bool haveNode = cn >= 0 || (part && st.tmin_bits[M + m] < dbits(args.fixed_step));
+            if (haveNode && tNode < tLink) { vs = tNode; cl = -1; } else cn = -1;
+            if (vs < net.opt.min_route_step) vs = net.opt.min_route_step;
+        }
+        st.crit_link[m] = cl; st.crit_node[m] = cn;
+        st.var_step[m] = floor(1000.0 * vs) / 1000.0;
+        // stats_updateCriticalTimeCount (stats.c:522-533; called from getVariableStep)
+        if (st.stat_node && (args.phases & PH_STATS)) {
+            if (cn >= 0) nstat(st, net, SWB_NS_TIME_COURANT, cn, m) += 1.0;
+            else if (cl >= 0) lstat(st, net, SWB_LS_TIME_COURANT, cl, m) += 1.0;
+        }
+    }
+}
+// NewRoutingTime += 1000 * routingStep (routing.c:301-302), kept in ms
+SWB_ENGINE inline void ph_advance_time(const State &st, int m, double dt)
+{
+    st.sim_time[m] = (1000.0 * st.sim_time[m] + 1000.0 * dt) / 1000.0;
+}
+
 template <class Ctx>
 SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs &args, Ctx &ctx)
 {
     const int M = st.M, nN = net.nN, nL = net.nL, nP = net.nP;
-    const int m = ctx.tid % M;
-    const int first = ctx.tid / M, stride = ctx.G / M;
-    const bool owner = (first == 0);             // the one thread that owns member m's scalars
+    const ThreadMap tm = thread_map(ctx, M);
+    const int m = tm.m;
+    const bool owner = tm.owner;
     const double *T = ctx.T;
-    const int maxTrials = net.opt.max_trials < SWB_MAX_TRIALS_CAP ? net.opt.max_trials
-                                                                  : SWB_MAX_TRIALS_CAP;
+    const int maxTrials = engine_max_trials(net);
     const bool withQual = (nP > 0) && !net.opt.ignore_quality;
     // partitioned network (M == 1): nodes [0, nNo) are this rank's, the rest are ghosts kept current
     // by halo_exchange; every decision that shapes the control flow is reduced over all ranks
@@ -379,168 +867,22 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
     for (int step = 0; step < args.n_steps; step++) {
         // ================= step prologue =======================================================
         if (args.phases & PH_ADVANCE) {
-            // execRouting (swmm5.c:528-546): step = variable step, shortened to end at t_end
-            if (owner) {
-                double t = st.sim_time[m];
-                int done = (t >= args.t_end) ? 1 : 0;
-                double dt = st.var_step[m];
-                if (net.opt.courant_factor == 0.0) dt = args.fixed_step;
-                else if (dt == 0.0) {      // first call of dynwave_getRoutingStep (dynwave.c:209-218)
-                    dt = floor(1000.0 * net.opt.min_route_step) / 1000.0;
-                    st.var_step[m] = dt;
-                }
-                // time is kept in milliseconds like NewRoutingTime (routing.c:301)
-                double tms = 1000.0 * t, nextms = tms + 1000.0 * dt, endms = 1000.0 * args.t_end;
-                if (!done && nextms > endms) {
-                    dt = (endms - tms) / 1000.0;
-                    dt = SWB_MAX(dt, 1. / 1000.0);
-                }
-                st.dt[m] = dt;
-                st.done[m] = done;
-            }
+            if (owner) ph_advance(net, st, args, m);
             ctx.grid_sync();
             // every member has reached t_end: leave the launch (grid-uniform decision)
             bool anyLeft = false;
             for (int mm = ctx.lane; mm < M; mm += ctx.block_size) anyLeft = anyLeft || !st.done[mm];
             if (!ctx.block_or(anyLeft)) break;
         }
-        const bool active = !((args.phases & PH_ADVANCE) && st.done[m]);
+        const bool active = member_active(st, args, m);
         const double dt = st.dt[m];
-        const int nMb = MB_FLOW_TERMS + MB_QUAL_TERMS * nP;
-        if ((args.phases & PH_MASSBAL) && owner && active) {
-            // massbal_updateRoutingTotals (massbal.c:587-617): the previous step's rates over the
-            // second half of that step (deferred from its end) and over the first half of this one
-            const double dtPrev = st.mb_dt_prev[m];
-            for (int q = 0; q < nMb; q++) {
-                const double r = st.mb_rate[q * M + m];
-                double tot = st.mb_total[q * M + m];
-                // (the mass moved to "final storage" is added unweighted by BOTH half-step
-                // updates, massbal.c:614 -- kept, it is what the reference reports)
-                const bool mass = q >= MB_FLOW_TERMS && (q - MB_FLOW_TERMS) % MB_QUAL_TERMS == MBQ_FINAL;
-                tot += mass ? r : r * (dtPrev / 2.);
-                tot += mass ? r : r * (dt / 2.);
-                st.mb_total[q * M + m] = tot;
-                st.mb_rate[q * M + m] = 0.0;
-            }
-            st.mb_dt_prev[m] = dt;
-        }
+        if ((args.phases & PH_MASSBAL) && owner && active) ph_massbal_fold(net, st, m, dt);
 
-        if (active && (args.phases & (PH_SWAP | PH_INFLOWS | PH_QSWAP | PH_DYNWAVE | PH_HOSTIN))) {
-            // getDateTime(NewRoutingTime): 1 ms after the routing time (swmm5.c:1551), in days
-            const double tNow = args.inflows.start_day +
-                (args.inflows.start_secs + (1000.0 * st.sim_time[m] + 1.0) / 1000.0) / 86400.0;
-            // Every body below issues ALL of its loads before its first store: the state arrays may
-            // alias as far as the compiler knows, so a load written after a store cannot be hoisted
-            // above it and each load/store pair would cost a full DRAM round trip.
-            const int ph = args.phases;
-            SWB_FOR_ITEMS(i, nN) {
-                const size_t ix = SWB_IX(i, m, M);
-                // ---- loads
-                double qv[SWB_MAX_POLLUT], hq[SWB_MAX_POLLUT];
-                const bool touchQual = (ph & (PH_QSWAP | PH_INFLOWS)) || ((ph & PH_HOSTIN) && args.host_qual);
-#pragma unroll
-                for (int p = 0; p < SWB_MAX_POLLUT; p++) {
-                    qv[p] = 0.0; hq[p] = 0.0;
-                    if (p < nP && touchQual) {
-                        size_t iq = SWB_IXP(p, i, nN, m, M);
-                        qv[p] = st.n_qual[iq];
-                        if ((ph & PH_HOSTIN) && args.host_qual) hq[p] = args.host_qual[iq];
-                    }
-                }
-                double depth = 0.0, volume = 0.0, inflow = 0.0, outflow = 0.0, lat = 0.0, losses = 0.0;
-                if (ph & PH_SWAP) {
-                    depth = st.n_depth[ix]; volume = st.n_volume[ix];
-                    inflow = st.n_inflow[ix]; outflow = st.n_outflow[ix];
-                }
-                bool newLat = false;
-                int slot = -1;
-                // Node.oldLatFlow = newLatFlow (routing.c:330), only where this step sets a new one
-                const double prevLat = (ph & (PH_INFLOWS | PH_HOSTIN)) ? st.n_latflow[ix] : 0.0;
-                if (ph & PH_INFLOWS) {
-                    // addExternalInflows (routing.c:435-490)
-                    slot = args.inflows.node_slot[i];
-                    if (slot >= 0) {
-                        double tsv = inflow_series(args.inflows, slot, tNow - args.inflows.member_shift[m])
-                                     * (args.inflows.sfactor[slot] * args.inflows.member_scale[m]);
-                        lat = tsv + args.inflows.baseline[slot];
-                        if (fabs(lat) < SWB_FLOW_TOL) lat = 0.0;
-                    }
-                    newLat = true;
-                }
-                if (ph & PH_HOSTIN) {
-                    lat = args.host_lat[ix];
-                    losses = args.host_losses ? args.host_losses[ix] : 0.0;
-                    newLat = true;
-                }
-                if (!newLat && (ph & PH_SWAP)) { lat = st.n_latflow[ix]; losses = st.n_losses[ix]; }
-                // ---- stores
-#pragma unroll
-                for (int p = 0; p < SWB_MAX_POLLUT; p++)
-                    if (p < nP && touchQual) {
-                        size_t iq = SWB_IXP(p, i, nN, m, M);
-                        double c = qv[p];
-                        if (ph & PH_QSWAP) { st.n_old_qual[iq] = c; c = 0.0; }      // routing.c:312-336
-                        if ((ph & PH_INFLOWS) && slot >= 0 && lat >= 0.0) c += args.inflows.concen[slot * nP + p] * lat;
-                        if ((ph & PH_HOSTIN) && args.host_qual) c += hq[p];
-                        st.n_qual[iq] = c;
-                    }
-                if (newLat) { st.n_latflow[ix] = lat; st.n_losses[ix] = losses; st.n_old_latflow[ix] = prevLat; }
-                if (ph & PH_SWAP) {
-                    // node_setOldHydState, node_initFlows, flowrout.c:153-162
-                    st.n_old_depth[ix] = depth;
-                    st.n_old_volume[ix] = volume;
-                    st.n_old_net_inflow[ix] = inflow - outflow;
-                    st.n_old_inflow[ix] = inflow;              // oldFlowInflow (node.c:302)
-                    st.n_inflow[ix] = lat;
-                    st.n_outflow[ix] = losses;
-                    double ov = 0.0, fullVolume = net.node_full_volume[i];
-                    if (net.node_type[i] != SWB_STORAGE && volume > fullVolume) ov = (volume - fullVolume) / dt;
-                    st.n_overflow[ix] = ov;
-                }
-                if (ph & PH_DYNWAVE) {                 // initRoutingStep (dynwave.c:276-293)
-                    st.n_converged[ix] = 0;
-                    st.n_dydt[ix] = 0.0;
-                }
-            }
-            SWB_FOR_ITEMS(j, nL) {
-                const size_t ix = SWB_IX(j, m, M);
-                // ---- loads
-                double qv[SWB_MAX_POLLUT];
-#pragma unroll
-                for (int p = 0; p < SWB_MAX_POLLUT; p++) {
-                    qv[p] = 0.0;
-                    if (p < nP && (ph & PH_QSWAP)) qv[p] = st.l_qual[SWB_IXP(p, j, nL, m, M)];
-                }
-                double depth = 0.0, flow = 0.0, volume = 0.0, a1 = 0.0;
-                const bool isConduit = (net.link_type[j] == SWB_CONDUIT);
-                if (ph & PH_SWAP) { depth = st.l_depth[ix]; flow = st.l_flow[ix]; volume = st.l_volume[ix]; }
-                if ((ph & PH_DYNWAVE) && isConduit) a1 = st.c_a1[ix];
-                // ---- stores
-#pragma unroll
-                for (int p = 0; p < SWB_MAX_POLLUT; p++)
-                    if (p < nP && (ph & PH_QSWAP)) {
-                        size_t iq = SWB_IXP(p, j, nL, m, M);
-                        st.l_old_qual[iq] = qv[p];
-                        st.l_qual[iq] = 0.0;
-                    }
-                if (ph & PH_SWAP) {                     // link_setOldHydState (link.c:564-583)
-                    st.l_old_depth[ix] = depth;
-                    st.l_old_flow[ix] = flow;
-                    st.l_old_volume[ix] = volume;
-                }
-                if (ph & PH_DYNWAVE) {
-                    st.l_bypassed[ix] = 0;
-                    if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) {
-                        st.l_surf_area1[ix] = 0.0;
-                        st.l_surf_area2[ix] = 0.0;
-                    }
-                    if (isConduit) st.c_a2[ix] = a1;    // dynwave.c:292
-                }
-            }
-        }
+        if (active && (args.phases & (PH_SWAP | PH_INFLOWS | PH_QSWAP | PH_DYNWAVE | PH_HOSTIN)))
+            ph_prologue(net, st, args, tm, dt);
         if (owner && (args.phases & PH_DYNWAVE))
             for (int k = 0; k < maxTrials; k++) st.not_conv[k * M + m] = 0;
-        for (int c = ctx.tid; c < 3 * SWB_MAX_TRIALS_CAP; c += ctx.G) st.tickets[c] = 0ull;
+        for (int c = ctx.tid; c < SWB_TICKETS_PER_TRIAL * SWB_MAX_TRIALS_CAP; c += ctx.G) st.tickets[c] = 0ull;
         ctx.grid_sync();
         SWB_TICK(TP_PROLOGUE);
 
@@ -552,19 +894,19 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
         // warp that drew cheap tiles (dry or bypassed conduits) simply draws more instead of
         // waiting at the barrier for the warps that drew surcharged ones.
         if (args.phases & PH_DYNWAVE) {
-            int nAlive = ctx.compact_members(M, [&](int mm) { return !((args.phases & PH_ADVANCE) && st.done[mm]); });
+            int nAlive = ctx.compact_members(M, [&](int mm) { return member_active(st, args, mm); });
             for (int k = 0; k < maxTrials && nAlive > 0; k++) {
-                unsigned long long *tickets = st.tickets + 3 * k;
+                unsigned long long *tickets = st.tickets + SWB_TICKETS_PER_TRIAL * k;
                 // ---- findLinkFlows, pass (i): true conduits (dynwave.c:387-395)
                 if (!(args.debug & DBG_SKIP_LINKS))
-                for_tiles(ctx, net.nTrue, nAlive, tickets + 0, [&](int jj, int mm) {
+                for_tiles(ctx, net.nTrue, nAlive, tickets + TK_LINKS, [&](int jj, int mm) {
                     picard_link(net, st, net.link_order[jj], mm, k, st.dt[mm], T);
                 });
                 ctx.grid_sync();
                 SWB_TICK(TP_LINKS);
                 // ---- networks with regulators / dummy links: ordered pass (A.4)
                 if (net.nNonConduit > 0) {
-                    for_tiles(ctx, nNo, nAlive, tickets + 1, [&](int ii, int mm) { picard_node_presum(net, st, nodeOrder[ii], mm); });
+                    for_tiles(ctx, nNo, nAlive, tickets + TK_PRESUM, [&](int ii, int mm) { picard_node_presum(net, st, nodeOrder[ii], mm); });
                     ctx.grid_sync();
                     if (ctx.tid < nAlive) {
                         int mm = ctx.alive_list[ctx.tid];
@@ -575,7 +917,7 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 }
                 // ---- findNodeDepths (dynwave.c:593-632)
                 if (!(args.debug & DBG_SKIP_NODES))
-                for_tiles(ctx, nNo, nAlive, tickets + 2, [&](int ii, int mm) {
+                for_tiles(ctx, nNo, nAlive, tickets + TK_NODES, [&](int ii, int mm) {
                     const int i = nodeOrder[ii];
                     if (!picard_node(net, st, i, mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
                     if (part && H.send_start[i + 1] > H.send_start[i]) {
@@ -612,56 +954,16 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 // Every CTA rebuilds the same ordered list of members that go on to trial k + 1.
                 if (k + 1 >= maxTrials) break;
                 if (k >= 1)
-                    nAlive = ctx.compact_members(M, [&](int mm) {
-                        bool a = !((args.phases & PH_ADVANCE) && st.done[mm]);
-                        for (int kk = 1; kk <= k && a; kk++) a = (st.not_conv[kk * M + mm] != 0);
-                        return a;
-                    });
+                    nAlive = ctx.compact_members(M, [&](int mm) { return member_iterates(st, args, mm, k); });
                 SWB_TICK(TP_CONTROL);
             }
-            // ---- updateConvergenceStats, findLimitedLinks (dynwave.c:257-260, 349-378)
-            if (active) {
-                if (owner) {
-                    // iterations used: first trial k >= 1 that ended converged, else MaxTrials
-                    int itersDone = maxTrials;
-                    for (int kk = 1; kk < maxTrials; kk++)
-                        if (st.not_conv[kk * M + m] == 0) { itersDone = kk + 1; break; }
-                    if (maxTrials == 1) itersDone = 1;
-                    st.iters[m] = itersDone;
-                    st.tot_iters[m] += itersDone;
-                    st.tot_steps[m] += 1;
-                    if (st.not_conv[(itersDone - 1) * M + m]) st.non_conv[m] += 1;
-                }
-                // stats_updateConvergenceStats (dynwave.c:266-272): every node that missed the
-                // tolerance in a step that ended without convergence (outfalls count: their flag is
-                // never raised, dynwave.c:611)
-                // (node-level convergence counts: see the statistics phase below)
-                SWB_FOR_ITEMS(j, nL) {
-                    if (!(net.link_flags[j] & LF_TRUE_CONDUIT)) continue;
-                    size_t ix = SWB_IX(j, m, M);
-                    unsigned char lim = 0;
-                    if (st.c_a1[ix] >= net.xs_afull[j]) {
-                        int n1 = net.link_node1[j], n2 = net.link_node2[j];
-                        double h1 = st.n_depth[SWB_IX(n1, m, M)] + net.node_invert[n1];
-                        double h2 = st.n_depth[SWB_IX(n2, m, M)] + net.node_invert[n2];
-                        // Conduit.length is the user's length (dynwave.c:374), not the true length
-                        if ((h1 - h2) > fabs(net.cond_slope[j]) * net.cond_user_length[j]) lim = 1;
-                    }
-                    st.c_cap_limited[ix] = lim;
-                }
-            }
+            if (active) ph_epilogue(net, st, tm);
         }
 
         SWB_TICK(TP_EPILOGUE);
         // ================= qualrout_execute (qualrout.c:100-142) ===============================
         if (withQual && (args.phases & PH_QUALITY)) {
-            // pollutant-major loops keep the three mass-balance partial sums in registers
-            if (active)
-                for (int p = 0; p < nP; p++) {
-                    QualAcc acc = {0.0, 0.0, 0.0};
-                    SWB_FOR_ITEMS(i, nNo) qual_node(net, st, i, m, p, dt, acc);
-                    qual_acc_flush(ctx, st, p, m, M, dt, acc);
-                }
+            if (active) ph_qual_nodes(net, st, ctx, tm, dt, nNo);
             ctx.grid_sync();
             SWB_TICK(TP_QUAL_NODES);
             if (part) {                // a cut conduit mixes with its upstream node's new quality
@@ -672,179 +974,19 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                     [&](const unsigned long long *) {});
                 SWB_TICK(TP_HALO);
             }
-            if (active)
-                for (int p = 0; p < nP; p++) {
-                    QualAcc acc = {0.0, 0.0, 0.0}, copy = {0.0, 0.0, 0.0};
-                    // the copy of a cut conduit is routed too, but only its owner reports the losses
-                    SWB_FOR_ITEMS(j, nL) qual_link(net, st, j, m, p, dt, (part && !H.link_owned[j]) ? copy : acc);
-                    qual_acc_flush(ctx, st, p, m, M, dt, acc);
-                }
+            if (active) ph_qual_links(net, st, ctx, tm, dt);
         }
 
-        // ================= removeSystemOutflows (routing.c:776-806, 812-925) =====================
-        // Step rates of everything that enters or leaves the system, summed per member: external
-        // inflows (routing.c:466-489), outfall discharge and flooding (node.c:438-493), negative
-        // lateral flows, storage and conduit losses.  Per-thread partial sums, one atomic per term.
-        if ((args.phases & PH_MASSBAL) && active) {
-            auto flush = [&](int q, double v) {
-                if (M == 1) v = ctx.warp_sum_f64(v);
-                if (v != 0.0 && (M != 1 || ctx.warp_lane == 0)) ctx.atomic_add_f64(&st.mb_rate[(size_t)q * M + m], v);
-            };
-            // pass 0: the flow terms and pollutants 0-1; further passes: two more pollutants each
-            // (keeps the partial sums in registers)
-            for (int p0 = 0; p0 == 0 || (withQual && p0 < nP); p0 += 2) {
-                double fl[MB_FLOW_TERMS] = {0.0, 0.0, 0.0, 0.0, 0.0};
-                double ql[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
-                SWB_FOR_ITEMS(i, nNo) {
-                    const size_t ix = SWB_IX(i, m, M);
-                    const double lat = st.n_latflow[ix];
-                    const int type = net.node_type[i];
-                    double q = 0.0;                       // node_getSystemOutflow (node.c:438-493)
-                    bool flooded = false;
-                    if (type == SWB_OUTFALL) {            // (warp-uniform: a warp holds one node)
-                        const double inflow = st.n_inflow[ix], outflow = st.n_outflow[ix];
-                        if (outflow == 0.0) q = inflow;
-                        else if (inflow == 0.0) q = -outflow;
-                    } else {
-                        // q = overflow if newVolume <= fullVolume: the volume only matters when
-                        // there is an overflow at all, so junctions cost two loads here
-                        const double ov = st.n_overflow[ix];
-                        if (ov != 0.0 && st.n_volume[ix] <= net.node_full_volume[i]) q = ov;
-                        flooded = q > 0.0;
-                    }
-                    if (p0 == 0) {
-                        if (lat >= 0.0) fl[MB_EX_INFLOW] += lat; else fl[MB_OUTFLOW] -= lat;      // routing.c:466-469
-                        if (q > 0.0) { if (flooded) fl[MB_FLOODING] += q; else fl[MB_OUTFLOW] += q; }  // :904
-                        else fl[MB_EX_INFLOW] -= q;                                                // :911
-                        if (type == SWB_STORAGE) {                                                 // :812-836
-                            fl[MB_EVAP] += st.n_evap_loss[ix] / dt;
-                            fl[MB_SEEP] += st.n_exfil_loss[ix] / dt;
-                        }
-                    }
-                    if (withQual) {
-                        const int slot = (args.phases & PH_INFLOWS) ? args.inflows.node_slot[i] : -1;
-#pragma unroll
-                        for (int pp = 0; pp < 2; pp++) {
-                            const int p = p0 + pp;
-                            if (p >= nP) continue;
-                            const size_t iq = SWB_IXP(p, i, nN, m, M);
-                            if (slot >= 0 && lat >= 0.0) ql[pp][MBQ_EX_INFLOW] += args.inflows.concen[slot * nP + p] * lat;
-                            if ((args.phases & PH_HOSTIN) && args.host_qual) ql[pp][MBQ_EX_INFLOW] += args.host_qual[iq];
-                            if (q > 0.0 || lat < 0.0) {   // the concentration only where mass leaves
-                                const double c = st.n_qual[iq];
-                                if (q > 0.0) ql[pp][flooded ? MBQ_FLOODING : MBQ_OUTFLOW] += q * c;  // :906-908
-                                if (lat < 0.0) ql[pp][MBQ_OUTFLOW] += -lat * c;                      // :915-922
-                            }
-                        }
-                    }
-                }
-                if (p0 == 0 && net.anyLossRate)                    // removeConduitLosses (:840-867)
-                    SWB_FOR_ITEMS(j, nL) {
-                        if (!(net.link_flags[j] & LF_HAS_LOSSRATE) || (part && !H.link_owned[j])) continue;
-                        const size_t ix = SWB_IX(j, m, M);
-                        const double barrels = (double)net.cond_barrels[j];
-                        fl[MB_EVAP] += st.c_evap_loss[ix] * barrels;
-                        fl[MB_SEEP] += st.c_seep_loss[ix] * barrels;
-                    }
-                if (p0 == 0)
-#pragma unroll
-                    for (int q = 0; q < MB_FLOW_TERMS; q++) flush(q, fl[q]);
-                if (withQual)
-#pragma unroll
-                    for (int pp = 0; pp < 2; pp++)
-                        if (p0 + pp < nP)
-#pragma unroll
-                            for (int t = 0; t < 3; t++) flush(MB_FLOW_TERMS + (p0 + pp) * MB_QUAL_TERMS + t, ql[pp][t]);
-            }
-        }
-
-        // ================= statistics (routing.c:256-260, stats.c:449-754) ======================
-        if ((args.phases & PH_STATS) && st.stat_node && active) {
-            // new routing time of this step in elapsed seconds, formed like NewRoutingTime (ms)
-            const double tNew = (1000.0 * st.sim_time[m] + 1000.0 * dt) / 1000.0;
-            if (tNew >= st.stat_report_start) {
-                // this thread's copy of "iterations used" (the owner's write to st.iters is not
-                // ordered against other CTAs): the step ended unconverged iff its last trial did
-                int itersDone = maxTrials;
-                for (int kk = 1; kk < maxTrials; kk++)
-                    if (st.not_conv[kk * M + m] == 0) { itersDone = kk + 1; break; }
-                if (maxTrials == 1) itersDone = 1;
-                const bool stepFailed = (args.phases & PH_DYNWAVE) && st.not_conv[(itersDone - 1) * M + m] != 0;
-                SWB_FOR_ITEMS(i, nNo) {
-                    stats_node(net, st, i, m, dt, tNew, withQual);
-                    if (stepFailed && !st.n_converged[SWB_IX(i, m, M)]) nstat(st, net, SWB_NS_NONCONV_COUNT, i, m) += 1.0;
-                }
-                SWB_FOR_ITEMS(j, nL) {
-                    if (part && !H.link_owned[j]) continue;
-                    stats_link(net, st, j, m, dt, tNew, T);
-                }
-                if (owner) {
-                    double *sys = st.stat_sys;
-                    sys[SWB_SS_REPORT_STEPS * M + m] += 1.0;
-                    sys[SWB_SS_ROUTING_SPAN * M + m] += dt;
-                    // SysOutfallFlow: the outfalls' inflows summed in node order like stats.c:626 (the
-                    // node phase wrote them several grid barriers ago); MaxOutfallFlow = running maximum
-                    double sysOut = 0.0;
-                    for (int k = 0; k < net.nOutfallNodes; k++) {
-                        const int i = net.outfall_nodes[k];
-                        if (i < nNo) sysOut += st.n_inflow[SWB_IX(i, m, M)];
-                    }
-                    double &mx = sys[SWB_SS_MAX_OUTFALL_FLOW * M + m];
-                    mx = SWB_MAX(mx, sysOut);
-                }
-            }
-            if (owner) {                      // stats_updateTimeStepStats (stats.c:486-518), no steady state
-                double *sys = st.stat_sys;
-                if (st.sim_time[m] > 0.0) {   // OldRoutingTime > 0: the first step does not set the minimum
-                    double &mn = sys[SWB_SS_MIN_DT * M + m];
-                    mn = SWB_MIN(mn, dt);
-                }
-                double &mx = sys[SWB_SS_MAX_DT * M + m];
-                mx = SWB_MAX(mx, dt);
-                sys[SWB_SS_ROUTING_TIME * M + m] += dt;
-                sys[SWB_SS_STEP_COUNT * M + m] += 1.0;
-                sys[SWB_SS_TRIALS * M + m] += (double)st.iters[m];
-            }
-        }
+        if ((args.phases & PH_MASSBAL) && active) ph_outflows(net, st, args, ctx, tm, dt, withQual, nNo);
+        if ((args.phases & PH_STATS) && st.stat_node) ph_stats(net, st, args, tm, active, dt, withQual, nNo, T);
 
         SWB_TICK(TP_QUAL_LINKS);
         // ================= dynwave_getRoutingStep (dynwave.c:195-220, 799-921) =================
-        // Two-level arg-min with integer atomics only (deterministic): the minimum itself as the
-        // ordered bit image of the positive double, then the smallest object index among the
-        // objects that attain it ("first index wins", like the reference's strict `<` loops).
         if (args.phases & PH_NEXTDT) {
-            if (owner) {
-                unsigned long long t0 = dbits(args.fixed_step);
-                st.tmin_bits[m] = t0;                 // links: min(maxStep, link candidates)
-                st.tmin_bits[M + m] = t0;             // nodes
-                st.crit_link[m] = 0x7fffffff; st.crit_node[m] = 0x7fffffff;
-            }
+            if (owner) ph_nextdt_reset(st, args, m);
             ctx.grid_sync();
-            const bool variable = !(net.opt.courant_factor == 0.0 || args.fixed_step < SWB_MINTIMESTEP);
-            const bool search = active && variable && st.var_step[m] != 0.0;
-            double tl = args.fixed_step, tn = args.fixed_step;
-            int il = -1, in = -1;
-            if (search) {
-                SWB_FOR_ITEMS(j, nL) {
-                    double t = link_step(net, st, j, m);
-                    if (t >= 0.0 && t < tl) { tl = t; il = j; }
-                }
-                SWB_FOR_ITEMS(i, nNo) {
-                    double t = node_step(net, st, i, m);
-                    if (t >= 0.0 && t < tn) { tn = t; in = i; }
-                }
-                unsigned long long bl = dbits(tl), bn = dbits(tn);
-                if (M == 1) {          // all lanes share the member: shuffle-reduce, one atomic per warp
-                    bl = ctx.warp_min_u64(bl); bn = ctx.warp_min_u64(bn);
-                    if (ctx.warp_lane == 0) {
-                        if (bl < dbits(args.fixed_step)) ctx.atomic_min_u64(&st.tmin_bits[m], bl);
-                        if (bn < dbits(args.fixed_step)) ctx.atomic_min_u64(&st.tmin_bits[M + m], bn);
-                    }
-                } else {
-                    if (il >= 0) ctx.atomic_min_u64(&st.tmin_bits[m], bl);
-                    if (in >= 0) ctx.atomic_min_u64(&st.tmin_bits[M + m], bn);
-                }
-            }
+            const bool search = active && nextdt_variable(net, args) && st.var_step[m] != 0.0;
+            const DtCand cand = ph_nextdt_search(net, st, args, ctx, tm, search, nNo);
             ctx.grid_sync();
             if (part) {                // MIN over the ranks (ordered bit images, like the atomics above)
                 unsigned long long rin[HALO_RED] = { st.tmin_bits[0], st.tmin_bits[M], 0ull, 0ull };
@@ -859,44 +1001,11 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                         st.tmin_bits[0] = a; st.tmin_bits[M] = b; });
                 SWB_TICK(TP_HALO);
             }
-            if (search) {
-                if (il >= 0 && dbits(tl) == st.tmin_bits[m]) ctx.atomic_min_i32(&st.crit_link[m], il);
-                if (in >= 0 && dbits(tn) == st.tmin_bits[M + m]) ctx.atomic_min_i32(&st.crit_node[m], in);
-            }
+            if (search) ph_nextdt_arg(st, ctx, m, cand);
             ctx.grid_sync();
-            if (owner && active) {
-                if (!variable) st.var_step[m] = args.fixed_step;
-                else {
-                    double vs;
-                    int cl = st.crit_link[m], cn = st.crit_node[m];
-                    if (cl == 0x7fffffff) cl = -1;
-                    if (cn == 0x7fffffff) cn = -1;
-                    if (st.var_step[m] == 0.0) { vs = net.opt.min_route_step; cl = cn = -1; }
-                    else {
-                        // getVariableStep (dynwave.c:813-831): a node wins only when strictly below
-                        // the link step, and then the link is dropped
-                        double tLink = dfrombits(st.tmin_bits[m]), tNode = dfrombits(st.tmin_bits[M + m]);
-                        vs = tLink;
-                        // (partitioned: the critical node may live on another rank; a node
-                        // candidate exists iff the reduced node minimum is below the fixed step)
-                        const bool haveNode = cn >= 0 || (part && st.tmin_bits[M + m] < dbits(args.fixed_step));
-                        if (haveNode && tNode < tLink) { vs = tNode; cl = -1; } else cn = -1;
-                        if (vs < net.opt.min_route_step) vs = net.opt.min_route_step;
-                    }
-                    st.crit_link[m] = cl; st.crit_node[m] = cn;
-                    st.var_step[m] = floor(1000.0 * vs) / 1000.0;
-                    // stats_updateCriticalTimeCount (stats.c:522-533; called from getVariableStep)
-                    if (st.stat_node && (args.phases & PH_STATS)) {
-                        if (cn >= 0) nstat(st, net, SWB_NS_TIME_COURANT, cn, m) += 1.0;
-                        else if (cl >= 0) lstat(st, net, SWB_LS_TIME_COURANT, cl, m) += 1.0;
-                    }
-                }
-            }
+            if (owner && active) ph_nextdt_final(net, st, args, m);
         }
-        if ((args.phases & PH_ADVANCE) && owner && active) {
-            // NewRoutingTime += 1000 * routingStep (routing.c:301-302), kept in ms
-            st.sim_time[m] = (1000.0 * st.sim_time[m] + 1000.0 * dt) / 1000.0;
-        }
+        if ((args.phases & PH_ADVANCE) && owner && active) ph_advance_time(st, m, dt);
         if (step + 1 < args.n_steps) ctx.grid_sync();
         SWB_TICK(TP_NEXTDT);
     }

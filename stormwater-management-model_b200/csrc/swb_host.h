@@ -160,6 +160,8 @@ inline void fill_net_scalars(Net &n, const swb_network_desc &d, const swb_option
     n.nShapeTbl = d.n_shape_tbls; n.shapeTblLen = d.shape_tbl_len;
     n.nTrue = r.nTrue; n.nNonConduit = r.nNonConduit; n.nOutfallLinks = 0;
     n.nOutfallNodes = (int)r.outfall_nodes.size();
+    n.lk_count[0] = n.lk_count[1] = n.lk_count[2] = 0;
+    for (int j : r.link_order) n.lk_count[r.link_kernel[j]]++;
     n.anyLossRate = 0;
     for (int f : r.link_flags) if (f & LF_HAS_LOSSRATE) n.anyLossRate = 1;
     n.opt = o;

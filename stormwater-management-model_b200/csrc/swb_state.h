@@ -71,6 +71,7 @@ struct alignas(16) AdjEntry {
 struct Net {
     int nN, nL, nP, nCurves, nShapeTbl, shapeTblLen;
     int nTrue;               // true conduits
+    int lk_count[3];         // of which per conduit-function class LK_* (link_order is grouped by class)
     int nNonConduit;         // links handled by the ordered regulator pass
     int nOutfallLinks;
     int anyLossRate;         // some conduit can evaporate / seep (LF_HAS_LOSSRATE)
@@ -143,9 +144,14 @@ struct Net {
 
 enum { MB_EX_INFLOW = 0, MB_FLOODING, MB_OUTFLOW, MB_EVAP, MB_SEEP, MB_FLOW_TERMS,
        MBQ_EX_INFLOW = 0, MBQ_FLOODING, MBQ_OUTFLOW, MBQ_REACTED, MBQ_SEEP, MBQ_FINAL, MB_QUAL_TERMS };
+enum { CTL_ANY_LEFT = 0,       // some member has not reached t_end: the step runs
+       CTL_N_ALIVE,            // entries of State::alive for the trial about to run
+       CTL_MARK_LO, CTL_MARK_HI,   // globaltimer at the start of the running phase (phase timers)
+       SWB_CTL_WORDS = 8 };
 enum { TP_PROLOGUE = 0, TP_LINKS, TP_REGULATORS, TP_NODES, TP_CONTROL, TP_EPILOGUE, TP_QUAL_NODES,
        TP_QUAL_LINKS, TP_NEXTDT, TP_HALO, TP_HALO_WAIT, SWB_N_PHASES = 12 };
-#define SWB_MAX_TRIALS_CAP 32     // alive / notConv bookkeeping rows (MaxTrials is 8 by default)
+#define SWB_MAX_TRIALS_CAP 32     // notConv bookkeeping rows (MaxTrials is 8 by default)
+#define SWB_TICKETS_PER_TRIAL 8    // ticket counters per Picard trial (swb_engine.h: TK_*)
 
 // One network partitioned over several GPUs (include/swmm_b200.h: swb_partition_desc).  Every rank
 // owns a receive WINDOW in its own memory that the peers write into directly (peer memory over
@@ -227,7 +233,11 @@ struct State {
     long long *tot_iters, *tot_steps, *non_conv;
     int    *crit_node, *crit_link;
     unsigned long long *tmin_bits;  // Courant search scratch (ordered bits of a positive double)
-    int    *alive;               // [SWB_MAX_TRIALS_CAP + 1][M] member still iterating at trial k
+    int    *alive;               // [M] staged kernels: ordered list of the members that iterate in the current trial
+    int    *ctl;                 // [SWB_CTL_WORDS] staged kernels: CTL_* words written by the control kernels
+    double *dt_cand;             // [4][threads] staged kernels: every thread's Courant candidates between the
+                                 // search and the arg-min kernels (DtCand as four planes)
+    int     dt_cand_stride;      // threads the planes were sized for
     int    *not_conv;            // [SWB_MAX_TRIALS_CAP][M] some node failed the head tolerance
     int    *done;                // member has reached t_end
     // mass-balance accumulators per member x pollutant (massbal.c:517-555)
@@ -246,7 +256,7 @@ struct State {
     double stat_report_start;        // statistics start at this elapsed simulated time (s)
     // device-side phase timers (ns, accumulated by thread 0 between grid barriers)
     unsigned long long *phase_ns;    // [SWB_N_PHASES]
-    unsigned long long *tickets;     // [3 * SWB_MAX_TRIALS_CAP] work-distribution counters of one step
+    unsigned long long *tickets;     // [SWB_TICKETS_PER_TRIAL * SWB_MAX_TRIALS_CAP] work-distribution counters of one step
 };
 
 // pollutant-plane index: field[(p * nItems + item) * M + m]

@@ -52,6 +52,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_get_routing_totals.argtypes = [C.c_void_p, C.c_int, C.c_int, _P_D, _P_D]
     lib.swb_conduit_updates.argtypes = [C.c_void_p]
     lib.swb_conduit_updates.restype = C.c_longlong
+    lib.swb_set_staged_min_members.argtypes = [C.c_int]
+    lib.swb_set_staged_min_members.restype = C.c_int
     lib.swb_launch_count.argtypes = [C.c_void_p]
     lib.swb_launch_count.restype = C.c_longlong
     lib.swb_last_kernel_ms.argtypes = [C.c_void_p]
@@ -360,6 +362,11 @@ class Solver:
 
     def conduit_updates(self) -> int:
         return int(self.lib.swb_conduit_updates(self._h))
+
+    def set_staged_min_members(self, n: int) -> int:
+        """Process-wide switch between the staged kernel chain (ensembles of >= n members) and the
+        persistent kernel (swb_set_staged_min_members); returns the previous value."""
+        return int(self.lib.swb_set_staged_min_members(int(n)))
 
     def launch_count(self) -> int:
         return int(self.lib.swb_launch_count(self._h))

@@ -165,8 +165,12 @@ struct EmulCtx {
     }
 };
 
-static bool launch(const Net &net, const State &st, const RunArgs &args, int, float *ms, std::string &, bool = true)
+static int staged_max_threads(int) { return 0; }
+static int set_staged_min_members(int) { return 0; }    // the staged kernels are CUDA only
+static bool launch(const Net &net, const State &st, const RunArgs &args, int, float *ms, std::string &, bool = true,
+                   int *n_kernels = nullptr)
 {
+    if (n_kernels) *n_kernels = 1;
     const int M = st.M;
     int k = 1;
     if (M < 4) k = 4 / M;

@@ -296,9 +296,83 @@ typedef struct swb_inflow_desc {
     const double *member_shift;     /* [n_members], days (NULL = 0)                          */
     double start_day;               /* floor(StartDateTime)                                  */
     double start_secs;              /* seconds of day of StartDateTime                       */
+    /* ---- everything below is optional (NULL / 0 = absent): baseline patterns, time-varying CONCEN /
+     * MASS pollutant inflows and dry-weather flow, evaluated on the device every step exactly like
+     * inflow_getExtInflow / inflow_getDwfInflow / getPatternFactor (inflow.c:207-234, 361-392, 456-486)
+     * and accumulated in the order of addExternalInflows / addDryWeatherInflows (routing.c:435-575).
+     * Member scale and shift act on the FLOW time series only. */
+    const double *cfactor;          /* per inflow node: TExtInflow.cFactor (NULL = 1)        */
+    const int    *base_pattern;     /* per inflow node: baseline pattern index or -1         */
+    int n_patterns;
+    const int    *pattern_type;     /* MONTHLY 0, DAILY 1, HOURLY 2, WEEKEND 3 (enums.h)     */
+    const double *pattern_factor;   /* [n_patterns][24]                                      */
+    int n_qual_inflows;             /* pollutant inflow records; when > 0 `concen` is ignored */
+    const int    *q_node, *q_pollut;
+    const int    *q_type;           /* 1 CONCEN_INFLOW, 2 MASS_INFLOW (enums.h)              */
+    const int    *q_series;         /* index into the series table below or -1               */
+    const int    *q_pattern;        /* baseline pattern or -1                                */
+    const double *q_cfactor, *q_sfactor, *q_baseline;
+    int n_series;                   /* time series used by the pollutant inflows             */
+    const int    *series_start;     /* n_series+1, CSR into series_t / series_v              */
+    const double *series_t, *series_v;
+    int n_dwf;                      /* dry-weather inflow records, a node's records in the   */
+    const int    *dwf_node;         /*   order of its TDwfInflow list                        */
+    const int    *dwf_param;        /* -1 flow, else pollutant index                         */
+    const double *dwf_avg;          /* avgValue, internal units                              */
+    const int    *dwf_patterns;     /* [n_dwf][4] pattern index per pattern type or -1       */
+    const double *pollut_dwf_concen;/* [n_pollut] Pollut.dwfConcen (NULL = 0)                */
 } swb_inflow_desc;
 
 int  swb_set_inflows(swb_solver *s, const swb_inflow_desc *inflows);
+
+/* ---- control rules and target settings on the device ------------------------------
+ * The part of evaluateControlRules (routing.c:269-308) an ensemble member needs every step:
+ * link_setTargetSetting (pump start-up / shut-off depths, link.c:604-624), controls_evaluate for rules
+ * whose premises test node / link / simulation-time variables against numbers or other variables and
+ * whose actions set a status / setting to a number, a curve of the control value, a time series or a PID
+ * output (controls.c:495-552, 1086-1164, 1243-1450), then link_setSetting with orifice opening rates and
+ * the weir's surcharge coefficient (link.c:626-639, 1729-1762, 2166-2190).  One thread per member walks
+ * the rules in order; priorities resolve conflicts like updateActionList (controls.c:1168-1202).
+ * RuleStep > 0 also shortens the routing step to land on rule times (routing.c:190-199).  The same pass sets
+ * the stage of TIDAL / TIMESERIES outfalls for the step.
+ * Not supported (rejected by the flattener): named variables / math expressions and rain-gage premises.
+ * Object / attribute / relation codes are the reference's own (controls.c:45-76). */
+enum { SWB_RULE_OBJ_SIM = -1, SWB_RULE_OBJ_GAGE = 0, SWB_RULE_OBJ_NODE = 1, SWB_RULE_OBJ_LINK = 2 };   /* TVariable.object as getPremiseVariable
+     * stores it (controls.c:680-790): r_GAGE, r_NODE, r_LINK for every link type, -1 for SIMULATION variables */
+typedef struct swb_controls_desc {
+    int n_rules, n_premises, n_actions;
+    double rule_step;               /* RuleStep, s (0 = rules are evaluated every routing step)          */
+    const double *rule_priority;    /* per rule                                                          */
+    const int    *rule_premise_start;   /* n_rules+1, CSR into the premise arrays                        */
+    const int    *rule_then_start, *rule_else_start;  /* n_rules+1 each, CSR into act_then / act_else    */
+    const int    *act_then, *act_else;  /* action indices, list order                                    */
+    const int    *prem_type;        /* r_AND 2 (also for IF), r_OR 3 (RuleState, controls.c:65)          */
+    const int    *prem_lhs_obj, *prem_lhs_index, *prem_lhs_attr;
+    const int    *prem_rhs_is_var, *prem_rhs_obj, *prem_rhs_index, *prem_rhs_attr;
+    const int    *prem_relation;    /* EQ NE LT LE GT GE = 0..5                                          */
+    const double *prem_value;
+    const int    *act_rule, *act_link, *act_attr, *act_curve, *act_tseries;
+    const double *act_value, *act_kp, *act_ki, *act_kd;
+    /* time series used by actions: CSR like the inflow series */
+    int n_series;
+    const int    *series_start;
+    const double *series_t, *series_v;
+    /* per link (n_links entries each) */
+    const double *pump_y_on, *pump_y_off;   /* Pump.yOn / yOff, ft (0 = none)                            */
+    const double *orif_orate;               /* Orifice.orate, s (0 = instantaneous)                      */
+    const double *link_time_last_set;       /* Link.timeLastSet at the start (DateTime, days)            */
+    /* clock */
+    double start_datetime;                  /* StartDateTime (DateTime, days)                            */
+    double start_day, start_secs;           /* floor(StartDateTime), seconds of day (as swb_inflow_desc) */
+    /* outfalls whose stage varies in time (node.c:1437-1458): evaluated per member at the start of a step */
+    int n_stage_nodes;
+    const int    *stage_node;               /* node index                                                */
+    const int    *stage_kind;               /* 1 TIDAL_OUTFALL (curve by hour of day), 2 TIMESERIES_OUTFALL */
+    const int    *stage_table;              /* kind 1: curve index of the network; kind 2: series index above */
+} swb_controls_desc;
+/* Installs the rules (a second call replaces them); swb_run_steps then evaluates them at the start of every
+ * routing step of every member.  Host-fed steps (swb_step_host) keep taking settings from the host. */
+int  swb_set_controls(swb_solver *s, const swb_controls_desc *controls);
 /* Advance every member n_steps routing steps entirely on the device (one cooperative launch):
  * dt from the Courant search, inflows from swb_set_inflows, dynamic wave + quality routing.
  * t_end: members stop stepping once their sim_time reaches it (last step shortened like

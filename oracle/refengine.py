@@ -70,6 +70,8 @@ class RefEngine:
         H.refhook_new_routing_time.restype = C.c_double
         H.refhook_inflows.restype = C.POINTER(self.abi.InflowDesc)
         H.refhook_total_duration.restype = C.c_double
+        H.refhook_inflows_full.restype = C.POINTER(self.abi.InflowDesc)
+        H.refhook_controls.restype = C.POINTER(self.abi.ControlsDesc)
         H.refhook_xsect_eval.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int,
                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]
         H.refhook_xsect_set.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double,
@@ -151,6 +153,19 @@ class RefEngine:
                     sfactor=arr(d.sfactor, n, np.float64), baseline=arr(d.baseline, n, np.float64),
                     concen=arr(d.concen, n * nP, np.float64) if nP else None,
                     start_day=d.start_day, start_secs=d.start_secs)
+
+    def inflows_desc(self):
+        """swb_inflow_desc of the open model from the shipped flattener (patterns, pollutant records, DWF):
+        a ctypes struct whose arrays live in the hook library until the next call."""
+        p = self.hook.refhook_inflows_full()
+        assert p, "swb_flatten_inflows failed"
+        return p.contents
+
+    def controls_desc(self):
+        """swb_controls_desc of the open model (rules, pump depths, orifice rates, timed outfall stages)."""
+        p = self.hook.refhook_controls()
+        assert p, "swb_flatten_controls: unsupported rule (named variable, expression or rain gage)"
+        return p.contents
 
     def results(self, f: float, n_nodes: int, n_links: int, n_pollut: int):
         """The engine's own report records: node_getResults (node.c:497) / link_getResults

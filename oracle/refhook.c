@@ -126,6 +126,25 @@ const swb_inflow_desc *refhook_inflows(void)
 }
 double refhook_total_duration(void) { return TotalDuration; }
 
+/* ---- the shipped flatteners (seam/flatten.c) for everything swb_run_steps evaluates on the device:
+ * external / dry-weather inflows with patterns and pollutant records, control rules, pump depths,
+ * timed outfall stages */
+static swb_flat g_flat_inf, g_flat_ctl;
+static swb_inflow_desc g_inf_full;
+static swb_controls_desc g_ctl;
+const swb_inflow_desc *refhook_inflows_full(void)
+{
+    swb_flat_free(&g_flat_inf);
+    if (swb_flatten_inflows(&g_flat_inf, &g_inf_full) != 0) return NULL;
+    return &g_inf_full;
+}
+const swb_controls_desc *refhook_controls(void)
+{
+    swb_flat_free(&g_flat_ctl);
+    if (swb_flatten_controls(&g_flat_ctl, &g_ctl) != 0) return NULL;
+    return &g_ctl;
+}
+
 /* ---- statistics of the live engine in the plane order of include/swmm_b200.h (swb_node_stat /
  * swb_link_stat): NodeStats / StorageStats / OutfallStats / LinkStats / PumpStats (stats.c:63-68).
  * Dates become elapsed seconds since StartDateTime. */

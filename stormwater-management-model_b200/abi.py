@@ -92,6 +92,10 @@ class InflowDesc(C.Structure):
     _fields_ = [(n, t) for (n, t, _, _) in _INFLOW_FIELDS]
 
 
+class ControlsDesc(C.Structure):
+    _fields_ = [(n, t) for (n, t, _, _) in _parse_struct(_TEXT, "swb_controls_desc")]
+
+
 class StepIO(C.Structure):
     _fields_ = [(n, t) for (n, t, _, _) in _STEPIO_FIELDS]
 

@@ -46,6 +46,8 @@ struct swb_solver {
     std::vector<void *> inflow_allocs;      // device arrays of the current swb_set_inflows call
     Inflows inflows;
     bool have_inflows;
+    std::vector<void *> control_allocs;     // device arrays of the current swb_set_controls call
+    Controls controls;
     long long launches;
     float last_ms;
     std::vector<double> h_dt;
@@ -188,6 +190,7 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     s->window = nullptr; s->window_bytes = 0;
     memset(s->peer_window, 0, sizeof(s->peer_window));
     memset(&s->inflows, 0, sizeof(s->inflows));
+    memset(&s->controls, 0, sizeof(s->controls));
     State &st = s->st;
     memset(&st, 0, sizeof(st));
     st.M = M;
@@ -201,6 +204,7 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     st.dt = dev_zero<double>(s->allocs, M);
     st.var_step = dev_zero<double>(s->allocs, M);
     st.sim_time = dev_zero<double>(s->allocs, M);
+    st.time_ms = dev_zero<double>(s->allocs, M);
     std::vector<double> ev(M, nw->net.opt.evap_rate), hc(M, nw->net.opt.hydcon_factor);
     st.evap_rate = dev_copy<double>(s->allocs, ev.data(), M);
     st.hydcon = dev_copy<double>(s->allocs, hc.data(), M);
@@ -245,6 +249,7 @@ void swb_solver_destroy(swb_solver *s)
     if (!s) return;
     for (void *p : s->allocs) backend::free_(p);
     for (void *p : s->inflow_allocs) backend::free_(p);
+    for (void *p : s->control_allocs) backend::free_(p);
     if (s->stream) backend::stream_destroy(s->stream);
     for (int p = 0; p < SWB_MAX_RANKS; p++) if (s->peer_window[p]) backend::window_close(s->peer_window[p]);
     if (s->window) backend::window_free(s->window, s->window_bytes, s->window_handle);
@@ -350,6 +355,7 @@ static int run(swb_solver *s, int phases, int n_steps, double t_end, double fixe
     a.host_lat = host_lat; a.host_losses = host_losses; a.host_qual = host_qual;
     a.phases = phases; a.n_steps = n_steps; a.t_end = t_end; a.fixed_step = fixed_step;
     a.inflows = s->inflows;
+    if (phases & PH_ADVANCE) a.controls = s->controls;      // (zeroed otherwise: inactive)
     std::string err;
     float ms = 0.f;
     if (s->st.halo.nRanks > 1) {
@@ -514,6 +520,20 @@ int swb_set_inflows(swb_solver *s, const swb_inflow_desc *d)
         if (d->node[k] < 0 || d->node[k] >= nN) return fail(SWB_ERR_ARG, "inflow node out of range");
         slot[d->node[k]] = k;
     }
+    auto pat_ok = [&](int p) { return p < d->n_patterns; };
+    for (int k = 0; k < n && d->base_pattern; k++)
+        if (!pat_ok(d->base_pattern[k])) return fail(SWB_ERR_ARG, "baseline pattern out of range");
+    for (int r = 0; r < d->n_qual_inflows; r++) {
+        if (d->q_node[r] < 0 || d->q_node[r] >= nN || d->q_pollut[r] < 0 || d->q_pollut[r] >= nP)
+            return fail(SWB_ERR_ARG, "pollutant inflow record out of range");
+        if (d->q_series[r] >= d->n_series || !pat_ok(d->q_pattern[r])) return fail(SWB_ERR_ARG, "pollutant inflow series / pattern out of range");
+    }
+    for (int r = 0; r < d->n_dwf; r++) {
+        if (d->dwf_node[r] < 0 || d->dwf_node[r] >= nN || d->dwf_param[r] >= nP) return fail(SWB_ERR_ARG, "dry-weather record out of range");
+        for (int q = 0; q < 4; q++) if (!pat_ok(d->dwf_patterns[(size_t)r * 4 + q])) return fail(SWB_ERR_ARG, "dry-weather pattern out of range");
+    }
+    for (int p = 0; p < d->n_patterns; p++)
+        if (d->pattern_type[p] < 0 || d->pattern_type[p] > 3) return fail(SWB_ERR_ARG, "pattern type out of range");
     SWB_ENTER(s);
     // a second call replaces the first: its device arrays are released, not leaked
     for (void *q : s->inflow_allocs) backend::free_(q);
@@ -535,6 +555,63 @@ int swb_set_inflows(swb_solver *s, const swb_inflow_desc *d)
         f.member_scale = dev_copy<double>(al, d->member_scale ? d->member_scale : one.data(), s->M);
         f.member_shift = dev_copy<double>(al, d->member_shift ? d->member_shift : zero.data(), s->M);
         f.node_slot = dev_copy<int>(al, slot.data(), nN);
+        // ---- optional parts: patterns, pollutant inflow records, dry-weather flow
+        f.general = 0;
+        f.cfactor = nullptr; f.base_pattern = nullptr; f.nPatterns = 0; f.pat_type = nullptr; f.pat_factor = nullptr;
+        f.node_q_start = nullptr; f.node_dwf_start = nullptr; f.pollut_dwf_concen = nullptr;
+        if (d->cfactor) { f.cfactor = dev_copy<double>(al, d->cfactor, n); f.general = 1; }
+        if (d->n_patterns > 0) {
+            f.nPatterns = d->n_patterns;
+            f.pat_type = dev_copy<int>(al, d->pattern_type, d->n_patterns);
+            f.pat_factor = dev_copy<double>(al, d->pattern_factor, (size_t)d->n_patterns * 24);
+        }
+        if (d->base_pattern) { f.base_pattern = dev_copy<int>(al, d->base_pattern, n); f.general = 1; }
+        if (d->n_qual_inflows > 0) {
+            // records grouped by node, a node's records in the order given (= the reference's list order)
+            const int nq = d->n_qual_inflows;
+            std::vector<int> start(nN + 1, 0), order(nq);
+            for (int r = 0; r < nq; r++) start[d->q_node[r] + 1]++;
+            for (int i = 0; i < nN; i++) start[i + 1] += start[i];
+            { std::vector<int> fill(start.begin(), start.end() - 1);
+              for (int r = 0; r < nq; r++) order[fill[d->q_node[r]]++] = r; }
+            auto gi = [&](const int *src) { std::vector<int> v(nq); for (int r = 0; r < nq; r++) v[r] = src[order[r]]; return v; };
+            auto gd = [&](const double *src) { std::vector<double> v(nq); for (int r = 0; r < nq; r++) v[r] = src[order[r]]; return v; };
+            f.node_q_start = dev_copy<int>(al, start.data(), nN + 1);
+            f.q_pollut = dev_copy<int>(al, gi(d->q_pollut).data(), nq);
+            f.q_type = dev_copy<int>(al, gi(d->q_type).data(), nq);
+            f.q_series = dev_copy<int>(al, gi(d->q_series).data(), nq);
+            f.q_pattern = dev_copy<int>(al, gi(d->q_pattern).data(), nq);
+            f.q_cfactor = dev_copy<double>(al, gd(d->q_cfactor).data(), nq);
+            f.q_sfactor = dev_copy<double>(al, gd(d->q_sfactor).data(), nq);
+            f.q_baseline = dev_copy<double>(al, gd(d->q_baseline).data(), nq);
+            const int ns = d->n_series;
+            std::vector<int> s0(1, 0);
+            f.series_start = dev_copy<int>(al, ns > 0 ? d->series_start : s0.data(), (ns > 0 ? ns : 0) + 1);
+            const int npts = ns > 0 ? d->series_start[ns] : 0;
+            f.series_t = dev_copy<double>(al, d->series_t, npts);
+            f.series_v = dev_copy<double>(al, d->series_v, npts);
+            f.general = 1;
+        }
+        if (d->n_dwf > 0) {
+            const int nd = d->n_dwf;
+            std::vector<int> start(nN + 1, 0), order(nd);
+            for (int r = 0; r < nd; r++) start[d->dwf_node[r] + 1]++;
+            for (int i = 0; i < nN; i++) start[i + 1] += start[i];
+            { std::vector<int> fill(start.begin(), start.end() - 1);
+              for (int r = 0; r < nd; r++) order[fill[d->dwf_node[r]]++] = r; }
+            std::vector<int> param(nd), pats((size_t)nd * 4);
+            std::vector<double> avg(nd);
+            for (int r = 0; r < nd; r++) {
+                param[r] = d->dwf_param[order[r]]; avg[r] = d->dwf_avg[order[r]];
+                for (int q = 0; q < 4; q++) pats[(size_t)r * 4 + q] = d->dwf_patterns[(size_t)order[r] * 4 + q];
+            }
+            f.node_dwf_start = dev_copy<int>(al, start.data(), nN + 1);
+            f.dwf_param = dev_copy<int>(al, param.data(), nd);
+            f.dwf_avg = dev_copy<double>(al, avg.data(), nd);
+            f.dwf_patterns = dev_copy<int>(al, pats.data(), (size_t)nd * 4);
+            if (d->pollut_dwf_concen && nP > 0) f.pollut_dwf_concen = dev_copy<double>(al, d->pollut_dwf_concen, nP);
+            f.general = 1;
+        }
     } catch (const DeviceError &e) {
         for (void *q : s->inflow_allocs) backend::free_(q);
         s->inflow_allocs.clear();
@@ -542,6 +619,134 @@ int swb_set_inflows(swb_solver *s, const swb_inflow_desc *d)
         return fail(SWB_ERR_CUDA, e.what);
     }
     s->have_inflows = true;
+    return SWB_OK;
+}
+
+// Control rules, pump start-up / shut-off depths and timed outfall stages for swb_run_steps.
+int swb_set_controls(swb_solver *s, const swb_controls_desc *d)
+{
+    if (!s || !d) return fail(SWB_ERR_ARG, "null argument");
+    const Net &n = s->net->net;
+    const int nL = n.nL, nN = n.nN, M = s->M;
+    const int nR = d->n_rules, nPr = d->n_premises, nA = d->n_actions;
+    if (nR < 0 || nPr < 0 || nA < 0 || d->n_series < 0 || d->n_stage_nodes < 0) return fail(SWB_ERR_ARG, "negative count");
+    if (!d->pump_y_on || !d->pump_y_off || !d->orif_orate) return fail(SWB_ERR_ARG, "per-link arrays missing");
+    if (s->st.halo.nRanks > 1) return fail(SWB_ERR_UNSUPP, "control rules on a partitioned network");
+    std::vector<int> ltype(nL);
+    backend::download(ltype.data(), n.link_type, sizeof(int) * nL);
+    for (int r = 0; r < nR; r++) {
+        if (d->rule_premise_start[r] > d->rule_premise_start[r + 1] || d->rule_then_start[r] > d->rule_then_start[r + 1] ||
+            d->rule_else_start[r] > d->rule_else_start[r + 1]) return fail(SWB_ERR_ARG, "rule CSR arrays not ascending");
+    }
+    if (nR > 0 && (d->rule_premise_start[nR] != nPr || d->rule_then_start[nR] + d->rule_else_start[nR] != nA))
+        return fail(SWB_ERR_ARG, "rule CSR arrays do not cover the premises / actions");
+    auto var_ok = [&](int obj, int idx, int attr) -> int {
+        if (obj == RO_GAGE) return SWB_ERR_UNSUPP;
+        if (obj != RO_NODE && obj != RO_LINK && obj != RO_SIM && obj != -1) return SWB_ERR_ARG;
+        if (obj == RO_NODE && (idx < 0 || idx >= nN)) return SWB_ERR_ARG;
+        if (obj == RO_LINK && (idx < 0 || idx >= nL)) return SWB_ERR_ARG;
+        if (attr < 0 || attr > RA_MONTH) return SWB_ERR_ARG;
+        return SWB_OK;
+    };
+    for (int p = 0; p < nPr; p++) {
+        int rc = var_ok(d->prem_lhs_obj[p], d->prem_lhs_index[p], d->prem_lhs_attr[p]);
+        if (!rc && d->prem_rhs_is_var[p]) rc = var_ok(d->prem_rhs_obj[p], d->prem_rhs_index[p], d->prem_rhs_attr[p]);
+        if (rc == SWB_ERR_UNSUPP) return fail(rc, "rain-gage premises are not supported on the device");
+        if (rc) return fail(rc, "premise variable out of range");
+        if (d->prem_relation[p] < 0 || d->prem_relation[p] > 5) return fail(SWB_ERR_ARG, "premise relation out of range");
+    }
+    for (int a = 0; a < nA; a++) {
+        if (d->act_link[a] < 0 || d->act_link[a] >= nL) return fail(SWB_ERR_ARG, "action link out of range");
+        if (d->act_rule[a] < 0 || d->act_rule[a] >= nR) return fail(SWB_ERR_ARG, "action rule out of range");
+        if (d->act_curve[a] >= n.nCurves) return fail(SWB_ERR_ARG, "action curve out of range");
+        if (d->act_tseries[a] >= d->n_series) return fail(SWB_ERR_ARG, "action time series out of range");
+    }
+    for (int k = 0; k < d->n_stage_nodes; k++) {
+        if (d->stage_node[k] < 0 || d->stage_node[k] >= nN) return fail(SWB_ERR_ARG, "stage node out of range");
+        const int kind = d->stage_kind[k], t = d->stage_table[k];
+        if (!((kind == 1 && t >= 0 && t < n.nCurves) || (kind == 2 && t >= 0 && t < d->n_series)))
+            return fail(SWB_ERR_ARG, "stage curve / series out of range");
+    }
+    // the watch list: links whose setting can change during the run
+    std::vector<int> link_watch(nL, -1), watch;
+    {
+        std::vector<char> mark(nL, 0);
+        for (int j = 0; j < nL; j++) if (ltype[j] == SWB_PUMP) mark[j] = 1;
+        for (int a = 0; a < nA; a++) mark[d->act_link[a]] = 1;
+        for (int j = 0; j < nL; j++) if (mark[j]) { link_watch[j] = (int)watch.size(); watch.push_back(j); }
+    }
+    const int nW = (int)watch.size();
+    SWB_ENTER(s);
+    for (void *q : s->control_allocs) backend::free_(q);
+    s->control_allocs.clear();
+    Controls &c = s->controls;
+    memset(&c, 0, sizeof(c));
+    try {
+        std::vector<void *> &al = s->control_allocs;
+        c.nRules = nR; c.nAct = nA; c.nWatch = nW; c.nStage = d->n_stage_nodes;
+        c.rule_step = d->rule_step; c.start_datetime = d->start_datetime;
+        c.start_day = d->start_day; c.start_secs = d->start_secs;
+        c.rule_priority = dev_copy<double>(al, d->rule_priority, nR);
+        c.rule_prem_start = dev_copy<int>(al, d->rule_premise_start, nR + 1);
+        c.rule_then_start = dev_copy<int>(al, d->rule_then_start, nR + 1);
+        c.rule_else_start = dev_copy<int>(al, d->rule_else_start, nR + 1);
+        c.act_then = dev_copy<int>(al, d->act_then, nR > 0 ? d->rule_then_start[nR] : 0);
+        c.act_else = dev_copy<int>(al, d->act_else, nR > 0 ? d->rule_else_start[nR] : 0);
+        c.prem_type = dev_copy<int>(al, d->prem_type, nPr);
+        c.prem_lhs_obj = dev_copy<int>(al, d->prem_lhs_obj, nPr);
+        c.prem_lhs_index = dev_copy<int>(al, d->prem_lhs_index, nPr);
+        c.prem_lhs_attr = dev_copy<int>(al, d->prem_lhs_attr, nPr);
+        c.prem_rhs_is_var = dev_copy<int>(al, d->prem_rhs_is_var, nPr);
+        c.prem_rhs_obj = dev_copy<int>(al, d->prem_rhs_obj, nPr);
+        c.prem_rhs_index = dev_copy<int>(al, d->prem_rhs_index, nPr);
+        c.prem_rhs_attr = dev_copy<int>(al, d->prem_rhs_attr, nPr);
+        c.prem_relation = dev_copy<int>(al, d->prem_relation, nPr);
+        c.prem_value = dev_copy<double>(al, d->prem_value, nPr);
+        c.act_rule = dev_copy<int>(al, d->act_rule, nA);
+        c.act_link = dev_copy<int>(al, d->act_link, nA);
+        c.act_attr = dev_copy<int>(al, d->act_attr, nA);
+        c.act_curve = dev_copy<int>(al, d->act_curve, nA);
+        c.act_tseries = dev_copy<int>(al, d->act_tseries, nA);
+        std::vector<int> slot(nA);
+        for (int a = 0; a < nA; a++) slot[a] = link_watch[d->act_link[a]];
+        c.act_slot = dev_copy<int>(al, slot.data(), nA);
+        c.act_kp = dev_copy<double>(al, d->act_kp, nA);
+        c.act_ki = dev_copy<double>(al, d->act_ki, nA);
+        c.act_kd = dev_copy<double>(al, d->act_kd, nA);
+        const int ns = d->n_series;
+        std::vector<int> s0(1, 0);
+        c.series_start = dev_copy<int>(al, ns > 0 ? d->series_start : s0.data(), ns + 1);
+        const int npts = ns > 0 ? d->series_start[ns] : 0;
+        c.series_t = dev_copy<double>(al, d->series_t, npts);
+        c.series_v = dev_copy<double>(al, d->series_v, npts);
+        c.pump_y_on = dev_copy<double>(al, d->pump_y_on, nL);
+        c.pump_y_off = dev_copy<double>(al, d->pump_y_off, nL);
+        c.orif_orate = dev_copy<double>(al, d->orif_orate, nL);
+        c.watch = dev_copy<int>(al, watch.data(), nW);
+        c.link_watch = dev_copy<int>(al, link_watch.data(), nL);
+        c.stage_node = dev_copy<int>(al, d->stage_node, d->n_stage_nodes);
+        c.stage_kind = dev_copy<int>(al, d->stage_kind, d->n_stage_nodes);
+        c.stage_table = dev_copy<int>(al, d->stage_table, d->n_stage_nodes);
+        // per-member rule state
+        c.control_value = dev_zero<double>(al, M);
+        c.set_point = dev_zero<double>(al, M);
+        std::vector<double> av((size_t)nA * M), tls((size_t)nW * M);
+        for (int a = 0; a < nA; a++) for (int m = 0; m < M; m++) av[(size_t)a * M + m] = d->act_value[a];
+        for (int w = 0; w < nW; w++)
+            for (int m = 0; m < M; m++) tls[(size_t)w * M + m] = d->link_time_last_set ? d->link_time_last_set[watch[w]] : d->start_datetime;
+        c.act_val = dev_copy<double>(al, av.data(), av.size());
+        c.act_e1 = dev_zero<double>(al, (size_t)nA * M);
+        c.act_e2 = dev_zero<double>(al, (size_t)nA * M);
+        c.time_last_set = dev_copy<double>(al, tls.data(), tls.size());
+        c.winner = dev_zero<int>(al, (size_t)nW * M);
+        c.new_rule_time = dev_zero<double>(al, M);
+        c.active = 1;
+    } catch (const DeviceError &e) {
+        for (void *q : s->control_allocs) backend::free_(q);
+        s->control_allocs.clear();
+        memset(&s->controls, 0, sizeof(s->controls));
+        return fail(SWB_ERR_CUDA, e.what);
+    }
     return SWB_OK;
 }
 

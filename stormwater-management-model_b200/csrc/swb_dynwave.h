@@ -252,9 +252,34 @@ SWB_FI FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int flags, d
 }
 
 // ---- K1: dwflow.c:57-293 (with findSurfArea :417-550, checkNormalFlow :637-686) ------------------
-template <int S>
-SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, double dt,
-                         const double *T)
+// Where the per-(conduit, member) inputs of the update come from.  CfLoad reads the state arrays at the
+// point of use (late loads keep the register budget of the persistent kernel); CfStaged reads this lane's
+// column of a shared-memory stage that cp.async filled while the warp was computing its previous tile
+// (swb_staged.cuh: sg_links_pf) -- the same values, hence the same bits.
+struct CfLoad {
+    const State &s;
+    size_t ix, ix1, ix2;
+    SWB_FI double qLast()   const { return s.c_q1[ix]; }
+    SWB_FI double depth1()  const { return s.n_depth[ix1]; }
+    SWB_FI double depth2()  const { return s.n_depth[ix2]; }
+    SWB_FI double setting() const { return s.l_setting[ix]; }
+    SWB_FI double aOld()    const { return s.c_a2[ix]; }
+    SWB_FI double oldFlow() const { return s.l_old_flow[ix]; }
+};
+enum { CF_QLAST = 0, CF_DEPTH1, CF_DEPTH2, CF_SETTING, CF_AOLD, CF_OLDFLOW, CF_DT, CF_FIELDS };
+struct CfStaged {
+    const double *b;             // &stage[lane]; field f of this lane is b[f * 32]
+    SWB_FI double qLast()   const { return b[CF_QLAST * 32]; }
+    SWB_FI double depth1()  const { return b[CF_DEPTH1 * 32]; }
+    SWB_FI double depth2()  const { return b[CF_DEPTH2 * 32]; }
+    SWB_FI double setting() const { return b[CF_SETTING * 32]; }
+    SWB_FI double aOld()    const { return b[CF_AOLD * 32]; }
+    SWB_FI double oldFlow() const { return b[CF_OLDFLOW * 32]; }
+};
+
+template <int S, class In>
+SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int steps, double dt,
+                            const double *T, const In &in)
 {
     const int M = s.M;
     const size_t ix = SWB_IX(j, m, M);
@@ -267,10 +292,10 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     // Register budget (64 per thread at 32 warps/SM): values that are only needed late (old flow,
     // old area, barrels, true length, end-node depths for the dry-node test) are loaded late or
     // re-read instead of being kept live across the geometry evaluation.
-    double qLast = s.c_q1[ix];
+    double qLast = in.qLast();
     double evapLoss = 0.0, seepLoss = 0.0;
 
-    const double depth1 = s.n_depth[SWB_IX(n1, m, M)], depth2 = s.n_depth[SWB_IX(n2, m, M)];
+    const double depth1 = in.depth1(), depth2 = in.depth2();
     const double inv1 = n.node_invert[n1], inv2 = n.node_invert[n2];
     double z1 = n.link_z1[j], z2 = n.link_z2[j];
     double h1 = depth1 + inv1, h2 = depth2 + inv2;
@@ -375,7 +400,7 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     bool isFull = (y1 >= x.yFull && y2 >= x.yFull);
 
     // --- dry / closed exit (dwflow.c:165-180)
-    const bool isClosed = (s.l_setting[ix] == 0);
+    const bool isClosed = (in.setting() == 0);
     const double barrels = (double)n.cond_barrels[j];
     if (flowClass == SWB_DRY || flowClass == SWB_UP_DRY || flowClass == SWB_DN_DRY || isClosed ||
         aMid <= SWB_FUDGE) {
@@ -421,9 +446,9 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
 
     // --- momentum terms (dwflow.c:210-236)
     const double trueLength = n.cond_length[j];
-    double aOld = s.c_a2[ix];
+    double aOld = in.aOld();
     aOld = SWB_MAX(aOld, SWB_FUDGE);
-    const double qOld = s.l_old_flow[ix] / barrels;
+    const double qOld = in.oldFlow() / barrels;
     double dq1;
     if (S < 0 && x.type == XS_FORCE_MAIN && isFull)
          dq1 = dt * forcemain_fric_slope(n, x, fabs(v), rMid);
@@ -486,8 +511,8 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     double qLimit = n.link_q_limit[j];
     if (qLimit > 0.0) { if (fabs(q) > qLimit) q = SWB_SGN(q) * qLimit; }
     if (link_flap_closed(flags, n.link_direction[j], q)) q = 0.0;
-    if (q >  SWB_FUDGE && s.n_depth[SWB_IX(n1, m, M)] <= SWB_FUDGE) q =  SWB_FUDGE;
-    if (q < -SWB_FUDGE && s.n_depth[SWB_IX(n2, m, M)] <= SWB_FUDGE) q = -SWB_FUDGE;
+    if (q >  SWB_FUDGE && in.depth1() <= SWB_FUDGE) q =  SWB_FUDGE;
+    if (q < -SWB_FUDGE && in.depth2() <= SWB_FUDGE) q = -SWB_FUDGE;
 
     // --- save (dwflow.c:283-292)
     s.c_a1[ix] = aMid;
@@ -506,6 +531,14 @@ SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, 
     s.l_normal_flow[ix] = normalFlow;
     if (hasCulvert) s.l_inlet_control[ix] = inletControl;     // 0 for ever on every other link
     if (flags & LF_HAS_LOSSRATE) { s.c_evap_loss[ix] = evapLoss; s.c_seep_loss[ix] = seepLoss; }
+}
+
+template <int S>
+SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, double dt,
+                         const double *T)
+{
+    const CfLoad in = { s, SWB_IX(j, m, s.M), SWB_IX(n.link_node1[j], m, s.M), SWB_IX(n.link_node2[j], m, s.M) };
+    conduit_flow_in<S>(n, s, j, m, steps, dt, T, in);
 }
 
 // Real (non-inlined) entry points: one compact function per specialised shape plus the generic one.

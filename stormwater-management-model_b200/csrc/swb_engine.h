@@ -26,6 +26,7 @@
 #include "swb_dynwave.h"
 #include "swb_qual.h"
 #include "swb_regulator.h"
+#include "swb_controls.h"
 #include "swb_stats.h"
 
 #ifdef __CUDACC__
@@ -61,6 +62,24 @@ struct Inflows {               // device image of swb_inflow_desc
     const double *member_scale, *member_shift;
     const int    *node_slot;   // per node: index into the inflow list or -1
     double start_day, start_secs;
+    // optional parts (null / 0 = absent); `general` is set when any of them is present: the step
+    // prologue then books the external quality mass itself (ph_outflows only does so in the plain case)
+    int general;
+    const double *cfactor;     // per inflow node
+    const int    *base_pattern;
+    int nPatterns;
+    const int    *pat_type;    // MONTHLY 0, DAILY 1, HOURLY 2, WEEKEND 3
+    const double *pat_factor;  // [nPatterns][24]
+    const int    *node_q_start;                      // [nN + 1] CSR: a node's pollutant inflow records
+    const int    *q_pollut, *q_type, *q_series, *q_pattern;
+    const double *q_cfactor, *q_sfactor, *q_baseline;
+    const int    *series_start;
+    const double *series_t, *series_v;
+    const int    *node_dwf_start;                    // [nN + 1] CSR: a node's dry-weather records
+    const int    *dwf_param;
+    const double *dwf_avg;
+    const int    *dwf_patterns;                      // [record][4]
+    const double *pollut_dwf_concen;                 // [nP]
 };
 
 enum { DBG_SKIP_LINKS = 1, DBG_SKIP_NODES = 2 };   // RunArgs.debug (profiling aid: isolate one Picard phase)
@@ -72,6 +91,7 @@ struct RunArgs {
     double t_end;              // PH_ADVANCE: members stop at this simulated time (s)
     double fixed_step;         // RouteStep for PH_NEXTDT / PH_ADVANCE
     Inflows inflows;
+    Controls controls;         // control rules, pump depths, timed outfall stages (PH_ADVANCE only)
     const double *host_lat, *host_losses, *host_qual;   // PH_HOSTIN images, device layout
     // host-layout landing zones of swb_step_host ([member][item(,p)]): when set, the kernel itself
     // transposes them into the images above before the first step, and the step's depths / flows
@@ -97,15 +117,34 @@ struct RunArgs {
 
 // hydrograph value at time t (s) for inflow slot k: linear between breakpoints, 0 outside
 // (table_tseriesLookup with extend = FALSE, table.c:745-806)
-SWB_HD double inflow_series(const Inflows &f, int k, double t)
+SWB_HD double inflow_series(const Inflows &f, int k, double t) { return series_lookup(f.ts_start, f.ts_t, f.ts_q, k, t); }
+
+// getPatternFactor (inflow.c:456-486)
+SWB_HD double pattern_factor(const Inflows &f, int p, const DateParts &d)
 {
-    int i0 = f.ts_start[k], i1 = f.ts_start[k + 1];
-    if (i1 <= i0) return 0.0;
-    if (t < f.ts_t[i0] || t > f.ts_t[i1 - 1]) return 0.0;
-    for (int i = i0 + 1; i < i1; i++) {
-        if (t <= f.ts_t[i]) return tbl_interp(t, f.ts_t[i - 1], f.ts_q[i - 1], f.ts_t[i], f.ts_q[i]);
+    const double *fac = f.pat_factor + (size_t)p * 24;
+    switch (f.pat_type[p]) {
+      case 0: if (d.month >= 0 && d.month < 12) return fac[d.month]; break;
+      case 1: if (d.day >= 0 && d.day < 7) return fac[d.day]; break;
+      case 2: if (d.hour >= 0 && d.hour < 24) return fac[d.hour]; break;
+      case 3: if (d.day == 0 || d.day == 6) { if (d.hour >= 0 && d.hour < 24) return fac[d.hour]; } break;
     }
-    return 0.0;
+    return 1.0;
+}
+// inflow_getDwfInflow (inflow.c:361-392)
+SWB_HD double dwf_value(const Inflows &f, int r, const DateParts &d)
+{
+    const int *pat = f.dwf_patterns + (size_t)r * 4;
+    double fac = 1.0;
+    if (pat[0] >= 0) fac *= pattern_factor(f, pat[0], d);
+    if (pat[1] >= 0) fac *= pattern_factor(f, pat[1], d);
+    const int p1 = pat[2], p2 = pat[3];
+    if (p2 >= 0) {
+        if (d.day == 0 || d.day == 6) fac *= pattern_factor(f, p2, d);
+        else if (p1 >= 0) fac *= pattern_factor(f, p1, d);
+    }
+    else if (p1 >= 0) fac *= pattern_factor(f, p1, d);
+    return fac * f.dwf_avg[r];
 }
 
 // ---- per-(object, member) bodies of the Picard phases --------------------------------------------
@@ -388,8 +427,8 @@ SWB_ENGINE inline bool member_active(const State &st, const RunArgs &args, int m
 // execRouting (swmm5.c:528-546): step = variable step, shortened to end at t_end (owner threads)
 SWB_ENGINE inline void ph_advance(const Net &net, const State &st, const RunArgs &args, int m)
 {
-    double t = st.sim_time[m];
-    int done = (t >= args.t_end) ? 1 : 0;
+    const double tms = st.time_ms[m];
+    int done = (st.sim_time[m] >= args.t_end) ? 1 : 0;
     double dt = st.var_step[m];
     if (net.opt.courant_factor == 0.0) dt = args.fixed_step;
     else if (dt == 0.0) {      // first call of dynwave_getRoutingStep (dynwave.c:209-218)
@@ -397,7 +436,8 @@ SWB_ENGINE inline void ph_advance(const Net &net, const State &st, const RunArgs
         st.var_step[m] = dt;
     }
     // time is kept in milliseconds like NewRoutingTime (routing.c:301)
-    double tms = 1000.0 * t, nextms = tms + 1000.0 * dt, endms = 1000.0 * args.t_end;
+    dt = ctl_clamp_step(args.controls, m, tms, dt);
+    double nextms = tms + 1000.0 * dt, endms = 1000.0 * args.t_end;
     if (!done && nextms > endms) {
         dt = (endms - tms) / 1000.0;
         dt = SWB_MAX(dt, 1. / 1000.0);
@@ -427,17 +467,25 @@ SWB_ENGINE inline void ph_massbal_fold(const Net &net, const State &st, int m, d
 }
 
 // old <- new, node_initFlows, overflow reset, lateral inflows + quality preload, initRoutingStep
-SWB_ENGINE inline void ph_prologue(const Net &net, const State &st, const RunArgs &args, const ThreadMap &tm, double dt)
+template <class Ctx>
+SWB_ENGINE inline void ph_prologue(const Net &net, const State &st, const RunArgs &args, Ctx &ctx, const ThreadMap &tm, double dt)
 {
     const int M = st.M, nN = net.nN, nL = net.nL, nP = net.nP;
     const int m = tm.m, first = tm.first, stride = tm.stride;
     // getDateTime(NewRoutingTime): 1 ms after the routing time (swmm5.c:1551), in days
     const double tNow = args.inflows.start_day +
-        (args.inflows.start_secs + (1000.0 * st.sim_time[m] + 1.0) / 1000.0) / 86400.0;
+        (args.inflows.start_secs + (st.time_ms[m] + 1.0) / 1000.0) / 86400.0;
     // Every body below issues ALL of its loads before its first store: the state arrays may
     // alias as far as the compiler knows, so a load written after a store cannot be hoisted
     // above it and each load/store pair would cost a full DRAM round trip.
     const int ph = args.phases;
+    const Inflows &F = args.inflows;
+    const bool general = (ph & PH_INFLOWS) && F.general;
+    DateParts dp = {0, 0, 0};
+    if (general && F.nPatterns > 0) dp = date_parts(tNow);
+    double exq[SWB_MAX_POLLUT];          // external quality mass rate booked by this thread (general inflows)
+#pragma unroll
+    for (int p = 0; p < SWB_MAX_POLLUT; p++) exq[p] = 0.0;
     SWB_FOR_ITEMS(i, nN) {
         const size_t ix = SWB_IX(i, m, M);
         // ---- loads
@@ -461,14 +509,35 @@ SWB_ENGINE inline void ph_prologue(const Net &net, const State &st, const RunArg
         int slot = -1;
         // Node.oldLatFlow = newLatFlow (routing.c:330), only where this step sets a new one
         const double prevLat = (ph & (PH_INFLOWS | PH_HOSTIN)) ? st.n_latflow[ix] : 0.0;
+        double extq = 0.0, dwfq = 0.0, revq = 0.0;
         if (ph & PH_INFLOWS) {
             // addExternalInflows (routing.c:435-490)
-            slot = args.inflows.node_slot[i];
+            slot = F.node_slot[i];
             if (slot >= 0) {
-                double tsv = inflow_series(args.inflows, slot, tNow - args.inflows.member_shift[m])
-                             * (args.inflows.sfactor[slot] * args.inflows.member_scale[m]);
-                lat = tsv + args.inflows.baseline[slot];
+                double tsv = inflow_series(F, slot, tNow - F.member_shift[m]) * (F.sfactor[slot] * F.member_scale[m]);
+                double blv = F.baseline[slot];
+                if (general && F.base_pattern && F.base_pattern[slot] >= 0) blv *= pattern_factor(F, F.base_pattern[slot], dp);
+                lat = tsv + blv;
+                if (general && F.cfactor) lat = F.cfactor[slot] * lat;
                 if (fabs(lat) < SWB_FLOW_TOL) lat = 0.0;
+            }
+            extq = lat;
+            if (general) {
+                // reverse flow through an outfall joins the flow that carries CONCEN inflows (routing.c:474);
+                // Node.oldNetInflow still holds the value of the step before the swap below
+                if (F.node_q_start && F.node_q_start[i + 1] > F.node_q_start[i] && net.node_type[i] == SWB_OUTFALL) {
+                    const double oni = st.n_old_net_inflow[ix];
+                    if (oni < 0.0) revq = oni;
+                }
+                // addDryWeatherInflows (routing.c:499-575): the flow record of the node's list
+                if (F.node_dwf_start)
+                    for (int r = F.node_dwf_start[i]; r < F.node_dwf_start[i + 1]; r++)
+                        if (F.dwf_param[r] < 0) {
+                            dwfq = dwf_value(F, r, dp);
+                            if (fabs(dwfq) < SWB_FLOW_TOL) dwfq = 0.0;
+                            lat += dwfq;
+                            break;
+                        }
             }
             newLat = true;
         }
@@ -485,7 +554,38 @@ SWB_ENGINE inline void ph_prologue(const Net &net, const State &st, const RunArg
                 size_t iq = SWB_IXP(p, i, nN, m, M);
                 double c = qv[p];
                 if (ph & PH_QSWAP) { st.n_old_qual[iq] = c; c = 0.0; }      // routing.c:312-336
-                if ((ph & PH_INFLOWS) && slot >= 0 && lat >= 0.0) c += args.inflows.concen[slot * nP + p] * lat;
+                if ((ph & PH_INFLOWS) && !general) { if (slot >= 0 && lat >= 0.0) c += F.concen[slot * nP + p] * lat; }
+                else if (ph & PH_INFLOWS) {
+                    double wsum = 0.0;                      // (for the routing totals; c is summed in the reference's order)
+                    if (extq >= 0.0) {                      // a negative external flow takes no pollutant inflow (:466-470)
+                        if (!F.node_q_start) { if (slot >= 0) { double w = F.concen[slot * nP + p] * extq; c += w; wsum += w; } }
+                        else {
+                            const double qq = extq - revq;
+                            for (int r = F.node_q_start[i]; r < F.node_q_start[i + 1]; r++) {
+                                if (F.q_pollut[r] != p) continue;
+                                // inflow_getExtInflow (inflow.c:207-234)
+                                double blv = F.q_baseline[r], tsv = 0.0;
+                                if (F.q_pattern[r] >= 0) blv *= pattern_factor(F, F.q_pattern[r], dp);
+                                if (F.q_series[r] >= 0)
+                                    tsv = series_lookup(F.series_start, F.series_t, F.series_v, F.q_series[r], tNow) * F.q_sfactor[r];
+                                double w = F.q_cfactor[r] * (tsv + blv);
+                                if (F.q_type[r] == 1) w *= qq;          // CONCEN_INFLOW
+                                c += w; wsum += w;
+                            }
+                        }
+                    }
+                    if (dwfq > 0.0) {                       // (:536-572)
+                        const double dc = F.pollut_dwf_concen ? F.pollut_dwf_concen[p] : 0.0;
+                        if (dc > 0.0) { double w = dwfq * dc; c += w; wsum += w; }
+                        for (int r = F.node_dwf_start[i]; r < F.node_dwf_start[i + 1]; r++) {
+                            if (F.dwf_param[r] != p) continue;
+                            double w = dwfq * dwf_value(F, r, dp);
+                            c += w; wsum += w;
+                            if (dc > 0.0) { w = dwfq * dc; c -= w; wsum -= w; }
+                        }
+                    }
+                    exq[p] += wsum;
+                }
                 if ((ph & PH_HOSTIN) && args.host_qual) c += hq[p];
                 st.n_qual[iq] = c;
             }
@@ -507,6 +607,15 @@ SWB_ENGINE inline void ph_prologue(const Net &net, const State &st, const RunArg
             st.n_dydt[ix] = 0.0;
         }
     }
+    if (general && (ph & PH_MASSBAL))
+#pragma unroll
+        for (int p = 0; p < SWB_MAX_POLLUT; p++)
+            if (p < nP) {
+                double v = exq[p];
+                if (M == 1) v = ctx.warp_sum_f64(v);
+                if (v != 0.0 && (M != 1 || ctx.warp_lane == 0))
+                    ctx.atomic_add_f64(&st.mb_rate[(size_t)(MB_FLOW_TERMS + p * MB_QUAL_TERMS + MBQ_EX_INFLOW) * M + m], v);
+            }
     SWB_FOR_ITEMS(j, nL) {
         const size_t ix = SWB_IX(j, m, M);
         // ---- loads
@@ -658,7 +767,7 @@ SWB_ENGINE inline void ph_outflows(const Net &net, const State &st, const RunArg
                     const int p = p0 + pp;
                     if (p >= nP) continue;
                     const size_t iq = SWB_IXP(p, i, nN, m, M);
-                    if (slot >= 0 && lat >= 0.0) ql[pp][MBQ_EX_INFLOW] += args.inflows.concen[slot * nP + p] * lat;
+                    if (slot >= 0 && lat >= 0.0 && !args.inflows.general) ql[pp][MBQ_EX_INFLOW] += args.inflows.concen[slot * nP + p] * lat;
                     if ((args.phases & PH_HOSTIN) && args.host_qual) ql[pp][MBQ_EX_INFLOW] += args.host_qual[iq];
                     if (q > 0.0 || lat < 0.0) {   // the concentration only where mass leaves
                         const double c = st.n_qual[iq];
@@ -698,7 +807,7 @@ SWB_ENGINE inline void ph_stats(const Net &net, const State &st, const RunArgs &
     const int maxTrials = engine_max_trials(net);
     if (!active) return;
     // new routing time of this step in elapsed seconds, formed like NewRoutingTime (ms)
-    const double tNew = (1000.0 * st.sim_time[m] + 1000.0 * dt) / 1000.0;
+    const double tNew = (st.time_ms[m] + 1000.0 * dt) / 1000.0;
     if (tNew >= st.stat_report_start) {
         // this thread's copy of "iterations used" (the owner's write to st.iters is not
         // ordered against other CTAs): the step ended unconverged iff its last trial did
@@ -832,7 +941,8 @@ SWB_ENGINE inline void ph_nextdt_final(const Net &net, const State &st, const Ru
 // NewRoutingTime += 1000 * routingStep (routing.c:301-302), kept in ms
 SWB_ENGINE inline void ph_advance_time(const State &st, int m, double dt)
 {
-    st.sim_time[m] = (1000.0 * st.sim_time[m] + 1000.0 * dt) / 1000.0;
+    st.time_ms[m] = st.time_ms[m] + 1000.0 * dt;
+    st.sim_time[m] = st.time_ms[m] / 1000.0;
 }
 
 template <class Ctx>
@@ -867,7 +977,15 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
     for (int step = 0; step < args.n_steps; step++) {
         // ================= step prologue =======================================================
         if (args.phases & PH_ADVANCE) {
-            if (owner) ph_advance(net, st, args, m);
+            if (owner) {
+                ph_advance(net, st, args, m);
+                // evaluateControlRules (routing.c:269-308): reads the previous step's results, before
+                // the prologue replaces them
+                if (args.controls.active && !st.done[m]) ph_controls(net, st, args.controls, m, st.dt[m], T);
+                // (before the barrier: the prologue of OTHER threads books external quality mass into the
+                // rates this fold zeroes)
+                if ((args.phases & PH_MASSBAL) && !st.done[m]) ph_massbal_fold(net, st, m, st.dt[m]);
+            }
             ctx.grid_sync();
             // every member has reached t_end: leave the launch (grid-uniform decision)
             bool anyLeft = false;
@@ -876,10 +994,10 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
         }
         const bool active = member_active(st, args, m);
         const double dt = st.dt[m];
-        if ((args.phases & PH_MASSBAL) && owner && active) ph_massbal_fold(net, st, m, dt);
+        if ((args.phases & PH_MASSBAL) && !(args.phases & PH_ADVANCE) && owner && active) ph_massbal_fold(net, st, m, dt);
 
         if (active && (args.phases & (PH_SWAP | PH_INFLOWS | PH_QSWAP | PH_DYNWAVE | PH_HOSTIN)))
-            ph_prologue(net, st, args, tm, dt);
+            ph_prologue(net, st, args, ctx, tm, dt);
         if (owner && (args.phases & PH_DYNWAVE))
             for (int k = 0; k < maxTrials; k++) st.not_conv[k * M + m] = 0;
         for (int c = ctx.tid; c < SWB_TICKETS_PER_TRIAL * SWB_MAX_TRIALS_CAP; c += ctx.G) st.tickets[c] = 0ull;

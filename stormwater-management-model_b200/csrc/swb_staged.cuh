@@ -28,7 +28,8 @@
 #define SWB_SG_LINK_BLOCK 256
 #endif
 #ifndef SWB_SG_LINK_MINB
-#define SWB_SG_LINK_MINB 2          // 128 registers: the specialised conduit update without spills to speak of
+#define SWB_SG_LINK_MINB 3          // 80 registers, 24 warps per SM: measured best with the cp.async pipeline
+                                    // (profiles/README.md round 2: 128 regs x 16 warps 298 ms, 80 x 24 267, 64 x 32 274)
 #endif
 #ifndef SWB_SG_NODE_BLOCK
 #define SWB_SG_NODE_BLOCK 256
@@ -92,7 +93,10 @@ sg_control(const __grid_constant__ Net net, const __grid_constant__ State st, co
     if (k == -1) {
         bool anyLeft = true;
         if (args.phases & PH_ADVANCE) {
-            for (int m = threadIdx.x; m < M; m += blockDim.x) ph_advance(net, st, args, m);
+            for (int m = threadIdx.x; m < M; m += blockDim.x) {
+                ph_advance(net, st, args, m);
+                if (args.controls.active && !st.done[m]) ph_controls(net, st, args.controls, m, st.dt[m], net.xs_tables);
+            }
             __syncthreads();
             anyLeft = false;
             for (int m = threadIdx.x; m < M; m += blockDim.x) anyLeft = anyLeft || !st.done[m];
@@ -135,7 +139,7 @@ sg_prologue(const __grid_constant__ Net net, const __grid_constant__ State st, c
     if (!st.ctl[CTL_ANY_LEFT]) return;
     CudaCtx ctx = sg_ctx(st, nullptr);
     const ThreadMap tm = thread_map(ctx, st.M);
-    if (member_active(st, args, tm.m)) ph_prologue(net, st, args, tm, st.dt[tm.m]);
+    if (member_active(st, args, tm.m)) ph_prologue(net, st, args, ctx, tm, st.dt[tm.m]);
 }
 
 // findLinkFlows pass (i) for the true conduits of one conduit-function class (dynwave.c:387-395)
@@ -163,6 +167,119 @@ sg_links(const __grid_constant__ Net net, const __grid_constant__ State st, int 
         else if (LK == LK_RECT_CLOSED) conduit_flow<XS_RECT_CLOSED>(net, st, j, mm, k, st.dt[mm], tab);
         else conduit_flow_generic(net, st, j, mm, k, st.dt[mm], tab);
     });
+}
+
+// The same pass as a software pipeline per warp (Blackwell / Hopper async copies, no register cost):
+//   tile i + 3   ticket atomic in flight
+//   tile i + 2   link / end-node / member indices being loaded (plain loads, consumed an iteration later)
+//   tile i + 1   its seven input rows on their way into the warp's shared-memory stage (cp.async, LDGSTS)
+//   tile i       conduit update reading its inputs from the stage (LDS)
+// so neither the ticket counter's round trip, nor the index chain link_order -> link_node -> alive, nor the
+// DRAM latency of the state rows sits on the critical path of a warp that has only 3 siblings per scheduler.
+#ifndef SWB_SG_LINK_PF
+#define SWB_SG_LINK_PF 1
+#endif
+struct PfIds { int j, n1, n2, mm; };     // mm < 0: lane has no member in this tile (or the conduit is bypassed)
+
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int LK>
+__global__ void __launch_bounds__(SWB_SG_LINK_BLOCK, SWB_SG_LINK_MINB)
+sg_links_pf(const __grid_constant__ Net net, const __grid_constant__ State st, int k, int prev)
+{
+    __shared__ double tab[XT_TOTAL];
+    __shared__ double stage_all[(SWB_SG_LINK_BLOCK / 32) * 2 * CF_FIELDS * 32];
+    sg_tick(st, prev);
+    const int nAlive = st.ctl[CTL_N_ALIVE];
+    if (!st.ctl[CTL_ANY_LEFT] || nAlive == 0) return;
+    sg_tables(tab, net);
+    const int M = st.M;
+    const int j0 = (LK > 0 ? net.lk_count[0] : 0) + (LK > 1 ? net.lk_count[1] : 0);
+    unsigned long long *ticket = st.tickets + SWB_TICKETS_PER_TRIAL * k + TK_LINKS + LK;
+    auto update = [&](int j, int mm, double dt, auto &&in) {
+        if (LK == LK_CIRCULAR) conduit_flow_in<XS_CIRCULAR>(net, st, j, mm, k, dt, tab, in);
+        else if (LK == LK_RECT_CLOSED) conduit_flow_in<XS_RECT_CLOSED>(net, st, j, mm, k, dt, tab, in);
+        else conduit_flow_in<-1>(net, st, j, mm, k, dt, tab, in);
+    };
+    if (nAlive < 32) {                     // few members left: several conduits per tile, plain loads
+        CudaCtx ctx = sg_ctx(st, tab);
+        for_tiles(ctx, net.lk_count[LK], nAlive, ticket, [&](int jj, int mm) {
+            const int j = net.link_order[j0 + jj];
+            if (k >= 2) {
+                const bool byp = st.n_converged[SWB_IX(net.link_node1[j], mm, M)] &&
+                                 st.n_converged[SWB_IX(net.link_node2[j], mm, M)];
+                st.l_bypassed[SWB_IX(j, mm, M)] = byp ? 1 : 0;
+                if (byp) return;
+            }
+            const CfLoad in = { st, SWB_IX(j, mm, M), SWB_IX(net.link_node1[j], mm, M), SWB_IX(net.link_node2[j], mm, M) };
+            update(j, mm, st.dt[mm], in);
+        });
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    double *my = stage_all + (size_t)(threadIdx.x >> 5) * 2 * CF_FIELDS * 32 + lane;
+    const int nChunks = (nAlive + 31) / 32;
+    const unsigned total = (unsigned)net.lk_count[LK] * (unsigned)nChunks;     // < 2^31 (checked by the launcher)
+    auto issue = [&]() -> unsigned long long { unsigned long long v = 0; if (lane == 0) v = atomicAdd(ticket, 1ull); return v; };
+    auto take = [&](unsigned long long v) -> unsigned {
+        v = __shfl_sync(0xffffffffu, v, 0);
+        return v < (unsigned long long)total ? (unsigned)v : total;
+    };
+    auto ids = [&](unsigned t) -> PfIds {
+        PfIds d;
+        const unsigned jj = t / (unsigned)nChunks;
+        const int slot = (int)(t - jj * (unsigned)nChunks) * 32 + lane;
+        d.j = net.link_order[j0 + (int)jj];
+        d.n1 = net.link_node1[d.j]; d.n2 = net.link_node2[d.j];
+        d.mm = slot < nAlive ? st.alive[slot] : -1;
+        if (k >= 2 && d.mm >= 0) {         // findBypassedLinks of the previous trial (dynwave.c:335-345)
+            const bool byp = st.n_converged[SWB_IX(d.n1, d.mm, M)] && st.n_converged[SWB_IX(d.n2, d.mm, M)];
+            st.l_bypassed[SWB_IX(d.j, d.mm, M)] = byp ? 1 : 0;
+            if (byp) d.mm = -1;
+        }
+        return d;
+    };
+    auto prefetch = [&](const PfIds &d, int stg) {
+        if (d.mm >= 0) {
+            double *b = my + stg * (CF_FIELDS * 32);
+            const size_t ix = SWB_IX(d.j, d.mm, M);
+            cp_async8(b + CF_QLAST * 32, &st.c_q1[ix]);
+            cp_async8(b + CF_DEPTH1 * 32, &st.n_depth[SWB_IX(d.n1, d.mm, M)]);
+            cp_async8(b + CF_DEPTH2 * 32, &st.n_depth[SWB_IX(d.n2, d.mm, M)]);
+            cp_async8(b + CF_SETTING * 32, &st.l_setting[ix]);
+            cp_async8(b + CF_AOLD * 32, &st.c_a2[ix]);
+            cp_async8(b + CF_OLDFLOW * 32, &st.l_old_flow[ix]);
+            cp_async8(b + CF_DT * 32, &st.dt[d.mm]);
+        }
+        cp_async_commit();
+    };
+    const PfIds none = { 0, 0, 0, -1 };
+    unsigned t0 = take(issue());
+    unsigned t1 = t0 < total ? take(issue()) : total;
+    unsigned t2 = t1 < total ? take(issue()) : total;
+    PfIds i0 = t0 < total ? ids(t0) : none, i1 = t1 < total ? ids(t1) : none, i2 = t2 < total ? ids(t2) : none;
+    prefetch(i0, 0);
+    int stg = 0;
+    while (t0 < total) {
+        const unsigned long long pend = (t2 < total) ? issue() : (unsigned long long)total;
+        prefetch(i1, stg ^ 1);             // (an empty group when there is no next tile)
+        cp_async_wait<1>();                // everything but the group just committed: tile t0's rows are in
+        if (i0.mm >= 0) {
+            const double *b = my + stg * (CF_FIELDS * 32);
+            const CfStaged in = { b };
+            update(i0.j, i0.mm, b[CF_DT * 32], in);
+        }
+        t0 = t1; i0 = i1; t1 = t2; i1 = i2; stg ^= 1;
+        t2 = (t2 < total) ? take(pend) : total;
+        i2 = t2 < total ? ids(t2) : none;
+    }
+    cp_async_wait<0>();
 }
 
 __global__ void __launch_bounds__(SWB_SG_NODE_BLOCK, SWB_SG_NODE_MINB)
@@ -274,6 +391,12 @@ sg_transpose(double *dst, const double *src, int R, int C, int planes, const __g
     }
 }
 
+#if SWB_SG_LINK_PF
+#define SG_LINKS_FAST sg_links_pf
+#else
+#define SG_LINKS_FAST sg_links
+#endif
+
 namespace swb { namespace backend {
 
 struct StagedInfo {
@@ -295,8 +418,13 @@ static void staged_init(int device)
     StagedInfo &S = g_staged[device];
     if (S.ready) return;
     const int sms = g_dev[device].sms;
+#if SWB_SG_LINK_PF
+    S.link_blocks[0] = sg_occupancy(sg_links_pf<0>, SWB_SG_LINK_BLOCK, sms);
+    S.link_blocks[1] = sg_occupancy(sg_links_pf<1>, SWB_SG_LINK_BLOCK, sms);
+#else
     S.link_blocks[0] = sg_occupancy(sg_links<0>, SWB_SG_LINK_BLOCK, sms);
     S.link_blocks[1] = sg_occupancy(sg_links<1>, SWB_SG_LINK_BLOCK, sms);
+#endif
     S.link_blocks[2] = sg_occupancy(sg_links<2>, SWB_SG_LINK_BLOCK, sms);
     S.node_blocks = sg_occupancy(sg_nodes, SWB_SG_NODE_BLOCK, sms);
     S.presum_blocks = sg_occupancy(sg_presum, SWB_SG_NODE_BLOCK, sms);
@@ -374,6 +502,7 @@ static bool launch_staged(const Net &net, const State &st, const RunArgs &args, 
     auto sblocks = [&](int maxBlocks) { return sg_stream_blocks(maxBlocks, SWB_SG_STREAM_BLOCK, M, items); };
     const int dtBlocks = sblocks(S.stream_blocks[SG_DT_SEARCH]);
     if ((long long)dtBlocks * SWB_SG_STREAM_BLOCK > st.dt_cand_stride) { err = "dt_cand too small"; return false; }
+    if ((long long)net.nTrue * ((M + 31) / 32) >= (1LL << 31)) { err = "more than 2^31 conduit tiles per trial"; return false; }
     const long long chunks = (M + 31) / 32;
     auto tblocks = [&](int maxBlocks, long long tiles) {
         return (int)std::max(1LL, std::min((long long)maxBlocks, (tiles * 32 + SWB_SG_LINK_BLOCK - 1) / SWB_SG_LINK_BLOCK));
@@ -397,8 +526,8 @@ static bool launch_staged(const Net &net, const State &st, const RunArgs &args, 
         }
         if (ph & PH_DYNWAVE) {
             for (int k = 0; k < maxTrials; k++) {
-                if (net.lk_count[0] > 0) { sg_links<0><<<tblocks(S.link_blocks[0], net.lk_count[0] * chunks), SWB_SG_LINK_BLOCK, 0, q>>>(net, st, k, prev); prev = TP_LINKS; launched++; }
-                if (net.lk_count[1] > 0) { sg_links<1><<<tblocks(S.link_blocks[1], net.lk_count[1] * chunks), SWB_SG_LINK_BLOCK, 0, q>>>(net, st, k, prev); prev = TP_LINKS; launched++; }
+                if (net.lk_count[0] > 0) { SG_LINKS_FAST<0><<<tblocks(S.link_blocks[0], net.lk_count[0] * chunks), SWB_SG_LINK_BLOCK, 0, q>>>(net, st, k, prev); prev = TP_LINKS; launched++; }
+                if (net.lk_count[1] > 0) { SG_LINKS_FAST<1><<<tblocks(S.link_blocks[1], net.lk_count[1] * chunks), SWB_SG_LINK_BLOCK, 0, q>>>(net, st, k, prev); prev = TP_LINKS; launched++; }
                 if (net.lk_count[2] > 0) { sg_links<2><<<tblocks(S.link_blocks[2], net.lk_count[2] * chunks), SWB_SG_LINK_BLOCK, 0, q>>>(net, st, k, prev); prev = TP_LINKS; launched++; }
                 if (net.nNonConduit > 0) {
                     sg_presum<<<tblocks(S.presum_blocks, nN * chunks), SWB_SG_NODE_BLOCK, 0, q>>>(net, st, k, prev); prev = TP_REGULATORS; launched++;

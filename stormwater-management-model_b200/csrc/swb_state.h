@@ -227,7 +227,8 @@ struct State {
     // per member
     double *dt;                  // routing step being taken
     double *var_step;            // VariableStep (dynwave.c:84); 0 before the first step
-    double *sim_time;            // elapsed simulated seconds
+    double *sim_time;            // elapsed simulated seconds (= time_ms / 1000, for reporting)
+    double *time_ms;             // NewRoutingTime: elapsed ms, accumulated like routing.c:301-302
     double *evap_rate, *hydcon;  // per-member climate scalars
     int    *iters;               // iterations used by the last dynwave_execute
     long long *tot_iters, *tot_steps, *non_conv;

@@ -339,6 +339,57 @@ def c3_mixed_inp() -> str:
     return C3_MIXED_INP
 
 
+# The same model with a rule base that exercises the rest of controls.c: conflicting rules resolved by
+# priority, CLOCKTIME windows, a right-hand-side variable, OR clauses, TIMEOPEN, conduit status, and the
+# three modulated settings (CURVE of the control value, TIMESERIES, PID), optionally with RULE_STEP.
+C3_RULES = """[CONTROLS]
+RULE R1
+IF NODE S1 DEPTH > 6
+THEN ORIFICE OR1 SETTING = 1.0
+ELSE ORIFICE OR1 SETTING = 0.3
+PRIORITY 1
+RULE R1B
+IF SIMULATION CLOCKTIME >= 06:00:00
+AND SIMULATION CLOCKTIME < 07:30:00
+THEN ORIFICE OR1 SETTING = 0.6
+PRIORITY 3
+RULE R2
+IF SIMULATION TIME > 12
+THEN PUMP P1 STATUS = OFF
+RULE R3
+IF NODE S2 DEPTH >= 0
+THEN WEIR W2 SETTING = CURVE WCURVE
+RULE R4
+IF NODE S1 DEPTH <> 5
+THEN ORIFICE OR2 SETTING = PID -0.5 10 0
+RULE R5
+IF SIMULATION TIME >= 0
+THEN WEIR W1 SETTING = TIMESERIES WTS
+RULE R6
+IF NODE J3 DEPTH > NODE J4 DEPTH
+OR PUMP P1 TIMEOPEN > 2:00
+THEN CONDUIT C8 STATUS = CLOSED
+ELSE CONDUIT C8 STATUS = OPEN
+RULE R7
+IF SIMULATION MONTH = 1
+AND SIMULATION DAY = 4
+AND LINK C3 VELOCITY > 3
+THEN OUTLET OL1 SETTING = 0.5
+ELSE OUTLET OL1 SETTING = 1.0
+"""
+
+
+def c3_rules_inp(rule_step: str | None = None) -> str:
+    a = C3_MIXED_INP.index("[CONTROLS]")
+    b = C3_MIXED_INP.index("[POLLUTANTS]")
+    txt = C3_MIXED_INP[:a] + C3_RULES + C3_MIXED_INP[b:]
+    txt = txt.replace("[CURVES]\n", "[CURVES]\nWCURVE CONTROL 0 1.0 2 0.8 5 0.4\n")
+    txt = txt.replace("[TIMESERIES]\n", "[TIMESERIES]\nWTS 0:00 1.0\nWTS 6:00 0.5\nWTS 12:00 1.0\n")
+    if rule_step:
+        txt = txt.replace("THREADS 1\n", f"THREADS 1\nRULE_STEP {rule_step}\n", 1)
+    return txt
+
+
 # A second mixed-element model that exercises what C3_MIXED_INP does not: pump types 1, 2, 4 and
 # ideal, SIDEFLOW / TRAPEZOIDAL weirs, flap-gated and slowly closing orifices, a TABULAR/HEAD outlet,
 # CYLINDRICAL / CONICAL / PYRAMIDAL storage with evaporation, open channels (trapezoid, rect_open,

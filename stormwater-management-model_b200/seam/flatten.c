@@ -377,3 +377,267 @@ static int field_rw(int field, double *buf, int set)
 
 int swb_engine_get_field(int field, double *buf)       { return field_rw(field, buf, 0); }
 int swb_engine_set_field(int field, const double *buf) { return field_rw(field, (double *)buf, 1); }
+
+/* ---- inflows (objects.h:430-453, inflow.c) -------------------------------------------------------- */
+static int series_len(int k)
+{
+    int n = 0;
+    const TTableEntry *e = Tseries[k].firstEntry;
+    while (e) { n++; e = e->next; }
+    return n;
+}
+
+int swb_flatten_inflows(swb_flat *f, swb_inflow_desc *d)
+{
+    int nN = Nobjects[NODE], nP = Nobjects[POLLUT], nPat = Nobjects[TIMEPATTERN], nTs = Nobjects[TSERIES];
+    int i, k, p, n = 0, npts = 0, nq = 0, nd = 0, anyCf = 0, anyPat = 0;
+    TExtInflow *x;
+    TDwfInflow *w;
+    int *node, *start, *bpat, *tsmap;
+    double *tt, *tq, *sf, *bl, *cf, *cc;
+    memset(d, 0, sizeof(*d));
+    for (i = 0; i < nN; i++) {
+        for (x = Node[i].extInflow; x; x = x->next) {
+            if (x->type == FLOW_INFLOW) { n++; if (x->tSeries >= 0) npts += series_len(x->tSeries); break; }
+        }
+        for (x = Node[i].extInflow; x; x = x->next) if (x->type != FLOW_INFLOW) nq++;
+        for (w = Node[i].dwfInflow; w; w = w->next) nd++;
+    }
+    node = IARR(n + 1); start = IARR(n + 2); bpat = IARR(n + 1);
+    tt = DARR(npts + 1); tq = DARR(npts + 1); sf = DARR(n + 1); bl = DARR(n + 1); cf = DARR(n + 1);
+    cc = DARR((size_t)(n + 1) * (nP ? nP : 1));
+    k = 0; npts = 0;
+    for (i = 0; i < nN; i++) {
+        TExtInflow *flow = NULL;
+        for (x = Node[i].extInflow; x; x = x->next) if (x->type == FLOW_INFLOW) { flow = x; break; }
+        if (!flow) continue;
+        node[k] = i; start[k] = npts;
+        sf[k] = flow->sFactor; bl[k] = flow->baseline; cf[k] = flow->cFactor; bpat[k] = flow->basePat;
+        if (flow->cFactor != 1.0) anyCf = 1;
+        if (flow->basePat >= 0) anyPat = 1;
+        if (flow->tSeries >= 0) {
+            const TTableEntry *e = Tseries[flow->tSeries].firstEntry;
+            while (e) { tt[npts] = e->x; tq[npts] = e->y; npts++; e = e->next; }
+        }
+        /* constant concentrations at the start date: the plain form kept for callers without records */
+        for (x = Node[i].extInflow; x; x = x->next)
+            if (x->type == CONCEN_INFLOW) cc[(size_t)k * nP + x->param] = inflow_getExtInflow(x, StartDateTime);
+        k++;
+    }
+    start[k] = npts;
+    d->n_inflow_nodes = n; d->n_ts_pts = npts; d->node = node; d->ts_start = start; d->ts_t = tt; d->ts_q = tq;
+    d->sfactor = sf; d->baseline = bl; d->concen = cc;
+    if (anyCf) d->cfactor = cf;
+    else for (k = 0; k < n; k++) { /* cFactor == 1: nothing to fold */ }
+    if (anyPat) d->base_pattern = bpat;
+    {
+        int h, mi, s;
+        datetime_decodeTime(StartDateTime, &h, &mi, &s);
+        d->start_day = floor(StartDateTime);
+        d->start_secs = 3600.0 * h + 60.0 * mi + s;
+    }
+    /* patterns */
+    if (nPat > 0) {
+        int *pt = IARR(nPat);
+        double *pf = DARR((size_t)nPat * 24);
+        for (p = 0; p < nPat; p++) {
+            pt[p] = Pattern[p].type;
+            for (i = 0; i < 24; i++) pf[(size_t)p * 24 + i] = Pattern[p].factor[i];
+        }
+        d->n_patterns = nPat; d->pattern_type = pt; d->pattern_factor = pf;
+    }
+    /* pollutant inflow records, a node's records in list order; their time series as a shared table */
+    if (nq > 0) {
+        int *qn = IARR(nq), *qp = IARR(nq), *qt = IARR(nq), *qs = IARR(nq), *qb = IARR(nq);
+        double *qc = DARR(nq), *qf = DARR(nq), *ql = DARR(nq);
+        int ns = 0, tot = 0, *ss;
+        double *st, *sv;
+        tsmap = IARR(nTs + 1);
+        for (i = 0; i < nTs; i++) tsmap[i] = -1;
+        k = 0;
+        for (i = 0; i < nN; i++)
+            for (x = Node[i].extInflow; x; x = x->next) {
+                if (x->type == FLOW_INFLOW) continue;
+                qn[k] = i; qp[k] = x->param; qt[k] = (x->type == CONCEN_INFLOW) ? 1 : 2;
+                qb[k] = x->basePat; qc[k] = x->cFactor; qf[k] = x->sFactor; ql[k] = x->baseline;
+                qs[k] = -1;
+                if (x->tSeries >= 0) {
+                    if (tsmap[x->tSeries] < 0) { tsmap[x->tSeries] = ns++; tot += series_len(x->tSeries); }
+                    qs[k] = tsmap[x->tSeries];
+                }
+                k++;
+            }
+        ss = IARR(ns + 1); st = DARR(tot + 1); sv = DARR(tot + 1);
+        tot = 0;
+        for (p = 0; p < ns; p++)
+            for (i = 0; i < nTs; i++)
+                if (tsmap[i] == p) {
+                    const TTableEntry *e = Tseries[i].firstEntry;
+                    ss[p] = tot;
+                    while (e) { st[tot] = e->x; sv[tot] = e->y; tot++; e = e->next; }
+                }
+        ss[ns] = tot;
+        d->n_qual_inflows = nq; d->q_node = qn; d->q_pollut = qp; d->q_type = qt; d->q_series = qs; d->q_pattern = qb;
+        d->q_cfactor = qc; d->q_sfactor = qf; d->q_baseline = ql;
+        d->n_series = ns; d->series_start = ss; d->series_t = st; d->series_v = sv;
+    }
+    /* dry-weather inflows */
+    if (nd > 0) {
+        int *dn = IARR(nd), *dp = IARR(nd), *dpat = IARR((size_t)nd * 4);
+        double *da = DARR(nd), *dc = DARR(nP + 1);
+        k = 0;
+        for (i = 0; i < nN; i++)
+            for (w = Node[i].dwfInflow; w; w = w->next) {
+                dn[k] = i; dp[k] = w->param; da[k] = w->avgValue;
+                for (p = 0; p < 4; p++) dpat[(size_t)k * 4 + p] = w->patterns[p];
+                k++;
+            }
+        for (p = 0; p < nP; p++) dc[p] = Pollut[p].dwfConcen;
+        d->n_dwf = nd; d->dwf_node = dn; d->dwf_param = dp; d->dwf_avg = da; d->dwf_patterns = dpat;
+        d->pollut_dwf_concen = dc;
+    }
+    return SWB_OK;
+}
+
+/* ---- control rules -----------------------------------------------------------------------------------
+ * controls.c keeps its rule base in structs private to that file (controls.c:95-160); the engine exports
+ * only the two globals below.  The layouts are restated here field for field so the list can be walked. */
+struct swb_TVariable { int object, index, attribute; };
+struct swb_TPremise {
+    int type, exprIndex;
+    struct swb_TVariable lhsVar, rhsVar;
+    int relation;
+    double value;
+    struct swb_TPremise *next;
+};
+struct swb_TAction {
+    int rule, link, attribute, curve, tseries;
+    double value, kp, ki, kd, e1, e2;
+    struct swb_TAction *next;
+};
+struct swb_TRule {
+    char *ID;
+    double priority;
+    struct swb_TPremise *firstPremise, *lastPremise;
+    struct swb_TAction *thenActions, *elseActions;
+};
+extern struct swb_TRule *Rules;        /* controls.c:163 */
+extern int RuleCount;                  /* controls.c:167 */
+
+int swb_flatten_controls(swb_flat *f, swb_controls_desc *d)
+{
+    int nL = Nobjects[LINK], nTs = Nobjects[TSERIES];
+    int r, j, k, nPrem = 0, nAct = 0, nThen = 0, nElse = 0, ns = 0, tot = 0;
+    struct swb_TPremise *p;
+    struct swb_TAction *a;
+    int *tsmap;
+    memset(d, 0, sizeof(*d));
+    for (r = 0; r < RuleCount; r++) {
+        for (p = Rules[r].firstPremise; p; p = p->next) {
+            nPrem++;
+            if (p->exprIndex >= 0) return SWB_ERR_UNSUPP;                     /* math expression */
+            if (p->lhsVar.object == 0 /* r_GAGE */) return SWB_ERR_UNSUPP;
+            if (p->value == MISSING && p->rhsVar.object == 0) return SWB_ERR_UNSUPP;
+        }
+        for (a = Rules[r].thenActions; a; a = a->next) { nAct++; nThen++; }
+        for (a = Rules[r].elseActions; a; a = a->next) { nAct++; nElse++; }
+    }
+    {
+        double *pri = DARR(RuleCount + 1), *pv = DARR(nPrem + 1);
+        int *ps = IARR(RuleCount + 2), *ts = IARR(RuleCount + 2), *es = IARR(RuleCount + 2);
+        int *at = IARR(nThen + 1), *ae = IARR(nElse + 1);
+        int *pt = IARR(nPrem + 1), *lo = IARR(nPrem + 1), *li = IARR(nPrem + 1), *la = IARR(nPrem + 1);
+        int *rv = IARR(nPrem + 1), *ro = IARR(nPrem + 1), *ri = IARR(nPrem + 1), *ra = IARR(nPrem + 1);
+        int *rel = IARR(nPrem + 1);
+        int *ar = IARR(nAct + 1), *al = IARR(nAct + 1), *aa = IARR(nAct + 1), *ac = IARR(nAct + 1), *ats = IARR(nAct + 1);
+        double *av = DARR(nAct + 1), *kp = DARR(nAct + 1), *ki = DARR(nAct + 1), *kd = DARR(nAct + 1);
+        int ip = 0, ia = 0, it = 0, ie = 0;
+        tsmap = IARR(nTs + 1);
+        for (j = 0; j < nTs; j++) tsmap[j] = -1;
+        for (r = 0; r < RuleCount; r++) {
+            int pass;
+            pri[r] = Rules[r].priority;
+            ps[r] = ip; ts[r] = it; es[r] = ie;
+            for (p = Rules[r].firstPremise; p; p = p->next) {
+                pt[ip] = p->type; lo[ip] = p->lhsVar.object; li[ip] = p->lhsVar.index; la[ip] = p->lhsVar.attribute;
+                rv[ip] = (p->value == MISSING); ro[ip] = p->rhsVar.object; ri[ip] = p->rhsVar.index;
+                ra[ip] = p->rhsVar.attribute; rel[ip] = p->relation; pv[ip] = p->value;
+                ip++;
+            }
+            for (pass = 0; pass < 2; pass++)
+                for (a = pass ? Rules[r].elseActions : Rules[r].thenActions; a; a = a->next) {
+                    ar[ia] = a->rule; al[ia] = a->link; aa[ia] = a->attribute; ac[ia] = a->curve; ats[ia] = -1;
+                    av[ia] = a->value; kp[ia] = a->kp; ki[ia] = a->ki; kd[ia] = a->kd;
+                    if (a->tseries >= 0) {
+                        if (tsmap[a->tseries] < 0) { tsmap[a->tseries] = ns++; tot += series_len(a->tseries); }
+                        ats[ia] = tsmap[a->tseries];
+                    }
+                    if (pass) ae[ie++] = ia; else at[it++] = ia;
+                    ia++;
+                }
+        }
+        ps[RuleCount] = ip; ts[RuleCount] = it; es[RuleCount] = ie;
+        /* outfalls with a tidal curve or a stage time series (node.c:1437-1458) */
+        {
+            int nN = Nobjects[NODE], i, nst = 0;
+            int *sn, *sk, *stb;
+            for (i = 0; i < nN; i++)
+                if (Node[i].type == OUTFALL && (Outfall[Node[i].subIndex].type == TIDAL_OUTFALL ||
+                                                Outfall[Node[i].subIndex].type == TIMESERIES_OUTFALL)) nst++;
+            sn = IARR(nst + 1); sk = IARR(nst + 1); stb = IARR(nst + 1);
+            nst = 0;
+            for (i = 0; i < nN; i++) {
+                if (Node[i].type != OUTFALL) continue;
+                k = Node[i].subIndex;
+                if (Outfall[k].type == TIDAL_OUTFALL) { sn[nst] = i; sk[nst] = 1; stb[nst] = Outfall[k].tideCurve; nst++; }
+                else if (Outfall[k].type == TIMESERIES_OUTFALL) {
+                    j = Outfall[k].stageSeries;
+                    if (tsmap[j] < 0) { tsmap[j] = ns++; tot += series_len(j); }
+                    sn[nst] = i; sk[nst] = 2; stb[nst] = tsmap[j]; nst++;
+                }
+            }
+            d->n_stage_nodes = nst; d->stage_node = sn; d->stage_kind = sk; d->stage_table = stb;
+        }
+        {
+            int h, mi, sec;
+            datetime_decodeTime(StartDateTime, &h, &mi, &sec);
+            d->start_datetime = StartDateTime;
+            d->start_day = floor(StartDateTime);
+            d->start_secs = 3600.0 * h + 60.0 * mi + sec;
+        }
+        d->n_rules = RuleCount; d->n_premises = nPrem; d->n_actions = nAct;
+        d->rule_step = RuleStep;
+        d->rule_priority = pri; d->rule_premise_start = ps; d->rule_then_start = ts; d->rule_else_start = es;
+        d->act_then = at; d->act_else = ae;
+        d->prem_type = pt; d->prem_lhs_obj = lo; d->prem_lhs_index = li; d->prem_lhs_attr = la;
+        d->prem_rhs_is_var = rv; d->prem_rhs_obj = ro; d->prem_rhs_index = ri; d->prem_rhs_attr = ra;
+        d->prem_relation = rel; d->prem_value = pv;
+        d->act_rule = ar; d->act_link = al; d->act_attr = aa; d->act_curve = ac; d->act_tseries = ats;
+        d->act_value = av; d->act_kp = kp; d->act_ki = ki; d->act_kd = kd;
+    }
+    {
+        int *ss = IARR(ns + 1);
+        double *st = DARR(tot + 1), *sv = DARR(tot + 1);
+        tot = 0;
+        for (k = 0; k < ns; k++)
+            for (j = 0; j < nTs; j++)
+                if (tsmap[j] == k) {
+                    const TTableEntry *e = Tseries[j].firstEntry;
+                    ss[k] = tot;
+                    while (e) { st[tot] = e->x; sv[tot] = e->y; tot++; e = e->next; }
+                }
+        ss[ns] = tot;
+        d->n_series = ns; d->series_start = ss; d->series_t = st; d->series_v = sv;
+    }
+    {
+        double *yon = DARR(nL + 1), *yoff = DARR(nL + 1), *orate = DARR(nL + 1), *tls = DARR(nL + 1);
+        for (j = 0; j < nL; j++) {
+            k = Link[j].subIndex;
+            if (Link[j].type == PUMP) { yon[j] = Pump[k].yOn; yoff[j] = Pump[k].yOff; }
+            if (Link[j].type == ORIFICE) orate[j] = Orifice[k].orate;
+            tls[j] = Link[j].timeLastSet;
+        }
+        d->pump_y_on = yon; d->pump_y_off = yoff; d->orif_orate = orate; d->link_time_last_set = tls;
+    }
+    return SWB_OK;
+}

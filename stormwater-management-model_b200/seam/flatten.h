@@ -18,6 +18,13 @@ typedef struct swb_flat {
 } swb_flat;
 
 int  swb_flatten_network(swb_flat *f);          /* 0 ok, SWB_ERR_UNSUPP if element unsupported */
+/* external + dry-weather inflows of the open project (Node[].extInflow / dwfInflow, Pattern[], Tseries[]);
+ * blocks are owned by `f` like the network's.  Member scale / shift are left NULL. */
+int  swb_flatten_inflows(swb_flat *f, swb_inflow_desc *out);
+/* control rules (controls.c keeps them in file-private structs: the layouts are restated in flatten.c),
+ * pump start-up / shut-off depths, orifice opening rates.  SWB_ERR_UNSUPP for rules that use named
+ * variables, math expressions or rain gages. */
+int  swb_flatten_controls(swb_flat *f, swb_controls_desc *out);
 void swb_flat_free(swb_flat *f);
 /* copy one dynamic field of the live engine (SWB_NODE_* / SWB_LINK_* ids) to/from buf */
 int  swb_engine_get_field(int field, double *buf);

@@ -46,6 +46,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_qualrout_execute.argtypes = [C.c_void_p, _P_D]
     lib.swb_get_routing_step.argtypes = [C.c_void_p, C.c_double, _P_D]
     lib.swb_set_inflows.argtypes = [C.c_void_p, C.POINTER(abi.InflowDesc)]
+    lib.swb_set_controls.argtypes = [C.c_void_p, C.POINTER(abi.ControlsDesc)]
     lib.swb_run_steps.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.swb_get_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.MemberStats)]
     lib.swb_get_massbal.argtypes = [C.c_void_p, C.c_int, C.c_int, _P_D, _P_D, _P_D]
@@ -245,6 +246,23 @@ class Solver:
                 setattr(d, name, arrs[name].ctypes.data_as(C.POINTER(ct)))
         self._keep.append(arrs)
         self._chk(self.lib.swb_set_inflows(self._h, C.byref(d)))
+
+    def set_inflows_desc(self, desc, member_scale=None, member_shift=None):
+        """swb_set_inflows with a ready swb_inflow_desc (e.g. from the seam's flattener); the per-member
+        scale / shift of the FLOW hydrographs are filled in here."""
+        d = abi.InflowDesc()
+        C.memmove(C.byref(d), C.byref(desc), C.sizeof(d))
+        keep = {}
+        for name, arr in (("member_scale", member_scale), ("member_shift", member_shift)):
+            if arr is not None:
+                keep[name] = np.ascontiguousarray(arr, dtype=np.float64)
+                assert keep[name].size == self.M
+                setattr(d, name, keep[name].ctypes.data_as(_P_D))
+        self._chk(self.lib.swb_set_inflows(self._h, C.byref(d)))
+
+    def set_controls_desc(self, desc):
+        """Control rules / pump depths / timed outfall stages for run_steps (swb_set_controls)."""
+        self._chk(self.lib.swb_set_controls(self._h, C.byref(desc)))
 
     def run_steps(self, n_steps: int, t_end: float):
         self._chk(self.lib.swb_run_steps(self._h, n_steps, t_end))

@@ -120,24 +120,31 @@ def open_reference(inp_text: str, lib: str = "libswmm5.so"):
     return e, d
 
 
-def make_solver_from_engine(e, lib_path, n_members=1, member_scale=None, member_shift=None):
+def make_solver_from_engine(e, lib_path, n_members=1, member_scale=None, member_shift=None, full=False):
+    """full=True: everything swb_run_steps can evaluate on the device comes from the shipped flatteners
+    (patterns, pollutant inflow records, dry-weather flow, control rules, pump depths, timed outfall
+    stages) instead of the plain FLOW-hydrograph extraction."""
     net = e.network()
     s = solver.Solver(net, n_members, lib_path=lib_path)
     s.load_state(grab_state(e))
-    inf = e.inflows()
-    s.set_inflows(member_scale=member_scale, member_shift=member_shift, **inf)
+    if full:
+        s.set_inflows_desc(e.inflows_desc(), member_scale=member_scale, member_shift=member_shift)
+        s.set_controls_desc(e.controls_desc())
+    else:
+        inf = e.inflows()
+        s.set_inflows(member_scale=member_scale, member_shift=member_shift, **inf)
     return s
 
 
 def lockstep_vs_reference(inp_text: str, lib_path, max_steps: int | None = None, every: int = 1,
-                          n_members: int = 1, continuity: bool = False) -> dict:
+                          n_members: int = 1, continuity: bool = False, full: bool = False) -> dict:
     """Step the reference and the solver (ensemble driver, one step per launch) side by side.
     continuity=True (whole runs only) adds the flow / quality continuity errors of the solver's
     device-side routing totals next to the reference's own swmm_getMassBalErr."""
     e, _ = open_reference(inp_text)
     out = None
     try:
-        s = make_solver_from_engine(e, lib_path, n_members)
+        s = make_solver_from_engine(e, lib_path, n_members, full=full)
         init_storage = s.storage() if continuity else None
         ref_iters = 0
         t_end = e.total_duration_s()

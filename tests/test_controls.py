@@ -1,0 +1,217 @@
+"""SURVEY 8(f) ranks 2 and 4 on the device: control rules, pump start-up / shut-off depths, orifice
+opening rates, weir surcharge coefficients, timed outfall stages, baseline / dry-weather patterns and
+time-varying pollutant inflows are evaluated per ensemble member inside swb_run_steps -- no host work
+per routing step.  Every test compares with the unmodified reference (oracle/_ref) running the same
+(or the member's perturbed) .inp: evaluateControlRules (routing.c:269-308), controls.c:495-552 and
+1086-1450, link.c:604-639 / 1729-1809 / 2166-2190, inflow.c:207-234 / 361-392 / 456-486,
+routing.c:435-575, node.c:1437-1458."""
+import re
+
+import numpy as np
+import pytest
+
+import parity_common as pc
+from swmm_b200 import abi, scenarios, solver
+
+TOL = 1e-6          # north_star tolerance for the GPU build
+
+
+def perturbed(inp: str, scale: float, shift_min: int) -> str:
+    """The .inp an ensemble member stands for: FLOW hydrograph scale factors times `scale` (written with
+    repr: the device multiplies sfactor * member_scale in double), storm series moved by whole minutes."""
+    out, section = [], ""
+    for line in inp.splitlines():
+        if line.startswith("["):
+            section = line.strip()
+        tok = line.split()
+        if section == "[INFLOWS]" and len(tok) >= 6 and tok[1] == "FLOW":
+            tok[5] = repr(float(tok[5]) * scale)
+            line = " ".join(tok)
+        elif section == "[TIMESERIES]" and len(tok) == 3 and tok[0] in ("TS1", "STORM") and shift_min:
+            h, m = tok[1].split(":")
+            total = int(h) * 60 + int(m) + shift_min
+            line = f"{tok[0]} {total // 60}:{total % 60:02d} {tok[2]}"
+        out.append(line)
+    return "\n".join(out) + "\n"
+
+
+def reference_run(inp: str, every: int, max_steps=None):
+    e, _ = pc.open_reference(inp)
+    times, iters, snaps = [], [], {}
+    fields = pc.SNAP_FIELDS + ["SWB_LINK_SETTING", "SWB_LINK_TARGET_SETTING"]
+    try:
+        step = 0
+        while True:
+            t = e.step()
+            step += 1
+            times.append(e.routing_time_ms() / 1000.0)
+            iters.append(e.last_iterations())
+            last = t == 0 or (max_steps and step >= max_steps)
+            if step % every == 0 or last:
+                snaps[step] = {f: e.field(f).copy() for f in fields}
+            if last:
+                break
+    finally:
+        e.end()
+        e.close()
+    return dict(times=np.array(times), iters=np.array(iters), snaps=snaps)
+
+
+def ensemble_vs_reference(inp, lib_path, scale, shift_min, sample, every, max_steps=None, chunk=1):
+    """Members `sample` of an ensemble stepped on the device (rules, inflows, stages all device side)
+    against the reference's own runs of their perturbed models."""
+    M = len(scale)
+    refs = {m: reference_run(perturbed(inp, float(scale[m]), int(shift_min[m])), every, max_steps) for m in sample}
+    e, _ = pc.open_reference(inp)
+    try:
+        s = pc.make_solver_from_engine(e, lib_path, M, member_scale=scale,
+                                       member_shift=np.asarray(shift_min, dtype=np.float64) / 1440.0, full=True)
+        t_end = e.total_duration_s()
+    finally:
+        e.end()
+        e.close()
+    n_max = max(len(r["times"]) for r in refs.values())
+    worst = {}
+    time_err, iters_ok = 0.0, True
+    prev = {m: 0 for m in sample}
+    step = 0
+    while step < n_max:
+        n = min(chunk, n_max - step)
+        if chunk > 1:                      # land exactly on the next snapshot
+            nxt = min(k for r in refs.values() for k in r["snaps"] if k > step)
+            n = min(n, nxt - step)
+        s.run_steps(n, t_end)
+        step += n
+        st = s.stats()
+        for m in sample:
+            r = refs[m]
+            if step > len(r["times"]):
+                continue
+            time_err = max(time_err, abs(st[m].sim_time - r["times"][step - 1]))
+            want = int(np.sum(r["iters"][:step]))
+            iters_ok = iters_ok and (st[m].iterations == want)
+            if step in r["snaps"]:
+                for f, ref in r["snaps"][step].items():
+                    got = s.get_field(f, m, 1)[0]
+                    floor = pc.FLOOR.get(f, 1e-6)
+                    worst[f] = max(worst.get(f, 0.0), pc.rel_err(got, ref, floor))
+    s.close()
+    return dict(steps=n_max, time_err_s=time_err, iters_match=iters_ok, max_rel=max(worst.values()), worst=worst)
+
+
+# ---- one model, everything on the device, against the live reference ---------------------------------
+@pytest.mark.parametrize("rule_step,max_steps", [(None, None), ("00:00:45", 6000)])
+def test_emulated_rules_and_general_inflows_equal_reference(rule_step, max_steps, emul_lib, have_reference):
+    """Conflicting priorities, CLOCKTIME windows, rhs variables, OR clauses, TIMEOPEN, conduit status,
+    CURVE / TIMESERIES / PID settings, pump on / off depths, a slowly closing orifice, the weir surcharge
+    coefficient, a TIDAL outfall, DWF with an hourly pattern, CONCEN series: bit for bit, 24 h."""
+    if not have_reference:
+        pytest.skip("oracle/_ref is not built")
+    r = pc.lockstep_vs_reference(scenarios.c3_rules_inp(rule_step), emul_lib, every=20, full=True,
+                                 max_steps=max_steps, continuity=max_steps is None)
+    print(r)
+    assert r["time_err_s"] == 0.0 and r["crit_mismatch"] == 0, r
+    assert r["iterations"] == r["ref_iterations"] and r["non_converged"] == r["ref_non_converged"], r
+    assert r["max_rel"] == 0.0, r
+    if max_steps is None:
+        assert abs(r["flow_error_pct"] - r["ref_flow_error_pct"]) < 1e-4, r
+        assert abs(r["qual_error_pct"] - r["ref_qual_error_pct"]) < 1e-4, r
+
+
+def test_emulated_controlled_ensemble_members_equal_reference(emul_lib, have_reference):
+    if not have_reference:
+        pytest.skip("oracle/_ref is not built")
+    scale = np.tile(np.array([1.0, 0.62, 1.37, 2.2, 0.85, 1.0, 0.5, 1.9]), 4)
+    shift = np.zeros(32, dtype=np.int64)
+    shift[5] = 17
+    r = ensemble_vs_reference(scenarios.c3_rules_inp(), emul_lib, scale, shift, sample=[1, 3], every=500, max_steps=5000)
+    print(r)
+    assert r["time_err_s"] < 1e-9 and r["iters_match"], r
+    assert r["max_rel"] == 0.0, r           # scale only: the member IS the perturbed model, bit for bit
+    r = ensemble_vs_reference(scenarios.c3_rules_inp(), emul_lib, scale, shift, sample=[5], every=500, max_steps=3000)
+    print(r)
+    assert r["time_err_s"] < 1e-9 and r["max_rel"] < 1e-7, r    # shifted hydrograph: DateTime values near 43 831 days resolve 7e-12 days, so the interpolated flows differ by ~1e-10
+
+
+def test_emulated_config3_full_size_with_device_controls(emul_lib, have_reference):
+    """973 links, 5 rules, pumps of 4 types with on / off depths, DWF patterns, TIDAL outfall: a member of a
+    32-member ensemble that never leaves the "device" equals the reference on its perturbed .inp."""
+    if not have_reference:
+        pytest.skip("oracle/_ref is not built")
+    M = 32
+    scale = np.round(np.random.default_rng(5).lognormal(0.0, 0.25, M), 6)
+    inp = scenarios.c3_large_inp(scenarios.C3Spec(hours=6.0))
+    r = ensemble_vs_reference(inp, emul_lib, scale, np.zeros(M, dtype=np.int64), sample=[3], every=200,
+                              max_steps=400, chunk=200)
+    print(r)
+    assert r["time_err_s"] == 0.0 and r["iters_match"] and r["max_rel"] == 0.0, r
+
+
+def test_controls_api_errors(emul_lib, have_reference):
+    if not have_reference:
+        pytest.skip("oracle/_ref is not built")
+    e, _ = pc.open_reference(scenarios.c3_rules_inp())
+    try:
+        s = pc.make_solver_from_engine(e, emul_lib, 1, full=True)
+        d = abi.ControlsDesc()
+        import ctypes as C
+        C.memmove(C.byref(d), C.byref(e.controls_desc()), C.sizeof(d))
+        obj = np.ctypeslib.as_array(d.prem_lhs_obj, shape=(d.n_premises,)).astype(np.int32).copy()
+        obj[0] = 0                                       # r_GAGE
+        d.prem_lhs_obj = obj.ctypes.data_as(C.POINTER(C.c_int))
+        with pytest.raises(solver.SwbError, match="rain-gage"):
+            s.set_controls_desc(d)
+        C.memmove(C.byref(d), C.byref(e.controls_desc()), C.sizeof(d))
+        link = np.ctypeslib.as_array(d.act_link, shape=(d.n_actions,)).astype(np.int32).copy()
+        link[0] = 10 ** 6
+        d.act_link = link.ctypes.data_as(C.POINTER(C.c_int))
+        with pytest.raises(solver.SwbError, match="action link"):
+            s.set_controls_desc(d)
+        s.set_controls_desc(e.controls_desc())           # a second good call replaces the first
+        s.run_steps(5, e.total_duration_s())
+        s.close()
+    finally:
+        e.end()
+        e.close()
+
+
+# ---- the same on the GPU -------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("rule_step", [None, "00:00:45"])
+def test_cuda_rules_and_general_inflows_vs_reference(rule_step, cuda_lib, have_reference):
+    assert have_reference, "oracle/_ref must travel to the GPU box"
+    r = pc.lockstep_vs_reference(scenarios.c3_rules_inp(rule_step), None, every=20, full=True, max_steps=9000)
+    print(r)
+    assert r["time_err_s"] == 0.0 and r["iterations"] == r["ref_iterations"], r
+    assert r["max_rel"] <= TOL, r
+
+
+@pytest.mark.gpu
+def test_cuda_controlled_ensemble_members_equal_reference(cuda_lib, have_reference):
+    """SURVEY 8(f) rank 4 done-criterion: the mixed-element model with its rule base as a 64-member
+    ensemble, whole 24 h in chunks of 1 000 steps per launch; sampled members equal the reference on
+    their perturbed .inp (settings included)."""
+    assert have_reference, "oracle/_ref must travel to the GPU box"
+    M = 64
+    rng = np.random.default_rng(11)
+    scale = np.round(rng.lognormal(0.0, 0.3, M), 6)
+    shift = np.zeros(M, dtype=np.int64)
+    shift[56:] = rng.integers(1, 30, M - 56)
+    r = ensemble_vs_reference(scenarios.c3_rules_inp(), None, scale, shift, sample=[0, 7, 23, 39, 60], every=1000, chunk=1000)
+    print(r)
+    assert r["time_err_s"] < 1e-9 and r["iters_match"], r
+    assert r["max_rel"] <= TOL, r
+
+
+@pytest.mark.gpu
+def test_cuda_config3_full_size_ensemble_with_device_controls(cuda_lib, have_reference):
+    """BASELINE config 3 at its stated size (973 links, 5 rules, DWF patterns, 3 outfall kinds) as an
+    ensemble that never leaves the device; two members against the reference for 6 simulated hours."""
+    assert have_reference, "oracle/_ref must travel to the GPU box"
+    M = 32
+    scale = np.round(np.random.default_rng(5).lognormal(0.0, 0.25, M), 6)
+    inp = scenarios.c3_large_inp(scenarios.C3Spec(hours=6.0))
+    r = ensemble_vs_reference(inp, None, scale, np.zeros(M, dtype=np.int64), sample=[3, 30], every=400, chunk=400)
+    print(r)
+    assert r["time_err_s"] < 1e-9 and r["iters_match"], r
+    assert r["max_rel"] <= TOL, r

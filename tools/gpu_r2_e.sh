@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round 2 call E: whole GPU suite on the staged default, default bench, launch list
+mkdir -p gpurun_out
+( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2e_gputests.log 2>&1
+tail -n 8 gpurun_out/r2e_gputests.log
+( time timeout 900 python bench.py --no-packed ) > gpurun_out/r2e_bench.json 2> gpurun_out/r2e_bench.err
+grep "bench \|real" gpurun_out/r2e_bench.err
+python - <<'PY'
+import json
+try:
+    d=json.loads(open('gpurun_out/r2e_bench.json').read().strip().splitlines()[-1])
+    for k in ('value','ms_per_step','picard_iterations_per_step','gpu_launches'): print(k, d[k])
+    print('e2e', d['e2e']['value'], 'roofline', d['roofline']['frac'], d['roofline']['phase_ms'])
+    print('weak', d.get('weak_512_per_gpu')); print('c2', d.get('c2_single')); print('c5', d.get('c5'))
+except Exception as e: print('failed', e)
+PY

@@ -133,6 +133,11 @@ def make_ensemble(args, device: int, member0: int, members: int | None = None):
     spec = scenarios.GridSpec(nx=args.grid, ny=args.grid, hours=args.hours, surcharge=args.surcharge)
     case = network.build_grid(spec)
     scale, shift_h = scenarios.c4_members(max(args.members_total, member0 + members), 2024)
+    if getattr(args, "member_order", "generated") == "scale":
+        # the same ensemble enumerated by storm intensity: members that need the same number of Picard trials
+        # become neighbours, so the member lists of the late trials touch whole sectors
+        order = np.argsort(-scale, kind="stable")
+        scale, shift_h = scale[order], shift_h[order]
     sl = slice(member0, member0 + members)
     s = solver.Solver(case.net, members, device=device)
     s.load_state(case.state0)
@@ -274,7 +279,10 @@ def run_ours(args):
                 "true_conduits": n_true, "routing_steps_per_step": rs, "spinup_sim_s": args.spinup,
                 "l2_policy": "state per GPU (%.2f GB) >> 126 MB L2, no flush needed" %
                              (4.8e-3 * args.members * (n_true / 19801.0)),
-                "timing": "CUDA events around each cooperative launch (library stream), max over ranks",
+                "timing": "CUDA events around each launch sequence of swb_run_steps (library stream), max over ranks",
+                "member_order": ("the 4096 members of c4_members(4096, 2024) enumerated by descending hydrograph scale "
+                                 "(neighbouring members need the same number of Picard trials)"
+                                 if args.member_order == "scale" else "as generated by c4_members(4096, 2024)"),
             },
             "picard_iterations_per_step": iters_all / max(msteps_all, 1),
             "e2e": {"value": e2e_cu / max(e2e_s, 1e-9), "unit": "conduit-updates/s",
@@ -679,6 +687,8 @@ def main():
     ap.add_argument("--cpu", type=int, default=-1, help="(reference-worker) core to pin to")
     ap.add_argument("--threads", type=int, default=1, help="(reference-worker) THREADS option of the model")
     ap.add_argument("--worker-warm", type=int, default=0, help="(reference-worker) untimed routing steps after spin-up")
+    ap.add_argument("--member-order", default="scale", choices=["generated", "scale"],
+                    help="enumeration of the config-4 members: as generated, or by descending hydrograph scale")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-packed", action="store_true")
     ap.add_argument("--no-weak", action="store_true")

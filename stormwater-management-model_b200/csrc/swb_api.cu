@@ -290,6 +290,10 @@ static bool zero(void *d, size_t b) { return !b || ok("cudaMemset", cudaMemset(d
 static bool copy2d(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, bool to_device)
 {
     if (!width || !height) return true;
+    // contiguous on both sides (all members of a field, or a single model): one linear copy -- a 2-D copy
+    // of 20 000 eight-byte rows costs ~0.3 ms, 60 of them per routing step made the drop-in seam 3x slower
+    if (dpitch == width && spitch == width)
+        return ok("cudaMemcpy", cudaMemcpy(d, s, width * height, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
     return ok("cudaMemcpy2D", cudaMemcpy2D(d, dpitch, s, spitch, width, height,
                                            to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
 }

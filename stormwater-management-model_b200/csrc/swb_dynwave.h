@@ -129,15 +129,19 @@ SWB_FI double link_froude(const Xs &x, bool isOpen, double v, double y, const do
 }
 
 // ---- link.c:770-804 -----------------------------------------------------------------------------
-SWB_NI double link_ynorm(const Net &n, int j, const Xs &x, double q, const double *T)
+SWB_NI double link_ynorm_vals(int flags, double qMax, double beta, const Xs &x, double q, const double *T)
 {
-    if (!(n.link_flags[j] & LF_TRUE_CONDUIT)) return 0.0;
+    if (!(flags & LF_TRUE_CONDUIT)) return 0.0;
     q = fabs(q);
-    if (q > n.cond_q_max[j]) q = n.cond_q_max[j];
+    if (q > qMax) q = qMax;
     if (q <= 0.0) return 0.0;
-    double s = q / n.cond_beta[j];
+    double s = q / beta;
     double a = xs_a_of_s_ni(x, s, T);
     return xs_y_of_a_ni(x, a, T);
+}
+SWB_FI double link_ynorm(const Net &n, int j, const Xs &x, double q, const double *T)
+{
+    return link_ynorm_vals(n.link_flags[j], n.cond_q_max[j], n.cond_beta[j], x, q, T);
 }
 
 // ---- link.c:643-670 with the node tests folded into link_flags ----------------------------------
@@ -151,7 +155,7 @@ SWB_FI bool link_flap_closed(int flags, int direction, double q)
 
 // ---- link.c:1334-1399 (DW branch) ---------------------------------------------------------------
 template <int S>
-SWB_FI double conduit_loss_rate(const Net &n, const State &s, int j, int m, const Xs &x,
+SWB_FI double conduit_loss_rate(const State &s, int j, int m, const Xs &x, double length, double seepRate,
                                        bool isOpen, double dt, double evapRate, double hydcon,
                                        double &evapLoss, double &seepLoss, const double *T)
 {
@@ -159,12 +163,10 @@ SWB_FI double conduit_loss_rate(const Net &n, const State &s, int j, int m, cons
     double depth = 0.5 * (s.l_old_depth[ix] + s.l_depth[ix]);
     double evapLossRate = 0.0, seepLossRate = 0.0, totalLossRate = 0.0;
     if (depth > SWB_FUDGE) {
-        double length = n.cond_length[j];
         if (isOpen && evapRate > 0.0) {
             double topWidth = xw<S>(x, depth, T);
             evapLossRate = topWidth * length * evapRate;
         }
-        double seepRate = n.link_seep_rate[j];
         if (seepRate > 0.0) {
             double width;
             if (x.type == XS_RECT_CLOSED) width = x.wMax;
@@ -196,33 +198,35 @@ struct FlowClassOut { int cls; double yC, yN, fasnh; };
 // never escapes, stays in registers, and its compile-time shape keeps folding every geometry
 // switch after the call (with a shared object the compiler had to reload x.type from the stack and
 // re-instantiated all 26 shapes behind every later lookup).
-SWB_FI void flow_class_depths(const Net &n, int j, Xs xc, double q, const double *T, double &yN, double &yC)
+template <class In>
+SWB_FI void flow_class_depths(const In &in, Xs xc, double q, const double *T, double &yN, double &yC)
 {
-    yN = link_ynorm(n, j, xc, q, T);
+    yN = link_ynorm_vals(in.flags(), in.qMax(), in.beta(), xc, q, T);
     yC = xs_ycrit_ni(xc, q, T);
 }
 
-SWB_FI FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int flags, double q,
+template <class In>
+SWB_FI FlowClassOut dw_flow_class(const In &in, const Xs &x, int flags, double q,
                                          double h1, double h2, double y1, double y2,
                                          double depth1, double depth2, double yMidGuess,
                                          const double *T)
 {
     FlowClassOut o;
     o.cls = SWB_SUBCRITICAL; o.fasnh = 1.0; o.yC = yMidGuess; o.yN = yMidGuess;
-    double z1 = n.link_offset1[j], z2 = n.link_offset2[j];
+    double z1 = in.offset1(), z2 = in.offset2();
     if (flags & LF_N1_OUTFALL) z1 = SWB_MAX(0.0, (z1 - depth1));
     if (flags & LF_N2_OUTFALL) z2 = SWB_MAX(0.0, (z2 - depth2));
 
     if (y1 > SWB_FUDGE && y2 > SWB_FUDGE) {
         if (q < 0.0) {
             if (z1 > 0.0) {
-                flow_class_depths(n, j, x, fabs(q), T, o.yN, o.yC);
+                flow_class_depths(in, x, fabs(q), T, o.yN, o.yC);
                 double ycMin = SWB_MIN(o.yN, o.yC);
                 if (y1 < ycMin) o.cls = SWB_UP_CRITICAL;
             }
         } else {
             if (z2 > 0.0) {
-                flow_class_depths(n, j, x, fabs(q), T, o.yN, o.yC);
+                flow_class_depths(in, x, fabs(q), T, o.yN, o.yC);
                 double ycMin = SWB_MIN(o.yN, o.yC);
                 double ycMax = SWB_MAX(o.yN, o.yC);
                 if (y2 < ycMin) o.cls = SWB_DN_CRITICAL;
@@ -235,16 +239,16 @@ SWB_FI FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int flags, d
     }
     else if (y1 <= SWB_FUDGE && y2 <= SWB_FUDGE) o.cls = SWB_DRY;
     else if (y2 > SWB_FUDGE) {
-        if (h2 < n.link_z1[j]) o.cls = SWB_UP_DRY;
+        if (h2 < in.z1()) o.cls = SWB_UP_DRY;
         else if (z1 > 0.0) {
-            flow_class_depths(n, j, x, fabs(q), T, o.yN, o.yC);
+            flow_class_depths(in, x, fabs(q), T, o.yN, o.yC);
             o.cls = SWB_UP_CRITICAL;
         }
     }
     else {
-        if (h1 < n.link_z2[j]) o.cls = SWB_DN_DRY;
+        if (h1 < in.z2()) o.cls = SWB_DN_DRY;
         else if (z2 > 0.0) {
-            flow_class_depths(n, j, x, fabs(q), T, o.yN, o.yC);
+            flow_class_depths(in, x, fabs(q), T, o.yN, o.yC);
             o.cls = SWB_DN_CRITICAL;
         }
     }
@@ -256,8 +260,23 @@ SWB_FI FlowClassOut dw_flow_class(const Net &n, int j, const Xs &x, int flags, d
 // point of use (late loads keep the register budget of the persistent kernel); CfStaged reads this lane's
 // column of a shared-memory stage that cp.async filled while the warp was computing its previous tile
 // (swb_staged.cuh: sg_links_pf) -- the same values, hence the same bits.
+// Static attributes of a true conduit packed into one 16-byte-aligned row (Net::link_rows, rows in
+// link_order order): the staged link kernel copies a conduit's row into shared memory with one cp.async per
+// lane while the warp works on its previous tile, so the update reads its ~40 static values with LDS at the
+// point of use instead of ~40 dependent global loads (and keeps none of them live across the geometry).
+enum { LR_YFULL = 0, LR_WMAX, LR_YWMAX, LR_AFULL, LR_RFULL, LR_SFULL, LR_SMAX, LR_YBOT, LR_ABOT, LR_SBOT, LR_RBOT,
+       LR_RCP_YFULL, LR_Z1, LR_Z2, LR_OFFSET1, LR_OFFSET2, LR_INV1, LR_INV2, LR_LENGTH, LR_MOD_LENGTH,
+       LR_RCP_MOD_LENGTH, LR_ROUGH, LR_BETA, LR_QMAX, LR_QLIMIT, LR_CLOSS_IN, LR_CLOSS_OUT, LR_CLOSS_AVG, LR_SEEP,
+       LR_DOUBLES,                       // 29 doubles, then 10 ints two per slot
+       LR_STRIDE = 36 };                 // doubles per row: 288 bytes = 18 lanes x 16 bytes
+enum { LRI_FLAGS = 0, LRI_XS_TYPE, LRI_BARRELS, LRI_HAS_LOSSES, LRI_DIRECTION, LRI_CULVERT, LRI_NODE1, LRI_NODE2, LRI_INTS };
+enum { CF_QLAST = 0, CF_DEPTH1, CF_DEPTH2, CF_SETTING, CF_AOLD, CF_OLDFLOW, CF_DT, CF_FIELDS };
+
 struct CfLoad {
+    static constexpr bool kStaged = false;
+    const Net &n;
     const State &s;
+    int j;
     size_t ix, ix1, ix2;
     SWB_FI double qLast()   const { return s.c_q1[ix]; }
     SWB_FI double depth1()  const { return s.n_depth[ix1]; }
@@ -265,16 +284,128 @@ struct CfLoad {
     SWB_FI double setting() const { return s.l_setting[ix]; }
     SWB_FI double aOld()    const { return s.c_a2[ix]; }
     SWB_FI double oldFlow() const { return s.l_old_flow[ix]; }
+    // static attributes
+    SWB_FI Xs     xs()        const { return load_xs(n, j); }
+    SWB_FI int    flags()     const { return n.link_flags[j]; }
+    SWB_FI double inv1()      const { return n.node_invert[n.link_node1[j]]; }
+    SWB_FI double inv2()      const { return n.node_invert[n.link_node2[j]]; }
+    SWB_FI double z1()        const { return n.link_z1[j]; }
+    SWB_FI double z2()        const { return n.link_z2[j]; }
+    SWB_FI double offset1()   const { return n.link_offset1[j]; }
+    SWB_FI double offset2()   const { return n.link_offset2[j]; }
+    SWB_FI double length()    const { return n.cond_length[j]; }
+    SWB_FI double modLength() const { return n.cond_mod_length[j]; }
+    SWB_FI double rcpModLength() const { return n.cond_rcp_mod_length[j]; }
+    SWB_FI double rough()     const { return n.cond_rough_factor[j]; }
+    SWB_FI double beta()      const { return n.cond_beta[j]; }
+    SWB_FI double qMax()      const { return n.cond_q_max[j]; }
+    SWB_FI double qLimit()    const { return n.link_q_limit[j]; }
+    SWB_FI double clossIn()   const { return n.link_closs_in[j]; }
+    SWB_FI double clossOut()  const { return n.link_closs_out[j]; }
+    SWB_FI double clossAvg()  const { return n.link_closs_avg[j]; }
+    SWB_FI double seepRate()  const { return n.link_seep_rate[j]; }
+    SWB_FI int    barrels()   const { return n.cond_barrels[j]; }
+    SWB_FI int    hasLosses() const { return n.cond_has_losses[j]; }
+    SWB_FI int    direction() const { return n.link_direction[j]; }
+    SWB_FI int    culvert()   const { return n.xs_culvert[j]; }
 };
-enum { CF_QLAST = 0, CF_DEPTH1, CF_DEPTH2, CF_SETTING, CF_AOLD, CF_OLDFLOW, CF_DT, CF_FIELDS };
+// Single models (M == 1): a warp holds 32 DIFFERENT conduits, consecutive in link_order.  The same packed
+// attributes stored column-wise in that order (Net::link_cols_d / link_cols_i) make every static load of the
+// warp one contiguous 256-byte request; indexed by the original link number the shape-grouped ticket order
+// reads the descriptor arrays with a stride of two or more and fetches twice the bytes.
+struct CfCols {
+    static constexpr bool kStaged = false;
+    const Net &n;
+    const State &s;
+    int j, k;                    // link index, position in link_order
+    size_t ix, ix1, ix2;
+    SWB_FI double qLast()   const { return s.c_q1[ix]; }
+    SWB_FI double depth1()  const { return s.n_depth[ix1]; }
+    SWB_FI double depth2()  const { return s.n_depth[ix2]; }
+    SWB_FI double setting() const { return s.l_setting[ix]; }
+    SWB_FI double aOld()    const { return s.c_a2[ix]; }
+    SWB_FI double oldFlow() const { return s.l_old_flow[ix]; }
+    SWB_FI double rd(int f) const { return n.link_cols_d[(size_t)f * n.nTrue + k]; }
+    SWB_FI int    ri(int f) const { return n.link_cols_i[(size_t)f * n.nTrue + k]; }
+    SWB_FI Xs xs() const
+    {
+        Xs x;
+        x.type = ri(LRI_XS_TYPE);
+        x.yFull = rd(LR_YFULL); x.wMax = rd(LR_WMAX); x.ywMax = rd(LR_YWMAX);
+        x.aFull = rd(LR_AFULL); x.rFull = rd(LR_RFULL); x.sFull = rd(LR_SFULL);
+        x.sMax = rd(LR_SMAX);   x.yBot = rd(LR_YBOT);   x.aBot = rd(LR_ABOT);
+        x.sBot = rd(LR_SBOT);   x.rBot = rd(LR_RBOT);   x.rYFull = rd(LR_RCP_YFULL);
+        x.ntbl = 0; x.atbl = x.rtbl = x.wtbl = nullptr;
+        return x;
+    }
+    SWB_FI int    flags()     const { return ri(LRI_FLAGS); }
+    SWB_FI double inv1()      const { return rd(LR_INV1); }
+    SWB_FI double inv2()      const { return rd(LR_INV2); }
+    SWB_FI double z1()        const { return rd(LR_Z1); }
+    SWB_FI double z2()        const { return rd(LR_Z2); }
+    SWB_FI double offset1()   const { return rd(LR_OFFSET1); }
+    SWB_FI double offset2()   const { return rd(LR_OFFSET2); }
+    SWB_FI double length()    const { return rd(LR_LENGTH); }
+    SWB_FI double modLength() const { return rd(LR_MOD_LENGTH); }
+    SWB_FI double rcpModLength() const { return rd(LR_RCP_MOD_LENGTH); }
+    SWB_FI double rough()     const { return rd(LR_ROUGH); }
+    SWB_FI double beta()      const { return rd(LR_BETA); }
+    SWB_FI double qMax()      const { return rd(LR_QMAX); }
+    SWB_FI double qLimit()    const { return rd(LR_QLIMIT); }
+    SWB_FI double clossIn()   const { return rd(LR_CLOSS_IN); }
+    SWB_FI double clossOut()  const { return rd(LR_CLOSS_OUT); }
+    SWB_FI double clossAvg()  const { return rd(LR_CLOSS_AVG); }
+    SWB_FI double seepRate()  const { return rd(LR_SEEP); }
+    SWB_FI int    barrels()   const { return ri(LRI_BARRELS); }
+    SWB_FI int    hasLosses() const { return ri(LRI_HAS_LOSSES); }
+    SWB_FI int    direction() const { return ri(LRI_DIRECTION); }
+    SWB_FI int    culvert()   const { return ri(LRI_CULVERT); }
+};
 struct CfStaged {
+    static constexpr bool kStaged = true;
     const double *b;             // &stage[lane]; field f of this lane is b[f * 32]
+    const double *r;             // the conduit's static row in shared memory (LR_*)
     SWB_FI double qLast()   const { return b[CF_QLAST * 32]; }
     SWB_FI double depth1()  const { return b[CF_DEPTH1 * 32]; }
     SWB_FI double depth2()  const { return b[CF_DEPTH2 * 32]; }
     SWB_FI double setting() const { return b[CF_SETTING * 32]; }
     SWB_FI double aOld()    const { return b[CF_AOLD * 32]; }
     SWB_FI double oldFlow() const { return b[CF_OLDFLOW * 32]; }
+    SWB_FI int ri(int k) const { return reinterpret_cast<const int *>(r + LR_DOUBLES)[k]; }
+    // only the specialised, table-free shapes run staged: no per-object tables
+    SWB_FI Xs xs() const
+    {
+        Xs x;
+        x.type = ri(LRI_XS_TYPE);
+        x.yFull = r[LR_YFULL]; x.wMax = r[LR_WMAX]; x.ywMax = r[LR_YWMAX];
+        x.aFull = r[LR_AFULL]; x.rFull = r[LR_RFULL]; x.sFull = r[LR_SFULL];
+        x.sMax = r[LR_SMAX];   x.yBot = r[LR_YBOT];   x.aBot = r[LR_ABOT];
+        x.sBot = r[LR_SBOT];   x.rBot = r[LR_RBOT];   x.rYFull = r[LR_RCP_YFULL];
+        x.ntbl = 0; x.atbl = x.rtbl = x.wtbl = nullptr;
+        return x;
+    }
+    SWB_FI int    flags()     const { return ri(LRI_FLAGS); }
+    SWB_FI double inv1()      const { return r[LR_INV1]; }
+    SWB_FI double inv2()      const { return r[LR_INV2]; }
+    SWB_FI double z1()        const { return r[LR_Z1]; }
+    SWB_FI double z2()        const { return r[LR_Z2]; }
+    SWB_FI double offset1()   const { return r[LR_OFFSET1]; }
+    SWB_FI double offset2()   const { return r[LR_OFFSET2]; }
+    SWB_FI double length()    const { return r[LR_LENGTH]; }
+    SWB_FI double modLength() const { return r[LR_MOD_LENGTH]; }
+    SWB_FI double rcpModLength() const { return r[LR_RCP_MOD_LENGTH]; }
+    SWB_FI double rough()     const { return r[LR_ROUGH]; }
+    SWB_FI double beta()      const { return r[LR_BETA]; }
+    SWB_FI double qMax()      const { return r[LR_QMAX]; }
+    SWB_FI double qLimit()    const { return r[LR_QLIMIT]; }
+    SWB_FI double clossIn()   const { return r[LR_CLOSS_IN]; }
+    SWB_FI double clossOut()  const { return r[LR_CLOSS_OUT]; }
+    SWB_FI double clossAvg()  const { return r[LR_CLOSS_AVG]; }
+    SWB_FI double seepRate()  const { return r[LR_SEEP]; }
+    SWB_FI int    barrels()   const { return ri(LRI_BARRELS); }
+    SWB_FI int    hasLosses() const { return ri(LRI_HAS_LOSSES); }
+    SWB_FI int    direction() const { return ri(LRI_DIRECTION); }
+    SWB_FI int    culvert()   const { return ri(LRI_CULVERT); }
 };
 
 template <int S, class In>
@@ -283,11 +414,13 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
 {
     const int M = s.M;
     const size_t ix = SWB_IX(j, m, M);
-    const int flags = n.link_flags[j];
-    Xs x = load_xs(n, j);
+    const int flags = in.flags();
+    Xs x = in.xs();
     if constexpr (S >= 0) x.type = S;        // compile-time shape: every geometry switch folds
+    // Staged inputs: the cross section is re-read from shared memory at the start of every block below, so
+    // none of its 12 values has to stay in a register (or a spill slot) across the blocks in between.
+#define SWB_XS_REFRESH() do { if constexpr (In::kStaged) { x = in.xs(); if constexpr (S >= 0) x.type = S; } } while (0)
     const bool isOpen = (flags & LF_OPEN_SHAPE) != 0;
-    const int n1 = n.link_node1[j], n2 = n.link_node2[j];
     const bool slot = (n.opt.surcharge_method == SWB_SLOT);
     // Register budget (64 per thread at 32 warps/SM): values that are only needed late (old flow,
     // old area, barrels, true length, end-node depths for the dry-node test) are loaded late or
@@ -296,8 +429,8 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
     double evapLoss = 0.0, seepLoss = 0.0;
 
     const double depth1 = in.depth1(), depth2 = in.depth2();
-    const double inv1 = n.node_invert[n1], inv2 = n.node_invert[n2];
-    double z1 = n.link_z1[j], z2 = n.link_z2[j];
+    const double inv1 = in.inv1(), inv2 = in.inv2();
+    double z1 = in.z1(), z2 = in.z2();
     double h1 = depth1 + inv1, h2 = depth2 + inv2;
     h1 = SWB_MAX(h1, z1);
     h2 = SWB_MAX(h2, z2);
@@ -306,7 +439,7 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
     y2 = SWB_MAX(y2, SWB_FUDGE);
     if (!slot) { y1 = SWB_MIN(y1, x.yFull); y2 = SWB_MIN(y2, x.yFull); }
 
-    const double length = n.cond_mod_length[j], rLength = n.cond_rcp_mod_length[j];
+    const double length = in.modLength(), rLength = in.rcpModLength();
 
     // --- findSurfArea (dwflow.c:417-550) on the previous iteration's flow
     int flowClass;
@@ -320,7 +453,7 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
         double normalDepth = (fd1 + fd2) / 2.0, criticalDepth = normalDepth, fasnh = 1.0;
         if (fd1 >= x.yFull && fd2 >= x.yFull) flowClass = SWB_SUBCRITICAL;
         else {
-            FlowClassOut fc = dw_flow_class(n, j, x, flags, qLast, h1, h2, y1, y2, depth1, depth2,
+            FlowClassOut fc = dw_flow_class(in, x, flags, qLast, h1, h2, y1, y2, depth1, depth2,
                                             normalDepth, T);
             flowClass = fc.cls; criticalDepth = fc.yC; normalDepth = fc.yN; fasnh = fc.fasnh;
         }
@@ -373,11 +506,11 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
                 break;
               case SWB_UP_DRY:
                 surfArea2 = (widthMid + width2) * length / 4.;
-                if (n.link_offset1[j] <= 0.0) surfArea1 = (width1 + widthMid) * length / 4.;
+                if (in.offset1() <= 0.0) surfArea1 = (width1 + widthMid) * length / 4.;
                 break;
               case SWB_DN_DRY:
                 surfArea1 = (widthMid + width1) * length / 4.;
-                if (n.link_offset2[j] <= 0.0) surfArea2 = (width2 + widthMid) * length / 4.;
+                if (in.offset2() <= 0.0) surfArea2 = (width2 + widthMid) * length / 4.;
                 break;
             }
         }
@@ -387,6 +520,7 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
     s.l_surf_area2[ix] = surfArea2;
 
     // --- areas and hydraulic radii (dwflow.c:142-153)
+    SWB_XS_REFRESH();
     if (ws1 < 0.0) ws1 = dw_slot_width(n, x, isOpen, y1);
     double a1 = dw_area<S>(x, y1, ws1, T);
     double r1 = dw_hyd_rad<S>(x, y1, T);
@@ -401,10 +535,10 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
 
     // --- dry / closed exit (dwflow.c:165-180)
     const bool isClosed = (in.setting() == 0);
-    const double barrels = (double)n.cond_barrels[j];
+    const double barrels = (double)in.barrels();
     if (flowClass == SWB_DRY || flowClass == SWB_UP_DRY || flowClass == SWB_DN_DRY || isClosed ||
         aMid <= SWB_FUDGE) {
-        const double trueLength = n.cond_length[j];
+        const double trueLength = in.length();
         double a1s = 0.5 * (a1 + a2);
         s.c_a1[ix] = a1s;
         s.c_q1[ix] = 0.0;
@@ -419,6 +553,7 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
     }
 
     // --- velocity, Froude number, inertial damping (dwflow.c:183-208)
+    SWB_XS_REFRESH();
     double v = qLast / aMid;
     if (fabs(v) > SWB_MAXVELOCITY) v = SWB_MAXVELOCITY * SWB_SGN(qLast);
     // link_getFroude (link.c:847-871); A(yMid) and W(yMid) are reused when they are the very values
@@ -445,14 +580,14 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
     if (isFull && !isOpen) sigma = 0.0;
 
     // --- momentum terms (dwflow.c:210-236)
-    const double trueLength = n.cond_length[j];
+    const double trueLength = in.length();
     double aOld = in.aOld();
     aOld = SWB_MAX(aOld, SWB_FUDGE);
     const double qOld = in.oldFlow() / barrels;
     double dq1;
     if (S < 0 && x.type == XS_FORCE_MAIN && isFull)
          dq1 = dt * forcemain_fric_slope(n, x, fabs(v), rMid);
-    else dq1 = dt * n.cond_rough_factor[j] / pow(rWtd, 1.33333) * fabs(v);
+    else dq1 = dt * in.rough() / pow(rWtd, 1.33333) * fabs(v);
     double dq2 = div_by(dt * SWB_GRAVITY * aWtd * (h2 - h1), length, rLength);
     double dq3 = 0.0, dq4 = 0.0;
     if (sigma > 0.0) {
@@ -460,16 +595,16 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
         dq4 = div_by(dt * v * v * (a2 - a1), length, rLength) * sigma;
     }
     double dq5 = 0.0;
-    if (n.cond_has_losses[j]) {
+    if (in.hasLosses()) {
         double losses = 0.0, qa = fabs(qLast);
-        if (a1 > SWB_FUDGE)   losses += n.link_closs_in[j]  * (qa / a1);
-        if (a2 > SWB_FUDGE)   losses += n.link_closs_out[j] * (qa / a2);
-        if (aMid > SWB_FUDGE) losses += n.link_closs_avg[j] * (qa / aMid);
+        if (a1 > SWB_FUDGE)   losses += in.clossIn()  * (qa / a1);
+        if (a2 > SWB_FUDGE)   losses += in.clossOut() * (qa / a2);
+        if (aMid > SWB_FUDGE) losses += in.clossAvg() * (qa / aMid);
         dq5 = div_by(losses / 2.0, length, rLength) * dt;
     }
     double dq6 = 0.0;
     if (flags & LF_HAS_LOSSRATE) {
-        double lossRate = conduit_loss_rate<S>(n, s, j, m, x, isOpen, dt, s.evap_rate[m], s.hydcon[m],
+        double lossRate = conduit_loss_rate<S>(s, j, m, x, trueLength, in.seepRate(), isOpen, dt, s.evap_rate[m], s.hydcon[m],
                                             evapLoss, seepLoss, T);
         dq6 = lossRate * 2.5 * dt * v / trueLength;
     }
@@ -479,8 +614,9 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
     double dqdh = div_by(1.0 / denom * SWB_GRAVITY * dt * aWtd, length, rLength) * barrels;
 
     // --- flow limitations (dwflow.c:245-259); culvert-coded links always run the generic instance
+    SWB_XS_REFRESH();
     unsigned char normalFlow = 0, inletControl = 0;
-    const bool hasCulvert = (S < 0) && n.xs_culvert[j] > 0;
+    const bool hasCulvert = (S < 0) && in.culvert() > 0;
     if (q > 0.0) {
         if (hasCulvert && !isFull) q = culvert_inflow(n, x, j, q, h1, dqdh, inletControl, T);
         else if (n.opt.normal_flow_ltd != SWB_NF_NEITHER && y1 < x.yFull &&
@@ -497,7 +633,7 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
                 }
             }
             if (check) {
-                double qNorm = n.cond_beta[j] * a1 * pow(r1, 2. / 3.);
+                double qNorm = in.beta() * a1 * pow(r1, 2. / 3.);
                 if (qNorm < q) { normalFlow = 1; q = qNorm; }
             }
         }
@@ -508,9 +644,9 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
         q = (1.0 - SWB_OMEGA) * qLast + SWB_OMEGA * q;
         if (q * qLast < 0.0) q = 0.001 * SWB_SGN(q);
     }
-    double qLimit = n.link_q_limit[j];
+    double qLimit = in.qLimit();
     if (qLimit > 0.0) { if (fabs(q) > qLimit) q = SWB_SGN(q) * qLimit; }
-    if (link_flap_closed(flags, n.link_direction[j], q)) q = 0.0;
+    if (link_flap_closed(flags, in.direction(), q)) q = 0.0;
     if (q >  SWB_FUDGE && in.depth1() <= SWB_FUDGE) q =  SWB_FUDGE;
     if (q < -SWB_FUDGE && in.depth2() <= SWB_FUDGE) q = -SWB_FUDGE;
 
@@ -531,13 +667,14 @@ SWB_FI void conduit_flow_in(const Net &n, const State &s, int j, int m, int step
     s.l_normal_flow[ix] = normalFlow;
     if (hasCulvert) s.l_inlet_control[ix] = inletControl;     // 0 for ever on every other link
     if (flags & LF_HAS_LOSSRATE) { s.c_evap_loss[ix] = evapLoss; s.c_seep_loss[ix] = seepLoss; }
+#undef SWB_XS_REFRESH
 }
 
 template <int S>
 SWB_FI void conduit_flow(const Net &n, const State &s, int j, int m, int steps, double dt,
                          const double *T)
 {
-    const CfLoad in = { s, SWB_IX(j, m, s.M), SWB_IX(n.link_node1[j], m, s.M), SWB_IX(n.link_node2[j], m, s.M) };
+    const CfLoad in = { n, s, j, SWB_IX(j, m, s.M), SWB_IX(n.link_node1[j], m, s.M), SWB_IX(n.link_node2[j], m, s.M) };
     conduit_flow_in<S>(n, s, j, m, steps, dt, T, in);
 }
 
@@ -554,6 +691,20 @@ SWB_CF void conduit_flow_rect_closed(const Net &n, const State &s, int j, int m,
 { conduit_flow<XS_RECT_CLOSED>(n, s, j, m, steps, dt, T); }
 SWB_NI void conduit_flow_generic(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
 { conduit_flow<-1>(n, s, j, m, steps, dt, T); }
+// the two table-free shapes of a single model, statics read column-wise (k = position in link_order)
+template <int S>
+SWB_NI void conduit_flow_cols(const Net &n, const State &s, int j, int k, int n1, int n2, int m, int steps, double dt, const double *T)
+{
+    const CfCols in = { n, s, j, k, SWB_IX(j, m, s.M), SWB_IX(n1, m, s.M), SWB_IX(n2, m, s.M) };
+    conduit_flow_in<S>(n, s, j, m, steps, dt, T, in);
+}
+SWB_FI void conduit_update_cols(const Net &n, const State &s, int j, int k, int n1, int n2, int m, int steps, double dt, const double *T)
+{
+    // link_order is grouped by conduit-function class: the class follows from the position
+    if (k < n.lk_count[0]) conduit_flow_cols<XS_CIRCULAR>(n, s, j, k, n1, n2, m, steps, dt, T);
+    else if (k < n.lk_count[0] + n.lk_count[1]) conduit_flow_cols<XS_RECT_CLOSED>(n, s, j, k, n1, n2, m, steps, dt, T);
+    else conduit_flow_generic(n, s, j, m, steps, dt, T);
+}
 SWB_FI void conduit_update(const Net &n, const State &s, int j, int m, int steps, double dt, const double *T)
 {
     switch (n.link_kernel[j]) {

@@ -160,6 +160,19 @@ SWB_FI void picard_link(const Net &net, const State &st, int j, int m, int k, do
     }
     conduit_update(net, st, j, m, k, dt, T);
 }
+// the same for a single model (M == 1), jj = position of the conduit in link_order: every static attribute,
+// the two end nodes included, comes from the column-wise copy in that order
+SWB_FI void picard_link_single(const Net &net, const State &st, int jj, int k, double dt, const double *T)
+{
+    const int j = net.link_order[jj];
+    const int n1 = net.link_cols_i[(size_t)LRI_NODE1 * net.nTrue + jj], n2 = net.link_cols_i[(size_t)LRI_NODE2 * net.nTrue + jj];
+    if (k >= 2) {
+        const bool byp = st.n_converged[n1] && st.n_converged[n2];
+        st.l_bypassed[j] = byp ? 1 : 0;
+        if (byp) return;
+    }
+    conduit_update_cols(net, st, j, jj, n1, n2, 0, k, dt, T);
+}
 // node sums over the true conduits only, stored for the ordered regulator pass
 SWB_FI void picard_node_presum(const Net &net, const State &st, int i, int m)
 {
@@ -1018,7 +1031,8 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 // ---- findLinkFlows, pass (i): true conduits (dynwave.c:387-395)
                 if (!(args.debug & DBG_SKIP_LINKS))
                 for_tiles(ctx, net.nTrue, nAlive, tickets + TK_LINKS, [&](int jj, int mm) {
-                    picard_link(net, st, net.link_order[jj], mm, k, st.dt[mm], T);
+                    if (M == 1) picard_link_single(net, st, jj, k, st.dt[0], T);
+                    else picard_link(net, st, net.link_order[jj], mm, k, st.dt[mm], T);
                 });
                 ctx.grid_sync();
                 SWB_TICK(TP_LINKS);

@@ -18,7 +18,8 @@ namespace swb {
 struct Derived {
     std::vector<int> outfall_nodes, link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link, link_order,
                      link_kernel, node_order;
-    std::vector<double> link_z1, link_z2, xs_tables, culvert_params, road_tables, xs_rcp_yfull, cond_rcp_mod_length;
+    std::vector<double> link_z1, link_z2, xs_tables, culvert_params, road_tables, xs_rcp_yfull, cond_rcp_mod_length, link_rows, link_cols_d;
+    std::vector<int> link_cols_i;
     std::vector<AdjEntry> adj_packed;
     int nTrue = 0, nNonConduit = 0;
 };
@@ -117,6 +118,42 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
                          if (r.link_kernel[a] != r.link_kernel[b]) return r.link_kernel[a] < r.link_kernel[b];
                          return d.xs_type[a] < d.xs_type[b];
                      });
+    // packed static rows of the true conduits, in ticket order (swb_dynwave.h: LR_*, CfStaged)
+    r.link_rows.assign(r.link_order.size() * (size_t)LR_STRIDE, 0.0);
+    for (size_t k = 0; k < r.link_order.size(); k++) {
+        const int j = r.link_order[k];
+        double *row = r.link_rows.data() + k * (size_t)LR_STRIDE;
+        row[LR_YFULL] = d.xs_yfull[j]; row[LR_WMAX] = d.xs_wmax[j]; row[LR_YWMAX] = d.xs_ywmax[j];
+        row[LR_AFULL] = d.xs_afull[j]; row[LR_RFULL] = d.xs_rfull[j]; row[LR_SFULL] = d.xs_sfull[j];
+        row[LR_SMAX] = d.xs_smax[j]; row[LR_YBOT] = d.xs_ybot[j]; row[LR_ABOT] = d.xs_abot[j];
+        row[LR_SBOT] = d.xs_sbot[j]; row[LR_RBOT] = d.xs_rbot[j]; row[LR_RCP_YFULL] = r.xs_rcp_yfull[j];
+        row[LR_Z1] = r.link_z1[j]; row[LR_Z2] = r.link_z2[j];
+        row[LR_OFFSET1] = d.link_offset1[j]; row[LR_OFFSET2] = d.link_offset2[j];
+        row[LR_INV1] = d.node_invert[d.link_node1[j]]; row[LR_INV2] = d.node_invert[d.link_node2[j]];
+        row[LR_LENGTH] = d.cond_length[j]; row[LR_MOD_LENGTH] = d.cond_mod_length[j];
+        row[LR_RCP_MOD_LENGTH] = r.cond_rcp_mod_length[j]; row[LR_ROUGH] = d.cond_rough_factor[j];
+        row[LR_BETA] = d.cond_beta[j]; row[LR_QMAX] = d.cond_q_max[j]; row[LR_QLIMIT] = d.link_q_limit[j];
+        row[LR_CLOSS_IN] = d.link_closs_in[j]; row[LR_CLOSS_OUT] = d.link_closs_out[j];
+        row[LR_CLOSS_AVG] = d.link_closs_avg[j]; row[LR_SEEP] = d.link_seep_rate[j];
+        int iv[LRI_INTS];
+        iv[LRI_FLAGS] = r.link_flags[j]; iv[LRI_XS_TYPE] = d.xs_type[j]; iv[LRI_BARRELS] = d.cond_barrels[j];
+        iv[LRI_HAS_LOSSES] = d.cond_has_losses[j]; iv[LRI_DIRECTION] = d.link_direction[j];
+        iv[LRI_CULVERT] = d.xs_culvert[j]; iv[LRI_NODE1] = d.link_node1[j]; iv[LRI_NODE2] = d.link_node2[j];
+        static_assert(LR_DOUBLES * sizeof(double) + LRI_INTS * sizeof(int) <= LR_STRIDE * sizeof(double), "row too small");
+        memcpy(row + LR_DOUBLES, iv, sizeof(iv));
+    }
+    {   // the same attributes column-wise (single models)
+        const size_t nT = r.link_order.size();
+        r.link_cols_d.assign(nT * (size_t)LR_DOUBLES, 0.0);
+        r.link_cols_i.assign(nT * (size_t)LRI_INTS, 0);
+        for (size_t k = 0; k < nT; k++) {
+            const double *row = r.link_rows.data() + k * (size_t)LR_STRIDE;
+            for (int f = 0; f < LR_DOUBLES; f++) r.link_cols_d[(size_t)f * nT + k] = row[f];
+            int iv[LRI_INTS];
+            memcpy(iv, row + LR_DOUBLES, sizeof(iv));
+            for (int f = 0; f < LRI_INTS; f++) r.link_cols_i[(size_t)f * nT + k] = iv[f];
+        }
+    }
     node_order_expensive_first(d.node_type, nN, nN, r.node_order);
     // CSR incidence.  adjq: ascending link index.  adj: true conduits first, then the rest.
     std::vector<std::vector<int>> inc(nN);

@@ -179,12 +179,18 @@ sg_links(const __grid_constant__ Net net, const __grid_constant__ State st, int 
 #ifndef SWB_SG_LINK_PF
 #define SWB_SG_LINK_PF 1
 #endif
-struct PfIds { int j, n1, n2, mm; };     // mm < 0: lane has no member in this tile (or the conduit is bypassed)
+struct PfIds { int j, n1, n2, mm, row; };   // mm < 0: lane has no member in this tile (or the conduit is bypassed);
+                                            // row = position of the conduit in link_order (its packed static row)
 
 __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double *dst_smem, const double *src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
@@ -195,6 +201,7 @@ sg_links_pf(const __grid_constant__ Net net, const __grid_constant__ State st, i
 {
     __shared__ double tab[XT_TOTAL];
     __shared__ double stage_all[(SWB_SG_LINK_BLOCK / 32) * 2 * CF_FIELDS * 32];
+    __shared__ __align__(16) double rows_all[(SWB_SG_LINK_BLOCK / 32) * 2 * LR_STRIDE];
     sg_tick(st, prev);
     const int nAlive = st.ctl[CTL_N_ALIVE];
     if (!st.ctl[CTL_ANY_LEFT] || nAlive == 0) return;
@@ -217,13 +224,13 @@ sg_links_pf(const __grid_constant__ Net net, const __grid_constant__ State st, i
                 st.l_bypassed[SWB_IX(j, mm, M)] = byp ? 1 : 0;
                 if (byp) return;
             }
-            const CfLoad in = { st, SWB_IX(j, mm, M), SWB_IX(net.link_node1[j], mm, M), SWB_IX(net.link_node2[j], mm, M) };
-            update(j, mm, st.dt[mm], in);
+            conduit_update(net, st, j, mm, k, st.dt[mm], tab);     // (out of line: this path is rare)
         });
         return;
     }
     const int lane = threadIdx.x & 31;
     double *my = stage_all + (size_t)(threadIdx.x >> 5) * 2 * CF_FIELDS * 32 + lane;
+    double *myRows = rows_all + (size_t)(threadIdx.x >> 5) * 2 * LR_STRIDE;
     const int nChunks = (nAlive + 31) / 32;
     const unsigned total = (unsigned)net.lk_count[LK] * (unsigned)nChunks;     // < 2^31 (checked by the launcher)
     auto issue = [&]() -> unsigned long long { unsigned long long v = 0; if (lane == 0) v = atomicAdd(ticket, 1ull); return v; };
@@ -235,7 +242,8 @@ sg_links_pf(const __grid_constant__ Net net, const __grid_constant__ State st, i
         PfIds d;
         const unsigned jj = t / (unsigned)nChunks;
         const int slot = (int)(t - jj * (unsigned)nChunks) * 32 + lane;
-        d.j = net.link_order[j0 + (int)jj];
+        d.row = j0 + (int)jj;
+        d.j = net.link_order[d.row];
         d.n1 = net.link_node1[d.j]; d.n2 = net.link_node2[d.j];
         d.mm = slot < nAlive ? st.alive[slot] : -1;
         if (k >= 2 && d.mm >= 0) {         // findBypassedLinks of the previous trial (dynwave.c:335-345)
@@ -245,7 +253,10 @@ sg_links_pf(const __grid_constant__ Net net, const __grid_constant__ State st, i
         }
         return d;
     };
-    auto prefetch = [&](const PfIds &d, int stg) {
+    auto prefetch = [&](const PfIds &d, int stg, bool valid) {
+        // the conduit's static row: 18 lanes x 16 bytes (warp-uniform source, every lane of the tile reads it)
+        if (valid && lane < LR_STRIDE / 2)
+            cp_async16(myRows + stg * LR_STRIDE + lane * 2, net.link_rows + (size_t)d.row * LR_STRIDE + lane * 2);
         if (d.mm >= 0) {
             double *b = my + stg * (CF_FIELDS * 32);
             const size_t ix = SWB_IX(d.j, d.mm, M);
@@ -259,20 +270,22 @@ sg_links_pf(const __grid_constant__ Net net, const __grid_constant__ State st, i
         }
         cp_async_commit();
     };
-    const PfIds none = { 0, 0, 0, -1 };
+    const PfIds none = { 0, 0, 0, -1, 0 };
     unsigned t0 = take(issue());
     unsigned t1 = t0 < total ? take(issue()) : total;
     unsigned t2 = t1 < total ? take(issue()) : total;
     PfIds i0 = t0 < total ? ids(t0) : none, i1 = t1 < total ? ids(t1) : none, i2 = t2 < total ? ids(t2) : none;
-    prefetch(i0, 0);
+    prefetch(i0, 0, t0 < total);
     int stg = 0;
     while (t0 < total) {
         const unsigned long long pend = (t2 < total) ? issue() : (unsigned long long)total;
-        prefetch(i1, stg ^ 1);             // (an empty group when there is no next tile)
+        __syncwarp();                      // every lane is done reading the static row the next copy overwrites
+        prefetch(i1, stg ^ 1, t1 < total); // (an empty group when there is no next tile)
         cp_async_wait<1>();                // everything but the group just committed: tile t0's rows are in
+        __syncwarp();                      // ... including the parts of the static row other lanes copied
         if (i0.mm >= 0) {
             const double *b = my + stg * (CF_FIELDS * 32);
-            const CfStaged in = { b };
+            const CfStaged in = { b, myRows + stg * LR_STRIDE };
             update(i0.j, i0.mm, b[CF_DT * 32], in);
         }
         t0 = t1; i0 = i1; t1 = t2; i1 = i2; stg ^= 1;

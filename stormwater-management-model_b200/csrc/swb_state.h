@@ -100,6 +100,10 @@ struct Net {
     const int    *outfall_nodes;           // outfall nodes in ascending index order
     int           nOutfallNodes;
     const int    *link_kernel;             // LK_*: which conduit function a true conduit runs
+    const double *link_rows;               // [nTrue][LR_STRIDE]: packed static row per true conduit, in
+                                           // link_order order (swb_dynwave.h: LR_*), 16-byte aligned
+    const double *link_cols_d;             // [LR_DOUBLES][nTrue] / [LRI_INTS][nTrue]: the same attributes column-wise
+    const int    *link_cols_i;             // in link_order order, for single models (CfCols)
     const double *culvert_params;          // [58][5] FHWA inlet-control coefficients (culvert.c:33)
     const double *road_tables;             // RT_TOTAL (x, y) pairs (roadway.c:42-69)
     const double *xs_tables;               // XT_TOTAL doubles (global copy of the shape tables)

@@ -379,10 +379,16 @@ ELSE OUTLET OL1 SETTING = 1.0
 """
 
 
-def c3_rules_inp(rule_step: str | None = None) -> str:
+def c3_rules_inp(rule_step: str | None = None, pid: bool = True) -> str:
+    """pid=False drops rule R4: the PID controller zeroes updates below 1e-4 (controls.c:1141), a
+    discontinuity that turns a last-bit difference in a depth into a 1e-4 difference in a setting."""
     a = C3_MIXED_INP.index("[CONTROLS]")
     b = C3_MIXED_INP.index("[POLLUTANTS]")
-    txt = C3_MIXED_INP[:a] + C3_RULES + C3_MIXED_INP[b:]
+    rules = C3_RULES
+    if not pid:
+        r4 = rules.index("RULE R4")
+        rules = rules[:r4] + rules[rules.index("RULE R5"):]
+    txt = C3_MIXED_INP[:a] + rules + C3_MIXED_INP[b:]
     txt = txt.replace("[CURVES]\n", "[CURVES]\nWCURVE CONTROL 0 1.0 2 0.8 5 0.4\n")
     txt = txt.replace("[TIMESERIES]\n", "[TIMESERIES]\nWTS 0:00 1.0\nWTS 6:00 0.5\nWTS 12:00 1.0\n")
     if rule_step:

@@ -373,6 +373,15 @@ typedef struct swb_controls_desc {
 /* Installs the rules (a second call replaces them); swb_run_steps then evaluates them at the start of every
  * routing step of every member.  Host-fed steps (swb_step_host) keep taking settings from the host. */
 int  swb_set_controls(swb_solver *s, const swb_controls_desc *controls);
+/* Re-enumerates the members of an ensemble on the device: afterwards member i is what member perm[i] was.  State,
+ * clocks, iteration counters, statistics, routing totals, inflow scale / shift and rule state move together, so
+ * every result of a member is the same bits as without the call -- only its index changes (the caller keeps the
+ * map).  Why: a Picard trial works on the members that have not converged yet (dynwave.c:242-256); when those
+ * sit next to each other a warp's 32 loads fill whole 32-byte sectors, when they are scattered each survivor
+ * costs a sector of its own.  Trial counts persist from step to step, so sorting the members by the trials they
+ * used recently (swb_get_stats: iterations) every few hundred steps keeps the late trials dense.  perm must be
+ * a permutation of 0 .. n_members-1. */
+int  swb_permute_members(swb_solver *s, const int *perm);
 /* Advance every member n_steps routing steps entirely on the device (one cooperative launch):
  * dt from the Courant search, inflows from swb_set_inflows, dynamic wave + quality routing.
  * t_end: members stop stepping once their sim_time reaches it (last step shortened like

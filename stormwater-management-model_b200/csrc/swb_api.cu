@@ -361,6 +361,34 @@ static void *window_open(const void *handle, size_t, std::string &err)
 static void window_close(void *p) { if (p) cudaIpcCloseMemHandle(p); }
 static void window_free(void *p, size_t, const void *) { if (p) cudaFree(p); }
 
+// dst[r][i] = src[r][perm[i]] for a batch of rows
+template <class T>
+__global__ void swb_permute_rows(T *dst, const T *src, const int *perm, int M, size_t rows)
+{
+    const size_t n = rows * (size_t)M;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = t / M;
+        const int i = (int)(t - r * M);
+        dst[t] = src[r * M + perm[i]];
+    }
+}
+static bool permute_members(void *p, size_t rows, int esz, int M, const int *d_perm, void *tmp, size_t tmp_bytes)
+{
+    const size_t row_bytes = (size_t)M * esz;
+    const size_t batch = std::max<size_t>(1, tmp_bytes / row_bytes);
+    for (size_t r0 = 0; r0 < rows; r0 += batch) {
+        const size_t nr = std::min(batch, rows - r0);
+        char *base = (char *)p + r0 * row_bytes;
+        const int blocks = (int)std::min<size_t>(148 * 8, (nr * M + 255) / 256);
+        if (esz == 8) swb_permute_rows<unsigned long long><<<blocks, 256>>>((unsigned long long *)tmp, (const unsigned long long *)base, d_perm, M, nr);
+        else if (esz == 4) swb_permute_rows<unsigned int><<<blocks, 256>>>((unsigned int *)tmp, (const unsigned int *)base, d_perm, M, nr);
+        else swb_permute_rows<unsigned char><<<blocks, 256>>>((unsigned char *)tmp, (const unsigned char *)base, d_perm, M, nr);
+        if (!ok("swb_permute_rows", cudaGetLastError())) return false;
+        if (!ok("cudaMemcpyAsync(D2D)", cudaMemcpyAsync(base, tmp, nr * row_bytes, cudaMemcpyDeviceToDevice, 0))) return false;
+    }
+    return true;
+}
+
 static void *host_alloc(size_t bytes)
 {
     void *p = nullptr;

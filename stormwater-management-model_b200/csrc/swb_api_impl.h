@@ -12,6 +12,7 @@
 //     bool  launch(const Net &, const State &, const RunArgs &, int device, float *ms, std::string &err);
 //     bool  sync(std::string &err);         int device_count();
 //     void *host_alloc(size_t);  void host_free(void *);
+//     bool permute_members(void *p, size_t rows, int esz, int M, const int *d_perm, void *tmp, size_t tmp_bytes);
 //     void  h2d_async(void *dst, const void *src, size_t bytes);  void d2h_async(...);
 //     bool  xsect_eval(int device, int fn, const Xs &x, int n, const double *args, double *out, std::string &err);
 //   } }
@@ -46,6 +47,8 @@ struct swb_solver {
     std::vector<void *> inflow_allocs;      // device arrays of the current swb_set_inflows call
     Inflows inflows;
     bool have_inflows;
+    void *xfer_buf = nullptr; size_t xfer_cap = 0;   // pinned staging of swb_set_field / swb_get_field
+    void *perm_tmp = nullptr; int *perm_idx = nullptr;   // scratch of swb_permute_members
     std::vector<void *> control_allocs;     // device arrays of the current swb_set_controls call
     Controls controls;
     long long launches;
@@ -157,7 +160,7 @@ int swb_network_create(const swb_network_desc *d, const swb_options *o, int devi
 #define D(name) ar.add(nw->net.name, r.name.data(), r.name.size());
         D(outfall_nodes) D(adj_packed) D(link_flags) D(link_z1) D(link_z2) D(xs_rcp_yfull) D(cond_rcp_mod_length) D(adj_start) D(adj)
         D(adjq_start) D(adjq) D(nc_links) D(node_order) D(link_order) D(outfall_link) D(xs_tables)
-        D(link_kernel) D(culvert_params) D(road_tables) D(link_rows) D(link_cols_d) D(link_cols_i)
+        D(link_kernel) D(culvert_params) D(road_tables) D(link_rows) D(link_cols_d) D(link_cols_i) D(outfall_slot) D(link_pre_node)
 #undef D
         nw->net.arena_bytes = ar.image.size();
         nw->net.arena = ar.commit(nw->allocs);
@@ -203,6 +206,8 @@ int swb_solver_create(swb_network *nw, int M, swb_solver **out)
     }
     st.dt = dev_zero<double>(s->allocs, M);
     st.var_step = dev_zero<double>(s->allocs, M);
+    st.o_ynorm = dev_zero<double>(s->allocs, (size_t)(nw->net.nOutfallNodes ? nw->net.nOutfallNodes : 1) * M);
+    st.o_ycrit = dev_zero<double>(s->allocs, (size_t)(nw->net.nOutfallNodes ? nw->net.nOutfallNodes : 1) * M);
     st.sim_time = dev_zero<double>(s->allocs, M);
     st.time_ms = dev_zero<double>(s->allocs, M);
     std::vector<double> ev(M, nw->net.opt.evap_rate), hc(M, nw->net.opt.hydcon_factor);
@@ -250,6 +255,7 @@ void swb_solver_destroy(swb_solver *s)
     for (void *p : s->allocs) backend::free_(p);
     for (void *p : s->inflow_allocs) backend::free_(p);
     for (void *p : s->control_allocs) backend::free_(p);
+    if (s->xfer_buf) backend::host_free(s->xfer_buf);
     if (s->stream) backend::stream_destroy(s->stream);
     for (int p = 0; p < SWB_MAX_RANKS; p++) if (s->peer_window[p]) backend::window_close(s->peer_window[p]);
     if (s->window) backend::window_free(s->window, s->window_bytes, s->window_handle);
@@ -276,10 +282,25 @@ static int field_xfer(swb_solver *s, int field, int m0, int nm, double *buf, con
     // member of a wide ensemble does not download the whole field
     const size_t esz = f->is_u8 ? 1 : sizeof(double);
     const size_t cols = (size_t)nm;
-    std::vector<double> h(items * cols);
-    std::vector<unsigned char> h8;
+    // one pinned staging buffer per solver (doubles, then the byte image of a flag field): the copies run at
+    // full PCIe rate without the driver's bounce buffer and nothing is allocated per call -- the drop-in seam
+    // moves ~100 fields per routing step through here
+    const size_t need = items * cols * (sizeof(double) + 1);
+    if (need > s->xfer_cap) {
+        if (s->xfer_buf) backend::host_free(s->xfer_buf);
+        s->xfer_cap = 0;
+        s->xfer_buf = backend::host_alloc(need);
+        if (!s->xfer_buf) return fail(SWB_ERR_CUDA, "pinned staging allocation failed");
+        s->xfer_cap = need;
+    }
+    struct Span { double *p; size_t n; double *data() const { return p; } size_t size() const { return n; }
+                  double &operator[](size_t i) const { return p[i]; } };
+    struct Span8 { unsigned char *p; size_t n; unsigned char *data() const { return p; } size_t size() const { return n; }
+                   unsigned char &operator[](size_t i) const { return p[i]; } };
+    const Span h = { (double *)s->xfer_buf, items * cols };
+    const Span8 h8 = { (unsigned char *)s->xfer_buf + items * cols * sizeof(double), f->is_u8 ? items * cols : 0 };
     void *hostp = h.data();
-    if (f->is_u8) { h8.resize(items * cols); hostp = h8.data(); }
+    if (f->is_u8) hostp = h8.data();
     char *devp = (char *)dev + (size_t)m0 * esz;
     if (!set) {
         if (!backend::copy2d(hostp, cols * esz, devp, (size_t)M * esz, cols * esz, items, false))
@@ -748,6 +769,72 @@ int swb_set_controls(swb_solver *s, const swb_controls_desc *d)
         return fail(SWB_ERR_CUDA, e.what);
     }
     return SWB_OK;
+}
+
+// ---- re-enumeration of the member axis ------------------------------------------------------------------
+// Every array with a member axis, as (pointer, rows, element size); built on demand so that arrays created
+// later (statistics, inflows, rule state) are covered.
+struct MemberArray { void *p; size_t rows; int esz; };
+static std::vector<MemberArray> member_arrays(swb_solver *s)
+{
+    const Net &n = s->net->net;
+    const State &st = s->st;
+    const int nN = n.nN, nL = n.nL, nP = n.nP;
+    std::vector<MemberArray> v;
+    auto add = [&](const void *p, size_t rows, int esz) { if (p && rows) v.push_back({const_cast<void *>(p), rows, esz}); };
+    for (const FieldInfo &f : field_table())
+        add(*(void **)((char *)&st + f.offset), field_items(f, nN, nL, nP), f.is_u8 ? 1 : 8);
+    add(st.dt, 1, 8); add(st.var_step, 1, 8); add(st.sim_time, 1, 8); add(st.time_ms, 1, 8);
+    add(st.evap_rate, 1, 8); add(st.hydcon, 1, 8); add(st.iters, 1, 4);
+    add(st.tot_iters, 1, 8); add(st.tot_steps, 1, 8); add(st.non_conv, 1, 8);
+    add(st.crit_node, 1, 4); add(st.crit_link, 1, 4); add(st.tmin_bits, 2, 8); add(st.done, 1, 4);
+    add(st.o_ynorm, n.nOutfallNodes, 8); add(st.o_ycrit, n.nOutfallNodes, 8);
+    add(st.not_conv, SWB_MAX_TRIALS_CAP, 4);
+    add(st.mb_reacted, nP ? nP : 1, 8); add(st.mb_seepage, nP ? nP : 1, 8); add(st.mb_final_storage, nP ? nP : 1, 8);
+    add(st.mb_rate, MB_FLOW_TERMS + MB_QUAL_TERMS * nP, 8); add(st.mb_total, MB_FLOW_TERMS + MB_QUAL_TERMS * nP, 8);
+    add(st.mb_dt_prev, 1, 8);
+    add(st.stat_node, (size_t)(SWB_NS_PLANES + nP) * nN, 8); add(st.stat_link, (size_t)SWB_LS_PLANES * nL, 8);
+    add(st.stat_sys, SWB_SS_PLANES, 8);
+    if (s->have_inflows) { add(s->inflows.member_scale, 1, 8); add(s->inflows.member_shift, 1, 8); }
+    const Controls &c = s->controls;
+    if (c.active) {
+        add(c.control_value, 1, 8); add(c.set_point, 1, 8); add(c.new_rule_time, 1, 8);
+        add(c.act_val, c.nAct, 8); add(c.act_e1, c.nAct, 8); add(c.act_e2, c.nAct, 8);
+        add(c.time_last_set, c.nWatch, 8); add(c.winner, c.nWatch, 4);
+    }
+    return v;
+}
+
+// After the call member i is what member perm[i] was: state, clocks, counters, statistics, routing totals,
+// inflow scale / shift and rule state move together (nothing else refers to a member by number).
+int swb_permute_members(swb_solver *s, const int *perm)
+{
+    if (!s || !perm) return fail(SWB_ERR_ARG, "null argument");
+    const int M = s->M;
+    if (s->st.halo.nRanks > 1) return fail(SWB_ERR_UNSUPP, "a partitioned solver holds one member");
+    std::vector<char> seen(M, 0);
+    for (int i = 0; i < M; i++) {
+        if (perm[i] < 0 || perm[i] >= M || seen[perm[i]]) return fail(SWB_ERR_ARG, "perm is not a permutation of the members");
+        seen[perm[i]] = 1;
+    }
+    SWB_ENTER(s);
+    { std::string err; if (!backend::sync(err)) return fail(SWB_ERR_CUDA, err); }     // nothing of this solver in flight
+    int rc = SWB_OK;
+    try {
+        // rows are permuted in batches through one scratch buffer (64 MB, or one row of the widest element) that
+        // stays with the solver: the call is meant to be repeated every few hundred steps
+        const size_t tmp_bytes = std::max<size_t>((size_t)64 << 20, (size_t)M * 8);
+        if (!s->perm_tmp) {
+            s->perm_idx = dev_zero<int>(s->allocs, M);
+            s->perm_tmp = checked_alloc(tmp_bytes);
+            s->allocs.push_back(s->perm_tmp);
+        }
+        checked(backend::upload(s->perm_idx, perm, sizeof(int) * M), "host -> device copy");
+        for (const MemberArray &a : member_arrays(s))
+            if (!backend::permute_members(a.p, a.rows, a.esz, M, s->perm_idx, s->perm_tmp, tmp_bytes)) { rc = fail(SWB_ERR_CUDA, backend::last_error()); break; }
+    } catch (const DeviceError &e) { rc = fail(SWB_ERR_CUDA, e.what); }
+    { std::string err; if (!backend::sync(err) && rc == SWB_OK) rc = fail(SWB_ERR_CUDA, err); }
+    return rc;
 }
 
 int swb_run_steps(swb_solver *s, int n_steps, double t_end)

@@ -931,6 +931,19 @@ SWB_FI void node_gather(const Net &n, const State &s, int e0, int e1, int m, Nod
     }
 }
 
+// link_setOutfallDepth's normal / critical depth (link.c:728-766) for the outfall served by true conduit j, at
+// the flow the update of j has just stored; called by whoever updated the conduit (flags says it ends at an outfall)
+SWB_NI void outfall_precompute(const Net &n, const State &s, int j, int m, const double *T)
+{
+    const int i = n.link_pre_node[j];
+    if (i < 0) return;
+    const size_t io = (size_t)n.outfall_slot[i] * s.M + m;
+    Xs x = load_xs(n, j);
+    double q = fabs(s.l_flow[SWB_IX(j, m, s.M)] / n.cond_barrels[j]);
+    s.o_ynorm[io] = link_ynorm(n, j, x, q, T);
+    s.o_ycrit[io] = xs_ycrit_ni(x, q, T);
+}
+
 // ---- K4: outfall boundary depth (link.c:728-766, node.c:1413-1492) ------------------------------
 SWB_NI void outfall_depth(const Net &n, const State &s, int i, int m, const double *T)
 {
@@ -940,10 +953,16 @@ SWB_NI void outfall_depth(const Net &n, const State &s, int i, int m, const doub
     double z = (n.link_node2[j] == i) ? n.link_offset2[j] : n.link_offset1[j];
     double yNorm = 0.0, yCrit = 0.0;
     if (n.link_type[j] == SWB_CONDUIT) {
-        Xs x = load_xs(n, j);
-        double q = fabs(s.l_flow[ixl] / n.cond_barrels[j]);
-        yNorm = link_ynorm(n, j, x, q, T);
-        yCrit = xs_ycrit_ni(x, q, T);
+        const int slot = n.outfall_slot[i];
+        if (slot >= 0) {             // computed by the link phase right after this conduit's update
+            yNorm = s.o_ynorm[(size_t)slot * s.M + m];
+            yCrit = s.o_ycrit[(size_t)slot * s.M + m];
+        } else {
+            Xs x = load_xs(n, j);
+            double q = fabs(s.l_flow[ixl] / n.cond_barrels[j]);
+            yNorm = link_ynorm(n, j, x, q, T);
+            yCrit = xs_ycrit_ni(x, q, T);
+        }
     }
     double yNew;
     switch (n.outfall_type[i]) {

@@ -159,6 +159,7 @@ SWB_FI void picard_link(const Net &net, const State &st, int j, int m, int k, do
         if (byp) return;
     }
     conduit_update(net, st, j, m, k, dt, T);
+    if (net.link_flags[j] & (LF_N1_OUTFALL | LF_N2_OUTFALL)) outfall_precompute(net, st, j, m, T);
 }
 // the same for a single model (M == 1), jj = position of the conduit in link_order: every static attribute,
 // the two end nodes included, comes from the column-wise copy in that order
@@ -172,6 +173,7 @@ SWB_FI void picard_link_single(const Net &net, const State &st, int jj, int k, d
         if (byp) return;
     }
     conduit_update_cols(net, st, j, jj, n1, n2, 0, k, dt, T);
+    if (net.link_cols_i[(size_t)LRI_FLAGS * net.nTrue + jj] & (LF_N1_OUTFALL | LF_N2_OUTFALL)) outfall_precompute(net, st, j, 0, T);
 }
 // node sums over the true conduits only, stored for the ordered regulator pass
 SWB_FI void picard_node_presum(const Net &net, const State &st, int i, int m)

@@ -17,6 +17,7 @@ namespace swb {
 
 struct Derived {
     std::vector<int> outfall_nodes, link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link, link_order,
+                     outfall_slot, link_pre_node,
                      link_kernel, node_order;
     std::vector<double> link_z1, link_z2, xs_tables, culvert_params, road_tables, xs_rcp_yfull, cond_rcp_mod_length, link_rows, link_cols_d;
     std::vector<int> link_cols_i;
@@ -111,11 +112,24 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
     r.nNonConduit = (int)r.nc_links.size();
     r.outfall_nodes.clear();
     for (int i = 0; i < nN; i++) if (d.node_type[i] == SWB_OUTFALL) r.outfall_nodes.push_back(i);
+    // the normal / critical depth an outfall needs (link.c:728-766) is a serial root search on its conduit's new
+    // flow: the link phase computes it right after that conduit's update, and such conduits are drawn FIRST, so
+    // the search overlaps the rest of the phase instead of stalling the node phase (and, partitioned, every rank)
+    r.outfall_slot.assign(nN, -1); r.link_pre_node.assign(nL, -1);
+    for (size_t k = 0; k < r.outfall_nodes.size(); k++) {
+        const int i = r.outfall_nodes[k], j = r.outfall_link[i];
+        if (j >= 0 && (r.link_flags[j] & LF_TRUE_CONDUIT) && r.link_pre_node[j] < 0) {
+            r.link_pre_node[j] = i;
+            r.outfall_slot[i] = (int)k;
+        }
+    }
     r.link_order.clear();
     for (int j = 0; j < nL; j++) if (r.link_flags[j] & LF_TRUE_CONDUIT) r.link_order.push_back(j);
     std::stable_sort(r.link_order.begin(), r.link_order.end(),
                      [&](int a, int b) {
                          if (r.link_kernel[a] != r.link_kernel[b]) return r.link_kernel[a] < r.link_kernel[b];
+                         const bool pa = r.link_pre_node[a] >= 0, pb = r.link_pre_node[b] >= 0;
+                         if (pa != pb) return pa;
                          return d.xs_type[a] < d.xs_type[b];
                      });
     // packed static rows of the true conduits, in ticket order (swb_dynwave.h: LR_*, CfStaged)

@@ -166,6 +166,7 @@ sg_links(const __grid_constant__ Net net, const __grid_constant__ State st, int 
         if (LK == LK_CIRCULAR) conduit_flow<XS_CIRCULAR>(net, st, j, mm, k, st.dt[mm], tab);
         else if (LK == LK_RECT_CLOSED) conduit_flow<XS_RECT_CLOSED>(net, st, j, mm, k, st.dt[mm], tab);
         else conduit_flow_generic(net, st, j, mm, k, st.dt[mm], tab);
+        if (net.link_flags[j] & (LF_N1_OUTFALL | LF_N2_OUTFALL)) outfall_precompute(net, st, j, mm, tab);
     });
 }
 
@@ -225,6 +226,7 @@ sg_links_pf(const __grid_constant__ Net net, const __grid_constant__ State st, i
                 if (byp) return;
             }
             conduit_update(net, st, j, mm, k, st.dt[mm], tab);     // (out of line: this path is rare)
+            if (net.link_flags[j] & (LF_N1_OUTFALL | LF_N2_OUTFALL)) outfall_precompute(net, st, j, mm, tab);
         });
         return;
     }
@@ -287,6 +289,7 @@ sg_links_pf(const __grid_constant__ Net net, const __grid_constant__ State st, i
             const double *b = my + stg * (CF_FIELDS * 32);
             const CfStaged in = { b, myRows + stg * LR_STRIDE };
             update(i0.j, i0.mm, b[CF_DT * 32], in);
+            if (in.flags() & (LF_N1_OUTFALL | LF_N2_OUTFALL)) outfall_precompute(net, st, i0.j, i0.mm, tab);
         }
         t0 = t1; i0 = i1; t1 = t2; i1 = i2; stg ^= 1;
         t2 = (t2 < total) ? take(pend) : total;

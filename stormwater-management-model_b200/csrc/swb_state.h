@@ -97,6 +97,9 @@ struct Net {
     const int    *node_order;              // node-phase ticket order: outfalls and storage nodes first
     const int    *nc_links;                // non-true-conduit links in ascending index order
     const int    *outfall_link;            // per node: its (single) link, or -1
+    const int    *outfall_slot;            // per node: row of State::o_ynorm / o_ycrit its link's update fills, or -1
+    const int    *link_pre_node;           // per link: the outfall node whose normal / critical depth follows this
+                                           // link's update (a true conduit that is that node's outfall_link), or -1
     const int    *outfall_nodes;           // outfall nodes in ascending index order
     int           nOutfallNodes;
     const int    *link_kernel;             // LK_*: which conduit function a true conduit runs
@@ -231,6 +234,8 @@ struct State {
     // per member
     double *dt;                  // routing step being taken
     double *var_step;            // VariableStep (dynwave.c:84); 0 before the first step
+    double *o_ynorm, *o_ycrit;   // [nOutfallNodes][M] normal / critical depth of an outfall's conduit at its new flow,
+                                 // written by the warp that updates that conduit (link phase), read by outfall_depth
     double *sim_time;            // elapsed simulated seconds (= time_ms / 1000, for reporting)
     double *time_ms;             // NewRoutingTime: elapsed ms, accumulated like routing.c:301-302
     double *evap_rate, *hydcon;  // per-member climate scalars

@@ -36,6 +36,7 @@ static swb_solver  *g_solver;
 static double      *g_buf;        /* staging, max(nodes, links) x max(1, pollutants) */
 static double      *g_mb_prev;    /* 3 x pollutants: cumulative mass-balance terms last seen */
 static int          g_ready;
+static int          g_hyd_current;   /* dynwave_execute ran in this routing step: device hydraulics are current */
 
 static void seam_fail(const char *what)
 {
@@ -50,10 +51,11 @@ static const int UP_HYD[] = {
     SWB_NODE_NEW_LATFLOW, SWB_NODE_LOSSES, SWB_NODE_INFLOW, SWB_NODE_OUTFLOW, SWB_NODE_OVERFLOW,
     SWB_NODE_OLD_NET_INFLOW, SWB_NODE_OUTFALL_STAGE,
     SWB_LINK_NEW_FLOW, SWB_LINK_OLD_FLOW, SWB_LINK_NEW_DEPTH, SWB_LINK_OLD_DEPTH, SWB_LINK_NEW_VOLUME,
-    SWB_LINK_OLD_VOLUME, SWB_LINK_SETTING, SWB_LINK_TARGET_SETTING, SWB_LINK_DQDH, SWB_LINK_FROUDE,
-    SWB_LINK_FLOW_CLASS, SWB_LINK_NORMAL_FLOW, SWB_LINK_INLET_CONTROL, SWB_COND_A1, SWB_COND_Q1,
-    SWB_COND_FULL_STATE, SWB_COND_EVAP_LOSS, SWB_COND_SEEP_LOSS, SWB_ORIF_CORIF, SWB_ORIF_CWEIR,
-    SWB_ORIF_HCRIT, SWB_REG_SURF_AREA, SWB_WEIR_CSURCHARGE };
+    SWB_LINK_OLD_VOLUME, SWB_LINK_SETTING, SWB_LINK_TARGET_SETTING, SWB_COND_A1, SWB_COND_Q1,
+    SWB_ORIF_CORIF, SWB_ORIF_CWEIR, SWB_ORIF_HCRIT, SWB_REG_SURF_AREA, SWB_WEIR_CSURCHARGE };
+/* (dqdh, Froude number, flow class, normal-flow / inlet-control flags, full state and the conduit loss rates are
+ * pure outputs of a routing step -- every link rewrites them in trial 0 before anything reads them -- so they
+ * only travel down; dynwave_init zeroes them on both sides) */
 /* fields the host engine reads after dynwave_execute (routing.c, stats.c, massbal.c, output.c) */
 static const int DOWN_HYD[] = {
     SWB_NODE_NEW_DEPTH, SWB_NODE_NEW_VOLUME, SWB_NODE_INFLOW, SWB_NODE_OUTFLOW, SWB_NODE_OVERFLOW,
@@ -151,7 +153,7 @@ void dynwave_close(void)                                      /* dynwave.c:165-1
     g_solver = NULL; g_net = NULL;
     if (g_ready) swb_flat_free(&g_flat);
     free(g_buf); free(g_mb_prev);
-    g_buf = NULL; g_mb_prev = NULL; g_ready = 0;
+    g_buf = NULL; g_mb_prev = NULL; g_ready = 0; g_hyd_current = 0;
 }
 
 double dynwave_getRoutingStep(double fixedStep)               /* dynwave.c:195-220 */
@@ -179,6 +181,7 @@ int dynwave_execute(double tStep)                             /* dynwave.c:224-2
     swb_get_stats(g_solver, 0, 1, &before);
     if (swb_dynwave_execute(g_solver, &tStep, &iters)) { seam_fail("dynwave_execute"); return 0; }
     if (pull(DOWN_HYD, COUNT(DOWN_HYD))) { seam_fail("state download"); return 0; }
+    g_hyd_current = 1;            /* the device's hydraulic image is this step's: qualrout_execute need not re-send it */
     swb_get_stats(g_solver, 0, 1, &after);
     if (after.non_converged > before.non_converged) {         /* updateConvergenceStats, :266-272 */
         NonConvergeCount++;
@@ -219,7 +222,8 @@ void qualrout_execute(double tStep)                           /* qualrout.c:100-
     if (!ensure_device()) return;
     /* steady-state periods skip dynwave_execute (routing.c:241-243): the hydraulic image the
      * quality step reads (flows, volumes, inflows) must then come from the host as well */
-    if (push(UP_HYD, COUNT(UP_HYD)) || push(UP_QUAL, COUNT(UP_QUAL))) { seam_fail("quality upload"); return; }
+    if ((!g_hyd_current && push(UP_HYD, COUNT(UP_HYD))) || push(UP_QUAL, COUNT(UP_QUAL))) { seam_fail("quality upload"); return; }
+    g_hyd_current = 0;
     if (swb_qualrout_execute(g_solver, &tStep)) { seam_fail("qualrout_execute"); return; }
     if (pull(DOWN_QUAL, COUNT(DOWN_QUAL))) { seam_fail("quality download"); return; }
     /* massbal_addReactedMass / addSeepageLoss take rates (mass/s), addToFinalStorage a mass */

@@ -47,6 +47,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.swb_get_routing_step.argtypes = [C.c_void_p, C.c_double, _P_D]
     lib.swb_set_inflows.argtypes = [C.c_void_p, C.POINTER(abi.InflowDesc)]
     lib.swb_set_controls.argtypes = [C.c_void_p, C.POINTER(abi.ControlsDesc)]
+    lib.swb_permute_members.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     lib.swb_run_steps.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.swb_get_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.MemberStats)]
     lib.swb_get_massbal.argtypes = [C.c_void_p, C.c_int, C.c_int, _P_D, _P_D, _P_D]
@@ -263,6 +264,12 @@ class Solver:
     def set_controls_desc(self, desc):
         """Control rules / pump depths / timed outfall stages for run_steps (swb_set_controls)."""
         self._chk(self.lib.swb_set_controls(self._h, C.byref(desc)))
+
+    def permute_members(self, perm):
+        """Re-enumerate the members: afterwards member i is what member perm[i] was (swb_permute_members)."""
+        p = np.ascontiguousarray(perm, dtype=np.int32)
+        assert p.size == self.M
+        self._chk(self.lib.swb_permute_members(self._h, p.ctypes.data_as(C.POINTER(C.c_int))))
 
     def run_steps(self, n_steps: int, t_end: float):
         self._chk(self.lib.swb_run_steps(self._h, n_steps, t_end))

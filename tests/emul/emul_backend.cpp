@@ -37,6 +37,16 @@ static void *stream_create() { return nullptr; }
 static void stream_destroy(void *) {}
 static void use_stream(void *) {}
 static int device_count() { return 1; }
+static bool permute_members(void *p, size_t rows, int esz, int M, const int *perm, void *, size_t)
+{
+    std::vector<char> row((size_t)M * esz);
+    for (size_t r = 0; r < rows; r++) {
+        char *base = (char *)p + r * (size_t)M * esz;
+        for (int i = 0; i < M; i++) memcpy(row.data() + (size_t)i * esz, base + (size_t)perm[i] * esz, esz);
+        memcpy(base, row.data(), row.size());
+    }
+    return true;
+}
 static void *host_alloc(size_t b) { return std::malloc(b ? b : 8); }
 static void host_free(void *p) { std::free(p); }
 static void h2d_async(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }

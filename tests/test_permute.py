@@ -1,0 +1,67 @@
+"""swb_permute_members: re-enumerating the members of an ensemble changes nothing but their index."""
+import numpy as np
+import pytest
+
+import parity_common as pc
+from swmm_b200 import solver
+
+
+def _golden_solver(case, M, scale, shift, lib_path):
+    net, g = pc.load_golden(case)
+    nP = net.n_pollut
+    s = solver.Solver(net, M, lib_path=lib_path)
+    s.load_state({k[3:]: g[k] for k in g if k.startswith("s0_")})
+    s.set_inflows(node=g["inf_node"], ts_start=g["inf_ts_start"], ts_t=g["inf_ts_t"], ts_q=g["inf_ts_q"],
+                  sfactor=g["inf_sfactor"], baseline=g["inf_baseline"], concen=g["inf_concen"] if nP else None,
+                  member_scale=scale, member_shift=shift,
+                  start_day=float(g["inf_start"][0]), start_secs=float(g["inf_start"][1]))
+    return s, net, g
+
+
+def _permute_check(lib_path, M, steps):
+    """swb_permute_members re-enumerates the members and nothing else: a permuted ensemble, stepped on, equals
+    the unpermuted one member by member (state, clocks, counters, statistics, routing totals) bit for bit."""
+    scale = np.linspace(0.3, 2.5, M)
+    shift = np.linspace(-0.02, 0.02, M)
+    a, net, g = _golden_solver("c2_grid12_slot", M, scale, shift, lib_path)
+    b, _, _ = _golden_solver("c2_grid12_slot", M, scale, shift, lib_path)
+    a.enable_statistics(0.0)
+    b.enable_statistics(0.0)
+    t_end = float(g["t_end"])
+    try:
+        a.run_steps(steps, t_end)
+        b.run_steps(steps, t_end)
+        rng = np.random.default_rng(3)
+        perm = rng.permutation(M).astype(np.int32)
+        b.permute_members(perm)
+        a.run_steps(steps, t_end)
+        b.run_steps(steps, t_end)
+        for f in ("SWB_NODE_NEW_DEPTH", "SWB_LINK_NEW_FLOW", "SWB_NODE_NEW_QUAL", "SWB_LINK_TOTAL_LOAD", "SWB_COND_Q1"):
+            if f.endswith("QUAL") and net.n_pollut == 0:
+                continue
+            assert np.array_equal(a.get_field(f)[perm], b.get_field(f)), f
+        sa, sb = a.stats(), b.stats()
+        for i in range(M):
+            x, y = sa[perm[i]], sb[i]
+            assert (x.sim_time, x.iterations, x.steps, x.non_converged, x.next_dt) == (y.sim_time, y.iterations, y.steps, y.non_converged, y.next_dt)
+        na, la_, ya = a.statistics()
+        nb, lb, yb = b.statistics()
+        assert np.array_equal(na[perm], nb) and np.array_equal(la_[perm], lb) and np.array_equal(ya[perm], yb)
+        ta, tb = a.routing_totals(), b.routing_totals()
+        for da, db in zip(ta, tb):          # (sums of unordered atomic adds: equal to rounding)
+            for k in da:
+                np.testing.assert_allclose(np.asarray(da[k])[perm], np.asarray(db[k]), rtol=1e-11, atol=1e-9, err_msg=k)
+        with pytest.raises(solver.SwbError):
+            b.permute_members(np.zeros(M, dtype=np.int32))
+    finally:
+        a.close()
+        b.close()
+
+
+def test_permute_members_emulated(emul_lib):
+    _permute_check(emul_lib, 32, 40)
+
+
+@pytest.mark.gpu
+def test_permute_members_cuda(cuda_lib):
+    _permute_check(None, 256, 150)

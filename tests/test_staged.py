@@ -141,3 +141,4 @@ def test_staged_step_host_batch(cuda_lib):
     finally:
         s.set_staged_min_members(256)
         s.close()
+

@@ -28,9 +28,10 @@ if a.lib:
     solver.CUDA_LIB = os.path.abspath(a.lib)
 import bench  # noqa: E402
 
-args = argparse.Namespace(grid=100, hours=6.0, surcharge="SLOT", members=a.members, members_total=a.members)
+args = argparse.Namespace(grid=100, hours=6.0, surcharge="SLOT", members=a.members, members_total=a.members,
+                          member_order="scale")
 s, case, spec = bench.make_ensemble(args, 0, 0)
-bench.spin_up(s, a.spinup)
+bench.spin_up(s, a.spinup, reorder_every=100)       # the bench's own configuration
 s.run_steps(a.routing_steps, case.t_end)
 s.sync()
 cu0 = s.conduit_updates()

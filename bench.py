@@ -5,7 +5,7 @@
 
 Workload (config.workload): BASELINE config 4, the 4 096-member rainfall ensemble of the config-2
 network (100 x 100 looped grid, 19 801 conduits, circular + rect_closed, SLOT, 2 pollutants), split in
-contiguous member blocks over the N GPUs ("scaling": "strong" -- every N runs the same 4 096 members;
+members interleaved over the N GPUs ("scaling": "strong" -- every N runs the same 4 096 members;
 one B200 holds all of them: 19.7 GB of state).  One bench "step" is ONE persistent launch per GPU that
 advances every member `--routing-steps` routing steps (Picard loops, quality routing, Courant search,
 all on the device).  The ensemble is first spun up, untimed, to `--spinup` simulated seconds so that
@@ -128,17 +128,19 @@ def dist_env():
 
 
 # ---------------------------------------------------------------------------------------------------
-def make_ensemble(args, device: int, member0: int, members: int | None = None):
+def make_ensemble(args, device: int, member0: int, members: int | None = None, stride: int = 1):
+    """Members member0, member0 + stride, ... of the enumerated config-4 ensemble (ranks take interleaved members,
+    so every GPU holds the same mix of light and heavy storms: the step time is the max over ranks)."""
     members = members or args.members
     spec = scenarios.GridSpec(nx=args.grid, ny=args.grid, hours=args.hours, surcharge=args.surcharge)
     case = network.build_grid(spec)
-    scale, shift_h = scenarios.c4_members(max(args.members_total, member0 + members), 2024)
+    scale, shift_h = scenarios.c4_members(max(args.members_total, member0 + stride * (members - 1) + 1), 2024)
     if getattr(args, "member_order", "generated") == "scale":
         # the same ensemble enumerated by storm intensity: members that need the same number of Picard trials
         # become neighbours, so the member lists of the late trials touch whole sectors
         order = np.argsort(-scale, kind="stable")
         scale, shift_h = scale[order], shift_h[order]
-    sl = slice(member0, member0 + members)
+    sl = member0 + stride * np.arange(members)
     s = solver.Solver(case.net, members, device=device)
     s.load_state(case.state0)
     inf = dict(case.inflows)
@@ -233,7 +235,7 @@ def run_ours(args):
     if args.members_total % (32 * world):
         raise SystemExit("--members-total must be a multiple of 32 x GPUs")
     args.members = args.members_total // world
-    s, case, spec = make_ensemble(args, device, rank * args.members)
+    s, case, spec = make_ensemble(args, device, rank, stride=world)
     n_true = int(case.net.true_conduit_mask().sum())
     t_end = case.t_end
     note(rank, T0, "ensemble built")
@@ -265,7 +267,8 @@ def run_ours(args):
     # ---- sub-records (each on every rank that takes part) ------------------------------------
     weak = None
     if not args.no_weak and args.members != 512:
-        w, _, _ = make_ensemble(args, device, rank * 512, members=512)
+        g = max(args.members_total // (512 * world), 1)      # every g-th member of the enumerated ensemble, interleaved over ranks
+        w, _, _ = make_ensemble(args, device, rank * g, members=512, stride=world * g)
         spin_up(w, args.spinup, reorder_every=args.reorder_every)
 
         def wbarrier():
@@ -312,7 +315,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"C4: {args.members_total}-member rainfall ensemble of the C2 {args.grid}x{args.grid} looped "
-                            f"grid ({n_true} conduits, 2 pollutants, {args.surcharge}), contiguous member blocks over "
+                            f"grid ({n_true} conduits, 2 pollutants, {args.surcharge}), members interleaved over "
                             f"{world} GPU(s), {args.members} members per GPU in lockstep",
                 "members_total": args.members_total, "members_per_gpu": args.members,
                 "true_conduits": n_true, "routing_steps_per_step": rs, "spinup_sim_s": args.spinup,

@@ -1033,7 +1033,8 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
                 // ---- findLinkFlows, pass (i): true conduits (dynwave.c:387-395)
                 if (!(args.debug & DBG_SKIP_LINKS))
                 for_tiles(ctx, net.nTrue, nAlive, tickets + TK_LINKS, [&](int jj, int mm) {
-                    if (M == 1) picard_link_single(net, st, jj, k, st.dt[0], T);
+                    if (M == 1) { int jr = jj + net.linkRot; if (jr >= net.nTrue) jr -= net.nTrue;
+                                  picard_link_single(net, st, jr, k, st.dt[0], T); }
                     else picard_link(net, st, net.link_order[jj], mm, k, st.dt[mm], T);
                 });
                 ctx.grid_sync();

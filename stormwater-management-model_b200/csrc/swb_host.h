@@ -213,6 +213,9 @@ inline void fill_net_scalars(Net &n, const swb_network_desc &d, const swb_option
     n.nOutfallNodes = (int)r.outfall_nodes.size();
     n.lk_count[0] = n.lk_count[1] = n.lk_count[2] = 0;
     for (int j : r.link_order) n.lk_count[r.link_kernel[j]]++;
+    n.linkRot = 0;
+    for (size_t k = 0; k < r.link_order.size(); k++)
+        if (r.link_pre_node[r.link_order[k]] >= 0) { n.linkRot = (int)k; break; }
     n.anyLossRate = 0;
     for (int f : r.link_flags) if (f & LF_HAS_LOSSRATE) n.anyLossRate = 1;
     n.opt = o;

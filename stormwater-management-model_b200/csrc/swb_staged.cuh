@@ -340,6 +340,152 @@ sg_nodes(const __grid_constant__ Net net, const __grid_constant__ State st, int 
     });
 }
 
+// findNodeDepths as a software pipeline per warp, for networks without regulators (the node sums then come
+// straight from the conduits, dynwave.c:528-589):
+//   tile i + 3   ticket atomic in flight
+//   tile i + 2   node, its incidence range and up to four packed incidence entries (plain loads)
+//   tile i + 1   its rows on their way into the warp's shared-memory stage (cp.async): depth, losses, lateral
+//                inflow, old depth, old net inflow of the node and flow / surface area / dqdh of each link end
+//   tile i       node_init_acc / node_apply_link_end / node_set_depth on the staged values
+// A tile the stage does not fit (outfall, more than four link ends, a conduit with a loss rate) runs picard_node
+// as before.  Same functions, same operand values, same order of the sums: the same bits.
+// MEASURED SLOWER than sg_nodes (profiles/README.md, round 2: node phase 281 -> 464 ms per 50 steps at 4 096
+// members, 78 -> 122 at 1 024): the plain kernel already keeps a node's 12-17 loads in flight per thread at 32
+// warps per SM, while the stage costs 17 LDGSTS + 17 LDS per thread and caps the SM at 24 warps.  Compiled out.
+#ifndef SWB_SG_NODE_PF
+#define SWB_SG_NODE_PF 0
+#endif
+#if SWB_SG_NODE_PF
+#define SWB_SG_NODEPF_BLOCK 128
+enum { NF_DEPTH = 0, NF_LOSSES, NF_LATFLOW, NF_OLD_DEPTH, NF_OLD_NET_INFLOW, NF_LINK0, NF_FIELDS = NF_LINK0 + 12 };
+struct NfIds { int i, mm, deg, plain; };     // plain: the tile runs picard_node (nothing staged)
+
+__global__ void __launch_bounds__(SWB_SG_NODEPF_BLOCK, 6)
+sg_nodes_pf(const __grid_constant__ Net net, const __grid_constant__ State st, int k, int prev)
+{
+    __shared__ double stage_all[(SWB_SG_NODEPF_BLOCK / 32) * 2 * NF_FIELDS * 32];
+    __shared__ __align__(16) AdjEntry adj_all[(SWB_SG_NODEPF_BLOCK / 32) * 2 * 4];
+    sg_tick(st, prev);
+    const int nAlive = st.ctl[CTL_N_ALIVE];
+    if (!st.ctl[CTL_ANY_LEFT] || nAlive == 0) return;
+    const int M = st.M;
+    const double *T = net.xs_tables;                 // (global copy: only an outfall without a precomputed depth reads it)
+    unsigned long long *ticket = st.tickets + SWB_TICKETS_PER_TRIAL * k + TK_NODES;
+    if (nAlive < 32) {                               // few members left: several nodes per tile, plain loads
+        CudaCtx ctx = sg_ctx(st, nullptr);
+        ctx.T = T;
+        for_tiles(ctx, net.nN, nAlive, ticket, [&](int ii, int mm) {
+            if (!picard_node(net, st, net.node_order[ii], mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
+        });
+        return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *my = stage_all + (size_t)warp * 2 * NF_FIELDS * 32 + lane;
+    AdjEntry *myAdj = adj_all + warp * 2 * 4;
+    const int nChunks = (nAlive + 31) / 32;
+    const unsigned total = (unsigned)net.nN * (unsigned)nChunks;
+    auto issue = [&]() -> unsigned long long { unsigned long long v = 0; if (lane == 0) v = atomicAdd(ticket, 1ull); return v; };
+    auto take = [&](unsigned long long v) -> unsigned {
+        v = __shfl_sync(0xffffffffu, v, 0);
+        return v < (unsigned long long)total ? (unsigned)v : total;
+    };
+    const AdjEntry noAdj = {0, 0, 0, -1};
+    struct Fetched { NfIds d; AdjEntry a0, a1, a2, a3; };
+    auto ids = [&](unsigned t) -> Fetched {
+        Fetched f;
+        const unsigned ii = t / (unsigned)nChunks;
+        const int slot = (int)(t - ii * (unsigned)nChunks) * 32 + lane;
+        const int i = net.node_order[(int)ii];
+        const int e0 = net.adj_start[i], e1 = net.adj_start[i + 1];
+        f.d.i = i; f.d.deg = e1 - e0;
+        f.d.mm = slot < nAlive ? st.alive[slot] : -1;
+        f.d.plain = (net.node_type[i] == SWB_OUTFALL || f.d.deg > 4) ? 1 : 0;
+        f.a0 = f.d.deg > 0 ? net.adj_packed[e0] : noAdj;
+        f.a1 = f.d.deg > 1 ? net.adj_packed[e0 + 1] : noAdj;
+        f.a2 = f.d.deg > 2 ? net.adj_packed[e0 + 2] : noAdj;
+        f.a3 = f.d.deg > 3 ? net.adj_packed[e0 + 3] : noAdj;
+        return f;
+    };
+    auto lossy = [&](const AdjEntry &a) { return a.kind >= 0 && (a.kind & 0xff) == SWB_CONDUIT && (a.flags & LF_HAS_LOSSRATE); };
+    auto end_rows = [&](double *b, int e, const AdjEntry &a, int mm) {
+        const size_t ix = SWB_IX(a.je >> 1, mm, M);
+        cp_async8(b + (NF_LINK0 + 3 * e + 0) * 32, &st.l_flow[ix]);
+        cp_async8(b + (NF_LINK0 + 3 * e + 1) * 32, (a.je & 1) == 0 ? &st.l_surf_area1[ix] : &st.l_surf_area2[ix]);
+        cp_async8(b + (NF_LINK0 + 3 * e + 2) * 32, &st.l_dqdh[ix]);
+    };
+    // returns the ids with `plain` finalised; stores the incidence entries for the compute stage
+    auto prefetch = [&](Fetched &f, int stg, bool valid) -> NfIds {
+        if (valid) {
+            if (lossy(f.a0) || lossy(f.a1) || lossy(f.a2) || lossy(f.a3)) f.d.plain = 1;
+            if (!f.d.plain) {
+                if (lane == 0) { AdjEntry *a = myAdj + stg * 4; a[0] = f.a0; a[1] = f.a1; a[2] = f.a2; a[3] = f.a3; }
+                if (f.d.mm >= 0) {
+                    double *b = my + stg * (NF_FIELDS * 32);
+                    const size_t ix = SWB_IX(f.d.i, f.d.mm, M);
+                    cp_async8(b + NF_DEPTH * 32, &st.n_depth[ix]);
+                    cp_async8(b + NF_LOSSES * 32, &st.n_losses[ix]);
+                    cp_async8(b + NF_LATFLOW * 32, &st.n_latflow[ix]);
+                    cp_async8(b + NF_OLD_DEPTH * 32, &st.n_old_depth[ix]);
+                    cp_async8(b + NF_OLD_NET_INFLOW * 32, &st.n_old_net_inflow[ix]);
+                    if (f.d.deg > 0) end_rows(b, 0, f.a0, f.d.mm);
+                    if (f.d.deg > 1) end_rows(b, 1, f.a1, f.d.mm);
+                    if (f.d.deg > 2) end_rows(b, 2, f.a2, f.d.mm);
+                    if (f.d.deg > 3) end_rows(b, 3, f.a3, f.d.mm);
+                }
+            }
+        }
+        cp_async_commit();
+        return f.d;
+    };
+    const NfIds none = { 0, -1, 0, 1 };
+    Fetched fnone; fnone.d = none; fnone.a0 = fnone.a1 = fnone.a2 = fnone.a3 = noAdj;
+    unsigned t0 = take(issue());
+    unsigned t1 = t0 < total ? take(issue()) : total;
+    unsigned t2 = t1 < total ? take(issue()) : total;
+    Fetched f0 = t0 < total ? ids(t0) : fnone, f1 = t1 < total ? ids(t1) : fnone, f2 = t2 < total ? ids(t2) : fnone;
+    NfIds i0 = prefetch(f0, 0, t0 < total);
+    int stg = 0;
+    while (t0 < total) {
+        const unsigned long long pend = (t2 < total) ? issue() : (unsigned long long)total;
+        __syncwarp();                      // every lane is done with the incidence entries the next tile overwrites
+        const NfIds i1 = prefetch(f1, stg ^ 1, t1 < total);
+        cp_async_wait<1>();                // tile t0's rows are in
+        __syncwarp();
+        if (i0.mm >= 0) {
+            const int i = i0.i, mm = i0.mm;
+            if (i0.plain) {
+                if (!picard_node(net, st, i, mm, k, st.dt[mm], T)) st.not_conv[k * M + mm] = 1;
+            } else {
+                const double *b = my + stg * (NF_FIELDS * 32);
+                const AdjEntry *a = myAdj + stg * 4;
+                // node_init_acc on the staged values (dynwave.c:297-331)
+                NodeAcc acc;
+                const double depth = b[NF_DEPTH * 32];
+                acc.surfArea = net.opt.allow_ponding ? node_ponded_area(net, i, depth) : node_surf_area(net, i, depth);
+                acc.inflow = 0.0;
+                acc.outflow = b[NF_LOSSES * 32];
+                const double lat = b[NF_LATFLOW * 32];
+                if (lat >= 0.0) acc.inflow += lat; else acc.outflow -= lat;
+                acc.sumdqdh = 0.0;
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (e < i0.deg) {
+                        const LinkEndData d = { b[(NF_LINK0 + 3 * e + 0) * 32], 0.0, b[(NF_LINK0 + 3 * e + 1) * 32],
+                                                b[(NF_LINK0 + 3 * e + 2) * 32] };
+                        node_apply_link_end(d, a[e], acc);
+                    }
+                const NodeOld old = { b[NF_OLD_DEPTH * 32], b[NF_OLD_NET_INFLOW * 32] };
+                if (!node_set_depth(net, st, i, mm, k, st.dt[mm], acc, old)) st.not_conv[k * M + mm] = 1;
+            }
+        }
+        t0 = t1; i0 = i1; f1 = f2; t1 = t2; stg ^= 1;
+        t2 = (t2 < total) ? take(pend) : total;
+        f2 = t2 < total ? ids(t2) : fnone;
+    }
+    cp_async_wait<0>();
+}
+#endif   // SWB_SG_NODE_PF
+
 enum { SG_EPILOGUE = 0, SG_QUAL_NODES, SG_QUAL_LINKS, SG_OUTFLOWS, SG_STATS, SG_DT_SEARCH, SG_DT_ARG };
 
 // the streaming phases after the Picard loop: one template, one instance (and register budget) per phase
@@ -417,7 +563,7 @@ namespace swb { namespace backend {
 
 struct StagedInfo {
     bool ready;
-    int link_blocks[3], node_blocks, presum_blocks, stream_blocks[8], prologue_blocks, transpose_blocks;
+    int link_blocks[3], node_blocks, nodepf_blocks, presum_blocks, stream_blocks[8], prologue_blocks, transpose_blocks;
 };
 static StagedInfo g_staged[SWB_MAX_DEVICES];
 
@@ -443,6 +589,9 @@ static void staged_init(int device)
 #endif
     S.link_blocks[2] = sg_occupancy(sg_links<2>, SWB_SG_LINK_BLOCK, sms);
     S.node_blocks = sg_occupancy(sg_nodes, SWB_SG_NODE_BLOCK, sms);
+#if SWB_SG_NODE_PF
+    S.nodepf_blocks = sg_occupancy(sg_nodes_pf, SWB_SG_NODEPF_BLOCK, sms);
+#endif
     S.presum_blocks = sg_occupancy(sg_presum, SWB_SG_NODE_BLOCK, sms);
     S.prologue_blocks = sg_occupancy(sg_prologue, SWB_SG_STREAM_BLOCK, sms);
     S.stream_blocks[SG_EPILOGUE] = sg_occupancy(sg_stream<SG_EPILOGUE>, SWB_SG_STREAM_BLOCK, sms);
@@ -549,7 +698,13 @@ static bool launch_staged(const Net &net, const State &st, const RunArgs &args, 
                     sg_presum<<<tblocks(S.presum_blocks, nN * chunks), SWB_SG_NODE_BLOCK, 0, q>>>(net, st, k, prev); prev = TP_REGULATORS; launched++;
                     sg_regulators<<<(M + 127) / 128, 128, 0, q>>>(net, st, k, prev); launched++;
                 }
-                sg_nodes<<<tblocks(S.node_blocks, nN * chunks), SWB_SG_NODE_BLOCK, 0, q>>>(net, st, k, prev); prev = TP_NODES; launched++;
+#if SWB_SG_NODE_PF
+                if (net.nNonConduit == 0)
+                    sg_nodes_pf<<<(int)std::max(1LL, std::min((long long)S.nodepf_blocks, (nN * chunks * 32 + SWB_SG_NODEPF_BLOCK - 1) / SWB_SG_NODEPF_BLOCK)), SWB_SG_NODEPF_BLOCK, 0, q>>>(net, st, k, prev);
+                else
+#endif
+                    sg_nodes<<<tblocks(S.node_blocks, nN * chunks), SWB_SG_NODE_BLOCK, 0, q>>>(net, st, k, prev);
+                prev = TP_NODES; launched++;
                 if (k + 1 >= maxTrials) break;
                 if (k >= 1) { sg_control<<<1, SWB_SG_CTL_BLOCK, 0, q>>>(net, st, args, k, prev); prev = TP_CONTROL; launched++; }
             }

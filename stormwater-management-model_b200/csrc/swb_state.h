@@ -73,6 +73,8 @@ struct Net {
     int nTrue;               // true conduits
     int lk_count[3];         // of which per conduit-function class LK_* (link_order is grouped by class)
     int nNonConduit;         // links handled by the ordered regulator pass
+    int linkRot;             // single models: position in link_order the link phase starts drawing at (the first
+                             // conduit that serves an outfall: its depth solve then overlaps the rest of the phase)
     int nOutfallLinks;
     int anyLossRate;         // some conduit can evaporate / seep (LF_HAS_LOSSRATE)
     swb_options opt;

@@ -65,3 +65,39 @@ def test_permute_members_emulated(emul_lib):
 @pytest.mark.gpu
 def test_permute_members_cuda(cuda_lib):
     _permute_check(None, 256, 150)
+
+
+@pytest.mark.gpu
+def test_two_solvers_on_two_devices_in_one_process(cuda_lib):
+    """Every entry point makes its solver's device current: two ensembles on two GPUs of one
+    process, calls interleaved, both equal a run on their own."""
+    lib = solver.load_library()
+    if lib.swb_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    M, steps = 64, 60
+    scale = np.linspace(0.5, 2.0, M)
+    net, g = pc.load_golden("c2_grid12_slot")
+    nP = net.n_pollut
+
+    def make(dev):
+        s = solver.Solver(net, M, device=dev)
+        s.load_state({k[3:]: g[k] for k in g if k.startswith("s0_")})
+        s.set_inflows(node=g["inf_node"], ts_start=g["inf_ts_start"], ts_t=g["inf_ts_t"], ts_q=g["inf_ts_q"],
+                      sfactor=g["inf_sfactor"], baseline=g["inf_baseline"], concen=g["inf_concen"] if nP else None,
+                      member_scale=scale, start_day=float(g["inf_start"][0]), start_secs=float(g["inf_start"][1]))
+        return s
+    a, b = make(0), make(1)
+    ref = make(0)
+    t_end = float(g["t_end"])
+    try:
+        ref.run_steps(steps, t_end)
+        for _ in range(steps // 10):          # interleaved: the current device flips between every call
+            a.run_steps(10, t_end)
+            b.run_steps(10, t_end)
+            a.get_field("SWB_NODE_NEW_DEPTH", 3, 1)
+        for f in ("SWB_NODE_NEW_DEPTH", "SWB_LINK_NEW_FLOW"):
+            want = ref.get_field(f)
+            assert np.array_equal(a.get_field(f), want) and np.array_equal(b.get_field(f), want), f
+        assert a.last_kernel_ms() > 0.0 and b.last_kernel_ms() > 0.0
+    finally:
+        a.close(); b.close(); ref.close()

@@ -160,7 +160,7 @@ int swb_network_create(const swb_network_desc *d, const swb_options *o, int devi
 #define D(name) ar.add(nw->net.name, r.name.data(), r.name.size());
         D(outfall_nodes) D(adj_packed) D(link_flags) D(link_z1) D(link_z2) D(xs_rcp_yfull) D(cond_rcp_mod_length) D(adj_start) D(adj)
         D(adjq_start) D(adjq) D(nc_links) D(node_order) D(link_order) D(outfall_link) D(xs_tables)
-        D(link_kernel) D(culvert_params) D(road_tables) D(link_rows) D(link_cols_d) D(link_cols_i) D(outfall_slot) D(link_pre_node)
+        D(link_kernel) D(culvert_params) D(road_tables) D(link_rows) D(link_cols_d) D(link_cols_i) D(outfall_slot) D(link_pre_node) D(pre_links)
 #undef D
         nw->net.arena_bytes = ar.image.size();
         nw->net.arena = ar.commit(nw->allocs);

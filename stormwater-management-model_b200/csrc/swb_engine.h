@@ -163,9 +163,14 @@ SWB_FI void picard_link(const Net &net, const State &st, int j, int m, int k, do
 }
 // the same for a single model (M == 1), jj = position of the conduit in link_order: every static attribute,
 // the two end nodes included, comes from the column-wise copy in that order
-SWB_FI void picard_link_single(const Net &net, const State &st, int jj, int k, double dt, const double *T)
+SWB_FI void picard_link_single(const Net &net, const State &st, int jj, int k, double dt, const double *T, bool wantPre)
 {
     const int j = net.link_order[jj];
+    // a conduit that serves an outfall runs on a thread of its own at the start of the phase (engine_run): its
+    // update plus the outfall's normal / critical depth solve is the longest dependent chain of the phase
+    const int lflags = net.link_cols_i[(size_t)LRI_FLAGS * net.nTrue + jj];
+    const bool isPre = (lflags & (LF_N1_OUTFALL | LF_N2_OUTFALL)) && net.link_pre_node[j] >= 0;
+    if (isPre != wantPre) return;
     const int n1 = net.link_cols_i[(size_t)LRI_NODE1 * net.nTrue + jj], n2 = net.link_cols_i[(size_t)LRI_NODE2 * net.nTrue + jj];
     if (k >= 2) {
         const bool byp = st.n_converged[n1] && st.n_converged[n2];
@@ -173,7 +178,7 @@ SWB_FI void picard_link_single(const Net &net, const State &st, int jj, int k, d
         if (byp) return;
     }
     conduit_update_cols(net, st, j, jj, n1, n2, 0, k, dt, T);
-    if (net.link_cols_i[(size_t)LRI_FLAGS * net.nTrue + jj] & (LF_N1_OUTFALL | LF_N2_OUTFALL)) outfall_precompute(net, st, j, 0, T);
+    if (isPre) outfall_precompute(net, st, j, 0, T);
 }
 // node sums over the true conduits only, stored for the ordered regulator pass
 SWB_FI void picard_node_presum(const Net &net, const State &st, int i, int m)
@@ -1031,10 +1036,11 @@ SWB_ENGINE inline void engine_run(const Net &net, const State &st, const RunArgs
             for (int k = 0; k < maxTrials && nAlive > 0; k++) {
                 unsigned long long *tickets = st.tickets + SWB_TICKETS_PER_TRIAL * k;
                 // ---- findLinkFlows, pass (i): true conduits (dynwave.c:387-395)
+                if (!(args.debug & DBG_SKIP_LINKS) && M == 1 && ctx.tid < net.nPre)
+                    picard_link_single(net, st, net.pre_links[ctx.tid], k, st.dt[0], T, true);
                 if (!(args.debug & DBG_SKIP_LINKS))
                 for_tiles(ctx, net.nTrue, nAlive, tickets + TK_LINKS, [&](int jj, int mm) {
-                    if (M == 1) { int jr = jj + net.linkRot; if (jr >= net.nTrue) jr -= net.nTrue;
-                                  picard_link_single(net, st, jr, k, st.dt[0], T); }
+                    if (M == 1) picard_link_single(net, st, jj, k, st.dt[0], T, false);
                     else picard_link(net, st, net.link_order[jj], mm, k, st.dt[mm], T);
                 });
                 ctx.grid_sync();

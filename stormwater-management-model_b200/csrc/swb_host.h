@@ -17,7 +17,7 @@ namespace swb {
 
 struct Derived {
     std::vector<int> outfall_nodes, link_flags, adj_start, adj, adjq_start, adjq, nc_links, outfall_link, link_order,
-                     outfall_slot, link_pre_node,
+                     outfall_slot, link_pre_node, pre_links,
                      link_kernel, node_order;
     std::vector<double> link_z1, link_z2, xs_tables, culvert_params, road_tables, xs_rcp_yfull, cond_rcp_mod_length, link_rows, link_cols_d;
     std::vector<int> link_cols_i;
@@ -132,6 +132,8 @@ inline void derive(const swb_network_desc &d, const swb_options &o, Derived &r)
                          if (pa != pb) return pa;
                          return d.xs_type[a] < d.xs_type[b];
                      });
+    r.pre_links.clear();
+    for (size_t k = 0; k < r.link_order.size(); k++) if (r.link_pre_node[r.link_order[k]] >= 0) r.pre_links.push_back((int)k);
     // packed static rows of the true conduits, in ticket order (swb_dynwave.h: LR_*, CfStaged)
     r.link_rows.assign(r.link_order.size() * (size_t)LR_STRIDE, 0.0);
     for (size_t k = 0; k < r.link_order.size(); k++) {
@@ -213,9 +215,7 @@ inline void fill_net_scalars(Net &n, const swb_network_desc &d, const swb_option
     n.nOutfallNodes = (int)r.outfall_nodes.size();
     n.lk_count[0] = n.lk_count[1] = n.lk_count[2] = 0;
     for (int j : r.link_order) n.lk_count[r.link_kernel[j]]++;
-    n.linkRot = 0;
-    for (size_t k = 0; k < r.link_order.size(); k++)
-        if (r.link_pre_node[r.link_order[k]] >= 0) { n.linkRot = (int)k; break; }
+    n.nPre = (int)r.pre_links.size();
     n.anyLossRate = 0;
     for (int f : r.link_flags) if (f & LF_HAS_LOSSRATE) n.anyLossRate = 1;
     n.opt = o;

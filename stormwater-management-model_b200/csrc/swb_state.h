@@ -73,8 +73,8 @@ struct Net {
     int nTrue;               // true conduits
     int lk_count[3];         // of which per conduit-function class LK_* (link_order is grouped by class)
     int nNonConduit;         // links handled by the ordered regulator pass
-    int linkRot;             // single models: position in link_order the link phase starts drawing at (the first
-                             // conduit that serves an outfall: its depth solve then overlaps the rest of the phase)
+    int nPre;                // conduits that serve an outfall (link_pre_node >= 0); pre_links = their positions in
+                             // link_order: a single model hands each to a thread of its own at the start of the phase
     int nOutfallLinks;
     int anyLossRate;         // some conduit can evaporate / seep (LF_HAS_LOSSRATE)
     swb_options opt;
@@ -100,6 +100,7 @@ struct Net {
     const int    *nc_links;                // non-true-conduit links in ascending index order
     const int    *outfall_link;            // per node: its (single) link, or -1
     const int    *outfall_slot;            // per node: row of State::o_ynorm / o_ycrit its link's update fills, or -1
+    const int    *pre_links;               // [nPre] positions in link_order
     const int    *link_pre_node;           // per link: the outfall node whose normal / critical depth follows this
                                            // link's update (a true conduit that is that node's outfall_link), or -1
     const int    *outfall_nodes;           // outfall nodes in ascending index order

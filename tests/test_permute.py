@@ -101,3 +101,19 @@ def test_two_solvers_on_two_devices_in_one_process(cuda_lib):
         assert a.last_kernel_ms() > 0.0 and b.last_kernel_ms() > 0.0
     finally:
         a.close(); b.close(); ref.close()
+
+
+@pytest.mark.gpu
+def test_solver_larger_than_device_memory_fails_cleanly(cuda_lib):
+    """allocations are checked -- an ensemble that does not fit the device returns SWB_ERR_CUDA
+    (nothing half-built, no sticky error) and the device stays usable."""
+    from swmm_b200 import network, scenarios
+    case = network.build_grid(scenarios.GridSpec(nx=230, ny=230, hours=1.0))        # ~25 MB of state per member
+    with pytest.raises(solver.SwbError, match="(?i)memory|alloc"):
+        solver.Solver(case.net, 8192)                                               # ~205 GB > 180 GB of HBM
+    s = solver.Solver(case.net, 32)
+    s.load_state(case.state0)
+    s.set_inflows(**case.inflows)
+    s.run_steps(5, case.t_end)
+    assert all(x.steps == 5 for x in s.stats())
+    s.close()

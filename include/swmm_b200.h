@@ -321,6 +321,14 @@ typedef struct swb_inflow_desc {
     const double *dwf_avg;          /* avgValue, internal units                              */
     const int    *dwf_patterns;     /* [n_dwf][4] pattern index per pattern type or -1       */
     const double *pollut_dwf_concen;/* [n_pollut] Pollut.dwfConcen (NULL = 0)                */
+    /* routing interface file ("runoff once, route many"): the records of an inflows file, linear in time between
+     * two records exactly like iface_getNumIfaceNodes / getIfaceFlow / getIfaceQual (iface.c:187-275), added after
+     * the external and dry-weather inflows like addIfaceInflows (routing.c:736-775).  Flows in internal units,
+     * concentrations per PROJECT pollutant (0 where the file carries none).  The same for every member. */
+    int n_iface_nodes, n_iface_records;
+    const int    *iface_node;       /* [n_iface_nodes] project node of each file node (-1: not in the project) */
+    const double *iface_date;       /* [n_iface_records] DateTime of each record, ascending   */
+    const double *iface_value;      /* [record][file node][1 + n_pollut]                      */
 } swb_inflow_desc;
 
 int  swb_set_inflows(swb_solver *s, const swb_inflow_desc *inflows);

@@ -555,6 +555,9 @@ int swb_set_inflows(swb_solver *s, const swb_inflow_desc *d)
     }
     for (int p = 0; p < d->n_patterns; p++)
         if (d->pattern_type[p] < 0 || d->pattern_type[p] > 3) return fail(SWB_ERR_ARG, "pattern type out of range");
+    if (d->n_iface_nodes < 0 || d->n_iface_records < 0) return fail(SWB_ERR_ARG, "negative interface-file count");
+    for (int r = 1; r < d->n_iface_records && d->n_iface_nodes > 0; r++)
+        if (!(d->iface_date[r] > d->iface_date[r - 1])) return fail(SWB_ERR_ARG, "interface-file records are not in ascending date order");
     SWB_ENTER(s);
     // a second call replaces the first: its device arrays are released, not leaked
     for (void *q : s->inflow_allocs) backend::free_(q);
@@ -631,6 +634,17 @@ int swb_set_inflows(swb_solver *s, const swb_inflow_desc *d)
             f.dwf_avg = dev_copy<double>(al, avg.data(), nd);
             f.dwf_patterns = dev_copy<int>(al, pats.data(), (size_t)nd * 4);
             if (d->pollut_dwf_concen && nP > 0) f.pollut_dwf_concen = dev_copy<double>(al, d->pollut_dwf_concen, nP);
+            f.general = 1;
+        }
+        f.nIfaceNodes = f.nIfaceRec = 0; f.if_slot = nullptr; f.if_date = f.if_val = nullptr;
+        if (d->n_iface_nodes > 0 && d->n_iface_records > 0) {
+            std::vector<int> islot(nN, -1);
+            for (int k = 0; k < d->n_iface_nodes; k++)
+                if (d->iface_node[k] >= 0 && d->iface_node[k] < nN) islot[d->iface_node[k]] = k;
+            f.nIfaceNodes = d->n_iface_nodes; f.nIfaceRec = d->n_iface_records;
+            f.if_slot = dev_copy<int>(al, islot.data(), nN);
+            f.if_date = dev_copy<double>(al, d->iface_date, d->n_iface_records);
+            f.if_val = dev_copy<double>(al, d->iface_value, (size_t)d->n_iface_records * d->n_iface_nodes * (1 + nP));
             f.general = 1;
         }
     } catch (const DeviceError &e) {

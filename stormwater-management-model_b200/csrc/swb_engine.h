@@ -80,6 +80,10 @@ struct Inflows {               // device image of swb_inflow_desc
     const double *dwf_avg;
     const int    *dwf_patterns;                      // [record][4]
     const double *pollut_dwf_concen;                 // [nP]
+    // routing interface file records (null / 0 = none)
+    int nIfaceNodes, nIfaceRec;
+    const int    *if_slot;                           // [nN] file node of a project node or -1
+    const double *if_date, *if_val;                  // [nIfaceRec], [record][file node][1 + nP]
 };
 
 enum { DBG_SKIP_LINKS = 1, DBG_SKIP_NODES = 2 };   // RunArgs.debug (profiling aid: isolate one Picard phase)
@@ -145,6 +149,34 @@ SWB_HD double dwf_value(const Inflows &f, int r, const DateParts &d)
     }
     else if (p1 >= 0) fac *= pattern_factor(f, p1, d);
     return fac * f.dwf_avg[r];
+}
+
+// iface_getNumIfaceNodes (iface.c:187-215) without the file cursor: the bracket of `date` in the record dates and
+// the fraction between its ends.  rec = index of the NEW record, or -1 when the file has no data for the date.
+struct IfaceAt { int rec; double frac; };
+SWB_HD IfaceAt iface_bracket(const Inflows &f, double date)
+{
+    IfaceAt a = { -1, 0.0 };
+    const int R = f.nIfaceRec;
+    if (R <= 0 || f.if_date[0] > date) return a;                 // file begins after the current date
+    int lo = 0, hi = R;                                          // first record with date >= current date
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (f.if_date[mid] < date) lo = mid + 1; else hi = mid; }
+    if (lo >= R) return a;                                       // past the last record (NO_DATE)
+    a.rec = lo;
+    const double dNew = f.if_date[lo], dOld = f.if_date[lo > 0 ? lo - 1 : 0];
+    double frac = (date - dOld) / (dNew - dOld);                 // (0 / 0 at the very first record: NaN -> 1 below)
+    frac = SWB_MAX(0.0, frac);
+    frac = SWB_MIN(frac, 1.0);
+    a.frac = frac;
+    return a;
+}
+// (1 - f) * old + f * new of column c of file node k (iface.c:233-275); before the first record "old" is zero
+SWB_HD double iface_value(const Inflows &f, const IfaceAt &a, int k, int c, int nP)
+{
+    const size_t w = (size_t)(1 + nP), row = (size_t)f.nIfaceNodes * w;
+    const double v2 = f.if_val[(size_t)a.rec * row + (size_t)k * w + c];
+    const double v1 = a.rec > 0 ? f.if_val[(size_t)(a.rec - 1) * row + (size_t)k * w + c] : 0.0;
+    return (1.0 - a.frac) * v1 + a.frac * v2;
 }
 
 // ---- per-(object, member) bodies of the Picard phases --------------------------------------------
@@ -503,6 +535,8 @@ SWB_ENGINE inline void ph_prologue(const Net &net, const State &st, const RunArg
     const bool general = (ph & PH_INFLOWS) && F.general;
     DateParts dp = {0, 0, 0};
     if (general && F.nPatterns > 0) dp = date_parts(tNow);
+    IfaceAt ifAt = { -1, 0.0 };
+    if (general && F.nIfaceRec > 0) ifAt = iface_bracket(F, tNow);
     double exq[SWB_MAX_POLLUT];          // external quality mass rate booked by this thread (general inflows)
 #pragma unroll
     for (int p = 0; p < SWB_MAX_POLLUT; p++) exq[p] = 0.0;
@@ -529,7 +563,8 @@ SWB_ENGINE inline void ph_prologue(const Net &net, const State &st, const RunArg
         int slot = -1;
         // Node.oldLatFlow = newLatFlow (routing.c:330), only where this step sets a new one
         const double prevLat = (ph & (PH_INFLOWS | PH_HOSTIN)) ? st.n_latflow[ix] : 0.0;
-        double extq = 0.0, dwfq = 0.0, revq = 0.0;
+        double extq = 0.0, dwfq = 0.0, revq = 0.0, ifq = 0.0;
+        bool ifOn = false;
         if (ph & PH_INFLOWS) {
             // addExternalInflows (routing.c:435-490)
             slot = F.node_slot[i];
@@ -558,6 +593,11 @@ SWB_ENGINE inline void ph_prologue(const Net &net, const State &st, const RunArg
                             lat += dwfq;
                             break;
                         }
+            }
+            if (general && F.if_slot && F.if_slot[i] >= 0 && ifAt.rec >= 0) {
+                // addIfaceInflows (routing.c:736-775)
+                const double q = iface_value(F, ifAt, F.if_slot[i], 0, nP);
+                if (!(fabs(q) < SWB_FLOW_TOL)) { ifq = q; lat += q; ifOn = true; }
             }
             newLat = true;
         }
@@ -604,6 +644,7 @@ SWB_ENGINE inline void ph_prologue(const Net &net, const State &st, const RunArg
                             if (dc > 0.0) { w = dwfq * dc; c -= w; wsum -= w; }
                         }
                     }
+                    if (ifOn) { const double w = ifq * iface_value(F, ifAt, F.if_slot[i], 1 + p, nP); c += w; wsum += w; }
                     exq[p] += wsum;
                 }
                 if ((ph & PH_HOSTIN) && args.host_qual) c += hq[p];

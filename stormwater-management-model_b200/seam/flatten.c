@@ -387,6 +387,81 @@ static int series_len(int k)
     return n;
 }
 
+extern double Qcf[];                        /* swmm5.c: flow units conversion factors (iface.c:23) */
+
+static int flatten_iface(swb_flat *f, swb_inflow_desc *d, const char *path)
+{
+    FILE *fp = fopen(path, "rt");
+    char line[MAXLINE + 1], s1[MAXLINE + 1], s2[MAXLINE + 1];
+    int nFilePol = -1, units, nNodes = 0, i, j, k, nP = Nobjects[POLLUT], cap = 0, nRec = 0, w = 1 + nP;
+    int *polCol, *nodes;
+    double *dates = NULL, *vals = NULL;
+    if (!fp) return SWB_ERR_ARG;
+    if (!fgets(line, MAXLINE, fp) || !sscanf(line, "%s", s1) || !strcomp(s1, "SWMM5")) { fclose(fp); return SWB_ERR_ARG; }
+    fgets(line, MAXLINE, fp);                                   /* title */
+    fgets(line, MAXLINE, fp);                                   /* reporting step */
+    fgets(line, MAXLINE, fp);                                   /* number of constituents, FLOW included */
+    if (sscanf(line, "%d", &nFilePol)) nFilePol--;
+    if (nFilePol < 0) { fclose(fp); return SWB_ERR_ARG; }
+    fgets(line, MAXLINE, fp);
+    if (sscanf(line, "%s %s", s1, s2) < 2 || !strcomp(s1, "FLOW") || (units = findmatch(s2, FlowUnitWords)) < 0) { fclose(fp); return SWB_ERR_ARG; }
+    polCol = IARR(nP + 1);
+    for (i = 0; i < nP; i++) polCol[i] = -1;
+    for (i = 0; i < nFilePol; i++) {
+        fgets(line, MAXLINE, fp);
+        if (sscanf(line, "%s %s", s1, s2) < 2) { fclose(fp); return SWB_ERR_ARG; }
+        j = project_findObject(POLLUT, s1);
+        if (j >= 0) polCol[j] = i;
+    }
+    fgets(line, MAXLINE, fp);
+    if (!sscanf(line, "%d", &nNodes) || nNodes <= 0) { fclose(fp); return SWB_ERR_ARG; }
+    nodes = IARR(nNodes);
+    for (i = 0; i < nNodes; i++) {
+        fgets(line, MAXLINE, fp);
+        if (!sscanf(line, "%s", s1)) { fclose(fp); return SWB_ERR_ARG; }
+        nodes[i] = project_findObject(NODE, s1);
+    }
+    fgets(line, MAXLINE, fp);                                   /* column headings */
+    for (;;) {                                                  /* one record = one line per file node */
+        int yr = 0, mon = 0, day = 0, hr = 0, mi = 0, sec = 0, ok = 1;
+        if (nRec == cap) {
+            cap = cap ? 2 * cap : 256;
+            dates = (double *)realloc(dates, sizeof(double) * cap);
+            vals = (double *)realloc(vals, sizeof(double) * (size_t)cap * nNodes * w);
+        }
+        for (i = 0; i < nNodes && ok; i++) {
+            char *t;
+            double *row = vals + ((size_t)nRec * nNodes + i) * w;
+            double filev[64];
+            if (feof(fp) || !fgets(line, MAXLINE, fp) || strtok(line, SEPSTR) == NULL) { ok = 0; break; }
+#define NEXT_TOK() ((t = strtok(NULL, SEPSTR)) != NULL)
+            if (!NEXT_TOK()) { ok = 0; break; } yr = atoi(t);
+            if (!NEXT_TOK()) { ok = 0; break; } mon = atoi(t);
+            if (!NEXT_TOK()) { ok = 0; break; } day = atoi(t);
+            if (!NEXT_TOK()) { ok = 0; break; } hr = atoi(t);
+            if (!NEXT_TOK()) { ok = 0; break; } mi = atoi(t);
+            if (!NEXT_TOK()) { ok = 0; break; } sec = atoi(t);
+            if (!NEXT_TOK()) { ok = 0; break; }
+            row[0] = atof(t) / Qcf[units];
+            for (j = 0; j < nFilePol && j < 64; j++) { if (!NEXT_TOK()) { ok = 0; break; } filev[j] = atof(t); }
+#undef NEXT_TOK
+            if (!ok) break;
+            for (k = 0; k < nP; k++) row[1 + k] = (polCol[k] >= 0 && polCol[k] < 64) ? filev[polCol[k]] : 0.0;
+        }
+        if (!ok) break;
+        dates[nRec] = datetime_encodeDate(yr, mon, day) + datetime_encodeTime(hr, mi, sec);
+        nRec++;
+    }
+    fclose(fp);
+    {
+        double *dd = DARR(nRec + 1), *vv = DARR((size_t)(nRec + 1) * nNodes * w);
+        if (nRec) { memcpy(dd, dates, sizeof(double) * nRec); memcpy(vv, vals, sizeof(double) * (size_t)nRec * nNodes * w); }
+        free(dates); free(vals);
+        d->n_iface_nodes = nNodes; d->n_iface_records = nRec; d->iface_node = nodes; d->iface_date = dd; d->iface_value = vv;
+    }
+    return SWB_OK;
+}
+
 int swb_flatten_inflows(swb_flat *f, swb_inflow_desc *d)
 {
     int nN = Nobjects[NODE], nP = Nobjects[POLLUT], nPat = Nobjects[TIMEPATTERN], nTs = Nobjects[TSERIES];
@@ -495,6 +570,12 @@ int swb_flatten_inflows(swb_flat *f, swb_inflow_desc *d)
         for (p = 0; p < nP; p++) dc[p] = Pollut[p].dwfConcen;
         d->n_dwf = nd; d->dwf_node = dn; d->dwf_param = dp; d->dwf_avg = da; d->dwf_patterns = dpat;
         d->pollut_dwf_concen = dc;
+    }
+    /* routing interface file with inflows ([FILES] USE INFLOWS): the engine keeps only a two-record window of
+     * it (iface.c), so the file is read again here, header and records exactly as iface.c:380-600 does */
+    if (Finflows.mode == USE_FILE) {
+        int rc = flatten_iface(f, d, Finflows.name);
+        if (rc) return rc;
     }
     return SWB_OK;
 }

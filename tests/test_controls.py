@@ -222,3 +222,59 @@ def test_cuda_config3_full_size_ensemble_with_device_controls(cuda_lib, have_ref
     print(r)
     assert r["time_err_s"] < 1e-9 and r["iters_match"], r
     assert r["max_rel"] <= TOL, r
+
+
+# ---- routing interface file ("runoff once, route many") --------------------------------------------------
+def _write_interface_file(path, nodes, hours0, hours1, step_min, with_dye=True):
+    """An inflows interface file in the reference's own format (iface.c: openFileForOutput / saveOutletResults):
+    records from hours0 to hours1 -- starting after and ending before the simulation -- every step_min minutes."""
+    cols = ["FLOW CFS", "TSS MG/L"] + (["DYE MG/L"] if with_dye else [])
+    L = ["SWMM5 Interface File", "synthetic upstream model", f"{step_min * 60:<4d} - reporting time step in sec",
+         f"{len(cols):<4d} - number of constituents as listed below:"] + cols
+    L += [f"{len(nodes):<4d} - number of nodes as listed below:"] + nodes
+    L += ["Node             Year Mon Day Hr  Min Sec FLOW       " + "  ".join(c.split()[0] for c in cols[1:])]
+    t = int(hours0 * 60)
+    k = 0
+    while t <= int(hours1 * 60):
+        for n, node in enumerate(nodes):
+            q = 2.0 + 1.5 * np.sin(0.37 * k + n) + 0.8 * n
+            vals = [f"{q:<10f}", f"{40.0 + 10.0 * np.cos(0.11 * k):<10f}"] + ([f"{5.0 + 0.05 * k:<10f}"] if with_dye else [])
+            L.append(f"{node:<16s} 2020 01  01  {t // 60:02d}  {t % 60:02d}  00  " + " ".join(vals))
+        t += step_min
+        k += 1
+    with open(path, "w") as f:
+        f.write("\n".join(L) + "\n")
+
+
+@pytest.mark.parametrize("with_dye", [True, False])
+def test_emulated_interface_file_inflows_equal_reference(with_dye, emul_lib, have_reference, tmp_path):
+    """[FILES] USE INFLOWS: the file's records are flattened once (seam/flatten.c) and interpolated per member on
+    the device like iface_getIfaceFlow / getIfaceQual; a file that starts after and ends before the simulation
+    and lacks one of the project's pollutants; bit for bit against the reference for the whole 24 h."""
+    if not have_reference:
+        pytest.skip("oracle/_ref is not built")
+    path = str(tmp_path / "upstream.txt")
+    _write_interface_file(path, ["J3", "J5"], 1.0, 20.0, 15, with_dye)
+    inp = scenarios.c3_rules_inp(pid=False).replace("[JUNCTIONS]", f'[FILES]\nUSE INFLOWS "{path}"\n[JUNCTIONS]', 1)
+    r = pc.lockstep_vs_reference(inp, emul_lib, every=25, full=True, continuity=True)
+    print(r)
+    assert r["time_err_s"] == 0.0 and r["iterations"] == r["ref_iterations"], r
+    assert r["max_rel"] == 0.0, r
+    assert abs(r["flow_error_pct"] - r["ref_flow_error_pct"]) < 1e-4, r
+    assert abs(r["qual_error_pct"] - r["ref_qual_error_pct"]) < 1e-4, r
+    if with_dye:       # the file really feeds the run: the same model without it takes a different path
+        base = pc.lockstep_vs_reference(scenarios.c3_rules_inp(pid=False), emul_lib, every=100, full=True, max_steps=4000)
+        fed = pc.lockstep_vs_reference(inp, emul_lib, every=100, full=True, max_steps=4000)
+        assert base["iterations"] != fed["iterations"], (base["iterations"], fed["iterations"])
+
+
+@pytest.mark.gpu
+def test_cuda_interface_file_inflows_vs_reference(cuda_lib, have_reference, tmp_path):
+    assert have_reference, "oracle/_ref must travel to the GPU box"
+    path = str(tmp_path / "upstream.txt")
+    _write_interface_file(path, ["J3", "J5"], 1.0, 20.0, 15, True)
+    inp = scenarios.c3_rules_inp(pid=False).replace("[JUNCTIONS]", f'[FILES]\nUSE INFLOWS "{path}"\n[JUNCTIONS]', 1)
+    r = pc.lockstep_vs_reference(inp, None, every=25, full=True, max_steps=9000)
+    print(r)
+    assert r["time_err_s"] == 0.0 and r["iterations"] == r["ref_iterations"], r
+    assert r["max_rel"] <= TOL, r

@@ -755,10 +755,18 @@ template <class Ctx>
 SWB_ENGINE inline void ph_qual_nodes(const Net &net, const State &st, Ctx &ctx, const ThreadMap &tm, double dt, int nNo)
 {
     const int M = st.M, m = tm.m, first = tm.first, stride = tm.stride;
-    for (int p = 0; p < net.nP; p++) {
-        QualAcc acc = {0.0, 0.0, 0.0};
-        SWB_FOR_ITEMS(i, nNo) qual_node(net, st, i, m, p, dt, acc);
-        qual_acc_flush(ctx, st, p, m, M, dt, acc);
+    // pollutants in pairs: one sweep over the nodes serves two of them (swb_qual.h)
+    for (int p0 = 0; p0 < net.nP; p0 += 2) {
+        if (p0 + 1 < net.nP) {
+            QualAcc acc[2] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+            SWB_FOR_ITEMS(i, nNo) qual_node<2>(net, st, i, m, p0, dt, acc);
+            qual_acc_flush(ctx, st, p0, m, M, dt, acc[0]);
+            qual_acc_flush(ctx, st, p0 + 1, m, M, dt, acc[1]);
+        } else {
+            QualAcc acc[1] = {{0.0, 0.0, 0.0}};
+            SWB_FOR_ITEMS(i, nNo) qual_node<1>(net, st, i, m, p0, dt, acc);
+            qual_acc_flush(ctx, st, p0, m, M, dt, acc[0]);
+        }
     }
 }
 template <class Ctx>
@@ -767,11 +775,20 @@ SWB_ENGINE inline void ph_qual_links(const Net &net, const State &st, Ctx &ctx, 
     const int M = st.M, nL = net.nL, m = tm.m, first = tm.first, stride = tm.stride;
     const Halo &H = st.halo;
     const bool part = H.nRanks > 1;
-    for (int p = 0; p < net.nP; p++) {
-        QualAcc acc = {0.0, 0.0, 0.0}, copy = {0.0, 0.0, 0.0};
+    for (int p0 = 0; p0 < net.nP; p0 += 2) {
         // the copy of a cut conduit is routed too, but only its owner reports the losses
-        SWB_FOR_ITEMS(j, nL) qual_link(net, st, j, m, p, dt, (part && !H.link_owned[j]) ? copy : acc);
-        qual_acc_flush(ctx, st, p, m, M, dt, acc);
+        if (p0 + 1 < net.nP) {
+            QualAcc acc[2] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}}, copy[2] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+            SWB_FOR_ITEMS(j, nL) { if (part && !H.link_owned[j]) qual_link<2>(net, st, j, m, p0, dt, copy);
+                                   else qual_link<2>(net, st, j, m, p0, dt, acc); }
+            qual_acc_flush(ctx, st, p0, m, M, dt, acc[0]);
+            qual_acc_flush(ctx, st, p0 + 1, m, M, dt, acc[1]);
+        } else {
+            QualAcc acc[1] = {{0.0, 0.0, 0.0}}, copy[1] = {{0.0, 0.0, 0.0}};
+            SWB_FOR_ITEMS(j, nL) { if (part && !H.link_owned[j]) qual_link<1>(net, st, j, m, p0, dt, copy);
+                                   else qual_link<1>(net, st, j, m, p0, dt, acc); }
+            qual_acc_flush(ctx, st, p0, m, M, dt, acc[0]);
+        }
     }
 }
 

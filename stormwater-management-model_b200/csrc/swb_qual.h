@@ -39,31 +39,38 @@ SWB_FI double qual_reacted(double kDecay, double c, double v1, double tStep, dou
     return c2;
 }
 
-// node i, pollutant p.  n_qual holds the external mass-rate preload on entry (routing.c:488 ...),
-// the new concentration on exit.
-SWB_FI void qual_node(const Net &n, const State &s, int i, int m, int p, double tStep,
-                             QualAcc &acc)
+// node i, pollutants p0 .. p0 + K - 1 in ONE pass over the node's fields and incident links (K = 1 or 2: the
+// hydraulic values -- link flows, node inflow, volumes, depth -- are the same for every pollutant, so a second
+// pollutant costs only its own concentrations instead of a second sweep over the state).  Per pollutant the
+// operations and their order are those of findLinkMassFlow / findNodeQual / findStorageQual (qualrout.c:
+// 179-249, 398-494).  n_qual holds the external mass-rate preload on entry (routing.c:488 ...), the new
+// concentration on exit.
+template <int K>
+SWB_FI void qual_node(const Net &n, const State &s, int i, int m, int p0, double tStep, QualAcc (&acc)[K])
 {
     const int M = s.M;
-    const size_t ix = SWB_IX(i, m, M), ixq = SWB_IXP(p, i, n.nN, m, M);
+    const size_t ix = SWB_IX(i, m, M);
+    size_t ixq[K];
+    double w[K];
+#pragma unroll
+    for (int t = 0; t < K; t++) { ixq[t] = SWB_IXP(p0 + t, i, n.nN, m, M); w[t] = s.n_qual[ixq[t]]; }
     // --- link mass flows into this node, ascending link index (qualrout.c:112, 179-217)
-    double w = s.n_qual[ixq];
     for (int k = n.adjq_start[i]; k < n.adjq_start[i + 1]; k++) {
         int e = n.adjq[k], j = e >> 1, end = e & 1;
         double q = s.l_flow[SWB_IX(j, m, M)];
         bool into = (q < 0.0) ? (end == 0) : (end == 1);
         if (!into) continue;
-        w += fabs(q) * s.l_old_qual[SWB_IXP(p, j, n.nL, m, M)];
+#pragma unroll
+        for (int t = 0; t < K; t++) w[t] += fabs(q) * s.l_old_qual[SWB_IXP(p0 + t, j, n.nL, m, M)];
     }
     double qIn = s.n_inflow[ix];                       // Node.qualInflow = Node.inflow (:118)
     double oldVolume = s.n_old_volume[ix];
     bool isStorage = (n.node_type[i] == SWB_STORAGE);
-    double c2;
     if (isStorage || oldVolume > SWB_ZERO_VOLUME) {
         // findStorageQual (qualrout.c:398-474)
         double v1 = oldVolume, qExfil = 0.0, vEvap = 0.0, fEvap = 1.0;
         if (isStorage) {
-            if (p == 0) {                              // updateHRT once per node (:478-494)
+            if (p0 == 0) {                             // updateHRT once per node (:478-494)
                 double hrt = s.n_hrt[ix];
                 if (v1 < SWB_ZERO) hrt = 0.0;
                 else hrt = (hrt + tStep) * v1 / (v1 + qIn * tStep);
@@ -73,42 +80,59 @@ SWB_FI void qual_node(const Net &n, const State &s, int i, int m, int p, double 
             vEvap = s.n_evap_loss[ix];
             if (vEvap > 0.0 && v1 > SWB_ZERO_VOLUME) fEvap += vEvap / v1;
         }
-        double c1 = s.n_old_qual[ixq];
-        acc.seepage += qExfil * c1;
-        c1 *= fEvap;
-        c1 = qual_reacted(n.pollut_kdecay[p], c1, v1, tStep, acc.reacted);
-        c2 = qual_mixed(c1, v1, w, qIn, tStep);
-        double newVolume = s.n_volume[ix];
-        if ((newVolume <= SWB_ZERO_VOLUME || s.n_depth[ix] <= SWB_ZERO_DEPTH) && qIn <= SWB_ZERO) {
-            acc.finalStorage += c2 * newVolume;
-            c2 = 0.0;
+        const double newVolume = s.n_volume[ix];
+        const bool emptied = (newVolume <= SWB_ZERO_VOLUME || s.n_depth[ix] <= SWB_ZERO_DEPTH) && qIn <= SWB_ZERO;
+        double cOld[K];                                 // (all loads before the first store)
+#pragma unroll
+        for (int t = 0; t < K; t++) cOld[t] = s.n_old_qual[ixq[t]];
+#pragma unroll
+        for (int t = 0; t < K; t++) {
+            double c1 = cOld[t];
+            acc[t].seepage += qExfil * c1;
+            c1 *= fEvap;
+            c1 = qual_reacted(n.pollut_kdecay[p0 + t], c1, v1, tStep, acc[t].reacted);
+            double c2 = qual_mixed(c1, v1, w[t], qIn, tStep);
+            if (emptied) { acc[t].finalStorage += c2 * newVolume; c2 = 0.0; }
+            s.n_qual[ixq[t]] = c2;
         }
     } else {
         // findNodeQual (qualrout.c:221-249)
-        if (qIn > SWB_ZERO) c2 = w / qIn;
-        else if (s.n_depth[ix] > SWB_ZERO_DEPTH) c2 = s.n_old_qual[ixq];
-        else c2 = 0.0;
+        const bool wet = s.n_depth[ix] > SWB_ZERO_DEPTH;
+#pragma unroll
+        for (int t = 0; t < K; t++) {
+            double c2;
+            if (qIn > SWB_ZERO) c2 = w[t] / qIn;
+            else if (wet) c2 = s.n_old_qual[ixq[t]];
+            else c2 = 0.0;
+            s.n_qual[ixq[t]] = c2;
+        }
     }
-    s.n_qual[ixq] = c2;
 }
 
-// link j, pollutant p
-SWB_FI void qual_link(const Net &n, const State &s, int j, int m, int p, double tStep, QualAcc &acc)
+// link j, pollutants p0 .. p0 + K - 1 (qualrout.c:253-394), one pass over the link's hydraulic values
+template <int K>
+SWB_FI void qual_link(const Net &n, const State &s, int j, int m, int p0, double tStep, QualAcc (&acc)[K])
 {
     const int M = s.M;
-    const size_t ix = SWB_IX(j, m, M), iq = SWB_IXP(p, j, n.nL, m, M);
+    const size_t ix = SWB_IX(j, m, M);
     const double newFlow = s.l_flow[ix];
     double qAbs = fabs(newFlow);                       // totalLoad (qualrout.c:210-214)
     int up = n.link_node1[j];
     if (newFlow < 0.0) up = n.link_node2[j];
-    double c1 = s.l_old_qual[iq];
     // every load of this link is issued before its first store (the arrays may alias as far as
     // the compiler knows, so a load placed after a store waits for a second DRAM round trip)
-    const double load0 = s.l_total_load[iq];
-    const double cUp = s.n_qual[SWB_IXP(p, up, n.nN, m, M)];
+    size_t iq[K];
+    double c1[K], load0[K], cUp[K];
+#pragma unroll
+    for (int t = 0; t < K; t++) {
+        iq[t] = SWB_IXP(p0 + t, j, n.nL, m, M);
+        c1[t] = s.l_old_qual[iq[t]];
+        load0[t] = s.l_total_load[iq[t]];
+        cUp[t] = s.n_qual[SWB_IXP(p0 + t, up, n.nN, m, M)];
+    }
     if (!(n.link_flags[j] & LF_TRUE_CONDUIT)) {
-        s.l_total_load[iq] = load0 + qAbs * c1 * tStep;
-        s.l_qual[iq] = cUp;
+#pragma unroll
+        for (int t = 0; t < K; t++) { s.l_total_load[iq[t]] = load0[t] + qAbs * c1[t] * tStep; s.l_qual[iq[t]] = cUp[t]; }
         return;
     }
     double barrels = (double)n.cond_barrels[j];
@@ -120,19 +144,25 @@ SWB_FI void qual_link(const Net &n, const State &s, int j, int m, int p, double 
     }
     double v1 = s.l_old_volume[ix], v2 = s.l_volume[ix];
     const double depth = s.l_depth[ix];
-    s.l_total_load[iq] = load0 + qAbs * c1 * tStep;
+#pragma unroll
+    for (int t = 0; t < K; t++) s.l_total_load[iq[t]] = load0[t] + qAbs * c1[t] * tStep;
     double vLosses = qSeep * tStep + vEvap;
     double fEvap = 1.0;
     if (vEvap > 0.0 && v1 > SWB_ZERO_VOLUME) fEvap += vEvap / v1;
     qIn = qIn + (v2 + vLosses - v1) / tStep;
     qIn = SWB_MAX(qIn, 0.0);
-    acc.seepage += qSeep * c1;
-    c1 *= fEvap;
-    double c2 = qual_reacted(n.pollut_kdecay[p], c1, v1, tStep, acc.reacted);
-    double wIn = cUp * qIn;
-    c2 = qual_mixed(c2, v1, wIn, qIn, tStep);
-    if (v2 < SWB_ZERO_VOLUME || depth <= SWB_ZERO_DEPTH) { acc.finalStorage += c2 * v2; c2 = 0.0; }
-    s.l_qual[iq] = c2;
+    const bool emptied = (v2 < SWB_ZERO_VOLUME || depth <= SWB_ZERO_DEPTH);
+#pragma unroll
+    for (int t = 0; t < K; t++) {
+        double c = c1[t];
+        acc[t].seepage += qSeep * c;
+        c *= fEvap;
+        double c2 = qual_reacted(n.pollut_kdecay[p0 + t], c, v1, tStep, acc[t].reacted);
+        double wIn = cUp[t] * qIn;
+        c2 = qual_mixed(c2, v1, wIn, qIn, tStep);
+        if (emptied) { acc[t].finalStorage += c2 * v2; c2 = 0.0; }
+        s.l_qual[iq[t]] = c2;
+    }
 }
 
 } // namespace swb

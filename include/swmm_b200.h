@@ -409,7 +409,9 @@ int  swb_get_massbal(swb_solver *s, int member0, int n_members, double *reacted,
  * NEW_VOLUME and NEW_VOLUME x NEW_QUAL over nodes and links) these give the continuity errors of
  * massbal_getFlowError / massbal_getQualError (massbal.c:858-960) for every member.  Either may be NULL. */
 int  swb_get_routing_totals(swb_solver *s, int member0, int n_members, double *flow, double *qual);
-/* conduit-updates performed so far: sum over members of iterations x true conduits */
+/* conduit-updates performed so far: sum over members of Picard iterations x true conduits -- the metric of
+ * BASELINE.json / SURVEY 8(d), i.e. trial SLOTS: a conduit the reference's bypass rule skips in a late trial
+ * (dynwave.c:335-345) still counts, for the device and for the reference arm of bench.py alike */
 long long swb_conduit_updates(swb_solver *s);
 
 /* ---- one network partitioned over several GPUs (BASELINE.json configs[4]) --------------

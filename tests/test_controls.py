@@ -278,3 +278,97 @@ def test_cuda_interface_file_inflows_vs_reference(cuda_lib, have_reference, tmp_
     print(r)
     assert r["time_err_s"] == 0.0 and r["iterations"] == r["ref_iterations"], r
     assert r["max_rel"] <= TOL, r
+
+
+def test_emulated_timeseries_outfall_stage_equals_reference(emul_lib, have_reference):
+    """A TIMESERIES outfall (node.c:1449-1455): its stage series is evaluated per member on the device with the
+    routing time already advanced, extended beyond both ends of the series like table_tseriesLookup(.., TRUE)."""
+    if not have_reference:
+        pytest.skip("oracle/_ref is not built")
+    inp = scenarios.c3_rules_inp(pid=False)
+    assert "O2 96 FIXED 97.5 YES" in inp
+    inp = inp.replace("O2 96 FIXED 97.5 YES", "O2 96 TIMESERIES STG YES")
+    inp = inp.replace("[TIMESERIES]\n", "[TIMESERIES]\nSTG 2:00 96.8\nSTG 6:00 98.4\nSTG 11:00 97.1\nSTG 18:30 98.0\n", 1)
+    r = pc.lockstep_vs_reference(inp, emul_lib, every=25, full=True, max_steps=None)
+    print(r)
+    assert r["time_err_s"] == 0.0 and r["iterations"] == r["ref_iterations"], r
+    assert r["max_rel"] == 0.0, r
+
+
+RULES_B = """[CONTROLS]
+RULE B1
+IF NODE S1 HEAD > 109.5
+AND NODE S1 VOLUME > 4000
+THEN ORIFICE OR1 SETTING = 0.9
+ELSE ORIFICE OR1 SETTING = 0.4
+RULE B2
+IF NODE J1 INFLOW > 12
+OR LINK C3 FLOW > 14
+THEN WEIR W1 SETTING = 0.6
+ELSE WEIR W1 SETTING = 1.0
+RULE B3
+IF LINK C3 DEPTH > LINK C3 FULLDEPTH
+THEN PUMP P1 SETTING = 1.3
+PRIORITY 2
+RULE B4
+IF PUMP P1 STATUS = ON
+AND ORIFICE OR1 SETTING >= 0.9
+THEN OUTLET OL1 SETTING = 0.7
+ELSE OUTLET OL1 SETTING = 1.0
+RULE B5
+IF PUMP P1 TIMECLOSED > 0:30
+THEN PUMP P1 STATUS = ON
+PRIORITY 1
+RULE B6
+IF SIMULATION DATE = 01/01/2020
+AND SIMULATION DAYOFYEAR = 1
+AND LINK C4 FULLFLOW > 1
+AND LINK C4 LENGTH > 100
+AND LINK C4 SLOPE > 0.0001
+AND NODE S2 DEPTH < NODE S2 MAXDEPTH
+THEN ORIFICE OR2 SETTING = 0.8
+ELSE ORIFICE OR2 SETTING = 0.2
+RULE B7
+IF SIMULATION TIME > 16
+THEN CONDUIT C8 STATUS = CLOSED
+"""
+
+
+def test_emulated_rule_vocabulary_b_equals_reference(emul_lib, have_reference):
+    """The premise attributes the first rule base does not use: HEAD, VOLUME, INFLOW, MAXDEPTH as a right-hand
+    side, link FLOW / DEPTH / FULLDEPTH / FULLFLOW / LENGTH / SLOPE, pump STATUS and orifice SETTING premises,
+    TIMECLOSED, DATE, DAYOFYEAR, a pump speed setting."""
+    if not have_reference:
+        pytest.skip("oracle/_ref is not built")
+    base = scenarios.c3_mixed_inp()
+    a, b = base.index("[CONTROLS]"), base.index("[POLLUTANTS]")
+    inp = base[:a] + RULES_B + base[b:]
+    r = pc.lockstep_vs_reference(inp, emul_lib, every=25, full=True)
+    print(r)
+    assert r["time_err_s"] == 0.0 and r["iterations"] == r["ref_iterations"], r
+    assert r["max_rel"] == 0.0, r
+
+
+def test_emulated_mass_inflows_patterns_and_dwf_quality_equal_reference(emul_lib, have_reference):
+    """What the mixed-element model's [INFLOWS] / [DWF] do not use: a MASS pollutant inflow with its own
+    series, a baseline pattern on a FLOW inflow, a pollutant baseline with a pattern, a dry-weather
+    concentration record with monthly + hourly patterns and the pollutant's default DWF concentration
+    (inflow.c:207-234, 361-392; routing.c:499-575)."""
+    if not have_reference:
+        pytest.skip("oracle/_ref is not built")
+    inp = scenarios.c3_mixed_inp()
+    for old, new in (("J1 TSS TSC CONCEN 1.0 1.0", "J1 TSS TSM MASS 2.5 1.0 0.3 DAILYP"),
+                     ("J2 FLOW TS1 FLOW 1.0 0.5 0.2", "J2 FLOW TS1 FLOW 1.0 0.5 0.2 DAILYP"),
+                     ("J2 DYE TSC CONCEN 1.0 0.5", "J2 DYE TSC CONCEN 1.0 0.5 20 MONP"),
+                     ("J3 FLOW 0.3 DAILYP", "J3 FLOW 0.3 MONP DAILYP\nJ3 TSS 25 DAILYP\nJ4 FLOW 0.1"),
+                     ("DAILYP HOURLY", "MONP MONTHLY 1.1 1.0 0.9 1.0 1.0 1.0 1.0 1.0 1.0 1.0 1.0 1.0\nDAILYP HOURLY"),
+                     ("TSC 0:00 100", "TSM 0:00 5\nTSM 6:00 40\nTSM 20:00 2\nTSC 0:00 100"),
+                     ("DYE MG/L 0 0 0 0", "DYE MG/L 0 0 0 0 NO * 0 7.5")):
+        assert old in inp, old
+        inp = inp.replace(old, new, 1)
+    r = pc.lockstep_vs_reference(inp, emul_lib, every=25, full=True, continuity=True)
+    print(r)
+    assert r["time_err_s"] == 0.0 and r["iterations"] == r["ref_iterations"], r
+    assert r["max_rel"] == 0.0, r
+    assert abs(r["flow_error_pct"] - r["ref_flow_error_pct"]) < 1e-4, r
+    assert abs(r["qual_error_pct"] - r["ref_qual_error_pct"]) < 1e-4, r
